@@ -1,0 +1,464 @@
+// C ABI of libimpop_b200.so (see include/impop_b200.h).  Host-side plumbing only: argument
+// checks, device tables, scratch ownership and kernel launches on the caller's stream.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace impop {
+cudaError_t launch_heavy_count(const uint32_t *, const int64_t *, const int32_t *, int32_t, int32_t *, cudaStream_t);
+cudaError_t launch_harmonic_table(double2 *, int32_t, cudaStream_t);
+cudaError_t launch_prep(const WindowTab &, int32_t *, cudaStream_t);
+cudaError_t configure_kernels();
+cudaError_t launch_pairs(const WindowTab &, const ItemParams &, int, int, cudaStream_t);
+cudaError_t launch_colstat(const WindowTab &, int64_t *, cudaStream_t);
+cudaError_t launch_window_sums(const WindowTab &, const double *, int, int, double *, cudaStream_t);
+cudaError_t launch_finalize(const WindowTab &, const double *, int, const int64_t *, double *, cudaStream_t);
+cudaError_t launch_export_a(const int32_t *, int32_t, int64_t *, cudaStream_t);
+cudaError_t launch_pack_bits(const uint8_t *, int32_t, int32_t, int64_t, uint32_t *, int32_t, cudaStream_t);
+int reduce_identity_blocks(int32_t n);
+cudaError_t launch_reduce_identity(const double *, int32_t, int64_t, const uint8_t *, const double *, int64_t, double,
+                                   const double2 *, int32_t, double *, double *, int64_t *, double *, cudaStream_t);
+cudaError_t launch_tajima(const int64_t *, const double *, const double *, int32_t, double *, double *, cudaStream_t);
+cudaError_t launch_site_counts(const uint64_t *, int64_t, int32_t, const uint64_t *, int32_t, int32_t *, double *, int,
+                               cudaStream_t);
+cudaError_t launch_cluster(const double *, int32_t, int64_t, double, int32_t *, int32_t *, cudaStream_t);
+cudaError_t launch_greedy_groups(const double *, int32_t, int64_t, double, int32_t *, double *, cudaStream_t);
+}  // namespace impop
+
+using namespace impop;
+
+constexpr int32_t HARM_N = 1 << 16;
+
+struct impop_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int32_t *err_dev = nullptr;
+    double2 *harm_dev = nullptr;
+    double *ri_scratch = nullptr;     // reduce_identity partials
+    int32_t *cluster_parent = nullptr;
+    int32_t cluster_cap = 0;
+    int64_t launches = 0;
+    std::string last_error;
+    // optional per-kernel timing (impop_timing_enable): event pairs recorded on the caller's stream
+    bool timing = false;
+    struct Slot { cudaEvent_t a, b; int kid; };
+    std::vector<Slot> slots;       // recorded launches since the last enable/read
+    std::vector<Slot> spare;       // recycled event pairs
+};
+
+constexpr size_t MAX_TIMING_SLOTS = 1 << 14;
+
+// Launch `fn` on `st`, bracketed by events when timing is on.  Events add no synchronisation.
+template <typename F>
+static cudaError_t timed(impop_ctx *ctx, int kid, cudaStream_t st, F fn) {
+    if (!ctx->timing || ctx->slots.size() >= MAX_TIMING_SLOTS) return fn();
+    impop_ctx::Slot s;
+    if (!ctx->spare.empty()) { s = ctx->spare.back(); ctx->spare.pop_back(); }
+    else {
+        cudaError_t e = cudaEventCreate(&s.a);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreate(&s.b);
+        if (e != cudaSuccess) return e;
+    }
+    s.kid = kid;
+    cudaEventRecord(s.a, st);
+    cudaError_t e = fn();
+    cudaEventRecord(s.b, st);
+    ctx->slots.push_back(s);
+    return e;
+}
+
+struct impop_batch {
+    WindowTab tab{};
+    std::vector<void *> owned;        // device allocations owned by the batch
+    std::vector<int64_t> item_off;    // host copy
+    std::vector<int32_t> n;
+    int64_t items = 0;
+    double *partials = nullptr;
+    double *sums_tmp = nullptr;
+    int64_t *counts_tmp = nullptr;
+    int32_t *counter = nullptr;
+};
+
+static int fail(impop_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+static int cuda_fail(impop_ctx *ctx, cudaError_t e, const char *where) {
+    return fail(ctx, IMPOP_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+static int64_t items_of(int32_t n) {
+    int64_t nb = (n + TILE_M - 1) / TILE_M, t = 0;
+    for (int64_t bi = 0; bi < nb; ++bi) t += (nb - bi + 1) / 2;
+    return t;
+}
+
+template <typename T>
+static cudaError_t upload(impop_batch *b, const std::vector<T> &host, const T **dev_out) {
+    T *d = nullptr;
+    size_t bytes = sizeof(T) * (host.empty() ? 1 : host.size());
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return e;
+    b->owned.push_back(d);
+    if (!host.empty()) e = cudaMemcpy(d, host.data(), sizeof(T) * host.size(), cudaMemcpyHostToDevice);
+    *dev_out = d;
+    return e;
+}
+
+template <typename T>
+static cudaError_t scratch(impop_batch *b, int64_t count, T **dev_out) {
+    T *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(T) * (size_t)(count > 0 ? count : 1));
+    if (e != cudaSuccess) return e;
+    b->owned.push_back(d);
+    *dev_out = d;
+    return cudaSuccess;
+}
+
+extern "C" {
+
+int impop_version(void) { return 100; }
+
+int impop_create(int device, impop_ctx_t **ctx_out) {
+    if (!ctx_out) return IMPOP_ERR_ARG;
+    *ctx_out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return IMPOP_ERR_CUDA;
+    impop_ctx *ctx = new (std::nothrow) impop_ctx();
+    if (!ctx) return IMPOP_ERR_NOMEM;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return IMPOP_ERR_CUDA;
+    }
+    if (prop.major != 10) {   // sm_100a cubin only: fail loudly rather than fall back
+        delete ctx;
+        return IMPOP_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaMalloc(&ctx->err_dev, sizeof(int32_t)) == cudaSuccess &&
+              cudaMemset(ctx->err_dev, 0, sizeof(int32_t)) == cudaSuccess &&
+              cudaMalloc(&ctx->harm_dev, sizeof(double2) * (HARM_N + 1)) == cudaSuccess &&
+              cudaMalloc(&ctx->ri_scratch, sizeof(double) * 16 * 148 * 4) == cudaSuccess &&
+              configure_kernels() == cudaSuccess && launch_harmonic_table(ctx->harm_dev, HARM_N, 0) == cudaSuccess &&
+              cudaDeviceSynchronize() == cudaSuccess;
+    if (!ok) {
+        cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->ri_scratch);
+        delete ctx;
+        return IMPOP_ERR_CUDA;
+    }
+    ctx->launches = 1;
+    *ctx_out = ctx;
+    return IMPOP_OK;
+}
+
+int impop_destroy(impop_ctx_t *ctx) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->ri_scratch); cudaFree(ctx->cluster_parent);
+    for (auto *v : {&ctx->slots, &ctx->spare})
+        for (auto &s : *v) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    delete ctx;
+    return IMPOP_OK;
+}
+
+int impop_timing_enable(impop_ctx_t *ctx, int32_t enable) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    for (auto &s : ctx->slots) ctx->spare.push_back(s);
+    ctx->slots.clear();
+    ctx->timing = enable != 0;
+    return IMPOP_OK;
+}
+
+int impop_timing_read(impop_ctx_t *ctx, int32_t kernel_id, double *total_ms, int64_t *launches) {
+    if (!ctx || !total_ms || !launches) return IMPOP_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    double tot = 0.0;
+    int64_t cnt = 0;
+    for (auto &s : ctx->slots) {
+        if (s.kid != kernel_id) continue;
+        CU(cudaEventSynchronize(s.b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s.a, s.b));
+        tot += ms;
+        ++cnt;
+    }
+    *total_ms = tot;
+    *launches = cnt;
+    return IMPOP_OK;
+}
+
+const char *impop_last_error(impop_ctx_t *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int64_t impop_launch_count(impop_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
+
+int impop_check(impop_ctx_t *ctx, void *stream) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    int32_t flag = 0;
+    CU(cudaMemcpy(&flag, ctx->err_dev, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag != DEV_OK) {
+        cudaMemset(ctx->err_dev, 0, sizeof(int32_t));
+        if (flag == DEV_ERR_RANGE) return fail(ctx, IMPOP_ERR_RANGE, "a window violates sum(node_len) < 2^31");
+        return fail(ctx, IMPOP_ERR_DEVICE, "device-side barrier time-out in the pairwise kernel");
+    }
+    return IMPOP_OK;
+}
+
+int impop_pack_bits(impop_ctx_t *ctx, const uint8_t *dense_dev, int32_t n, int32_t m, int64_t dense_pitch,
+                    uint32_t *x_dev, int32_t pitch_words, void *stream) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    if (n < 0 || m < 0 || pitch_words < 0 || (n > 0 && m > 0 && (!dense_dev || !x_dev)) || dense_pitch < m ||
+        (int64_t)pitch_words * 32 < m)
+        return fail(ctx, IMPOP_ERR_ARG, "impop_pack_bits: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_pack_bits(dense_dev, n, m, dense_pitch, x_dev, pitch_words, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return IMPOP_OK;
+}
+
+int impop_batch_destroy(impop_ctx_t *ctx, impop_batch_t *batch) {
+    if (!ctx || !batch) return IMPOP_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    for (void *p : batch->owned) cudaFree(p);
+    delete batch;
+    return IMPOP_OK;
+}
+
+int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batch_t **batch_out) {
+    if (!ctx || !d || !batch_out) return IMPOP_ERR_ARG;
+    *batch_out = nullptr;
+    const int32_t W = d->windows;
+    if (W < 0) return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: negative window count");
+    if (W > 0 && (!d->n_host || !d->m_host || !d->pitch_words_host || !d->x_off_host || !d->len_off_host ||
+                  !d->lab_off_host || !d->length_host))
+        return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: null descriptor array");
+    std::vector<int32_t> n(d->n_host, d->n_host + W), m(d->m_host, d->m_host + W),
+        pitch(d->pitch_words_host, d->pitch_words_host + W);
+    std::vector<int64_t> x_off(d->x_off_host, d->x_off_host + W), len_off(d->len_off_host, d->len_off_host + W),
+        lab_off(d->lab_off_host, d->lab_off_host + W), L(d->length_host, d->length_host + W);
+    std::vector<int64_t> row_off(W + 1, 0), w8_off(W + 1, 0), item_off(W + 1, 0), heavy_off(W + 1, 0);
+    bool any_rows = false, any_nodes = false;
+    for (int32_t w = 0; w < W; ++w) {
+        if (n[w] < 0 || m[w] < 0 || n[w] > (1 << 24) || m[w] > (1 << 24))
+            return fail(ctx, IMPOP_ERR_RANGE, "impop_batch_create: n or m out of range (max 2^24)");
+        if (pitch[w] % 4 != 0 || x_off[w] % 4 != 0 || (int64_t)pitch[w] * 32 < m[w])
+            return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: pitch_words / x_off must be multiples of 4 and cover m");
+        if (x_off[w] < 0 || len_off[w] < 0 || lab_off[w] < 0)
+            return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: negative offset");
+        row_off[w + 1] = row_off[w] + n[w];
+        w8_off[w + 1] = w8_off[w] + ((int64_t)(m[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
+        item_off[w + 1] = item_off[w] + items_of(n[w]);
+        any_rows |= n[w] > 0;
+        any_nodes |= m[w] > 0;
+    }
+    if ((any_rows && any_nodes && !d->x_dev) || (any_nodes && !d->node_len_dev) || (any_rows && !d->labels_dev))
+        return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: null device array");
+    CU(cudaSetDevice(ctx->device));
+    impop_batch *b = new (std::nothrow) impop_batch();
+    if (!b) return fail(ctx, IMPOP_ERR_NOMEM, "impop_batch_create: out of host memory");
+    WindowTab &t = b->tab;
+    cudaError_t e = cudaSuccess;
+    auto bail = [&](cudaError_t err, const char *where) {
+        impop_batch_destroy(ctx, b);
+        return cuda_fail(ctx, err, where);
+    };
+    if ((e = upload(b, n, &t.n)) != cudaSuccess) return bail(e, "upload n");
+    if ((e = upload(b, m, &t.m)) != cudaSuccess) return bail(e, "upload m");
+    if ((e = upload(b, pitch, &t.pitch)) != cudaSuccess) return bail(e, "upload pitch");
+    if ((e = upload(b, x_off, &t.x_off)) != cudaSuccess) return bail(e, "upload x_off");
+    if ((e = upload(b, len_off, &t.len_off)) != cudaSuccess) return bail(e, "upload len_off");
+    if ((e = upload(b, lab_off, &t.lab_off)) != cudaSuccess) return bail(e, "upload lab_off");
+    if ((e = upload(b, L, &t.L)) != cudaSuccess) return bail(e, "upload L");
+    if ((e = upload(b, row_off, &t.row_off)) != cudaSuccess) return bail(e, "upload row_off");
+    if ((e = upload(b, w8_off, &t.w8_off)) != cudaSuccess) return bail(e, "upload w8_off");
+    if ((e = upload(b, item_off, &t.item_off)) != cudaSuccess) return bail(e, "upload item_off");
+    t.x = d->x_dev; t.len = d->node_len_dev; t.labels = d->labels_dev;
+    t.W = W; t.err = ctx->err_dev; t.harm = ctx->harm_dev; t.harm_n = HARM_N;
+    // heavy-node table size: count on device, prefix on host
+    {
+        int32_t *cnt_dev = nullptr;
+        if ((e = scratch(b, W, &cnt_dev)) != cudaSuccess) return bail(e, "alloc heavy counts");
+        if ((e = launch_heavy_count(t.len, t.len_off, t.m, W, cnt_dev, 0)) != cudaSuccess) return bail(e, "heavy_count");
+        ctx->launches += (W > 0);
+        std::vector<int32_t> cnt(W, 0);
+        if (W > 0 && (e = cudaMemcpy(cnt.data(), cnt_dev, sizeof(int32_t) * W, cudaMemcpyDeviceToHost)) != cudaSuccess)
+            return bail(e, "read heavy counts");
+        for (int32_t w = 0; w < W; ++w)
+            heavy_off[w + 1] = heavy_off[w] + ((int64_t)(cnt[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
+    }
+    if ((e = upload(b, heavy_off, &t.heavy_off)) != cudaSuccess) return bail(e, "upload heavy_off");
+    b->items = item_off[W];
+    if ((e = scratch(b, row_off[W], &t.A)) != cudaSuccess) return bail(e, "alloc A");
+    if ((e = scratch(b, w8_off[W] + 64, &t.w8)) != cudaSuccess) return bail(e, "alloc w8");
+    if ((e = scratch(b, heavy_off[W] + 64, &t.heavy)) != cudaSuccess) return bail(e, "alloc heavy");
+    if ((e = scratch(b, b->items * 4, &b->partials)) != cudaSuccess) return bail(e, "alloc partials");
+    if ((e = scratch(b, (int64_t)W * 4, &b->sums_tmp)) != cudaSuccess) return bail(e, "alloc sums");
+    if ((e = scratch(b, (int64_t)W * IMPOP_NCOUNTS, &b->counts_tmp)) != cudaSuccess) return bail(e, "alloc counts");
+    if ((e = scratch(b, 1, &b->counter)) != cudaSuccess) return bail(e, "alloc counter");
+    b->item_off = item_off;
+    b->n = n;
+    *batch_out = b;
+    return IMPOP_OK;
+}
+
+int64_t impop_batch_items(const impop_batch_t *batch) { return batch ? batch->items : 0; }
+
+static int run_sums(impop_ctx_t *ctx, impop_batch_t *b, int32_t algo, int32_t rank, int32_t world, double *sums_dev,
+                    cudaStream_t st) {
+    if (algo != IMPOP_ALGO_TCGEN05 && algo != IMPOP_ALGO_SIMT) return fail(ctx, IMPOP_ERR_ARG, "unknown algo");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, IMPOP_ERR_ARG, "bad rank/world");
+    if (b->tab.W == 0) return IMPOP_OK;
+    CU(timed(ctx, IMPOP_KERNEL_PREP, st, [&] { return launch_prep(b->tab, b->counter, st); }));
+    ItemParams prm{};
+    prm.partials = b->partials; prm.counter = b->counter;
+    prm.item_begin = 0; prm.item_end = b->items; prm.rank = rank; prm.world = world;
+    prm.dumpI = nullptr; prm.dumpPi = nullptr;
+    CU(timed(ctx, IMPOP_KERNEL_PAIRS, st, [&] { return launch_pairs(b->tab, prm, algo, ctx->sm_count, st); }));
+    CU(timed(ctx, IMPOP_KERNEL_SUMS, st, [&] { return launch_window_sums(b->tab, b->partials, rank, world, sums_dev, st); }));
+    ctx->launches += 3;
+    return IMPOP_OK;
+}
+
+int impop_window_sums(impop_ctx_t *ctx, impop_batch_t *batch, int32_t algo, int32_t rank, int32_t world,
+                      double *sums_dev, void *stream) {
+    if (!ctx || !batch || (!sums_dev && batch->tab.W > 0)) return fail(ctx, IMPOP_ERR_ARG, "impop_window_sums: null argument");
+    CU(cudaSetDevice(ctx->device));
+    return run_sums(ctx, batch, algo, rank, world, sums_dev, (cudaStream_t)stream);
+}
+
+int impop_window_finalize(impop_ctx_t *ctx, impop_batch_t *batch, const double *sums_dev, int32_t parts,
+                          double *stats_dev, int64_t *counts_dev, void *stream) {
+    if (!ctx || !batch) return IMPOP_ERR_ARG;
+    if (batch->tab.W == 0) return IMPOP_OK;
+    if (!sums_dev || !stats_dev || parts < 1) return fail(ctx, IMPOP_ERR_ARG, "impop_window_finalize: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t *counts = counts_dev ? counts_dev : batch->counts_tmp;
+    CU(timed(ctx, IMPOP_KERNEL_COLSTAT, st, [&] { return launch_colstat(batch->tab, counts, st); }));
+    CU(timed(ctx, IMPOP_KERNEL_FINALIZE, st, [&] { return launch_finalize(batch->tab, sums_dev, parts, counts, stats_dev, st); }));
+    ctx->launches += 2;
+    return IMPOP_OK;
+}
+
+int impop_window_stats(impop_ctx_t *ctx, impop_batch_t *batch, int32_t algo, double *stats_dev, int64_t *counts_dev,
+                       void *stream) {
+    if (!ctx || !batch) return IMPOP_ERR_ARG;
+    if (batch->tab.W == 0) return IMPOP_OK;
+    if (!stats_dev) return fail(ctx, IMPOP_ERR_ARG, "impop_window_stats: null stats_dev");
+    CU(cudaSetDevice(ctx->device));
+    int rc = run_sums(ctx, batch, algo, 0, 1, batch->sums_tmp, (cudaStream_t)stream);
+    if (rc != IMPOP_OK) return rc;
+    return impop_window_finalize(ctx, batch, batch->sums_tmp, 1, stats_dev, counts_dev, stream);
+}
+
+int impop_pairwise(impop_ctx_t *ctx, impop_batch_t *batch, int32_t window, int32_t algo, int64_t *I_dev,
+                   int64_t *A_dev, double *pi_dev, void *stream) {
+    if (!ctx || !batch) return IMPOP_ERR_ARG;
+    if (window < 0 || window >= batch->tab.W) return fail(ctx, IMPOP_ERR_ARG, "impop_pairwise: window out of range");
+    if (algo != IMPOP_ALGO_TCGEN05 && algo != IMPOP_ALGO_SIMT) return fail(ctx, IMPOP_ERR_ARG, "unknown algo");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(launch_prep(batch->tab, batch->counter, st));
+    ctx->launches += 1;
+    if (I_dev || pi_dev) {
+        ItemParams prm{};
+        prm.partials = batch->partials; prm.counter = batch->counter;
+        prm.item_begin = batch->item_off[window]; prm.item_end = batch->item_off[window + 1];
+        prm.rank = 0; prm.world = 1; prm.dumpI = I_dev; prm.dumpPi = pi_dev;
+        CU(launch_pairs(batch->tab, prm, algo, ctx->sm_count, st));
+        ctx->launches += 1;
+    }
+    if (A_dev) {
+        int64_t off = 0;
+        for (int32_t w = 0; w < window; ++w) off += batch->n[w];
+        CU(launch_export_a(batch->tab.A + off, batch->n[window], A_dev, st));
+        ctx->launches += 1;
+    }
+    return IMPOP_OK;
+}
+
+int impop_reduce_identity(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t ld, const uint8_t *labels_dev,
+                          const double *weight_dev, int64_t length, double seg_sites, double *stats_dev,
+                          int64_t *counts_dev, double *wsum_dev, void *stream) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    if (n < 0 || ld < n || (n > 0 && !ident_dev)) return fail(ctx, IMPOP_ERR_ARG, "impop_reduce_identity: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_reduce_identity(ident_dev, n, ld, labels_dev, weight_dev, length, seg_sites, ctx->harm_dev, HARM_N,
+                              ctx->ri_scratch, stats_dev, counts_dev, wsum_dev, (cudaStream_t)stream));
+    ctx->launches += 2;
+    return IMPOP_OK;
+}
+
+int impop_tajima_d(impop_ctx_t *ctx, const int64_t *n_dev, const double *S_dev, const double *pi_dev, int32_t count,
+                   double *D_dev, double *parts_dev, void *stream) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    if (count < 0 || (count > 0 && (!n_dev || !S_dev || !pi_dev || !D_dev)))
+        return fail(ctx, IMPOP_ERR_ARG, "impop_tajima_d: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_tajima(n_dev, S_dev, pi_dev, count, D_dev, parts_dev, (cudaStream_t)stream));
+    ctx->launches += (count > 0);
+    return IMPOP_OK;
+}
+
+int impop_site_counts(impop_ctx_t *ctx, const uint64_t *sites_dev, int64_t sites, int32_t words,
+                      const uint64_t *masks_dev, int32_t pops, int32_t *counts_dev, double *freq_dev, void *stream) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    if (sites < 0 || words < 1 || pops < 1 || pops > 64 || (int64_t)pops * words > 2048 ||
+        (sites > 0 && (!sites_dev || !masks_dev || !counts_dev)))
+        return fail(ctx, IMPOP_ERR_ARG, "impop_site_counts: bad argument (pops <= 64, pops * words <= 2048)");
+    CU(cudaSetDevice(ctx->device));
+    CU(timed(ctx, IMPOP_KERNEL_SITES, (cudaStream_t)stream, [&] {
+        return launch_site_counts(sites_dev, sites, words, masks_dev, pops, counts_dev, freq_dev, ctx->sm_count,
+                                  (cudaStream_t)stream);
+    }));
+    ctx->launches += (sites > 0);
+    return IMPOP_OK;
+}
+
+int impop_cluster(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t ld, double threshold,
+                  int32_t *comp_dev, void *stream) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    if (n < 0 || ld < n || (n > 0 && (!ident_dev || !comp_dev))) return fail(ctx, IMPOP_ERR_ARG, "impop_cluster: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    if (n > ctx->cluster_cap) {
+        CU(cudaStreamSynchronize((cudaStream_t)stream));
+        cudaFree(ctx->cluster_parent);
+        ctx->cluster_parent = nullptr;
+        ctx->cluster_cap = 0;
+        CU(cudaMalloc(&ctx->cluster_parent, sizeof(int32_t) * (size_t)n));
+        ctx->cluster_cap = n;
+    }
+    CU(launch_cluster(ident_dev, n, ld, threshold, ctx->cluster_parent, comp_dev, (cudaStream_t)stream));
+    ctx->launches += (n > 0) ? 3 : 0;
+    return IMPOP_OK;
+}
+
+int impop_greedy_groups(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t ld, double threshold,
+                        int32_t *group_dev, double *weight_dev, void *stream) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    if (n < 0 || ld < n || (n > 0 && (!ident_dev || !group_dev)))
+        return fail(ctx, IMPOP_ERR_ARG, "impop_greedy_groups: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_greedy_groups(ident_dev, n, ld, threshold, group_dev, weight_dev, (cudaStream_t)stream));
+    ctx->launches += (n > 0);
+    return IMPOP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// Auxiliary kernels: bit packing (ingest), TSV-mode reductions over a dense identity matrix,
+// stand-alone Tajima's D, per-site allele counts, and threshold clustering.
+#include "common.cuh"
+#include "stats_math.cuh"
+
+namespace impop {
+
+// ------------------------------------------------------------------------------------------
+// K1: dense 0/1 bytes -> bit-packed rows.  One warp per 32 columns: coalesced byte loads, ballot.
+// ------------------------------------------------------------------------------------------
+__global__ void pack_bits_kernel(const uint8_t *dense, int32_t n, int32_t m, int64_t dpitch, uint32_t *x,
+                                 int32_t pitch_words) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = (int64_t)n * pitch_words;
+    for (int64_t t = warp_global; t < total; t += nwarps) {
+        const int i = (int)(t / pitch_words), wd = (int)(t % pitch_words);
+        const int k = wd * 32 + lane;
+        const bool bit = (k < m) && dense[(size_t)i * dpitch + k] != 0;
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) x[(size_t)i * pitch_words + wd] = word;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 alone (TSV mode).  Stage 1: one CTA per row stripe, fixed thread->pair mapping, partials to
+// scratch; stage 2: one CTA adds the partials in order and finalizes.  Deterministic.
+// partial layout per block: [0..3] sums S AA BB AB, [4] weighted sum, [5..8] pair counts, [9] weighted count
+// ------------------------------------------------------------------------------------------
+constexpr int RI_THREADS = 256;
+constexpr int RI_VALS = 10;
+
+__global__ void __launch_bounds__(RI_THREADS) reduce_identity_stage1(const double *ident, int32_t n, int64_t ld,
+                                                                     const uint8_t *labels, const double *weight,
+                                                                     double *partials) {
+    __shared__ double s_red[RI_THREADS / 32][RI_VALS];
+    double v[RI_VALS];
+#pragma unroll
+    for (int k = 0; k < RI_VALS; ++k) v[k] = 0.0;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t fi = labels ? labels[i] : 0u;
+        const double wi = weight ? weight[i] : 0.0;
+        for (int j = i + 1 + threadIdx.x; j < n; j += RI_THREADS) {
+            const double s = ident[(size_t)i * ld + j];
+            if (s != s) continue;  // pair absent from the table: skipped, not counted (h-fst.py:147-153)
+            const double p = __dadd_rn(1.0, -s);
+            const uint32_t fj = labels ? labels[j] : 0u;
+            if (fi & fj & IMPOP_LAB_SUBSET) { v[0] = __dadd_rn(v[0], p); v[5] += 1.0; }
+            if (fi & fj & IMPOP_LAB_A) { v[1] = __dadd_rn(v[1], p); v[6] += 1.0; }
+            if (fi & fj & IMPOP_LAB_B) { v[2] = __dadd_rn(v[2], p); v[7] += 1.0; }
+            if (((fi & IMPOP_LAB_A) && (fj & IMPOP_LAB_B)) || ((fi & IMPOP_LAB_B) && (fj & IMPOP_LAB_A))) {
+                v[3] = __dadd_rn(v[3], p); v[8] += 1.0;
+            }
+            if (weight) {
+                const double wj = weight[j];
+                if (wi != 0.0 && wj != 0.0) {
+                    v[4] = __dadd_rn(v[4], __dmul_rn(__dmul_rn(p, wi), wj));  // pica2.py:139
+                    v[9] += 1.0;
+                }
+            }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < RI_VALS; ++k) {
+        double t = warp_sum(v[k]);
+        if (lane == 0) s_red[warp][k] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < RI_VALS) {
+        double t = 0.0;
+        for (int wgt = 0; wgt < RI_THREADS / 32; ++wgt) t = __dadd_rn(t, s_red[wgt][threadIdx.x]);
+        partials[(size_t)blockIdx.x * RI_VALS + threadIdx.x] = t;
+    }
+}
+
+__global__ void reduce_identity_stage2(const double *partials, int32_t blocks, const uint8_t *labels, int32_t n,
+                                       int64_t L, double seg, const double2 *harm, int32_t harm_n, double *stats,
+                                       int64_t *counts, double *wsum) {
+    __shared__ double s_tot[RI_VALS];
+    __shared__ int s_n[3];
+    if (threadIdx.x < 3) s_n[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < RI_VALS) {
+        double t = 0.0;
+        for (int b = 0; b < blocks; ++b) t = __dadd_rn(t, partials[(size_t)b * RI_VALS + threadIdx.x]);
+        s_tot[threadIdx.x] = t;
+    }
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        uint32_t f = labels ? labels[i] : 0u;
+        c0 += (f & IMPOP_LAB_SUBSET) != 0; c1 += (f & IMPOP_LAB_A) != 0; c2 += (f & IMPOP_LAB_B) != 0;
+    }
+    if (c0) atomicAdd(&s_n[0], c0);
+    if (c1) atomicAdd(&s_n[1], c1);
+    if (c2) atomicAdd(&s_n[2], c2);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t cnt[IMPOP_NCOUNTS];
+        cnt[0] = s_n[0]; cnt[1] = s_n[1]; cnt[2] = s_n[2];
+        cnt[3] = (int64_t)s_tot[5]; cnt[4] = (int64_t)s_tot[6]; cnt[5] = (int64_t)s_tot[7]; cnt[6] = (int64_t)s_tot[8];
+        cnt[7] = (int64_t)seg;
+        double sums[4] = {s_tot[0], s_tot[1], s_tot[2], s_tot[3]};
+        double st[IMPOP_NSTATS];
+        finalize_row(sums, cnt, L, seg, harm, harm_n, st);
+        if (stats) for (int k = 0; k < IMPOP_NSTATS; ++k) stats[k] = st[k];
+        if (counts) for (int k = 0; k < IMPOP_NCOUNTS; ++k) counts[k] = cnt[k];
+        if (wsum) {   // pica2.py:137-164 with group frequencies as weights; n = every element of the table
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            double pw = 0.0;
+            if (s_tot[9] > 0.0 && n >= 2) {
+                double dn = (double)n;
+                pw = __dmul_rn(__ddiv_rn(dn, __dadd_rn(dn, -1.0)), __dmul_rn(2.0, s_tot[4]));   // pica2.py:154
+            }
+            wsum[0] = s_tot[4]; wsum[1] = s_tot[9]; wsum[2] = pw;
+            wsum[3] = (L > 0) ? __ddiv_rn(pw, (double)L) : nan;                                 // pica2.py:163-164
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// tj_d.py:47-69 for independent triples (the tj_d.py CLI path).
+// ------------------------------------------------------------------------------------------
+__global__ void tajima_kernel(const int64_t *n, const double *S, const double *pi, int32_t count, double *D,
+                              double *parts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int64_t nn = n[t];
+    double t1 = 0.0, c1 = 0.0, t2 = 0.0, c2 = 0.0;
+    for (int64_t i = 1; i < nn; ++i) {
+        double di = (double)i;
+        neumaier_add(t1, c1, __ddiv_rn(1.0, di));
+        neumaier_add(t2, c2, __ddiv_rn(1.0, __dmul_rn(di, di)));
+    }
+    double a1 = neumaier_value(t1, c1), a2 = neumaier_value(t2, c2);
+    D[t] = tajima_from_harmonics((double)nn, S[t], pi[t], a1, a2, parts ? parts + (size_t)t * 10 : nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: per-site allele counts.  Thread per site; masks staged in shared memory.
+// ------------------------------------------------------------------------------------------
+constexpr int SITE_THREADS = 256;
+constexpr int SITE_MAX_MASK_WORDS = 2048;  // pops * words (u64) held in shared memory
+
+__global__ void __launch_bounds__(SITE_THREADS) site_counts_kernel(const uint64_t *sites, int64_t M, int32_t words,
+                                                                   const uint64_t *masks, int32_t P, int32_t *counts,
+                                                                   double *freq) {
+    __shared__ uint64_t s_mask[SITE_MAX_MASK_WORDS];
+    __shared__ double s_size[64];
+    for (int k = threadIdx.x; k < P * words; k += SITE_THREADS) s_mask[k] = masks[k];
+    __syncthreads();
+    if (threadIdx.x < P) {
+        int c = 0;
+        for (int w = 0; w < words; ++w) c += __popcll(s_mask[threadIdx.x * words + w]);
+        s_size[threadIdx.x] = (double)c;
+    }
+    __syncthreads();
+    for (int64_t s = (int64_t)blockIdx.x * SITE_THREADS + threadIdx.x; s < M; s += (int64_t)gridDim.x * SITE_THREADS) {
+        const uint64_t *row = sites + (size_t)s * words;
+        for (int p = 0; p < P; ++p) {
+            int c = 0;
+            for (int w = 0; w < words; ++w) c += __popcll(__ldg(row + w) & s_mask[p * words + w]);
+            counts[(size_t)s * P + p] = c;
+            if (freq) freq[(size_t)s * P + p] = s_size[p] > 0.0 ? __ddiv_rn((double)c, s_size[p]) : 0.0;
+        }
+    }
+}
+
+// Fast path for words == 8 (up to 512 haplotypes, the HPRC panel): the 64-byte site row is read
+// once as four 16-byte loads and every population is counted from registers.
+template <int P>
+__global__ void __launch_bounds__(SITE_THREADS) site_counts_w8_kernel(const uint64_t *sites, int64_t M,
+                                                                      const uint64_t *masks, int32_t *counts,
+                                                                      double *freq) {
+    __shared__ uint64_t s_mask[P * 8];
+    __shared__ double s_size[P];
+    for (int k = threadIdx.x; k < P * 8; k += SITE_THREADS) s_mask[k] = masks[k];
+    __syncthreads();
+    if (threadIdx.x < P) {
+        int c = 0;
+        for (int w = 0; w < 8; ++w) c += __popcll(s_mask[threadIdx.x * 8 + w]);
+        s_size[threadIdx.x] = (double)c;
+    }
+    __syncthreads();
+    for (int64_t s = (int64_t)blockIdx.x * SITE_THREADS + threadIdx.x; s < M; s += (int64_t)gridDim.x * SITE_THREADS) {
+        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(sites + (size_t)s * 8);
+        ulonglong2 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2), r3 = __ldg(row + 3);
+        uint64_t v[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            int c = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) c += __popcll(v[w] & s_mask[p * 8 + w]);
+            counts[(size_t)s * P + p] = c;
+            if (freq) freq[(size_t)s * P + p] = s_size[p] > 0.0 ? __ddiv_rn((double)c, s_size[p]) : 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: connected components of {identity >= threshold} (af.py:35-44).  Lock-free union-find that
+// always links the larger root under the smaller, so every root is its component's smallest index.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(volatile int32_t *parent, int v) {
+    int p = parent[v];
+    while (p != v) { v = p; p = parent[v]; }
+    return v;
+}
+
+__global__ void cluster_init_kernel(int32_t *parent, int32_t n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) parent[i] = i;
+}
+
+__global__ void cluster_link_kernel(const double *ident, int32_t n, int64_t ld, double threshold, int32_t *parent) {
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+            const double s = ident[(size_t)i * ld + j];
+            if (!(s >= threshold)) continue;  // NaN (absent pair) never links
+            int a = i, b = j;
+            while (true) {
+                a = uf_find(parent, a);
+                b = uf_find(parent, b);
+                if (a == b) break;
+                const int hi = a > b ? a : b, lo = a > b ? b : a;
+                if (atomicCAS(&parent[hi], hi, lo) == hi) break;
+            }
+        }
+    }
+}
+
+__global__ void cluster_flatten_kernel(int32_t *parent, int32_t n, int32_t *comp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) comp[i] = uf_find(parent, i);
+}
+
+// ------------------------------------------------------------------------------------------
+// pica2.py:94-112 star grouping, made deterministic: the seed is always the smallest remaining
+// index (names are sorted, so index order is name order).  The seed loop is
+// sequential by definition; each step scans the seed's row in parallel.  One CTA.
+// group[i] = seed index of i's group (the seed is the group's smallest member = its
+// representative, pica2.py:110/128); weight[i] = |G|/N on seeds, 0 elsewhere (pica2.py:137-138).
+// ------------------------------------------------------------------------------------------
+constexpr int GROUP_THREADS = 1024;
+
+__global__ void __launch_bounds__(GROUP_THREADS) greedy_groups_kernel(const double *ident, int32_t n, int64_t ld,
+                                                                      double threshold, int32_t *group,
+                                                                      double *weight) {
+    for (int i = threadIdx.x; i < n; i += GROUP_THREADS) {
+        group[i] = -1;
+        if (weight) weight[i] = 0.0;
+    }
+    __syncthreads();
+    for (int s = 0; s < n; ++s) {
+        if (group[s] != -1) continue;   // uniform: written before the last barrier
+        for (int j = s + 1 + threadIdx.x; j < n; j += GROUP_THREADS) {
+            if (group[j] != -1) continue;
+            const double v = ident[(size_t)s * ld + j];
+            if (v > threshold) group[j] = s;   // strict; NaN (absent pair) never joins (pica2.py:106)
+        }
+        if (threadIdx.x == 0) group[s] = s;
+        __syncthreads();
+    }
+    if (!weight) return;
+    for (int i = threadIdx.x; i < n; i += GROUP_THREADS) atomicAdd(&weight[group[i]], 1.0);   // exact small integers
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += GROUP_THREADS) weight[i] = __ddiv_rn(weight[i], (double)n);
+}
+
+// ------------------------------------------------------------------------------------------
+// Launchers
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_pack_bits(const uint8_t *dense, int32_t n, int32_t m, int64_t dpitch, uint32_t *x,
+                             int32_t pitch_words, cudaStream_t st) {
+    int64_t total = (int64_t)n * pitch_words;
+    if (total == 0) return cudaSuccess;
+    int64_t blocks = (total + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pack_bits_kernel<<<(int)blocks, 256, 0, st>>>(dense, n, m, dpitch, x, pitch_words);
+    return cudaGetLastError();
+}
+
+int reduce_identity_blocks(int32_t n) { return n < 1 ? 1 : (n < 148 * 4 ? n : 148 * 4); }
+
+cudaError_t launch_reduce_identity(const double *ident, int32_t n, int64_t ld, const uint8_t *labels,
+                                   const double *weight, int64_t L, double seg, const double2 *harm, int32_t harm_n,
+                                   double *scratch, double *stats, int64_t *counts, double *wsum, cudaStream_t st) {
+    int blocks = reduce_identity_blocks(n);
+    reduce_identity_stage1<<<blocks, RI_THREADS, 0, st>>>(ident, n, ld, labels, weight, scratch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    reduce_identity_stage2<<<1, 128, 0, st>>>(scratch, blocks, labels, n, L, seg, harm, harm_n, stats, counts, wsum);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tajima(const int64_t *n, const double *S, const double *pi, int32_t count, double *D, double *parts,
+                          cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    tajima_kernel<<<(count + 63) / 64, 64, 0, st>>>(n, S, pi, count, D, parts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_site_counts(const uint64_t *sites, int64_t M, int32_t words, const uint64_t *masks, int32_t P,
+                               int32_t *counts, double *freq, int sm_count, cudaStream_t st) {
+    if (M == 0) return cudaSuccess;
+    int64_t blocks = (M + SITE_THREADS - 1) / SITE_THREADS;
+    int64_t cap = (int64_t)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (words == 8 && P == 5) site_counts_w8_kernel<5><<<(int)blocks, SITE_THREADS, 0, st>>>(sites, M, masks, counts, freq);
+    else if (words == 8 && P == 1) site_counts_w8_kernel<1><<<(int)blocks, SITE_THREADS, 0, st>>>(sites, M, masks, counts, freq);
+    else if (words == 8 && P == 2) site_counts_w8_kernel<2><<<(int)blocks, SITE_THREADS, 0, st>>>(sites, M, masks, counts, freq);
+    else site_counts_kernel<<<(int)blocks, SITE_THREADS, 0, st>>>(sites, M, words, masks, P, counts, freq);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cluster(const double *ident, int32_t n, int64_t ld, double threshold, int32_t *parent, int32_t *comp,
+                           cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    cluster_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(parent, n);
+    cluster_link_kernel<<<n < 148 * 8 ? n : 148 * 8, 128, 0, st>>>(ident, n, ld, threshold, parent);
+    cluster_flatten_kernel<<<(n + 255) / 256, 256, 0, st>>>(parent, n, comp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_greedy_groups(const double *ident, int32_t n, int64_t ld, double threshold, int32_t *group,
+                                 double *weight, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    greedy_groups_kernel<<<1, GROUP_THREADS, 0, st>>>(ident, n, ld, threshold, group, weight);
+    return cudaGetLastError();
+}
+
+}  // namespace impop

@@ -1,0 +1,281 @@
+"""Device engine: thin Python objects over the C ABI of libimpop_b200.so (include/impop_b200.h).
+
+PyTorch is used only for device memory, streams and (in distributed.py) the process group;
+every computation below is a call into the hand-written sm_100a library.  There is no CPU
+fallback: constructing a Context without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+LAB_SUBSET, LAB_A, LAB_B, LAB_SEG = N.LAB_SUBSET, N.LAB_A, N.LAB_B, N.LAB_SEG
+ALGO_TCGEN05, ALGO_SIMT = N.ALGO_TCGEN05, N.ALGO_SIMT
+NSTATS, NCOUNTS, ST = N.NSTATS, N.NCOUNTS, N.ST
+
+
+def _ptr(t):
+    """Raw pointer of a torch tensor / numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _u32_tensor(a: np.ndarray) -> torch.Tensor:
+    """numpy uint32 -> torch int32 view (torch's uint32 support is partial; the bits are what matter)."""
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint32).view(np.int32))
+
+
+def _u64_tensor(a: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64))
+
+
+class Context:
+    """One impop_ctx_t per device (impop_create / impop_destroy)."""
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("impop_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = N.lib()
+        self.device = int(device)
+        self.torch_device = torch.device("cuda", self.device)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.torch_device)          # make sure the primary context exists
+        h = C.c_void_p()
+        rc = self.lib.impop_create(self.device, C.byref(h))
+        if rc != 0:
+            raise N.NativeError(rc, "impop_create", "no sm_100a device or CUDA failure")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.impop_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover - interpreter shutdown order
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _call(self, name, *args):
+        rc = getattr(self.lib, name)(self.handle, *args)
+        if rc != 0:
+            raise N.NativeError(rc, name, self.lib.impop_last_error(self.handle).decode())
+
+    def check(self, stream=None):
+        """Synchronise the stream and raise on sticky device-side errors (impop_check)."""
+        self._call("impop_check", _stream_ptr(stream))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.impop_launch_count(self.handle))
+
+    def timing(self, enable: bool = True):
+        """Start (or stop) recording per-kernel CUDA-event timings; clears earlier records."""
+        self._call("impop_timing_enable", 1 if enable else 0)
+
+    def timing_read(self, kernel: str):
+        """(total milliseconds, launches) of one kernel (see _native.KERNELS) since timing(True)."""
+        ms, cnt = C.c_double(0.0), C.c_int64(0)
+        self._call("impop_timing_read", N.KERNELS[kernel], C.byref(ms), C.byref(cnt))
+        return ms.value, cnt.value
+
+    # ------------------------------------------------------------------ stand-alone kernels
+    def pack_bits(self, dense: torch.Tensor, pitch_words: int | None = None, stream=None) -> torch.Tensor:
+        """K1: dense 0/1 uint8 [n, m] (device) -> bit-packed int32 [n, pitch_words]."""
+        assert dense.dtype == torch.uint8 and dense.dim() == 2 and dense.is_cuda
+        n, m = dense.shape
+        if pitch_words is None:
+            pitch_words = ((m + 127) // 128) * 4
+        out = torch.empty((n, pitch_words), dtype=torch.int32, device=dense.device)
+        self._call("impop_pack_bits", _ptr(dense), n, m, dense.stride(0) if n else max(m, 1), _ptr(out), pitch_words,
+                   _stream_ptr(stream))
+        return out
+
+    def reduce_identity(self, ident: torch.Tensor, labels: torch.Tensor | None, weight: torch.Tensor | None = None,
+                        length: int = 0, seg_sites: float = 0.0, stream=None):
+        """K3 alone (TSV mode): (stats[NSTATS] f64, counts[NCOUNTS] i64, wsum[4] f64) device tensors.
+        wsum = weighted sum, weighted pair count, grouped pi, grouped pi / length (see include/impop_b200.h)."""
+        assert ident.dtype == torch.float64 and ident.dim() == 2 and ident.is_cuda
+        n = ident.shape[0]
+        stats = torch.empty(NSTATS, dtype=torch.float64, device=ident.device)
+        counts = torch.empty(NCOUNTS, dtype=torch.int64, device=ident.device)
+        wsum = torch.zeros(4, dtype=torch.float64, device=ident.device)
+        self._call("impop_reduce_identity", _ptr(ident), n, ident.stride(0) if n else 0, _ptr(labels), _ptr(weight),
+                   int(length or 0), float(seg_sites), _ptr(stats), _ptr(counts), _ptr(wsum), _stream_ptr(stream))
+        return stats, counts, wsum
+
+    def tajima_d(self, n: torch.Tensor, S: torch.Tensor, pi: torch.Tensor, with_parts: bool = False, stream=None):
+        count = n.numel()
+        D = torch.empty(count, dtype=torch.float64, device=n.device)
+        parts = torch.empty((count, 10), dtype=torch.float64, device=n.device) if with_parts else None
+        self._call("impop_tajima_d", _ptr(n), _ptr(S), _ptr(pi), count, _ptr(D), _ptr(parts), _stream_ptr(stream))
+        return (D, parts) if with_parts else D
+
+    def site_counts(self, sites: torch.Tensor, masks: torch.Tensor, want_freq: bool = True, stream=None,
+                    out_counts: torch.Tensor | None = None, out_freq: torch.Tensor | None = None):
+        """K4: sites [M, words] int64 (u64 bits), masks [P, words] -> counts [M, P] i32, freq [M, P] f64."""
+        M, words = sites.shape
+        P = masks.shape[0]
+        counts = out_counts if out_counts is not None else torch.empty((M, P), dtype=torch.int32, device=sites.device)
+        freq = out_freq if out_freq is not None else (
+            torch.empty((M, P), dtype=torch.float64, device=sites.device) if want_freq else None)
+        self._call("impop_site_counts", _ptr(sites), M, words, _ptr(masks), P, _ptr(counts), _ptr(freq),
+                   _stream_ptr(stream))
+        return counts, freq
+
+    def greedy_groups(self, ident: torch.Tensor, threshold: float, stream=None):
+        """pica2 step 1 on the device: (group [n] i32 = seed index, weight [n] f64 = |G|/n on seeds)."""
+        n = ident.shape[0]
+        group = torch.empty(n, dtype=torch.int32, device=ident.device)
+        weight = torch.empty(n, dtype=torch.float64, device=ident.device)
+        self._call("impop_greedy_groups", _ptr(ident), n, ident.stride(0) if n else 0, float(threshold), _ptr(group),
+                   _ptr(weight), _stream_ptr(stream))
+        return group, weight
+
+    def cluster(self, ident: torch.Tensor, threshold: float, stream=None) -> torch.Tensor:
+        """K5: component label (= smallest member index) per row of a dense identity matrix."""
+        n = ident.shape[0]
+        comp = torch.empty(n, dtype=torch.int32, device=ident.device)
+        self._call("impop_cluster", _ptr(ident), n, ident.stride(0) if n else 0, float(threshold), _ptr(comp),
+                   _stream_ptr(stream))
+        return comp
+
+
+class WindowBatch:
+    """A batch of windows resident on the device (impop_batch_t).
+
+    x: int32 tensor holding the u32 presence words of every window; node_len: int32 (u32) tensor;
+    labels: uint8 tensor.  Per-window descriptor arrays are host numpy arrays.
+    """
+
+    def __init__(self, ctx: Context, n, m, pitch_words, x_off, len_off, lab_off, length,
+                 x: torch.Tensor, node_len: torch.Tensor, labels: torch.Tensor):
+        self.ctx = ctx
+        self.n = np.ascontiguousarray(n, dtype=np.int32)
+        self.m = np.ascontiguousarray(m, dtype=np.int32)
+        self.pitch_words = np.ascontiguousarray(pitch_words, dtype=np.int32)
+        self.x_off = np.ascontiguousarray(x_off, dtype=np.int64)
+        self.len_off = np.ascontiguousarray(len_off, dtype=np.int64)
+        self.lab_off = np.ascontiguousarray(lab_off, dtype=np.int64)
+        self.length = np.ascontiguousarray(length, dtype=np.int64)
+        self.windows = int(self.n.shape[0])
+        self.x, self.node_len, self.labels = x, node_len, labels      # keep the device buffers alive
+        d = N.BatchDesc(self.windows, _ptr(self.n), _ptr(self.m), _ptr(self.pitch_words), _ptr(self.x_off),
+                        _ptr(self.len_off), _ptr(self.lab_off), _ptr(self.length), _ptr(x), _ptr(node_len),
+                        _ptr(labels))
+        h = C.c_void_p()
+        rc = ctx.lib.impop_batch_create(ctx.handle, C.byref(d), C.byref(h))
+        if rc != 0:
+            raise N.NativeError(rc, "impop_batch_create", ctx.lib.impop_last_error(ctx.handle).decode())
+        self.handle = h
+
+    # ------------------------------------------------------------------ constructors
+    @classmethod
+    def from_uniform(cls, ctx: Context, x_bits, node_len, labels, length, m: int | None = None):
+        """W same-shape windows: x_bits [W, n, pitch] u32, node_len [W, m_pad] u32, labels [n] or [W, n] u8.
+
+        Arguments may be numpy arrays (copied to the device) or device tensors (used in place).
+        """
+        W, n, pitch = x_bits.shape
+        m_pad = node_len.shape[1]
+        dev = ctx.torch_device
+        xd = x_bits if isinstance(x_bits, torch.Tensor) else _u32_tensor(x_bits).to(dev)
+        ld = node_len if isinstance(node_len, torch.Tensor) else _u32_tensor(node_len).to(dev)
+        lab = labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(labels, dtype=np.uint8)).to(dev)
+        per_window_labels = lab.dim() == 2
+        ar = np.arange(W, dtype=np.int64)
+        L = np.full(W, int(length or 0), dtype=np.int64) if np.isscalar(length) or length is None else np.asarray(length)
+        return cls(ctx, np.full(W, n), np.full(W, m_pad if m is None else m), np.full(W, pitch), ar * (n * pitch),
+                   ar * m_pad, ar * n if per_window_labels else np.zeros(W, dtype=np.int64), L, xd, ld, lab)
+
+    @classmethod
+    def from_windows(cls, ctx: Context, windows):
+        """Ragged batch from a list of (x_bits [n, pitch] u32, node_len [m] u32, labels [n] u8, L) host arrays."""
+        n, m, pitch, x_off, len_off, lab_off, L = [], [], [], [], [], [], []
+        xs, ls, labs = [], [], []
+        xo = lo = bo = 0
+        for xb, nl, lab, length in windows:
+            xb = np.ascontiguousarray(xb, dtype=np.uint32)
+            if xb.ndim != 2:
+                xb = xb.reshape(len(lab), -1)
+            nn, pw = xb.shape
+            if pw % 4:                                     # rows must be 16-byte multiples
+                pad = np.zeros((nn, (pw + 3) // 4 * 4), dtype=np.uint32)
+                pad[:, :pw] = xb
+                xb, pw = pad, pad.shape[1]
+            n.append(nn); m.append(len(nl)); pitch.append(pw)
+            x_off.append(xo); len_off.append(lo); lab_off.append(bo); L.append(int(length or 0))
+            xs.append(xb.ravel()); ls.append(np.asarray(nl, dtype=np.uint32)); labs.append(np.asarray(lab, dtype=np.uint8))
+            xo += xb.size
+            lo += len(nl)
+            bo += nn
+        cat = lambda parts, dt: np.concatenate(parts).astype(dt, copy=False) if parts and sum(p.size for p in parts) else np.zeros(4, dtype=dt)
+        dev = ctx.torch_device
+        x = _u32_tensor(cat(xs, np.uint32)).to(dev)
+        nl = _u32_tensor(cat(ls, np.uint32)).to(dev)
+        lab = torch.from_numpy(cat(labs, np.uint8)).to(dev)
+        return cls(ctx, n, m, pitch, x_off, len_off, lab_off, L, x, nl, lab)
+
+    # ------------------------------------------------------------------ life cycle
+    def close(self):
+        if getattr(self, "handle", None) and self.ctx.handle:
+            self.ctx.lib.impop_batch_destroy(self.ctx.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def items(self) -> int:
+        return int(self.ctx.lib.impop_batch_items(self.handle))
+
+    # ------------------------------------------------------------------ kernels
+    def stats(self, algo: int = ALGO_TCGEN05, stream=None, out_stats=None, out_counts=None):
+        """Fused K2+K3 over every window: (stats [W, NSTATS] f64, counts [W, NCOUNTS] i64) on the device."""
+        dev = self.ctx.torch_device
+        stats = out_stats if out_stats is not None else torch.empty((self.windows, NSTATS), dtype=torch.float64, device=dev)
+        counts = out_counts if out_counts is not None else torch.empty((self.windows, NCOUNTS), dtype=torch.int64, device=dev)
+        self.ctx._call("impop_window_stats", self.handle, algo, _ptr(stats), _ptr(counts), _stream_ptr(stream))
+        return stats, counts
+
+    def window_sums(self, rank: int, world: int, algo: int = ALGO_TCGEN05, stream=None) -> torch.Tensor:
+        """Raw pair sums [W, 4] over the work items t with t % world == rank (tile-grid split)."""
+        sums = torch.empty((self.windows, 4), dtype=torch.float64, device=self.ctx.torch_device)
+        self.ctx._call("impop_window_sums", self.handle, algo, rank, world, _ptr(sums), _stream_ptr(stream))
+        return sums
+
+    def finalize(self, sums_parts: torch.Tensor, stream=None):
+        """sums_parts [parts, W, 4] -> (stats, counts); parts are added in index order (reproducible)."""
+        assert sums_parts.dim() == 3 and sums_parts.shape[1:] == (self.windows, 4) and sums_parts.is_contiguous()
+        dev = self.ctx.torch_device
+        stats = torch.empty((self.windows, NSTATS), dtype=torch.float64, device=dev)
+        counts = torch.empty((self.windows, NCOUNTS), dtype=torch.int64, device=dev)
+        self.ctx._call("impop_window_finalize", self.handle, _ptr(sums_parts), sums_parts.shape[0], _ptr(stats),
+                       _ptr(counts), _stream_ptr(stream))
+        return stats, counts
+
+    def pairwise(self, window: int, algo: int = ALGO_TCGEN05, want_i=True, want_pi=True, stream=None):
+        """Materialise one window: (I [n, n] i64, A [n] i64, pi [n, n] f64); the table `impg similarity` prints."""
+        n = int(self.n[window])
+        dev = self.ctx.torch_device
+        I = torch.zeros((n, n), dtype=torch.int64, device=dev) if want_i else None
+        A = torch.zeros(n, dtype=torch.int64, device=dev)
+        pi = torch.zeros((n, n), dtype=torch.float64, device=dev) if want_pi else None
+        self.ctx._call("impop_pairwise", self.handle, window, algo, _ptr(I), _ptr(A), _ptr(pi), _stream_ptr(stream))
+        return I, A, pi

@@ -154,3 +154,86 @@ def make_site_matrix(sites: int, n: int, seed: int, pops: np.ndarray | None = No
         d[:n] = pops == p
         masks[p] = np.packbits(d, bitorder="little").view("<u8")
     return out, masks
+
+
+def make_windows_device(ctx, n: int, length: int, windows: int, seed: int, n_sites_override: int | None = None,
+                        chunk: int = 512, pops: np.ndarray | None = None, max_sv_len: int = 10000):
+    """The same window model generated ON the device with torch's RNG (bench-scale batches: the numpy
+    generator needs ~16 ms per window).  Returns (x_bits int32 [W, n, pitch], node_len int32 [W, m_pad],
+    pops numpy, m, m_pad) with the tensors on ctx.torch_device; rows are bit-packed by impop_pack_bits.
+    Backbone lengths are a uniform random composition of the spare length (sum(backbone + ref) == L)."""
+    import torch
+    dev = ctx.torch_device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    if pops is None:
+        pops, _ = panel(n)
+    pops_t = torch.from_numpy(np.asarray(pops)).to(dev)
+    npop = int(pops.max()) + 1
+    K = n_sites_override if n_sites_override is not None else n_sites(n, length)
+    m = 3 * K + 1
+    m_pad = ((m + 127) // 128) * 128
+    pitch = m_pad // 32
+    x_bits = torch.empty((windows, n, pitch), dtype=torch.int32, device=dev)
+    node_len = torch.zeros((windows, m_pad), dtype=torch.int32, device=dev)
+    sfs = 1.0 / torch.arange(1, n, device=dev, dtype=torch.float64)
+    sfs = sfs / sfs.sum()
+    a_bn = (1.0 - FST_BN) / FST_BN
+    ref_col = 1 + 3 * torch.arange(K, device=dev)
+    for w0 in range(0, windows, chunk):
+        wc = min(chunk, windows - w0)
+        cls = torch.rand((wc, K), generator=gen, device=dev)
+        indel = (cls >= 0.90) & (cls < 0.98)
+        sv = cls >= 0.98
+        ind_len = torch.randint(1, 51, (wc, K), generator=gen, device=dev)
+        ins = torch.rand((wc, K), generator=gen, device=dev) < 0.5
+        one = torch.ones((wc, K), dtype=torch.int64, device=dev)
+        alt_len = torch.where(indel & ins, ind_len, one)
+        ref_len = torch.where(indel & ~ins, ind_len, one)
+        lo, hi = float(np.log(50.0)), float(np.log(float(max_sv_len)))
+        sv_len = torch.exp(lo + (hi - lo) * torch.rand((wc, K), generator=gen, device=dev, dtype=torch.float64)).to(torch.int64)
+        alt_len = torch.where(sv, sv_len, alt_len)
+        spare = (length - ref_len.sum(dim=1)).clamp_min(0)
+        cuts = (torch.rand((wc, K), generator=gen, device=dev, dtype=torch.float64) * (spare[:, None] + 1).to(torch.float64)).to(torch.int64)
+        cuts = torch.minimum(cuts, spare[:, None]).sort(dim=1).values
+        edges = torch.cat([torch.zeros((wc, 1), dtype=torch.int64, device=dev), cuts, spare[:, None]], dim=1)
+        bb = edges[:, 1:] - edges[:, :-1]                       # (wc, K + 1), sums to spare
+        nl = node_len[w0:w0 + wc]
+        nl[:, 0] = bb[:, 0].to(torch.int32)
+        nl[:, ref_col] = ref_len.to(torch.int32)
+        nl[:, ref_col + 1] = alt_len.to(torch.int32)
+        nl[:, ref_col + 2] = bb[:, 1:].to(torch.int32)
+        k_anc = torch.multinomial(sfs, wc * K, replacement=True, generator=gen).reshape(wc, K) + 1
+        p_anc = (k_anc.to(torch.float64) / n).clamp(1e-6, 1 - 1e-6)
+        ga = torch._standard_gamma((p_anc[:, None, :] * a_bn).expand(wc, npop, K).contiguous(), generator=gen)
+        gb = torch._standard_gamma(((1.0 - p_anc[:, None, :]) * a_bn).expand(wc, npop, K).contiguous(), generator=gen)
+        p_pop = (ga / (ga + gb).clamp_min(1e-300)).to(torch.float32)          # Beta(a, b) = Ga / (Ga + Gb)
+        u = torch.rand((wc, n, K), generator=gen, device=dev)
+        alt = u < p_pop[:, pops_t, :]
+        dense = torch.zeros((wc, n, m_pad), dtype=torch.uint8, device=dev)
+        dense[:, :, 0] = 1
+        dense[:, :, ref_col] = (~alt).to(torch.uint8)
+        dense[:, :, ref_col + 1] = alt.to(torch.uint8)
+        dense[:, :, ref_col + 2] = 1
+        x_bits[w0:w0 + wc] = ctx.pack_bits(dense.view(wc * n, m_pad), pitch).view(wc, n, pitch)
+        del dense, u, alt
+    ctx.check()
+    return x_bits, node_len, pops, m, m_pad
+
+
+class HostGenerator:
+    """Stand-in for a device Context so make_windows_device can run on the host (CPU torch + numpy
+    packbits): used where no GPU work is wanted, e.g. the CPU reference arm of bench.py."""
+
+    def __init__(self):
+        import torch
+        self.torch_device = torch.device("cpu")
+
+    def pack_bits(self, dense, pitch):
+        import torch
+        d = dense.numpy()
+        packed = np.packbits(d, axis=1, bitorder="little")
+        return torch.from_numpy(packed.view("<u4").view(np.int32).reshape(d.shape[0], pitch))
+
+    def check(self):
+        pass

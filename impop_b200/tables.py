@@ -1,0 +1,160 @@
+"""All-pairs similarity tables (the text hand-off the reference scripts consume), kept as a
+dense identity matrix so the reductions run on the device.
+
+The reference scripts hold the table as ``dict[(min_name, max_name)] -> float``
+(pica2.py:6-58, h-fst.py:84-119).  `SimilarityTable` offers the same mapping interface
+(so code written against the reference's return value keeps working) and additionally owns
+the dense n x n fp64 matrix (NaN = pair absent) that libimpop_b200 reduces on the GPU.
+Only parsing and name handling happen here; no statistic is computed on the host.
+"""
+from __future__ import annotations
+
+import csv
+from collections.abc import Mapping
+
+import numpy as np
+
+REQUIRED_COLUMNS = ("group.a", "group.b", "estimated.identity")
+
+
+class SimilarityTable(Mapping):
+    """Mapping (name_a, name_b) -> estimated.identity backed by a dense matrix over sorted names."""
+
+    def __init__(self, names, matrix: np.ndarray):
+        self.names = list(names)
+        self.index = {s: i for i, s in enumerate(self.names)}
+        self.matrix = matrix
+        self._device = {}          # (device index, round_digits) -> torch tensor
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_rows(cls, rows, combine: str = "last"):
+        """rows: iterable of (a, b, value).  combine='last' (pica2.py:44 / h-fst.py:112: a repeated pair
+        keeps the last value) or 'max' (af.py:37-39 links on ANY row reaching the threshold)."""
+        rows = list(rows)
+        names = sorted({r[0] for r in rows} | {r[1] for r in rows})
+        index = {s: i for i, s in enumerate(names)}
+        n = len(names)
+        mat = np.full((n, n), np.nan, dtype=np.float64)
+        if rows:
+            ia = np.fromiter((index[r[0]] for r in rows), dtype=np.int64, count=len(rows))
+            ib = np.fromiter((index[r[1]] for r in rows), dtype=np.int64, count=len(rows))
+            v = np.fromiter((r[2] for r in rows), dtype=np.float64, count=len(rows))
+            if combine == "max":
+                order = np.argsort(v, kind="stable")       # later (larger) assignments win
+                ia, ib, v = ia[order], ib[order], v[order]
+            lo, hi = np.minimum(ia, ib), np.maximum(ia, ib)
+            mat[lo, hi] = v                                # repeated index: the last assignment stays
+            mat = np.where(np.isnan(mat), mat.T, mat)      # mirror the upper triangle
+        return cls(names, mat)
+
+    @classmethod
+    def from_mapping(cls, similarity, elements=None):
+        """Accept what the reference's read_similarity_file returns: a dict keyed by name pairs."""
+        if isinstance(similarity, cls):
+            return similarity
+        rows = [(a, b, float(v)) for (a, b), v in similarity.items()]
+        tab = cls.from_rows(rows)
+        if elements is not None:
+            extra = sorted(set(elements) - set(tab.names))
+            if extra:                                       # elements that occur in no pair
+                names = sorted(tab.names + extra)
+                mat = np.full((len(names), len(names)), np.nan)
+                where = [names.index(s) for s in tab.names]
+                mat[np.ix_(where, where)] = tab.matrix
+                tab = cls(names, mat)
+        return tab
+
+    # ------------------------------------------------------------------ Mapping interface
+    def _key(self, key):
+        a, b = key
+        i, j = self.index.get(a), self.index.get(b)
+        if i is None or j is None:
+            return None
+        return (i, j)
+
+    def __getitem__(self, key):
+        ij = self._key(key)
+        if ij is None:
+            raise KeyError(key)
+        v = self.matrix[ij]
+        if v != v:
+            raise KeyError(key)
+        return float(v)
+
+    def __iter__(self):
+        n = len(self.names)
+        for i in range(n):
+            for j in range(i, n):
+                if self.matrix[i, j] == self.matrix[i, j]:
+                    yield (self.names[i], self.names[j])
+
+    def __len__(self):
+        iu = np.triu_indices(len(self.names))
+        return int(np.count_nonzero(~np.isnan(self.matrix[iu])))
+
+    # ------------------------------------------------------------------ device side
+    def rounded(self, digits) -> np.ndarray:
+        """round(sim, r) exactly as CPython rounds (pica2.py:81-83, h-fst.py:149-150): correctly
+        rounded decimal, which rint(x * 10^r) / 10^r is not.  Text-level ingest."""
+        if digits is None:
+            return self.matrix
+        flat = [v if v != v else round(v, digits) for v in self.matrix.ravel().tolist()]
+        return np.array(flat, dtype=np.float64).reshape(self.matrix.shape)
+
+    def device(self, ctx, round_digits=None):
+        """The (optionally rounded) matrix as a device tensor, uploaded once per context."""
+        import torch
+        key = (ctx.device, round_digits)
+        if key not in self._device:
+            host = np.ascontiguousarray(self.rounded(round_digits))
+            if host.size == 0:
+                host = np.zeros((0, 0), dtype=np.float64)
+            self._device[key] = torch.from_numpy(host).to(ctx.torch_device)
+        return self._device[key]
+
+    def labels(self, ctx, **classes):
+        """uint8 label vector on the device from name collections: subset=..., a=..., b=..., seg=..."""
+        import torch
+        bits = {"subset": 1, "a": 2, "b": 4, "seg": 8}
+        lab = np.zeros(len(self.names), dtype=np.uint8)
+        for cls_name, members in classes.items():
+            if members is None:
+                continue
+            idx = [self.index[s] for s in members if s in self.index]
+            lab[idx] |= bits[cls_name]
+        return torch.from_numpy(lab).to(ctx.torch_device)
+
+
+class TableFormatError(Exception):
+    """A similarity table the reference scripts would refuse (message mirrors theirs)."""
+
+
+def read_rows(handle, on_bad_value: str = "error", strip_coords: bool = False):
+    """Parse a tab-separated table with a header; columns are found by name, extras ignored.
+
+    on_bad_value: 'error' (pica2.py:37-41), 'skip' (h-fst.py:107-109) or 'raise' (af.py:15, a bare
+    float() -> ValueError).  Returns (rows, row_count, bad) where bad lists (line_number, text)."""
+    reader = csv.DictReader(handle, delimiter="\t")
+    if not reader.fieldnames:
+        raise TableFormatError("empty")
+    missing = set(REQUIRED_COLUMNS) - set(reader.fieldnames)
+    if missing:
+        raise TableFormatError(("columns", list(reader.fieldnames)))
+    rows, bad, count = [], [], 0
+    for line_no, rec in enumerate(reader, start=2):
+        count += 1
+        a, b, text = rec["group.a"], rec["group.b"], rec["estimated.identity"]
+        try:
+            v = float(text)
+        except (TypeError, ValueError):
+            if on_bad_value == "raise":
+                raise
+            bad.append((line_no, text))
+            if on_bad_value == "error":
+                break
+            continue
+        if strip_coords:
+            a, b = a.split(":", 1)[0], b.split(":", 1)[0]
+        rows.append((a, b, v))
+    return rows, count, bad

@@ -1,0 +1,188 @@
+/* impop_b200 -- C ABI of the B200-native windowed population-statistics library.
+ *
+ * The reference (pangenome/impop) has NO library / plugin / FFI boundary on this path:
+ * layers talk through process spawns and text (SURVEY.md section 8 b).  Each entry point
+ * below therefore cites the reference *process or function* it replaces; INTEGRATION.md
+ * shows the ctypes stub a maintainer of the reference scripts would add.
+ *
+ * Conventions
+ *  - Every call returns 0 (IMPOP_OK) or a negative error code; impop_last_error(ctx) gives text.
+ *  - The caller owns every buffer.  Pointers named *_dev are device pointers on the
+ *    context's device; pointers named *_host are host pointers.  The library never
+ *    frees caller memory and keeps no global state (one context per device / thread).
+ *  - All work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL =
+ *    default stream).  Calls are asynchronous unless stated; impop_check() synchronises
+ *    the stream and reports device-side errors (bad input, barrier time-out).
+ *  - Bit layout of a window's presence matrix: haplotype i, node k -> bit (k & 31) of the
+ *    32-bit word x[x_off + i * pitch_words + (k >> 5)].  pitch_words and x_off must be
+ *    multiples of 4 (16-byte rows); bits at k >= m must be zero.
+ *  - Exactness: intersections, path lengths and unions are exact integers; a window must
+ *    satisfy sum(node_len) < 2^31 (checked on device -> IMPOP_ERR_RANGE at impop_check).
+ *  - There is no CPU fallback anywhere: without a CUDA device impop_create fails.
+ */
+#ifndef IMPOP_B200_H
+#define IMPOP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMPOP_OK 0
+#define IMPOP_ERR_ARG (-1)      /* bad argument (null pointer, misaligned pitch, ...) */
+#define IMPOP_ERR_CUDA (-2)     /* CUDA runtime error; see impop_last_error */
+#define IMPOP_ERR_NOMEM (-3)
+#define IMPOP_ERR_RANGE (-4)    /* window violates sum(node_len) < 2^31, or n/m limits */
+#define IMPOP_ERR_DEVICE (-5)   /* device-side failure flag (barrier time-out) */
+
+/* Haplotype label bits (one byte per haplotype). */
+#define IMPOP_LAB_SUBSET 1u /* counted in pi / n (pica2.py sample subset, run_tajd.sh -l list) */
+#define IMPOP_LAB_A 2u      /* population A of h-fst.py -a */
+#define IMPOP_LAB_B 4u      /* population B of h-fst.py -b */
+#define IMPOP_LAB_SEG 8u    /* rows that define segregating nodes S (run_tajd.sh:126-148 uses all) */
+
+/* Columns of one statistics row (fp64). */
+#define IMPOP_NSTATS 20
+#define IMPOP_ST_PI 0           /* pica2.py:154, all-singleton groups (threshold >= max identity) */
+#define IMPOP_ST_PI_PER_SITE 1  /* pica2.py:163-164; NaN when L == 0 */
+#define IMPOP_ST_PI_A 2         /* h-fst.py:197; divided by L when L > 0 (h-fst.py:225-240) */
+#define IMPOP_ST_PI_B 3
+#define IMPOP_ST_PI_XY 4
+#define IMPOP_ST_DXY 5
+#define IMPOP_ST_DA 6
+#define IMPOP_ST_FST 7          /* h-fst.py:214-222 */
+#define IMPOP_ST_S 8            /* segregating nodes (replaces run_tajd.sh:148) */
+#define IMPOP_ST_TAJIMA_D 9     /* tj_d.py:47-69 on (n, S, per-site pi if L > 0 else pi) as run_tajd.sh:166-180 */
+#define IMPOP_ST_A1 10
+#define IMPOP_ST_E1 11
+#define IMPOP_ST_E2 12
+#define IMPOP_ST_N 13
+#define IMPOP_ST_SUM_S 14       /* raw sum of pi_ij over subset pairs */
+#define IMPOP_ST_SUM_AA 15
+#define IMPOP_ST_SUM_BB 16
+#define IMPOP_ST_SUM_AB 17
+#define IMPOP_ST_TAJIMA_D_RAW 18 /* tj_d.py on (n, S, pi) with pi not divided by L */
+#define IMPOP_ST_RESERVED 19
+
+/* Columns of one counts row (int64). */
+#define IMPOP_NCOUNTS 8 /* nS nA nB pairsS pairsAA pairsBB pairsAB S */
+
+/* Pairwise-kernel implementations (both are CUDA kernels; there is no CPU path). */
+#define IMPOP_ALGO_TCGEN05 0 /* tcgen05.mma kind::i8, accumulators in TMEM (default) */
+#define IMPOP_ALGO_SIMT 1    /* dp4a shared-memory tiles; cross-check and bring-up path */
+
+typedef struct impop_ctx impop_ctx_t;
+typedef struct impop_batch impop_batch_t;
+
+/* A batch of W windows.  Descriptor arrays are HOST arrays of length `windows`; the bulk
+ * arrays are DEVICE pointers and must stay valid and unchanged (x, node_len) for the
+ * lifetime of the batch.  labels may be rewritten between calls. */
+typedef struct {
+    int32_t windows;
+    const int32_t *n_host;           /* haplotypes per window */
+    const int32_t *m_host;           /* nodes per window */
+    const int32_t *pitch_words_host; /* row pitch in 32-bit words (multiple of 4) */
+    const int64_t *x_off_host;       /* offset of the window in x_dev, in 32-bit words (multiple of 4) */
+    const int64_t *len_off_host;     /* offset of the window in node_len_dev (elements) */
+    const int64_t *lab_off_host;     /* offset of the window in labels_dev (bytes) */
+    const int64_t *length_host;      /* BED window length L per window (0 = no per-site normalisation) */
+    const uint32_t *x_dev;
+    const uint32_t *node_len_dev;
+    const uint8_t *labels_dev;
+} impop_batch_desc_t;
+
+int impop_version(void);
+int impop_create(int device, impop_ctx_t **ctx_out);
+int impop_destroy(impop_ctx_t *ctx);
+const char *impop_last_error(impop_ctx_t *ctx);
+/* Synchronise `stream`, then report sticky device-side errors raised by earlier kernels. */
+int impop_check(impop_ctx_t *ctx, void *stream);
+/* Number of kernels this library has launched on ctx so far (bench.py's gpu_launches). */
+int64_t impop_launch_count(impop_ctx_t *ctx);
+
+/* Optional per-kernel device timing for bench.py's roofline line: when enabled, every launch of the
+ * kernels below is bracketed by CUDA events on the caller's stream (no synchronisation added).
+ * impop_timing_read sums the elapsed time of the launches of one kernel recorded since the last
+ * impop_timing_enable call (which also clears the record). */
+#define IMPOP_KERNEL_PREP 0      /* path lengths, byte weights, heavy-node table */
+#define IMPOP_KERNEL_PAIRS 1     /* fused pairwise + fp64 reduction (tcgen05 or SIMT) */
+#define IMPOP_KERNEL_SUMS 2      /* per-window fixed-order sum of tile partials */
+#define IMPOP_KERNEL_COLSTAT 3   /* segregating nodes + label counts */
+#define IMPOP_KERNEL_FINALIZE 4  /* derived statistics */
+#define IMPOP_KERNEL_SITES 5     /* per-site allele counts */
+int impop_timing_enable(impop_ctx_t *ctx, int32_t enable);
+int impop_timing_read(impop_ctx_t *ctx, int32_t kernel_id, double *total_ms, int64_t *launches);
+
+/* K1 ingest.  Replaces the text hand-off `impg similarity ... > tmp.sim` (run_pica2_impg.sh:162-168):
+ * a dense 0/1 coverage matrix (n x m bytes, row pitch dense_pitch bytes) becomes bit-packed rows. */
+int impop_pack_bits(impop_ctx_t *ctx, const uint8_t *dense_dev, int32_t n, int32_t m, int64_t dense_pitch,
+                    uint32_t *x_dev, int32_t pitch_words, void *stream);
+
+/* Batch set-up: uploads the descriptor tables, sizes the scratch (path lengths, byte weights,
+ * heavy-node table, per-item partial sums).  Synchronous (one small device->host read). */
+int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *desc, impop_batch_t **batch_out);
+int impop_batch_destroy(impop_ctx_t *ctx, impop_batch_t *batch);
+int64_t impop_batch_items(const impop_batch_t *batch); /* number of 128 x 256 tile work items */
+
+/* K2+K3 fused.  Replaces, per window, `impg similarity` / `odgi similarity` (a-0) followed by
+ * pica2.analyze_similarity_matrix (pica2.py:60-169, threshold >= max identity), h-fst.calculate_fst
+ * (h-fst.py:173-249), the segregating-site count (run_tajd.sh:126-148) and tj_d.tajimas_d
+ * (tj_d.py:47-69).  stats_dev: W x IMPOP_NSTATS fp64; counts_dev: W x IMPOP_NCOUNTS int64. */
+int impop_window_stats(impop_ctx_t *ctx, impop_batch_t *batch, int32_t algo, double *stats_dev,
+                       int64_t *counts_dev, void *stream);
+
+/* The same in two steps, for splitting one batch's tile grid over several GPUs (SURVEY.md 8 e):
+ * rank r of `world` processes work items t with t % world == r and writes raw sums
+ * (W x 4: S, AA, BB, AB).  After an all-gather, impop_window_finalize adds `parts` such arrays
+ * ([parts][W][4], fixed order => run-to-run reproducible) and derives the statistics. */
+int impop_window_sums(impop_ctx_t *ctx, impop_batch_t *batch, int32_t algo, int32_t rank, int32_t world,
+                      double *sums_dev, void *stream);
+int impop_window_finalize(impop_ctx_t *ctx, impop_batch_t *batch, const double *sums_dev, int32_t parts,
+                          double *stats_dev, int64_t *counts_dev, void *stream);
+
+/* Materialising variant for one window of the batch (`--dump-similarity`, bit-exact tests):
+ * I_dev n x n int64 (diagonal = path length), A_dev n int64, pi_dev n x n fp64 (diagonal 0).
+ * Any output pointer may be NULL.  The table `impg similarity` would print is (I, A) -> identity = 1 - pi. */
+int impop_pairwise(impop_ctx_t *ctx, impop_batch_t *batch, int32_t window, int32_t algo, int64_t *I_dev,
+                   int64_t *A_dev, double *pi_dev, void *stream);
+
+/* K3 alone ("TSV mode"): reductions of pica2.py:118-164 / h-fst.py:130-249 over a dense identity
+ * matrix (n x n fp64, row stride ld, NaN = pair absent from the table; only i < j is read).
+ * weight_dev (nullable, n fp64): pica2 group frequencies |G|/N on representatives, 0 elsewhere;
+ * when given, wsum_dev[0] = sum_{i<j} (1 - s_ij) * w_i * w_j over present pairs (pica2.py:137-139),
+ * wsum_dev[1] = number of such pairs with w_i * w_j != 0, wsum_dev[2] = pica2's grouped
+ * pi = n/(n-1) * 2 * wsum_dev[0] (pica2.py:154; 0 when no pair) and wsum_dev[3] = pi / length (NaN when length == 0).
+ * wsum_dev holds 4 doubles.  stats_dev: IMPOP_NSTATS, counts_dev: IMPOP_NCOUNTS (S and Tajima columns use seg_sites as S). */
+int impop_reduce_identity(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t ld,
+                          const uint8_t *labels_dev, const double *weight_dev, int64_t length, double seg_sites,
+                          double *stats_dev, int64_t *counts_dev, double *wsum_dev, void *stream);
+
+/* tj_d.tajimas_d (tj_d.py:47-69) for `count` independent (n, S, pi) triples.
+ * parts_dev (nullable): count x 10 = a1 a2 b1 b2 c1 c2 e1 e2 numerator denominator. */
+int impop_tajima_d(impop_ctx_t *ctx, const int64_t *n_dev, const double *S_dev, const double *pi_dev,
+                   int32_t count, double *D_dev, double *parts_dev, void *stream);
+
+/* K4, BASELINE config 4: per-site allele counts of a site-major bit matrix (sites x words u64,
+ * bit h of a row = haplotype h carries the allele) under `pops` population masks (pops x words u64).
+ * counts_dev sites x pops int32; freq_dev (nullable) sites x pops fp64 = count / |mask|.
+ * The only per-site allele-count semantics in the reference is scripts/wip/op-afs.py:26-45. */
+int impop_site_counts(impop_ctx_t *ctx, const uint64_t *sites_dev, int64_t sites, int32_t words,
+                      const uint64_t *masks_dev, int32_t pops, int32_t *counts_dev, double *freq_dev, void *stream);
+
+/* K5: af.cluster (af.py:35-44): connected components of {identity >= threshold} over a dense
+ * identity matrix (NaN = absent).  comp_dev[i] = smallest member index of i's component. */
+int impop_cluster(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t ld, double threshold,
+                  int32_t *comp_dev, void *stream);
+
+/* pica2.analyze_similarity_matrix step 1 (pica2.py:94-112): greedy star grouping on `identity > threshold`
+ * (strict), seeds taken in index order (= sorted-name order; the reference's set.pop() order is
+ * hash-seed dependent).  group_dev[i] = index of the seed of i's group (its smallest
+ * member, the representative pica2.py:128 uses); weight_dev (nullable, n fp64) = |G|/n on seeds, 0 elsewhere. */
+int impop_greedy_groups(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t ld, double threshold,
+                        int32_t *group_dev, double *weight_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMPOP_B200_H */
