@@ -308,7 +308,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     if ((e = scratch(b, row_off[W], &t.A)) != cudaSuccess) return bail(e, "alloc A");
     if ((e = scratch(b, w8_off[W] + 64, &t.w8)) != cudaSuccess) return bail(e, "alloc w8");
     if ((e = scratch(b, heavy_off[W] + 64, &t.heavy)) != cudaSuccess) return bail(e, "alloc heavy");
-    if ((e = scratch(b, b->items * 4, &b->partials)) != cudaSuccess) return bail(e, "alloc partials");
+    if ((e = scratch(b, b->items * 8, &b->partials)) != cudaSuccess) return bail(e, "alloc partials");
     if ((e = scratch(b, (int64_t)W * 4, &b->sums_tmp)) != cudaSuccess) return bail(e, "alloc sums");
     if ((e = scratch(b, (int64_t)W * IMPOP_NCOUNTS, &b->counts_tmp)) != cudaSuccess) return bail(e, "alloc counts");
     if ((e = scratch(b, 1, &b->counter)) != cudaSuccess) return bail(e, "alloc counter");

@@ -26,18 +26,21 @@ __global__ void pack_bits_kernel(const uint8_t *dense, int32_t n, int32_t m, int
 // ------------------------------------------------------------------------------------------
 // K3 alone (TSV mode).  Stage 1: one CTA per row stripe, fixed thread->pair mapping, partials to
 // scratch; stage 2: one CTA adds the partials in order and finalizes.  Deterministic.
-// partial layout per block: [0..3] sums S AA BB AB, [4] weighted sum, [5..8] pair counts, [9] weighted count
 // ------------------------------------------------------------------------------------------
 constexpr int RI_THREADS = 256;
-constexpr int RI_VALS = 10;
+constexpr int RI_SUMS = 5;    // S AA BB AB weighted: compensated (hi, lo)
+constexpr int RI_CNTS = 5;    // matching pair counts (exact small integers in fp64)
+constexpr int RI_VALS = 2 * RI_SUMS + RI_CNTS;   // per block: hi[5], lo[5], counts[5]
 
 __global__ void __launch_bounds__(RI_THREADS) reduce_identity_stage1(const double *ident, int32_t n, int64_t ld,
                                                                      const uint8_t *labels, const double *weight,
                                                                      double *partials) {
-    __shared__ double s_red[RI_THREADS / 32][RI_VALS];
-    double v[RI_VALS];
+    __shared__ dd s_sum[RI_THREADS / 32][RI_SUMS];
+    __shared__ double s_cnt[RI_THREADS / 32][RI_CNTS];
+    dd v[RI_SUMS];
+    double c[RI_CNTS];
 #pragma unroll
-    for (int k = 0; k < RI_VALS; ++k) v[k] = 0.0;
+    for (int k = 0; k < RI_SUMS; ++k) { v[k].hi = 0.0; v[k].lo = 0.0; c[k] = 0.0; }
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint32_t fi = labels ? labels[i] : 0u;
         const double wi = weight ? weight[i] : 0.0;
@@ -46,46 +49,58 @@ __global__ void __launch_bounds__(RI_THREADS) reduce_identity_stage1(const doubl
             if (s != s) continue;  // pair absent from the table: skipped, not counted (h-fst.py:147-153)
             const double p = __dadd_rn(1.0, -s);
             const uint32_t fj = labels ? labels[j] : 0u;
-            if (fi & fj & IMPOP_LAB_SUBSET) { v[0] = __dadd_rn(v[0], p); v[5] += 1.0; }
-            if (fi & fj & IMPOP_LAB_A) { v[1] = __dadd_rn(v[1], p); v[6] += 1.0; }
-            if (fi & fj & IMPOP_LAB_B) { v[2] = __dadd_rn(v[2], p); v[7] += 1.0; }
+            if (fi & fj & IMPOP_LAB_SUBSET) { dd_add(v[0], p); c[0] += 1.0; }
+            if (fi & fj & IMPOP_LAB_A) { dd_add(v[1], p); c[1] += 1.0; }
+            if (fi & fj & IMPOP_LAB_B) { dd_add(v[2], p); c[2] += 1.0; }
             if (((fi & IMPOP_LAB_A) && (fj & IMPOP_LAB_B)) || ((fi & IMPOP_LAB_B) && (fj & IMPOP_LAB_A))) {
-                v[3] = __dadd_rn(v[3], p); v[8] += 1.0;
+                dd_add(v[3], p); c[3] += 1.0;
             }
             if (weight) {
                 const double wj = weight[j];
                 if (wi != 0.0 && wj != 0.0) {
-                    v[4] = __dadd_rn(v[4], __dmul_rn(__dmul_rn(p, wi), wj));  // pica2.py:139
-                    v[9] += 1.0;
+                    dd_add(v[4], __dmul_rn(__dmul_rn(p, wi), wj));  // pica2.py:139
+                    c[4] += 1.0;
                 }
             }
         }
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < RI_VALS; ++k) {
-        double t = warp_sum(v[k]);
-        if (lane == 0) s_red[warp][k] = t;
+    for (int k = 0; k < RI_SUMS; ++k) {
+        dd t = warp_sum_dd(v[k]);
+        double tc = warp_sum(c[k]);
+        if (lane == 0) { s_sum[warp][k] = t; s_cnt[warp][k] = tc; }
     }
     __syncthreads();
-    if (threadIdx.x < RI_VALS) {
-        double t = 0.0;
-        for (int wgt = 0; wgt < RI_THREADS / 32; ++wgt) t = __dadd_rn(t, s_red[wgt][threadIdx.x]);
-        partials[(size_t)blockIdx.x * RI_VALS + threadIdx.x] = t;
+    if (threadIdx.x < RI_SUMS) {
+        dd t = s_sum[0][threadIdx.x];
+        double tc = s_cnt[0][threadIdx.x];
+        for (int wgt = 1; wgt < RI_THREADS / 32; ++wgt) { dd_merge(t, s_sum[wgt][threadIdx.x]); tc += s_cnt[wgt][threadIdx.x]; }
+        double *out = partials + (size_t)blockIdx.x * RI_VALS;
+        out[threadIdx.x] = t.hi;
+        out[RI_SUMS + threadIdx.x] = t.lo;
+        out[2 * RI_SUMS + threadIdx.x] = tc;
     }
 }
 
 __global__ void reduce_identity_stage2(const double *partials, int32_t blocks, const uint8_t *labels, int32_t n,
                                        int64_t L, double seg, const double2 *harm, int32_t harm_n, double *stats,
                                        int64_t *counts, double *wsum) {
-    __shared__ double s_tot[RI_VALS];
+    __shared__ double s_tot[RI_SUMS], s_pairs[RI_CNTS];
     __shared__ int s_n[3];
     if (threadIdx.x < 3) s_n[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x < RI_VALS) {
-        double t = 0.0;
-        for (int b = 0; b < blocks; ++b) t = __dadd_rn(t, partials[(size_t)b * RI_VALS + threadIdx.x]);
-        s_tot[threadIdx.x] = t;
+    if (threadIdx.x < RI_SUMS) {
+        dd t = {0.0, 0.0};
+        double tc = 0.0;
+        for (int b = 0; b < blocks; ++b) {
+            const double *in = partials + (size_t)b * RI_VALS;
+            dd p = {in[threadIdx.x], in[RI_SUMS + threadIdx.x]};
+            dd_merge(t, p);
+            tc += in[2 * RI_SUMS + threadIdx.x];
+        }
+        s_tot[threadIdx.x] = dd_value(t);
+        s_pairs[threadIdx.x] = tc;
     }
     int c0 = 0, c1 = 0, c2 = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -99,7 +114,7 @@ __global__ void reduce_identity_stage2(const double *partials, int32_t blocks, c
     if (threadIdx.x == 0) {
         int64_t cnt[IMPOP_NCOUNTS];
         cnt[0] = s_n[0]; cnt[1] = s_n[1]; cnt[2] = s_n[2];
-        cnt[3] = (int64_t)s_tot[5]; cnt[4] = (int64_t)s_tot[6]; cnt[5] = (int64_t)s_tot[7]; cnt[6] = (int64_t)s_tot[8];
+        cnt[3] = (int64_t)s_pairs[0]; cnt[4] = (int64_t)s_pairs[1]; cnt[5] = (int64_t)s_pairs[2]; cnt[6] = (int64_t)s_pairs[3];
         cnt[7] = (int64_t)seg;
         double sums[4] = {s_tot[0], s_tot[1], s_tot[2], s_tot[3]};
         double st[IMPOP_NSTATS];
@@ -109,11 +124,11 @@ __global__ void reduce_identity_stage2(const double *partials, int32_t blocks, c
         if (wsum) {   // pica2.py:137-164 with group frequencies as weights; n = every element of the table
             const double nan = __longlong_as_double(0x7ff8000000000000ll);
             double pw = 0.0;
-            if (s_tot[9] > 0.0 && n >= 2) {
+            if (s_pairs[4] > 0.0 && n >= 2) {
                 double dn = (double)n;
                 pw = __dmul_rn(__ddiv_rn(dn, __dadd_rn(dn, -1.0)), __dmul_rn(2.0, s_tot[4]));   // pica2.py:154
             }
-            wsum[0] = s_tot[4]; wsum[1] = s_tot[9]; wsum[2] = pw;
+            wsum[0] = s_tot[4]; wsum[1] = s_pairs[4]; wsum[2] = pw;
             wsum[3] = (L > 0) ? __ddiv_rn(pw, (double)L) : nan;                                 // pica2.py:163-164
         }
     }

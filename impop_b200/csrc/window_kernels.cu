@@ -154,8 +154,13 @@ __device__ __forceinline__ uint32_t gather_heavy_bits(const uint32_t *row, const
 
 // Per-pair epilogue shared by both implementations.  Column class flags are warp-uniform
 // (every lane of a warp looks at the same column j), so the branches do not diverge.
+// Accumulation is two-level: plain adds into a chunk-local sum (<= 32 columns, terms of similar
+// size), then a compensated add of the chunk sum into the running total (see dd in common.cuh).
 struct PairAcc {
     double s, a, b;  // sums over columns carrying SUBSET / A / B, for this thread's row
+};
+struct PairTot {
+    dd s, a, b;
 };
 
 __device__ __forceinline__ void pair_step(PairAcc &acc, uint32_t inter, uint32_t ai, uint32_t aj, uint32_t fj,
@@ -165,6 +170,11 @@ __device__ __forceinline__ void pair_step(PairAcc &acc, uint32_t inter, uint32_t
     if (fj & IMPOP_LAB_SUBSET) acc.s = __dadd_rn(acc.s, p);
     if (fj & IMPOP_LAB_A) acc.a = __dadd_rn(acc.a, p);
     if (fj & IMPOP_LAB_B) acc.b = __dadd_rn(acc.b, p);
+}
+
+__device__ __forceinline__ void pair_fold(PairTot &tot, PairAcc &acc) {
+    dd_add(tot.s, acc.s); dd_add(tot.a, acc.a); dd_add(tot.b, acc.b);
+    acc.s = 0.0; acc.a = 0.0; acc.b = 0.0;
 }
 
 __device__ __forceinline__ void pair_dump(const ItemParams &p, int n, int i, int j, uint32_t inter, uint32_t ai,
@@ -184,20 +194,27 @@ __device__ __forceinline__ void pair_dump(const ItemParams &p, int n, int i, int
 
 // Row-side combination + block reduction into partials[item][4] (fixed order => deterministic).
 template <int NWARPS>
-__device__ __forceinline__ void item_reduce(const PairAcc &acc, uint32_t fi, double (*s_red)[4], double *out4) {
-    double v0 = (fi & IMPOP_LAB_SUBSET) ? acc.s : 0.0;
-    double v1 = (fi & IMPOP_LAB_A) ? acc.a : 0.0;
-    double v2 = (fi & IMPOP_LAB_B) ? acc.b : 0.0;
-    double v3 = __dadd_rn((fi & IMPOP_LAB_A) ? acc.b : 0.0, (fi & IMPOP_LAB_B) ? acc.a : 0.0);
-    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+__device__ __forceinline__ void item_reduce(const PairTot &tot, uint32_t fi, dd (*s_red)[4], double *out4) {
+    const dd zero = {0.0, 0.0};
+    dd v[4];
+    v[0] = (fi & IMPOP_LAB_SUBSET) ? tot.s : zero;
+    v[1] = (fi & IMPOP_LAB_A) ? tot.a : zero;
+    v[2] = (fi & IMPOP_LAB_B) ? tot.b : zero;
+    v[3] = (fi & IMPOP_LAB_A) ? tot.b : zero;
+    if (fi & IMPOP_LAB_B) dd_merge(v[3], tot.a);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { s_red[warp][0] = v0; s_red[warp][1] = v1; s_red[warp][2] = v2; s_red[warp][3] = v3; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = warp_sum_dd(v[k]);
+        if (lane == 0) s_red[warp][k] = v[k];
+    }
     __syncthreads();
     if (threadIdx.x < 4) {
-        double t = 0.0;
+        dd t = s_red[0][threadIdx.x];
 #pragma unroll
-        for (int wgt = 0; wgt < NWARPS; ++wgt) t = __dadd_rn(t, s_red[wgt][threadIdx.x]);
-        out4[threadIdx.x] = t;
+        for (int wgt = 1; wgt < NWARPS; ++wgt) dd_merge(t, s_red[wgt][threadIdx.x]);
+        out4[threadIdx.x] = t.hi;          // partials are stored as (hi[4], lo[4])
+        out4[4 + threadIdx.x] = t.lo;
     }
 }
 
@@ -223,7 +240,7 @@ struct TcShared {
     long long item_id;
     int32_t a_col[TILE_N];
     uint8_t f_col[TILE_N];
-    double red[TC_THREADS / 32][4];
+    dd red[TC_THREADS / 32][4];
 };
 constexpr int TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + (int)sizeof(TcShared) + 1024;
 
@@ -368,6 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) window_pairs_tc_kernel(WindowTa
         const int warp_row_min = bi * TILE_M + q4 * 32;
         const bool dump = (prm.dumpI != nullptr) || (prm.dumpPi != nullptr);
         PairAcc acc = {0.0, 0.0, 0.0};
+        PairTot tot = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
         for (int cc = hsel * half_cols; cc < (hsel + 1) * half_cols; cc += 16) {
             const int jbase = cb0 * TILE_M + cc;
             if (jbase >= n) break;
@@ -388,10 +406,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) window_pairs_tc_kernel(WindowTa
                 pair_step(acc, r[t], ai, aj, fj, rvalid && j < n && j > i);
                 if (dump) pair_dump(prm, n, i, j, r[t], ai, aj);
             }
+            pair_fold(tot, acc);
         }
         tc_fence_before();
         __syncthreads();   // all TMEM reads done before the next item's first MMA overwrites the accumulator
-        item_reduce<TC_THREADS / 32>(acc, fi, sh.red, prm.partials + item_id * 4);
+        item_reduce<TC_THREADS / 32>(tot, fi, sh.red, prm.partials + item_id * 8);
         __syncthreads();
     }
 
@@ -410,7 +429,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(WindowT
     __shared__ __align__(16) uint32_t s_b[SIMT_COLS][KCHUNK / 4 + 4];  // +4 words: rows stay 16-byte aligned
     __shared__ int32_t s_item[4];
     __shared__ long long s_item_id;
-    __shared__ double s_red[SIMT_THREADS / 32][4];
+    __shared__ dd s_red[SIMT_THREADS / 32][4];
     const int tid = threadIdx.x;
 
     while (true) {
@@ -445,6 +464,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(WindowT
         const uint32_t fi = rvalid ? (uint32_t)lab[i] : 0u;
         const bool dump = (prm.dumpI != nullptr) || (prm.dumpPi != nullptr);
         PairAcc acc = {0.0, 0.0, 0.0};
+        PairTot tot = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
 
         for (int sub = 0; sub < ncb * (TILE_M / SIMT_COLS); ++sub) {
             const int jbase = cb0 * TILE_M + sub * SIMT_COLS;
@@ -524,9 +544,10 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(WindowT
                 pair_step(acc, cnt[t], ai, aj, fj, rvalid && jv && j > i);
                 if (dump) pair_dump(prm, n, i, j, cnt[t], ai, aj);
             }
+            pair_fold(tot, acc);
         }
         __syncthreads();
-        item_reduce<SIMT_THREADS / 32>(acc, fi, s_red, prm.partials + item_id * 4);
+        item_reduce<SIMT_THREADS / 32>(tot, fi, s_red, prm.partials + item_id * 8);
         __syncthreads();
     }
 }
@@ -591,25 +612,36 @@ __global__ void window_sums_kernel(WindowTab tab, const double *partials, int32_
     const int lane = threadIdx.x & 31;
     for (int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < tab.W; w += gridDim.x * warps_per_block) {
         const int64_t t0 = tab.item_off[w], t1 = tab.item_off[w + 1];
-        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
         // first item of this window handled by `rank`
         int64_t first = t0 + ((rank - (t0 % world)) % world + world) % world;
         for (int64_t t = first + (int64_t)lane * world; t < t1; t += 32ll * world) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = __dadd_rn(v[k], partials[t * 4 + k]);
+            for (int k = 0; k < 4; ++k) {
+                dd p = {partials[t * 8 + k], partials[t * 8 + 4 + k]};
+                dd_merge(v[k], p);
+            }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
-        if (lane < 4) sums[(size_t)w * 4 + lane] = v[lane];
+        for (int k = 0; k < 4; ++k) v[k] = warp_sum_dd(v[k]);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sums[(size_t)w * 4 + k] = dd_value(v[k]);
+        }
     }
 }
 
 __global__ void finalize_kernel(WindowTab tab, const double *sums, int32_t parts, const int64_t *counts, double *stats) {
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < tab.W; w += gridDim.x * blockDim.x) {
-        double s[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int p = 0; p < parts; ++p)
+        double s[4];
+        {
+            dd acc[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+            for (int p = 0; p < parts; ++p)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s[k] = __dadd_rn(s[k], sums[((size_t)p * tab.W + w) * 4 + k]);
+                for (int k = 0; k < 4; ++k) dd_add(acc[k], sums[((size_t)p * tab.W + w) * 4 + k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[k] = dd_value(acc[k]);
+        }
         int64_t cnt[IMPOP_NCOUNTS];
 #pragma unroll
         for (int k = 0; k < IMPOP_NCOUNTS; ++k) cnt[k] = counts[(size_t)w * IMPOP_NCOUNTS + k];

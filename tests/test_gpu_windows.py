@@ -14,6 +14,7 @@ torch = pytest.importorskip("torch")
 
 from impop_b200 import synth  # noqa: E402
 from oracle import clib, similarity  # noqa: E402
+from oracle.compare import row_mismatches  # noqa: E402
 
 LAB_SUBSET, LAB_A, LAB_B, LAB_SEG = 1, 2, 4, 8
 TOL = 1e-12
@@ -52,8 +53,9 @@ def _random_window(n, m, seed, heavy_frac=0.1, max_len=200000, density=0.6):
 
 
 def _assert_stats(got, want, ctxmsg=""):
-    for k in range(len(want)):
-        assert rel_close(float(got[k]), float(want[k]), TOL), (ctxmsg, k, float(got[k]), float(want[k]))
+    """1e-12 relative per column; da / fst / D relative to their operands' scale (oracle/compare.py)."""
+    bad = row_mismatches(got, want, TOL)
+    assert not bad, (ctxmsg, bad)
 
 
 @pytest.mark.parametrize("algo", ALGOS)
