@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) window_pairs_tc_kernel(WindowTa
             int j = cb0 * TILE_M + tid;
             bool ok = tid < ncols && j < n;
             sh.a_col[tid] = ok ? Aw[j] : 0;
-            sh.f_col[tid] = ok ? lab[j] : (uint8_t)0;
+            sh.f_col[tid] = ok ? (uint8_t)clean_label(lab[j]) : (uint8_t)0;
         }
         __syncthreads();
 
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) window_pairs_tc_kernel(WindowTa
         const int i = bi * TILE_M + q4 * 32 + lane;
         const bool rvalid = i < n;
         const uint32_t ai = rvalid ? (uint32_t)Aw[i] : 0u;
-        const uint32_t fi = rvalid ? (uint32_t)lab[i] : 0u;
+        const uint32_t fi = rvalid ? clean_label(lab[i]) : 0u;
         const int half_cols = ncols / 2;
         const int warp_row_min = bi * TILE_M + q4 * 32;
         const bool dump = (prm.dumpI != nullptr) || (prm.dumpPi != nullptr);
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(WindowT
         const bool rvalid = i < n;
         const uint32_t *myrow = x + (size_t)i * pitch;
         const uint32_t ai = rvalid ? (uint32_t)Aw[i] : 0u;
-        const uint32_t fi = rvalid ? (uint32_t)lab[i] : 0u;
+        const uint32_t fi = rvalid ? clean_label(lab[i]) : 0u;
         const bool dump = (prm.dumpI != nullptr) || (prm.dumpPi != nullptr);
         PairAcc acc = {0.0, 0.0, 0.0};
         PairTot tot = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(WindowT
                 const int j = jbase + t;
                 const bool jv = j < n;
                 const uint32_t aj = jv ? (uint32_t)__ldg(Aw + j) : 0u;
-                const uint32_t fj = jv ? (uint32_t)__ldg(lab + j) : 0u;
+                const uint32_t fj = jv ? clean_label(__ldg(lab + j)) : 0u;
                 pair_step(acc, cnt[t], ai, aj, fj, rvalid && jv && j > i);
                 if (dump) pair_dump(prm, n, i, j, cnt[t], ai, aj);
             }
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(COL_THREADS) colstat_kernel(WindowTab tab, int
         __syncthreads();
         int c0 = 0, c1 = 0, c2 = 0;
         for (int i = threadIdx.x; i < n; i += COL_THREADS) {
-            uint32_t f = lab[i];
+            uint32_t f = clean_label(lab[i]);
             c0 += (f & IMPOP_LAB_SUBSET) != 0; c1 += (f & IMPOP_LAB_A) != 0; c2 += (f & IMPOP_LAB_B) != 0;
         }
         if (c0) atomicAdd(&s_cnt[0], c0);

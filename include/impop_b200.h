@@ -36,7 +36,8 @@ extern "C" {
 #define IMPOP_ERR_RANGE (-4)    /* window violates sum(node_len) < 2^31, or n/m limits */
 #define IMPOP_ERR_DEVICE (-5)   /* device-side failure flag (barrier time-out) */
 
-/* Haplotype label bits (one byte per haplotype). */
+/* Haplotype label bits (one byte per haplotype).  In the window kernels a haplotype carrying both
+ * IMPOP_LAB_A and IMPOP_LAB_B is dropped from both populations, as h-fst.py:181-185 does. */
 #define IMPOP_LAB_SUBSET 1u /* counted in pi / n (pica2.py sample subset, run_tajd.sh -l list) */
 #define IMPOP_LAB_A 2u      /* population A of h-fst.py -a */
 #define IMPOP_LAB_B 4u      /* population B of h-fst.py -b */

@@ -222,6 +222,11 @@ void oracle_finalize(const double sums[4], const int64_t cnt[8], int64_t L, doub
     stats[17] = sums[3]; stats[18] = d_raw; stats[19] = 0.0;
 }
 
+/* h-fst.py:181-185: a sequence listed in both populations is removed from both. */
+static inline unsigned clean_label(unsigned f) {
+    return ((f & (LAB_A | LAB_B)) == (LAB_A | LAB_B)) ? (f & ~(LAB_A | LAB_B)) : f;
+}
+
 /* One window end to end (fused: nothing n x n is stored). */
 int oracle_window_stats(const uint32_t *x, int n, int m, int pitch_words, const uint32_t *len,
                         const uint8_t *labels, int64_t L, double *stats, int64_t *counts) {
@@ -233,17 +238,17 @@ int oracle_window_stats(const uint32_t *x, int n, int m, int pitch_words, const 
     for (int i = 0; i < n; ++i) {
         const uint32_t *xi = x + (size_t)i * pitch_words;
         A[i] = lut_intersection(&lut, xi, xi, pitch_words);
-        cnt[0] += (labels[i] & LAB_SUBSET) != 0;
-        cnt[1] += (labels[i] & LAB_A) != 0;
-        cnt[2] += (labels[i] & LAB_B) != 0;
+        cnt[0] += (clean_label(labels[i]) & LAB_SUBSET) != 0;
+        cnt[1] += (clean_label(labels[i]) & LAB_A) != 0;
+        cnt[2] += (clean_label(labels[i]) & LAB_B) != 0;
     }
     nsum_t acc[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
     for (int i = 0; i < n; ++i) {
         const uint32_t *xi = x + (size_t)i * pitch_words;
-        unsigned li = labels[i];
+        unsigned li = clean_label(labels[i]);
         if (!(li & (LAB_SUBSET | LAB_A | LAB_B))) continue;
         for (int j = i + 1; j < n; ++j) {
-            unsigned lj = labels[j];
+            unsigned lj = clean_label(labels[j]);
             int inS = (li & lj & LAB_SUBSET) != 0;
             int inAA = (li & lj & LAB_A) != 0;
             int inBB = (li & lj & LAB_B) != 0;
