@@ -13,7 +13,8 @@
 namespace impop {
 cudaError_t launch_heavy_count(const uint32_t *, const int64_t *, const int32_t *, int32_t, int32_t *, cudaStream_t);
 cudaError_t launch_harmonic_table(double2 *, int32_t, cudaStream_t);
-cudaError_t launch_prep(const WindowTab &, int32_t *, cudaStream_t);
+cudaError_t launch_prep(const WindowTab &, int, cudaStream_t);
+cudaError_t launch_division_selftest(uint64_t, int64_t, unsigned long long *, cudaStream_t);
 cudaError_t configure_kernels();
 cudaError_t launch_pairs(const WindowTab &, const ItemParams &, int, int, cudaStream_t);
 cudaError_t launch_colstat(const WindowTab &, int64_t *, cudaStream_t);
@@ -83,7 +84,6 @@ struct impop_batch {
     double *partials = nullptr;
     double *sums_tmp = nullptr;
     int64_t *counts_tmp = nullptr;
-    int32_t *counter = nullptr;
 };
 
 static int fail(impop_ctx *ctx, int code, const std::string &msg) {
@@ -103,7 +103,7 @@ static int cuda_fail(impop_ctx *ctx, cudaError_t e, const char *where) {
 
 static int64_t items_of(int32_t n) {
     int64_t nb = (n + TILE_M - 1) / TILE_M, t = 0;
-    for (int64_t bi = 0; bi < nb; ++bi) t += (nb - bi + 1) / 2;
+    for (int64_t bi = 0; bi < nb; ++bi) t += items_of_rowblock(n, (int)bi);
     return t;
 }
 
@@ -253,7 +253,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
         pitch(d->pitch_words_host, d->pitch_words_host + W);
     std::vector<int64_t> x_off(d->x_off_host, d->x_off_host + W), len_off(d->len_off_host, d->len_off_host + W),
         lab_off(d->lab_off_host, d->lab_off_host + W), L(d->length_host, d->length_host + W);
-    std::vector<int64_t> row_off(W + 1, 0), w8_off(W + 1, 0), item_off(W + 1, 0), heavy_off(W + 1, 0);
+    std::vector<int64_t> row_off(W + 1, 0), w8_off(W + 1, 0), item_off(W + 1, 0), heavy_off(W + 1, 0), xh_off(W + 1, 0);
     bool any_rows = false, any_nodes = false;
     for (int32_t w = 0; w < W; ++w) {
         if (n[w] < 0 || m[w] < 0 || n[w] > (1 << 24) || m[w] > (1 << 24))
@@ -263,7 +263,6 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
         if (x_off[w] < 0 || len_off[w] < 0 || lab_off[w] < 0)
             return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: negative offset");
         row_off[w + 1] = row_off[w] + n[w];
-        w8_off[w + 1] = w8_off[w] + ((int64_t)(m[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
         item_off[w + 1] = item_off[w] + items_of(n[w]);
         any_rows |= n[w] > 0;
         any_nodes |= m[w] > 0;
@@ -287,7 +286,6 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     if ((e = upload(b, lab_off, &t.lab_off)) != cudaSuccess) return bail(e, "upload lab_off");
     if ((e = upload(b, L, &t.L)) != cudaSuccess) return bail(e, "upload L");
     if ((e = upload(b, row_off, &t.row_off)) != cudaSuccess) return bail(e, "upload row_off");
-    if ((e = upload(b, w8_off, &t.w8_off)) != cudaSuccess) return bail(e, "upload w8_off");
     if ((e = upload(b, item_off, &t.item_off)) != cudaSuccess) return bail(e, "upload item_off");
     t.x = d->x_dev; t.len = d->node_len_dev; t.labels = d->labels_dev;
     t.W = W; t.err = ctx->err_dev; t.harm = ctx->harm_dev; t.harm_n = HARM_N;
@@ -300,18 +298,25 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
         std::vector<int32_t> cnt(W, 0);
         if (W > 0 && (e = cudaMemcpy(cnt.data(), cnt_dev, sizeof(int32_t) * W, cudaMemcpyDeviceToHost)) != cudaSuccess)
             return bail(e, "read heavy counts");
-        for (int32_t w = 0; w < W; ++w)
-            heavy_off[w + 1] = heavy_off[w] + ((int64_t)(cnt[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
+        for (int32_t w = 0; w < W; ++w) {
+            const int64_t hpad = ((int64_t)(cnt[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
+            const int64_t m64 = ((int64_t)(m[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
+            heavy_off[w + 1] = heavy_off[w] + hpad;
+            w8_off[w + 1] = w8_off[w] + m64 + hpad;                 // virtual columns: dense | heavy
+            xh_off[w + 1] = xh_off[w] + (int64_t)n[w] * (hpad / 32);
+        }
     }
     if ((e = upload(b, heavy_off, &t.heavy_off)) != cudaSuccess) return bail(e, "upload heavy_off");
+    if ((e = upload(b, w8_off, &t.w8_off)) != cudaSuccess) return bail(e, "upload w8_off");
+    if ((e = upload(b, xh_off, &t.xh_off)) != cudaSuccess) return bail(e, "upload xh_off");
     b->items = item_off[W];
     if ((e = scratch(b, row_off[W], &t.A)) != cudaSuccess) return bail(e, "alloc A");
     if ((e = scratch(b, w8_off[W] + 64, &t.w8)) != cudaSuccess) return bail(e, "alloc w8");
     if ((e = scratch(b, heavy_off[W] + 64, &t.heavy)) != cudaSuccess) return bail(e, "alloc heavy");
-    if ((e = scratch(b, b->items * 8, &b->partials)) != cudaSuccess) return bail(e, "alloc partials");
+    if ((e = scratch(b, xh_off[W] + 4, &t.xh)) != cudaSuccess) return bail(e, "alloc heavy bits");
+    if ((e = scratch(b, b->items * PART_STRIDE, &b->partials)) != cudaSuccess) return bail(e, "alloc partials");
     if ((e = scratch(b, (int64_t)W * 4, &b->sums_tmp)) != cudaSuccess) return bail(e, "alloc sums");
     if ((e = scratch(b, (int64_t)W * IMPOP_NCOUNTS, &b->counts_tmp)) != cudaSuccess) return bail(e, "alloc counts");
-    if ((e = scratch(b, 1, &b->counter)) != cudaSuccess) return bail(e, "alloc counter");
     b->item_off = item_off;
     b->n = n;
     *batch_out = b;
@@ -325,9 +330,9 @@ static int run_sums(impop_ctx_t *ctx, impop_batch_t *b, int32_t algo, int32_t ra
     if (algo != IMPOP_ALGO_TCGEN05 && algo != IMPOP_ALGO_SIMT) return fail(ctx, IMPOP_ERR_ARG, "unknown algo");
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, IMPOP_ERR_ARG, "bad rank/world");
     if (b->tab.W == 0) return IMPOP_OK;
-    CU(timed(ctx, IMPOP_KERNEL_PREP, st, [&] { return launch_prep(b->tab, b->counter, st); }));
+    CU(timed(ctx, IMPOP_KERNEL_PREP, st, [&] { return launch_prep(b->tab, ctx->sm_count, st); }));
     ItemParams prm{};
-    prm.partials = b->partials; prm.counter = b->counter;
+    prm.partials = b->partials;
     prm.item_begin = 0; prm.item_end = b->items; prm.rank = rank; prm.world = world;
     prm.dumpI = nullptr; prm.dumpPi = nullptr;
     CU(timed(ctx, IMPOP_KERNEL_PAIRS, st, [&] { return launch_pairs(b->tab, prm, algo, ctx->sm_count, st); }));
@@ -375,11 +380,11 @@ int impop_pairwise(impop_ctx_t *ctx, impop_batch_t *batch, int32_t window, int32
     if (algo != IMPOP_ALGO_TCGEN05 && algo != IMPOP_ALGO_SIMT) return fail(ctx, IMPOP_ERR_ARG, "unknown algo");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CU(launch_prep(batch->tab, batch->counter, st));
+    CU(launch_prep(batch->tab, ctx->sm_count, st));
     ctx->launches += 1;
     if (I_dev || pi_dev) {
         ItemParams prm{};
-        prm.partials = batch->partials; prm.counter = batch->counter;
+        prm.partials = batch->partials;
         prm.item_begin = batch->item_off[window]; prm.item_end = batch->item_off[window + 1];
         prm.rank = 0; prm.world = 1; prm.dumpI = I_dev; prm.dumpPi = pi_dev;
         CU(launch_pairs(batch->tab, prm, algo, ctx->sm_count, st));
@@ -458,6 +463,23 @@ int impop_greedy_groups(impop_ctx_t *ctx, const double *ident_dev, int32_t n, in
     CU(cudaSetDevice(ctx->device));
     CU(launch_greedy_groups(ident_dev, n, ld, threshold, group_dev, weight_dev, (cudaStream_t)stream));
     ctx->launches += (n > 0);
+    return IMPOP_OK;
+}
+
+int impop_selftest_division(impop_ctx_t *ctx, uint64_t seed, int64_t count, int64_t *mismatches_host, void *stream) {
+    if (!ctx || !mismatches_host) return IMPOP_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long *dev = nullptr;
+    CU(cudaMalloc(&dev, sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(dev, 0, sizeof(unsigned long long), (cudaStream_t)stream);
+    if (e == cudaSuccess) e = launch_division_selftest(seed, count, dev, (cudaStream_t)stream);
+    unsigned long long host = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&host, dev, sizeof(host), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "impop_selftest_division");
+    ctx->launches += 1;
+    *mismatches_host = (int64_t)host;
     return IMPOP_OK;
 }
 

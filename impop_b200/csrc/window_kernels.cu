@@ -1,6 +1,6 @@
-// Windowed pairwise kernels: prep (path lengths, byte weights, heavy-node table), the fused
-// pairwise + fp64 reduction kernel in two implementations (tcgen05 / TMEM and dp4a SIMT),
-// segregating-node counts, and the per-window finalize.
+// Windowed pairwise kernels: prep (path lengths, byte weights, heavy-node table and bits), the fused
+// pairwise + fp64 reduction kernel in two implementations (warp-specialised tcgen05 / TMEM, and dp4a
+// SIMT as cross-check), segregating-node counts, and the per-window finalize.
 //
 // Replaces, per window: `impg similarity` / `odgi similarity` (reference call sites
 // run_pica2_impg.sh:162-168, run_h-fst.sh:65-67, run_tajd.sh:160) + pica2.py:118-164 +
@@ -17,26 +17,34 @@ namespace impop {
 
 // ==========================================================================================
 // Prep: one CTA per window.
+//   (a) byte weights of the dense columns, heavy-node table, range check sum(len) < 2^31
+//   (b) path lengths A_i through a nibble look-up table of node lengths held in shared memory
+//       (lane l of a warp looks up nibble position 32 q + l, so the 32 look-ups of a warp hit 32
+//       different banks)
+//   (c) presence bits of the heavy columns, gathered once per row (ballot)
 // ==========================================================================================
 constexpr int PREP_THREADS = 256;
+constexpr int LUT_POS = 512;                 // nibble positions per table pass = 2048 nodes = 64 words
 
-__global__ void __launch_bounds__(PREP_THREADS) prep_kernel(WindowTab tab, int32_t *counter) {
+__global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constant__ WindowTab tab) {
+    __shared__ uint32_t s_lut[16][LUT_POS];   // 32 KB
     __shared__ int s_heavy;
     __shared__ unsigned long long s_total;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int w = blockIdx.x; w < tab.W; w += gridDim.x) {
         const int n = tab.n[w], m = tab.m[w], pitch = tab.pitch[w];
         const uint32_t *len = tab.len + tab.len_off[w];
         const uint32_t *x = tab.x + tab.x_off[w];
         uint8_t *w8 = tab.w8 + tab.w8_off[w];
         uint32_t *heavy = tab.heavy + tab.heavy_off[w];
-        const int m64 = (int)(tab.w8_off[w + 1] - tab.w8_off[w]);
+        const int m64 = ((m + KCHUNK - 1) / KCHUNK) * KCHUNK;
         const int hpad = (int)(tab.heavy_off[w + 1] - tab.heavy_off[w]);
         if (threadIdx.x == 0) { s_heavy = 0; s_total = 0ull; }
         __syncthreads();
+        // ---- (a)
         unsigned long long tot = 0;
         for (int k = threadIdx.x; k < m64; k += PREP_THREADS) {
-            uint32_t l = (k < m) ? len[k] : 0u;
+            uint32_t l = (k < m) ? __ldg(len + k) : 0u;
             tot += l;
             w8[k] = (uint8_t)(l % HEAVY_Q);
             uint32_t q = l / HEAVY_Q;
@@ -50,25 +58,55 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(WindowTab tab, int32
         if (tot) atomicAdd(&s_total, tot);
         __syncthreads();
         if (threadIdx.x == 0 && (s_total >= (1ull << 31) || s_heavy > hpad)) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);
-        for (int s = s_heavy + threadIdx.x; s < hpad; s += PREP_THREADS) heavy[s] = 0u;
-        // path lengths: one warp per haplotype
+        const int nh = s_heavy < hpad ? s_heavy : hpad;
+        for (int s = nh + threadIdx.x; s < hpad; s += PREP_THREADS) heavy[s] = 0u;
+        __syncthreads();
+        for (int s = threadIdx.x; s < hpad; s += PREP_THREADS) w8[m64 + s] = (uint8_t)(heavy[s] & 255u);
+        // ---- (b)
         int32_t *A = tab.A + tab.row_off[w];
-        const int words = (m + 31) >> 5;
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int c0 = 0; c0 < m || c0 == 0; c0 += 4 * LUT_POS) {
+            for (int p = threadIdx.x; p < LUT_POS; p += PREP_THREADS) {
+                const int k = c0 + 4 * p;
+                const uint32_t l0 = (k < m) ? __ldg(len + k) : 0u, l1 = (k + 1 < m) ? __ldg(len + k + 1) : 0u;
+                const uint32_t l2 = (k + 2 < m) ? __ldg(len + k + 2) : 0u, l3 = (k + 3 < m) ? __ldg(len + k + 3) : 0u;
+#pragma unroll
+                for (int v = 0; v < 16; ++v)
+                    s_lut[v][p] = ((v & 1) ? l0 : 0u) + ((v & 2) ? l1 : 0u) + ((v & 4) ? l2 : 0u) + ((v & 8) ? l3 : 0u);
+            }
+            __syncthreads();
+            const int w0 = c0 >> 5;                       // first word of this pass
+            const int passes = (m - c0 > 1024) ? 2 : 1;   // 32 words (1024 nodes) per warp pass
+            for (int i = warp; i < n; i += PREP_THREADS / 32) {
+                const uint32_t *row = x + (size_t)i * pitch + w0;
+                uint32_t acc = 0;
+                for (int ps = 0; ps < passes; ++ps) {
+                    const int wd = ps * 32 + lane;
+                    const uint32_t word = (w0 + wd < pitch) ? __ldg(row + wd) : 0u;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t src = __shfl_sync(0xffffffffu, word, q * 4 + (lane >> 3));
+                        const uint32_t nib = (src >> ((lane & 7) * 4)) & 15u;
+                        acc += s_lut[nib][ps * 256 + q * 32 + lane];
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                if (lane == 0) A[i] = (int32_t)(acc + (c0 ? (uint32_t)A[i] : 0u));
+            }
+            __syncthreads();
+        }
+        // ---- (c)
+        const int hwords = hpad >> 5;
+        uint32_t *xh = tab.xh + tab.xh_off[w];
         for (int i = warp; i < n; i += PREP_THREADS / 32) {
             const uint32_t *row = x + (size_t)i * pitch;
-            uint32_t acc = 0;
-            for (int wd = lane; wd < words; wd += 32) {
-                uint32_t v = __ldg(row + wd);
-                while (v) {
-                    int k = wd * 32 + (__ffs(v) - 1);
-                    if (k < m) acc += __ldg(len + k);
-                    v &= v - 1;
-                }
+            for (int hw = 0; hw < hwords; ++hw) {
+                const uint32_t ent = heavy[hw * 32 + lane];
+                const uint32_t col = ent >> 8;
+                const bool bit = (ent & 255u) && ((__ldg(row + (col >> 5)) >> (col & 31u)) & 1u);
+                const uint32_t word = __ballot_sync(0xffffffffu, bit);
+                if (lane == 0) xh[(size_t)i * hwords + hw] = word;
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-            if (lane == 0) A[i] = (int32_t)acc;
         }
         __syncthreads();
     }
@@ -111,7 +149,7 @@ __global__ void harmonic_table_kernel(double2 *harm, int32_t nmax) {
 // Work-item bookkeeping
 // ==========================================================================================
 struct Item {
-    int w, bi, cb0, ncb;
+    int w, bi, col0, ncols;   // window, row block, first column, columns (multiple of 16, <= 256)
 };
 
 __device__ Item decode_item(const WindowTab &tab, int64_t t) {
@@ -122,59 +160,19 @@ __device__ Item decode_item(const WindowTab &tab, int64_t t) {
     }
     Item it;
     it.w = lo;
-    int64_t r = t - tab.item_off[lo];
-    int nb = (tab.n[lo] + TILE_M - 1) / TILE_M;
+    int r = (int)(t - tab.item_off[lo]);
+    const int n = tab.n[lo];
     int bi = 0;
-    while (bi < nb) {
-        int u = (nb - bi + 1) >> 1;
-        if (r < u) break;
-        r -= u;
+    while (true) {
+        const int cnt = items_of_rowblock(n, bi);
+        if (r < cnt) break;
+        r -= cnt;
         ++bi;
     }
     it.bi = bi;
-    it.cb0 = bi + 2 * (int)r;
-    it.ncb = min(2, nb - it.cb0);
+    it.ncols = width_of_rowblock(n, bi);
+    it.col0 = bi * TILE_M + r * it.ncols;
     return it;
-}
-
-// Gather 32 presence bits of one haplotype row for 32 heavy-table entries.
-__device__ __forceinline__ uint32_t gather_heavy_bits(const uint32_t *row, const uint32_t *entries, bool row_valid) {
-    uint32_t bits = 0;
-    if (row_valid) {
-#pragma unroll 4
-        for (int e = 0; e < 32; ++e) {
-            uint32_t ent = __ldg(entries + e);
-            uint32_t col = ent >> 8;
-            uint32_t word = __ldg(row + (col >> 5));
-            bits |= ((word >> (col & 31u)) & 1u) << e;
-        }
-    }
-    return bits;
-}
-
-// Per-pair epilogue shared by both implementations.  Column class flags are warp-uniform
-// (every lane of a warp looks at the same column j), so the branches do not diverge.
-// Accumulation is two-level: plain adds into a chunk-local sum (<= 32 columns, terms of similar
-// size), then a compensated add of the chunk sum into the running total (see dd in common.cuh).
-struct PairAcc {
-    double s, a, b;  // sums over columns carrying SUBSET / A / B, for this thread's row
-};
-struct PairTot {
-    dd s, a, b;
-};
-
-__device__ __forceinline__ void pair_step(PairAcc &acc, uint32_t inter, uint32_t ai, uint32_t aj, uint32_t fj,
-                                          bool valid) {
-    if (fj == 0u) return;
-    double p = valid ? pi_from_counts(inter, ai, aj) : 0.0;
-    if (fj & IMPOP_LAB_SUBSET) acc.s = __dadd_rn(acc.s, p);
-    if (fj & IMPOP_LAB_A) acc.a = __dadd_rn(acc.a, p);
-    if (fj & IMPOP_LAB_B) acc.b = __dadd_rn(acc.b, p);
-}
-
-__device__ __forceinline__ void pair_fold(PairTot &tot, PairAcc &acc) {
-    dd_add(tot.s, acc.s); dd_add(tot.a, acc.a); dd_add(tot.b, acc.b);
-    acc.s = 0.0; acc.a = 0.0; acc.b = 0.0;
 }
 
 __device__ __forceinline__ void pair_dump(const ItemParams &p, int n, int i, int j, uint32_t inter, uint32_t ai,
@@ -192,334 +190,336 @@ __device__ __forceinline__ void pair_dump(const ItemParams &p, int n, int i, int
     }
 }
 
-// Row-side combination + block reduction into partials[item][4] (fixed order => deterministic).
-template <int NWARPS>
-__device__ __forceinline__ void item_reduce(const PairTot &tot, uint32_t fi, dd (*s_red)[4], double *out4) {
+// Row-side combination of one warp's per-row totals (s, a, b = sums over the columns carrying
+// SUBSET / A / B) into the four pair sums S, AA, BB, AB, reduced over the warp's 32 rows and
+// written as one partial record (hi[4], lo[4]).
+__device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const dd &tb, uint32_t fi, double *out8) {
     const dd zero = {0.0, 0.0};
     dd v[4];
-    v[0] = (fi & IMPOP_LAB_SUBSET) ? tot.s : zero;
-    v[1] = (fi & IMPOP_LAB_A) ? tot.a : zero;
-    v[2] = (fi & IMPOP_LAB_B) ? tot.b : zero;
-    v[3] = (fi & IMPOP_LAB_A) ? tot.b : zero;
-    if (fi & IMPOP_LAB_B) dd_merge(v[3], tot.a);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    v[0] = (fi & IMPOP_LAB_SUBSET) ? ts : zero;
+    v[1] = (fi & IMPOP_LAB_A) ? ta : zero;
+    v[2] = (fi & IMPOP_LAB_B) ? tb : zero;
+    v[3] = (fi & IMPOP_LAB_A) ? tb : zero;
+    if (fi & IMPOP_LAB_B) dd_merge(v[3], ta);
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         v[k] = warp_sum_dd(v[k]);
-        if (lane == 0) s_red[warp][k] = v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        dd t = s_red[0][threadIdx.x];
-#pragma unroll
-        for (int wgt = 1; wgt < NWARPS; ++wgt) dd_merge(t, s_red[wgt][threadIdx.x]);
-        out4[threadIdx.x] = t.hi;          // partials are stored as (hi[4], lo[4])
-        out4[4 + threadIdx.x] = t.lo;
+        if (lane == 0) { out8[k] = v[k].hi; out8[4 + k] = v[k].lo; }
     }
 }
 
 // ==========================================================================================
-// tcgen05 implementation.  256 threads, 2 CTAs per SM (each owns 256 TMEM columns), so one
-// CTA's fp64 epilogue overlaps the other's operand expansion + MMA.
+// tcgen05 implementation, warp specialised.  One CTA per SM:
+//   warps 0-11   producers: expand presence bits into the u8 operand tiles of a ring of stages
+//                (warps 0-3: the 128 A rows, warps 4-11: up to 256 B rows; lane = row)
+//   warp  12     MMA issuer (one elected lane): tcgen05.mma kind::i8 into one of two TMEM buffers
+//   warps 13-20  epilogue: tcgen05.ld, exact integer union, fp64 pi_ij, compensated sums
+// The integer pipes (expansion) and the fp64 pipe (epilogue) so run concurrently on different
+// warps, and items flow through without CTA-wide barriers.
 // ==========================================================================================
-constexpr int TC_THREADS = 256;
-constexpr int TC_STAGES = 4;
+constexpr int WS_PROD_WARPS = 12;
+constexpr int WS_EPI_WARPS = 8;
+constexpr int WS_MMA_WARP = WS_PROD_WARPS;
+constexpr int WS_THREADS = 32 * (WS_PROD_WARPS + 1 + WS_EPI_WARPS);   // 672
+constexpr int WS_STAGES = 6;
 constexpr int A_STAGE_BYTES = TILE_M * KCHUNK;                  // 8 KB
 constexpr int B_STAGE_BYTES = TILE_N * KCHUNK;                  // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;      // 24 KB
 constexpr uint32_t LBO_A = TILE_M * 16;                         // next 16-byte K slab of the A tile
 constexpr uint32_t LBO_B = TILE_N * 16;
 constexpr uint32_t SBO_AB = 128;                                // next 8-row group
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;                             // two accumulator buffers of 256 columns
+constexpr int EPI_COLS = 128;                                   // columns one epilogue warp can own
 
-struct TcShared {
-    uint64_t stage_free[TC_STAGES];
-    uint64_t acc_full;
-    uint32_t tmem_base;
-    int32_t item_w, item_bi, item_cb0, item_ncb;
-    long long item_id;
-    int32_t a_col[TILE_N];
-    uint8_t f_col[TILE_N];
-    dd red[TC_THREADS / 32][4];
+struct __align__(16) ColInfo {
+    uint32_t aj, flags;
+    double fs, fa, fb;       // 1.0 / 0.0: column carries SUBSET / A / B
 };
-constexpr int TC_SMEM_BYTES = TC_STAGES * STAGE_BYTES + (int)sizeof(TcShared) + 1024;
 
-__global__ void __launch_bounds__(TC_THREADS, 2) window_pairs_tc_kernel(WindowTab tab, ItemParams prm) {
-    extern __shared__ uint8_t smem_raw[];
-    // operand stages need 128-byte alignment (16-byte core-matrix rows); align generously
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    TcShared &sh = *reinterpret_cast<TcShared *>(smem + TC_STAGES * STAGE_BYTES);
+struct WsShared {
+    uint64_t full[WS_STAGES], empty[WS_STAGES];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+    ColInfo col[WS_EPI_WARPS][EPI_COLS];      // 32 KB
+};
+constexpr int WS_SMEM_BYTES = WS_STAGES * STAGE_BYTES + (int)sizeof(WsShared);
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_constant__ ItemParams prm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    WsShared &sh = *reinterpret_cast<WsShared *>(smem + WS_STAGES * STAGE_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) mbar_init(&sh.stage_free[s], 1);
-        mbar_init(&sh.acc_full, 1);
+        for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&sh.full[s], WS_PROD_WARPS); mbar_init(&sh.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sh.acc_full[b], 1); mbar_init(&sh.acc_empty[b], WS_EPI_WARPS); }
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc(&sh.tmem_base, TMEM_COLS);
+    if (warp == WS_MMA_WARP) tmem_alloc(&sh.tmem_base, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sh.tmem_base;
-    const uint32_t smem_base_u32 = smem_u32(smem);
-
-    uint32_t gchunk = 0;      // chunks issued so far by this CTA (stage = gchunk % STAGES)
-    uint32_t acc_uses = 0;    // completed phases of acc_full (items with at least one MMA)
+    const int64_t stride = (int64_t)gridDim.x * prm.world;
+    const int64_t first = prm.item_begin + (int64_t)blockIdx.x * prm.world + prm.rank;
     bool alive = true;
 
-    while (true) {
-        if (tid == 0) {
-            int64_t t = prm.item_begin + ((int64_t)atomicAdd(prm.counter, 1) * prm.world + prm.rank);
-            if (t < prm.item_end) {
-                Item it = decode_item(tab, t);
-                sh.item_w = it.w; sh.item_bi = it.bi; sh.item_cb0 = it.cb0; sh.item_ncb = it.ncb;
-            } else {
-                sh.item_w = -1;
-            }
-            sh.item_id = (long long)t;
-        }
-        __syncthreads();
-        const int w = sh.item_w;
-        if (w < 0) break;
-        const int64_t item_id = sh.item_id;
-        const int bi = sh.item_bi, cb0 = sh.item_cb0, ncb = sh.item_ncb;
-        const int n = tab.n[w], pitch = tab.pitch[w];
-        const uint32_t *x = tab.x + tab.x_off[w];
-        const uint8_t *w8 = tab.w8 + tab.w8_off[w];
-        const uint32_t *heavy = tab.heavy + tab.heavy_off[w];
-        const int32_t *Aw = tab.A + tab.row_off[w];
-        const uint8_t *lab = tab.labels + tab.lab_off[w];
-        const int dense_chunks = (int)((tab.w8_off[w + 1] - tab.w8_off[w]) / KCHUNK);
-        const int heavy_chunks = (int)((tab.heavy_off[w + 1] - tab.heavy_off[w]) / KCHUNK);
-        const int nch = dense_chunks + heavy_chunks;
-        const int ncols = ncb * TILE_M;
-        const uint32_t idesc = make_idesc_u8(TILE_M, (uint32_t)ncols);
-
-        {   // column-side path lengths and labels for the epilogue
-            int j = cb0 * TILE_M + tid;
-            bool ok = tid < ncols && j < n;
-            sh.a_col[tid] = ok ? Aw[j] : 0;
-            sh.f_col[tid] = ok ? (uint8_t)clean_label(lab[j]) : (uint8_t)0;
-        }
-        __syncthreads();
-
-        // ------------------------------------------------------------------ K loop
-        for (int c = 0; c < nch; ++c) {
-            const uint32_t s = gchunk % TC_STAGES, use = gchunk / TC_STAGES;
-            if (use >= 1 && alive) alive = mbar_wait(&sh.stage_free[s], (use - 1) & 1u, tab.err);
-            uint8_t *stA = smem + s * STAGE_BYTES;
-            uint8_t *stB = stA + A_STAGE_BYTES;
-            const bool is_heavy = c >= dense_chunks;
-            const int hc = c - dense_chunks;
-            // 24 warp tasks: (operand, 32-row group, 32-column half)
-            const int b_groups = ncb * 4;
-            for (int task = warp; task < 8 + 2 * b_groups; task += TC_THREADS / 32) {
-                const bool isA = task < 8;
-                const int tt = isA ? task : task - 8;
-                const int rg = tt >> 1, half = tt & 1;
-                const int rl = rg * 32 + lane;
-                const int grow = (isA ? bi : cb0) * TILE_M + rl;
-                const bool rvalid = grow < n;
-                const uint32_t *row = x + (size_t)grow * pitch;
-                uint32_t bits = 0;
-                uint32_t wv[8];
-                if (!is_heavy) {
-                    const int wd = c * 2 + half;
-                    if (rvalid && wd < pitch) bits = __ldg(row + wd);
-                    if (!isA) {
-                        const uint4 *wp = reinterpret_cast<const uint4 *>(w8 + c * KCHUNK + half * 32);
-                        uint4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-                        wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
-                        wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
-                    }
-                } else {
-                    const uint32_t *ent = heavy + hc * KCHUNK + half * 32;
-                    bits = gather_heavy_bits(row, ent, rvalid);
-                    if (!isA) {
+    if (warp < WS_PROD_WARPS) {
+        // ================================================================ producers
+        const bool isA = warp < 4;
+        const int rl = (isA ? warp : warp - 4) * 32 + lane;          // row of the operand tile
+        const uint32_t lbo = isA ? LBO_A : LBO_B;
+        uint32_t g = 0;                                               // chunks produced so far
+        for (int64_t t = first; t < prm.item_end; t += stride) {
+            const Item it = decode_item(tab, t);
+            const int n = tab.n[it.w], pitch = tab.pitch[it.w], m = tab.m[it.w];
+            const int dense_chunks = (m + KCHUNK - 1) / KCHUNK;
+            const int hwords = (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 5);
+            const int nch = dense_chunks + (hwords >> 1);
+            const int grow = (isA ? it.bi * TILE_M : it.col0) + rl;
+            const bool active = isA || rl < it.ncols;
+            const bool rvalid = active && grow < n;
+            const uint32_t *row = tab.x + tab.x_off[it.w] + (size_t)grow * pitch;
+            const uint32_t *hrow = tab.xh + tab.xh_off[it.w] + (size_t)grow * hwords;
+            const uint8_t *w8 = tab.w8 + tab.w8_off[it.w];
+            for (int c = 0; c < nch; ++c, ++g) {
+                const uint32_t s = g % WS_STAGES;
+                if (alive) alive = mbar_wait(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
+                if (active) {
+                    const bool is_heavy = c >= dense_chunks;
+                    uint2 bits = make_uint2(0u, 0u);
+                    if (rvalid)
+                        bits = is_heavy ? *reinterpret_cast<const uint2 *>(hrow + 2 * (c - dense_chunks))
+                                        : __ldg(reinterpret_cast<const uint2 *>(row + 2 * c));
+                    uint8_t *dst = smem + s * STAGE_BYTES + (isA ? 0 : A_STAGE_BYTES) + rl * 16;
+                    if (isA) {
+                        const uint32_t mul = is_heavy ? 255u : 1u;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            wv[q] = (__ldg(ent + 4 * q) & 255u) | ((__ldg(ent + 4 * q + 1) & 255u) << 8) |
-                                    ((__ldg(ent + 4 * q + 2) & 255u) << 16) | ((__ldg(ent + 4 * q + 3) & 255u) << 24);
+                        for (int slab = 0; slab < 4; ++slab) {
+                            const uint32_t b16 = ((slab & 2) ? bits.y : bits.x) >> ((slab & 1) * 16);
+                            uint4 o;
+                            o.x = nibble_to_bytes01(b16 & 0xFu) * mul;
+                            o.y = nibble_to_bytes01((b16 >> 4) & 0xFu) * mul;
+                            o.z = nibble_to_bytes01((b16 >> 8) & 0xFu) * mul;
+                            o.w = nibble_to_bytes01((b16 >> 12) & 0xFu) * mul;
+                            *reinterpret_cast<uint4 *>(dst + slab * lbo) = o;
+                        }
+                    } else {
+                        const uint4 *wp = reinterpret_cast<const uint4 *>(w8 + (size_t)c * KCHUNK);
+#pragma unroll
+                        for (int slab = 0; slab < 4; ++slab) {
+                            const uint32_t b16 = ((slab & 2) ? bits.y : bits.x) >> ((slab & 1) * 16);
+                            const uint4 wv = __ldg(wp + slab);
+                            uint4 o;
+                            o.x = (nibble_to_bytes01(b16 & 0xFu) * 255u) & wv.x;
+                            o.y = (nibble_to_bytes01((b16 >> 4) & 0xFu) * 255u) & wv.y;
+                            o.z = (nibble_to_bytes01((b16 >> 8) & 0xFu) * 255u) & wv.z;
+                            o.w = (nibble_to_bytes01((b16 >> 12) & 0xFu) * 255u) & wv.w;
+                            *reinterpret_cast<uint4 *>(dst + slab * lbo) = o;
                         }
                     }
+                    fence_proxy_async_smem();
                 }
-                uint32_t out[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    uint32_t b01 = nibble_to_bytes01((bits >> (4 * q)) & 0xFu);
-                    if (isA) out[q] = is_heavy ? b01 * 255u : b01;
-                    else out[q] = (b01 * 255u) & wv[q];
-                }
-                uint8_t *dst = (isA ? stA : stB) + (uint32_t)(half * 2) * (isA ? LBO_A : LBO_B) + rl * 16;
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
-                *reinterpret_cast<uint4 *>(dst + (isA ? LBO_A : LBO_B)) = make_uint4(out[4], out[5], out[6], out[7]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.full[s]);
             }
-            fence_proxy_async_smem();
-            __syncthreads();
-            if (tid == 0) {
+        }
+    } else if (warp == WS_MMA_WARP) {
+        // ================================================================ MMA issuer
+        const uint32_t smem_base_u32 = smem_u32(smem);
+        uint32_t g = 0, acc_uses = 0;
+        for (int64_t t = first; t < prm.item_end; t += stride) {
+            const Item it = decode_item(tab, t);
+            const int m = tab.m[it.w];
+            const int dense_chunks = (m + KCHUNK - 1) / KCHUNK;
+            const int nch = dense_chunks + (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 6);
+            if (nch == 0) continue;
+            const uint32_t buf = acc_uses & 1u;
+            if (alive) alive = mbar_wait(&sh.acc_empty[buf], ((acc_uses >> 1) & 1u) ^ 1u, tab.err);
+            tc_fence_after();
+            const uint32_t idesc = make_idesc_u8(TILE_M, (uint32_t)it.ncols);
+            const uint32_t tmem_d = tmem_base + buf * TILE_N;
+            for (int c = 0; c < nch; ++c, ++g) {
+                const uint32_t s = g % WS_STAGES;
+                if (alive) alive = mbar_wait(&sh.full[s], (g / WS_STAGES) & 1u, tab.err);
                 tc_fence_after();
-                const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
-                const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
-                for (int k32 = 0; k32 < KCHUNK / 32; ++k32) {
-                    uint64_t da = make_smem_desc(a_addr + k32 * 2 * LBO_A, LBO_A, SBO_AB);
-                    uint64_t db = make_smem_desc(b_addr + k32 * 2 * LBO_B, LBO_B, SBO_AB);
-                    tc_mma_i8(tmem_base, da, db, idesc, (c > 0 || k32 > 0) ? 1u : 0u);
+                    for (int k32 = 0; k32 < KCHUNK / 32; ++k32) {
+                        uint64_t da = make_smem_desc(a_addr + k32 * 2 * LBO_A, LBO_A, SBO_AB);
+                        uint64_t db = make_smem_desc(b_addr + k32 * 2 * LBO_B, LBO_B, SBO_AB);
+                        tc_mma_i8(tmem_d, da, db, idesc, (c > 0 || k32 > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&sh.empty[s]);
+                    if (c == nch - 1) tc_commit(&sh.acc_full[buf]);
                 }
-                tc_commit(&sh.stage_free[s]);
-                if (c == nch - 1) tc_commit(&sh.acc_full);
+                __syncwarp();
             }
-            ++gchunk;
+            ++acc_uses;
         }
-
-        // ------------------------------------------------------------------ epilogue
-        if (nch > 0 && alive) alive = mbar_wait(&sh.acc_full, acc_uses & 1u, tab.err);
-        if (nch > 0) ++acc_uses;
-        tc_fence_after();
-        const int q4 = warp & 3, hsel = warp >> 2;
-        const int i = bi * TILE_M + q4 * 32 + lane;
-        const bool rvalid = i < n;
-        const uint32_t ai = rvalid ? (uint32_t)Aw[i] : 0u;
-        const uint32_t fi = rvalid ? clean_label(lab[i]) : 0u;
-        const int half_cols = ncols / 2;
-        const int warp_row_min = bi * TILE_M + q4 * 32;
+    } else {
+        // ================================================================ epilogue
+        const int e = warp - (WS_MMA_WARP + 1);         // 0..7
+        const int q4 = warp & 3;                          // TMEM lane quarter this warp may read
+        const int hsel = e >> 2;                          // column half
+        ColInfo *col = sh.col[e];
         const bool dump = (prm.dumpI != nullptr) || (prm.dumpPi != nullptr);
-        PairAcc acc = {0.0, 0.0, 0.0};
-        PairTot tot = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-        for (int cc = hsel * half_cols; cc < (hsel + 1) * half_cols; cc += 16) {
-            const int jbase = cb0 * TILE_M + cc;
-            if (jbase >= n) break;
-            if (!dump && jbase + 15 <= warp_row_min) continue;  // every j <= every i of this warp
-            uint32_t r[16];
+        uint32_t acc_uses = 0;
+        for (int64_t t = first; t < prm.item_end; t += stride) {
+            const Item it = decode_item(tab, t);
+            const int n = tab.n[it.w], m = tab.m[it.w];
+            const int nch = (m + KCHUNK - 1) / KCHUNK + (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 6);
+            const int32_t *Aw = tab.A + tab.row_off[it.w];
+            const uint8_t *lab = tab.labels + tab.lab_off[it.w];
+            const int half0 = (((it.ncols >> 4) + 1) >> 1) << 4;        // columns of half 0 (multiple of 16)
+            const int cbeg = hsel ? half0 : 0, cend = hsel ? it.ncols : half0;
+            // column table of this warp: path length and class flags of each of its columns
+            uint32_t anyA = 0, anyB = 0;                                 // bit k: 16-column chunk k holds an A / B column
+            for (int cc = lane; cc < EPI_COLS; cc += 32) {
+                const int j = it.col0 + cbeg + cc;
+                const bool ok = (cbeg + cc < cend) && j < n;
+                const uint32_t f = ok ? clean_label(__ldg(lab + j)) : 0u;
+                ColInfo ci;
+                ci.aj = ok ? (uint32_t)__ldg(Aw + j) : 0u;
+                ci.flags = f;
+                ci.fs = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
+                ci.fa = (f & IMPOP_LAB_A) ? 1.0 : 0.0;
+                ci.fb = (f & IMPOP_LAB_B) ? 1.0 : 0.0;
+                col[cc] = ci;
+                const uint32_t ba = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_A) != 0u);
+                const uint32_t bb = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_B) != 0u);
+                const int k0 = (cc - lane) >> 4;
+                anyA |= (((ba & 0xFFFFu) ? 1u : 0u) << k0) | (((ba >> 16) ? 1u : 0u) << (k0 + 1));
+                anyB |= (((bb & 0xFFFFu) ? 1u : 0u) << k0) | (((bb >> 16) ? 1u : 0u) << (k0 + 1));
+            }
+            __syncwarp();
+            const int r0 = it.bi * TILE_M + q4 * 32;
+            const int i = r0 + lane;
+            const bool rvalid = i < n;
+            const uint32_t ai = rvalid ? (uint32_t)__ldg(Aw + i) : 0u;
+            const uint32_t fi = rvalid ? clean_label(__ldg(lab + i)) : 0u;
+            const uint32_t buf = acc_uses & 1u;
             if (nch > 0) {
-                tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cc, r);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int t = 0; t < 16; ++t) r[t] = 0u;
+                if (alive) alive = mbar_wait(&sh.acc_full[buf], (acc_uses >> 1) & 1u, tab.err);
+                tc_fence_after();
             }
+            dd ts = {0.0, 0.0}, ta = {0.0, 0.0}, tb = {0.0, 0.0};
+            for (int cc = cbeg; cc < cend; cc += 16) {
+                const int jbase = it.col0 + cc;
+                if (jbase >= n) break;
+                if (jbase + 15 < r0) continue;                     // every j below every i of this warp
+                uint32_t r[16];
+                if (nch > 0) {
+                    tmem_ld16(tmem_base + buf * TILE_N + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cc, r);
+                    tmem_ld_wait();
+                } else {
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int j = jbase + t;
-                const uint32_t aj = (uint32_t)sh.a_col[cc + t];
-                const uint32_t fj = sh.f_col[cc + t];
-                pair_step(acc, r[t], ai, aj, fj, rvalid && j < n && j > i);
-                if (dump) pair_dump(prm, n, i, j, r[t], ai, aj);
+                    for (int k = 0; k < 16; ++k) r[k] = 0u;
+                }
+                const ColInfo *ck = col + (cc - cbeg);
+                const int kc = (cc - cbeg) >> 4;
+                const bool tri = jbase <= r0 + 31;                 // the chunk touches the diagonal of this warp's rows
+                const bool hasA = (anyA >> kc) & 1u, hasB = (anyB >> kc) & 1u;
+                double cs = 0.0, ca = 0.0, cb = 0.0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const ColInfo ci = ck[k];
+                    double p = pi_from_counts_fast(r[k], ai, ci.aj);
+                    if (tri) p = (jbase + k > i) ? p : 0.0;
+                    cs = __fma_rn(p, ci.fs, cs);                   // p * 1.0 or p * 0.0: exact
+                    if (hasA) ca = __fma_rn(p, ci.fa, ca);
+                    if (hasB) cb = __fma_rn(p, ci.fb, cb);
+                    if (dump) pair_dump(prm, n, i, jbase + k, r[k], ai, ci.aj);
+                }
+                dd_add(ts, cs);
+                if (hasA) dd_add(ta, ca);
+                if (hasB) dd_add(tb, cb);
             }
-            pair_fold(tot, acc);
+            if (nch > 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.acc_empty[buf]);
+                ++acc_uses;
+            }
+            warp_partial(ts, ta, tb, fi, prm.partials + t * PART_STRIDE + e * 8);
         }
-        tc_fence_before();
-        __syncthreads();   // all TMEM reads done before the next item's first MMA overwrites the accumulator
-        item_reduce<TC_THREADS / 32>(tot, fi, sh.red, prm.partials + item_id * 8);
-        __syncthreads();
     }
 
+    tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == WS_MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ==========================================================================================
-// SIMT implementation (dp4a).  128 threads = the 128 rows of the item's row block; columns are
-// processed 32 at a time with u32 accumulators in registers.  Same items, same epilogue.
+// SIMT implementation (dp4a), the cross-check path.  128 threads = the 128 rows of the item's row
+// block; columns are processed 16 at a time with u32 accumulators in registers.  Same items, same
+// virtual columns, same contract arithmetic (__ddiv_rn).
 // ==========================================================================================
 constexpr int SIMT_THREADS = 128;
-constexpr int SIMT_COLS = 32;
+constexpr int SIMT_COLS = 16;
 
-__global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(WindowTab tab, ItemParams prm) {
+__global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const __grid_constant__ WindowTab tab,
+                                                                         const __grid_constant__ ItemParams prm) {
     __shared__ __align__(16) uint32_t s_b[SIMT_COLS][KCHUNK / 4 + 4];  // +4 words: rows stay 16-byte aligned
-    __shared__ int32_t s_item[4];
-    __shared__ long long s_item_id;
-    __shared__ dd s_red[SIMT_THREADS / 32][4];
-    const int tid = threadIdx.x;
-
-    while (true) {
-        if (tid == 0) {
-            int64_t t = prm.item_begin + ((int64_t)atomicAdd(prm.counter, 1) * prm.world + prm.rank);
-            s_item_id = t;
-            if (t < prm.item_end) {
-                Item it = decode_item(tab, t);
-                s_item[0] = it.w; s_item[1] = it.bi; s_item[2] = it.cb0; s_item[3] = it.ncb;
-            } else {
-                s_item[0] = -1;
-            }
-        }
-        __syncthreads();
-        const int w = s_item[0];
-        if (w < 0) break;
-        const int64_t item_id = s_item_id;
-        const int bi = s_item[1], cb0 = s_item[2], ncb = s_item[3];
-        const int n = tab.n[w], pitch = tab.pitch[w];
-        const uint32_t *x = tab.x + tab.x_off[w];
-        const uint8_t *w8 = tab.w8 + tab.w8_off[w];
-        const uint32_t *heavy = tab.heavy + tab.heavy_off[w];
-        const int32_t *Aw = tab.A + tab.row_off[w];
-        const uint8_t *lab = tab.labels + tab.lab_off[w];
-        const int dense_chunks = (int)((tab.w8_off[w + 1] - tab.w8_off[w]) / KCHUNK);
-        const int heavy_chunks = (int)((tab.heavy_off[w + 1] - tab.heavy_off[w]) / KCHUNK);
-        const int nch = dense_chunks + heavy_chunks;
-        const int i = bi * TILE_M + tid;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t stride = (int64_t)gridDim.x * prm.world;
+    for (int64_t t = prm.item_begin + (int64_t)blockIdx.x * prm.world + prm.rank; t < prm.item_end; t += stride) {
+        const Item it = decode_item(tab, t);
+        const int n = tab.n[it.w], pitch = tab.pitch[it.w], m = tab.m[it.w];
+        const uint32_t *x = tab.x + tab.x_off[it.w];
+        const int dense_chunks = (m + KCHUNK - 1) / KCHUNK;
+        const int hwords = (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 5);
+        const int nch = dense_chunks + (hwords >> 1);
+        const uint32_t *xh = tab.xh + tab.xh_off[it.w];
+        const uint8_t *w8 = tab.w8 + tab.w8_off[it.w];
+        const int32_t *Aw = tab.A + tab.row_off[it.w];
+        const uint8_t *lab = tab.labels + tab.lab_off[it.w];
+        const int i = it.bi * TILE_M + tid;
         const bool rvalid = i < n;
-        const uint32_t *myrow = x + (size_t)i * pitch;
         const uint32_t ai = rvalid ? (uint32_t)Aw[i] : 0u;
         const uint32_t fi = rvalid ? clean_label(lab[i]) : 0u;
         const bool dump = (prm.dumpI != nullptr) || (prm.dumpPi != nullptr);
-        PairAcc acc = {0.0, 0.0, 0.0};
-        PairTot tot = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+        dd ts = {0.0, 0.0}, ta = {0.0, 0.0}, tb = {0.0, 0.0};
 
-        for (int sub = 0; sub < ncb * (TILE_M / SIMT_COLS); ++sub) {
-            const int jbase = cb0 * TILE_M + sub * SIMT_COLS;
+        for (int cc = 0; cc < it.ncols; cc += SIMT_COLS) {
+            const int jbase = it.col0 + cc;
             if (jbase >= n) break;
-            if (!dump && jbase + SIMT_COLS - 1 <= bi * TILE_M) continue;
+            if (jbase + SIMT_COLS - 1 < it.bi * TILE_M) continue;
             uint32_t cnt[SIMT_COLS];
 #pragma unroll
             for (int j = 0; j < SIMT_COLS; ++j) cnt[j] = 0u;
             for (int c = 0; c < nch; ++c) {
                 const bool is_heavy = c >= dense_chunks;
-                const int hc = c - dense_chunks;
                 __syncthreads();
-                {   // stage B': thread -> (column row = tid / 4, 16-byte slab = tid % 4)
-                    const int jr = tid >> 2, slab = tid & 3;
+                {   // stage B': thread -> (column jr = tid / 8, 8 virtual columns = one byte of bits)
+                    const int jr = tid >> 3, slab = tid & 7;
                     const int gj = jbase + jr;
-                    const bool jvalid = gj < n;
-                    const uint32_t *jrow = x + (size_t)gj * pitch;
-                    uint32_t bits16 = 0, wv[4];
-                    if (!is_heavy) {
-                        const int wd = c * 2 + (slab >> 1);
-                        if (jvalid && wd < pitch) bits16 = (__ldg(jrow + wd) >> ((slab & 1) * 16)) & 0xFFFFu;
-                        uint4 wq = __ldg(reinterpret_cast<const uint4 *>(w8 + c * KCHUNK + slab * 16));
-                        wv[0] = wq.x; wv[1] = wq.y; wv[2] = wq.z; wv[3] = wq.w;
-                    } else {
-                        const uint32_t *ent = heavy + hc * KCHUNK + slab * 16;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) wv[q] = 0u;
-                        for (int e = 0; e < 16; ++e) {
-                            uint32_t en = __ldg(ent + e);
-                            uint32_t col = en >> 8;
-                            if (jvalid) bits16 |= ((__ldg(jrow + (col >> 5)) >> (col & 31u)) & 1u) << e;
-                            wv[e >> 2] |= (en & 255u) << ((e & 3) * 8);
-                        }
-                    }
-                    uint32_t o[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) o[q] = (nibble_to_bytes01((bits16 >> (4 * q)) & 0xFu) * 255u) & wv[q];
-                    *reinterpret_cast<uint4 *>(&s_b[jr][slab * 4]) = make_uint4(o[0], o[1], o[2], o[3]);
+                    uint32_t word = 0;
+                    if (gj < n)
+                        word = is_heavy ? xh[(size_t)gj * hwords + 2 * (c - dense_chunks) + (slab >> 2)]
+                                        : __ldg(x + (size_t)gj * pitch + 2 * c + (slab >> 2));
+                    const uint32_t b8 = (word >> ((slab & 3) * 8)) & 0xFFu;
+                    const uint2 wv = *reinterpret_cast<const uint2 *>(w8 + (size_t)c * KCHUNK + slab * 8);
+                    uint2 o;
+                    o.x = (nibble_to_bytes01(b8 & 0xFu) * 255u) & wv.x;
+                    o.y = (nibble_to_bytes01(b8 >> 4) * 255u) & wv.y;
+                    *reinterpret_cast<uint2 *>(&s_b[jr][slab * 2]) = o;
                 }
-                // own A' words for this chunk
                 uint32_t a[KCHUNK / 4];
                 {
-                    uint32_t b0 = 0, b1 = 0;
-                    if (!is_heavy) {
-                        if (rvalid && c * 2 < pitch) b0 = __ldg(myrow + c * 2);
-                        if (rvalid && c * 2 + 1 < pitch) b1 = __ldg(myrow + c * 2 + 1);
-                    } else {
-                        b0 = gather_heavy_bits(myrow, heavy + hc * KCHUNK, rvalid);
-                        b1 = gather_heavy_bits(myrow, heavy + hc * KCHUNK + 32, rvalid);
-                    }
+                    uint2 bits = make_uint2(0u, 0u);
+                    if (rvalid)
+                        bits = is_heavy ? *reinterpret_cast<const uint2 *>(xh + (size_t)i * hwords + 2 * (c - dense_chunks))
+                                        : __ldg(reinterpret_cast<const uint2 *>(x + (size_t)i * pitch + 2 * c));
                     const uint32_t mul = is_heavy ? 255u : 1u;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        a[q] = nibble_to_bytes01((b0 >> (4 * q)) & 0xFu) * mul;
-                        a[8 + q] = nibble_to_bytes01((b1 >> (4 * q)) & 0xFu) * mul;
+                        a[q] = nibble_to_bytes01((bits.x >> (4 * q)) & 0xFu) * mul;
+                        a[8 + q] = nibble_to_bytes01((bits.y >> (4 * q)) & 0xFu) * mul;
                     }
                 }
                 __syncthreads();
@@ -535,20 +535,27 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(WindowT
                     }
                 }
             }
+            double cs = 0.0, ca = 0.0, cb = 0.0;
 #pragma unroll
-            for (int t = 0; t < SIMT_COLS; ++t) {
-                const int j = jbase + t;
+            for (int k = 0; k < SIMT_COLS; ++k) {
+                const int j = jbase + k;
                 const bool jv = j < n;
                 const uint32_t aj = jv ? (uint32_t)__ldg(Aw + j) : 0u;
                 const uint32_t fj = jv ? clean_label(__ldg(lab + j)) : 0u;
-                pair_step(acc, cnt[t], ai, aj, fj, rvalid && jv && j > i);
-                if (dump) pair_dump(prm, n, i, j, cnt[t], ai, aj);
+                if (fj != 0u) {
+                    const double p = (rvalid && j > i) ? pi_from_counts(cnt[k], ai, aj) : 0.0;
+                    if (fj & IMPOP_LAB_SUBSET) cs = __dadd_rn(cs, p);
+                    if (fj & IMPOP_LAB_A) ca = __dadd_rn(ca, p);
+                    if (fj & IMPOP_LAB_B) cb = __dadd_rn(cb, p);
+                }
+                if (dump) pair_dump(prm, n, i, j, cnt[k], ai, aj);
             }
-            pair_fold(tot, acc);
+            dd_add(ts, cs); dd_add(ta, ca); dd_add(tb, cb);
         }
         __syncthreads();
-        item_reduce<SIMT_THREADS / 32>(tot, fi, s_red, prm.partials + item_id * 8);
-        __syncthreads();
+        warp_partial(ts, ta, tb, fi, prm.partials + t * PART_STRIDE + warp * 8);
+        if (tid < (PART_SLOTS - SIMT_THREADS / 32) * 8)             // unused partial slots of this item
+            prm.partials[t * PART_STRIDE + (SIMT_THREADS / 32) * 8 + tid] = 0.0;
     }
 }
 
@@ -557,7 +564,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(WindowT
 // ==========================================================================================
 constexpr int COL_THREADS = 128;
 
-__global__ void __launch_bounds__(COL_THREADS) colstat_kernel(WindowTab tab, int64_t *counts) {
+__global__ void __launch_bounds__(COL_THREADS) colstat_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
     __shared__ int s_cnt[4];
     for (int w = blockIdx.x; w < tab.W; w += gridDim.x) {
         const int n = tab.n[w], m = tab.m[w], pitch = tab.pitch[w];
@@ -605,20 +612,24 @@ __global__ void __launch_bounds__(COL_THREADS) colstat_kernel(WindowTab tab, int
 }
 
 // ==========================================================================================
-// Window sums (fixed-order reduction of item partials) and finalize.
+// Window sums (fixed-order reduction of the items' partial records) and finalize.
 // ==========================================================================================
-__global__ void window_sums_kernel(WindowTab tab, const double *partials, int32_t rank, int32_t world, double *sums) {
+__global__ void window_sums_kernel(const __grid_constant__ WindowTab tab, const double *partials, int32_t rank,
+                                   int32_t world, double *sums) {
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < tab.W; w += gridDim.x * warps_per_block) {
         const int64_t t0 = tab.item_off[w], t1 = tab.item_off[w + 1];
         dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-        // first item of this window handled by `rank`
-        int64_t first = t0 + ((rank - (t0 % world)) % world + world) % world;
-        for (int64_t t = first + (int64_t)lane * world; t < t1; t += 32ll * world) {
+        // items of this window handled by `rank`: t == rank (mod world); lane -> (item, slot)
+        const int64_t first = t0 + ((rank - (t0 % world)) % world + world) % world;
+        const int64_t mine = (t1 > first) ? (t1 - first + world - 1) / world : 0;
+        for (int64_t r = lane; r < mine * PART_SLOTS; r += 32) {
+            const int64_t t = first + (r / PART_SLOTS) * world;
+            const double *rec = partials + t * PART_STRIDE + (r % PART_SLOTS) * 8;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                dd p = {partials[t * 8 + k], partials[t * 8 + 4 + k]};
+                dd p = {rec[k], rec[4 + k]};
                 dd_merge(v[k], p);
             }
         }
@@ -631,7 +642,8 @@ __global__ void window_sums_kernel(WindowTab tab, const double *partials, int32_
     }
 }
 
-__global__ void finalize_kernel(WindowTab tab, const double *sums, int32_t parts, const int64_t *counts, double *stats) {
+__global__ void finalize_kernel(const __grid_constant__ WindowTab tab, const double *sums, int32_t parts,
+                                const int64_t *counts, double *stats) {
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < tab.W; w += gridDim.x * blockDim.x) {
         double s[4];
         {
@@ -655,6 +667,32 @@ __global__ void export_a_kernel(const int32_t *A, int32_t n, int64_t *out) {
     if (i < n) out[i] = (int64_t)A[i];
 }
 
+// Self-test of div_rn_inrange / pi_from_counts_fast against __ddiv_rn / pi_from_counts on pseudo-random
+// in-range operands; out[0] += number of mismatching results.
+__global__ void division_selftest_kernel(uint64_t seed, int64_t count, unsigned long long *out) {
+    unsigned long long bad = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(t + 1);   // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const uint32_t sh1 = (uint32_t)(z & 31u), sh2 = (uint32_t)((z >> 5) & 31u);
+        uint32_t ai = ((uint32_t)(z >> 10) & 0x3FFFFFFFu) >> (sh1 % 30u);
+        uint32_t aj = ((uint32_t)(z >> 33) & 0x3FFFFFFFu) >> (sh2 % 30u);
+        uint64_t z2 = z * 0xD6E8FEB86659FD93ull;
+        uint32_t lim = ai < aj ? ai : aj;
+        uint32_t inter = lim ? (uint32_t)((z2 >> 20) % ((uint64_t)lim + 1u)) : 0u;
+        if ((z2 & 7u) == 0u) inter = lim;                    // one path contained in the other
+        if ((z2 & 15u) == 1u) inter = 0u;
+        const double p0 = pi_from_counts(inter, ai, aj), p1 = pi_from_counts_fast(inter, ai, aj);
+        if (__double_as_longlong(p0) != __double_as_longlong(p1)) ++bad;
+        const uint32_t uni = ai + aj - inter;
+        const double a = u32_to_double(inter), b = u32_to_double(uni ? uni : 1u);
+        if (__double_as_longlong(__ddiv_rn(a, b)) != __double_as_longlong(div_rn_inrange(a, b))) ++bad;
+    }
+    if (bad) atomicAdd(out, bad);
+}
+
 // ------------------------------------------------------------------------------------------
 // Launchers (called from api.cu)
 // ------------------------------------------------------------------------------------------
@@ -670,22 +708,22 @@ cudaError_t launch_harmonic_table(double2 *harm, int32_t nmax, cudaStream_t st) 
     return cudaGetLastError();
 }
 
-cudaError_t launch_prep(const WindowTab &tab, int32_t *counter, cudaStream_t st) {
-    prep_kernel<<<max(1, min(tab.W, 148 * 8)), PREP_THREADS, 0, st>>>(tab, counter);
+cudaError_t launch_prep(const WindowTab &tab, int sm_count, cudaStream_t st) {
+    prep_kernel<<<max(1, min(tab.W, sm_count * 6)), PREP_THREADS, 0, st>>>(tab);
     return cudaGetLastError();
 }
 
 cudaError_t configure_kernels() {
-    return cudaFuncSetAttribute(window_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    return cudaFuncSetAttribute(window_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
 }
 
 cudaError_t launch_pairs(const WindowTab &tab, const ItemParams &prm, int algo, int sm_count, cudaStream_t st) {
     if (prm.item_end <= prm.item_begin) return cudaSuccess;
-    int64_t items = (prm.item_end - prm.item_begin + prm.world - 1) / prm.world;
+    int64_t items = (prm.item_end - prm.item_begin - prm.rank + prm.world - 1) / prm.world;
+    if (items <= 0) return cudaSuccess;
     if (algo == IMPOP_ALGO_TCGEN05) {
-        int64_t cap = (int64_t)sm_count * 2;
-        int grid = (int)(items < cap ? items : cap);
-        window_pairs_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(tab, prm);
+        int grid = (int)(items < sm_count ? items : sm_count);
+        window_pairs_tc_kernel<<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(tab, prm);
     } else {
         int64_t cap = (int64_t)sm_count * 8;
         int grid = (int)(items < cap ? items : cap);
@@ -718,6 +756,12 @@ cudaError_t launch_finalize(const WindowTab &tab, const double *sums, int parts,
 cudaError_t launch_export_a(const int32_t *A, int32_t n, int64_t *out, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     export_a_kernel<<<(n + 127) / 128, 128, 0, st>>>(A, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_division_selftest(uint64_t seed, int64_t count, unsigned long long *out, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    division_selftest_kernel<<<148 * 4, 256, 0, st>>>(seed, count, out);
     return cudaGetLastError();
 }
 

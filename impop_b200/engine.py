@@ -136,6 +136,12 @@ class Context:
                    _stream_ptr(stream))
         return counts, freq
 
+    def selftest_division(self, count: int = 1 << 24, seed: int = 1, stream=None) -> int:
+        """Mismatches between the epilogue's in-range division and __ddiv_rn over `count` random triples."""
+        bad = C.c_int64(-1)
+        self._call("impop_selftest_division", C.c_uint64(seed), int(count), C.byref(bad), _stream_ptr(stream))
+        return int(bad.value)
+
     def greedy_groups(self, ident: torch.Tensor, threshold: float, stream=None):
         """pica2 step 1 on the device: (group [n] i32 = seed index, weight [n] f64 = |G|/n on seeds)."""
         n = ident.shape[0]

@@ -121,10 +121,10 @@ int impop_pack_bits(impop_ctx_t *ctx, const uint8_t *dense_dev, int32_t n, int32
                     uint32_t *x_dev, int32_t pitch_words, void *stream);
 
 /* Batch set-up: uploads the descriptor tables, sizes the scratch (path lengths, byte weights,
- * heavy-node table, per-item partial sums).  Synchronous (one small device->host read). */
+ * heavy-node table and bits, per-item partial sums).  Synchronous (one small device->host read). */
 int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *desc, impop_batch_t **batch_out);
 int impop_batch_destroy(impop_ctx_t *ctx, impop_batch_t *batch);
-int64_t impop_batch_items(const impop_batch_t *batch); /* number of 128 x 256 tile work items */
+int64_t impop_batch_items(const impop_batch_t *batch); /* number of 128 x (<= 256) tile work items */
 
 /* K2+K3 fused.  Replaces, per window, `impg similarity` / `odgi similarity` (a-0) followed by
  * pica2.analyze_similarity_matrix (pica2.py:60-169, threshold >= max identity), h-fst.calculate_fst
@@ -182,6 +182,10 @@ int impop_cluster(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t 
  * member, the representative pica2.py:128 uses); weight_dev (nullable, n fp64) = |G|/n on seeds, 0 elsewhere. */
 int impop_greedy_groups(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t ld, double threshold,
                         int32_t *group_dev, double *weight_dev, void *stream);
+
+/* Device self-test: the epilogue's range-restricted division against __ddiv_rn on `count` pseudo-random
+ * in-range operand triples (I, A_i, A_j).  *mismatches_host must come back 0.  Synchronous. */
+int impop_selftest_division(impop_ctx_t *ctx, uint64_t seed, int64_t count, int64_t *mismatches_host, void *stream);
 
 #ifdef __cplusplus
 }

@@ -250,6 +250,47 @@ def test_edge_cases(ctx):
     empty.close()
 
 
+def test_division_selftest(ctx):
+    """The epilogue's range-restricted division (no slow-path checks) is bit-identical to __ddiv_rn on
+    2^26 pseudo-random (I, A_i, A_j) triples incl. I == 0, I == min(A), tiny and huge paths."""
+    assert ctx.selftest_division(1 << 26, seed=7) == 0
+    assert ctx.selftest_division(1 << 24, seed=12345) == 0
+
+
+def test_many_small_windows_and_wide_rows(ctx):
+    """Ragged batch that exercises every row-block / column-split shape of the tile scheduler
+    (n from 1 to 700) with few nodes, plus one window with m > 2048 (two passes of the length table)."""
+    from impop_b200.engine import WindowBatch
+    rng = np.random.default_rng(21)
+    wins = []
+    for n in (1, 2, 15, 16, 17, 31, 33, 64, 100, 128, 129, 130, 200, 255, 256, 257, 300, 383, 384, 385, 400, 512, 513, 640, 700):
+        m = int(rng.integers(1, 90))
+        x = (rng.random((n, m)) < 0.5).astype(np.uint8)
+        nl = rng.integers(0, 300, size=m).astype(np.uint32)
+        lab = _labels(n, range(0, n, 2), range(1, n, 2))
+        wins.append((similarity.pack_bits(x), nl, lab, 777))
+    x = (rng.random((150, 3000)) < 0.3).astype(np.uint8)
+    nl = rng.integers(0, 500, size=3000).astype(np.uint32)
+    wins.append((similarity.pack_bits(x), nl, _labels(150, range(0, 70), range(70, 150)), 9999))
+    batch = WindowBatch.from_windows(ctx, wins)
+    want_s, want_c = clib.batch_stats(batch.n, batch.m, batch.pitch_words, batch.x_off, batch.len_off, batch.lab_off,
+                                      batch.length, batch.x.cpu().numpy().view(np.uint32),
+                                      batch.node_len.cpu().numpy().view(np.uint32), batch.labels.cpu().numpy(), 4)
+    for algo in ALGOS:
+        stats, counts = batch.stats(algo)
+        ctx.check()
+        assert (counts.cpu().numpy() == want_c).all()
+        got = stats.cpu().numpy()
+        for w in range(len(wins)):
+            _assert_stats(got[w], want_s[w], f"algo {algo} window {w} n={wins[w][0].shape[0]}")
+    w = len(wins) - 1
+    A0, I0, pi0 = clib.window_pairwise(wins[w][0], 3000, wins[w][1])
+    I, A, pi = batch.pairwise(w, 0)
+    ctx.check()
+    assert (A.cpu().numpy() == A0).all() and (I.cpu().numpy() == I0).all() and (pi.cpu().numpy() == pi0).all()
+    batch.close()
+
+
 def test_range_error_is_reported(ctx):
     """sum(node_len) >= 2^31 is refused loudly (exactness bound of the int32 accumulators)."""
     from impop_b200 import _native
