@@ -29,7 +29,7 @@ class BatchDesc(C.Structure):
     """impop_batch_desc_t"""
     _fields_ = [("windows", _i32), ("n_host", _p), ("m_host", _p), ("pitch_words_host", _p), ("x_off_host", _p),
                 ("len_off_host", _p), ("lab_off_host", _p), ("length_host", _p), ("x_dev", _p), ("node_len_dev", _p),
-                ("labels_dev", _p)]
+                ("labels_dev", _p), ("node_len_host", _p), ("stream", _p)]
 
 
 # name -> (restype, argtypes); every symbol include/impop_b200.h declares

@@ -51,7 +51,54 @@ struct impop_ctx {
     struct Slot { cudaEvent_t a, b; int kid; };
     std::vector<Slot> slots;       // recorded launches since the last enable/read
     std::vector<Slot> spare;       // recycled event pairs
+    // device scratch pool and pinned staging buffers, recycled across batches (no cudaMalloc / cudaFree,
+    // which synchronise the device, on the per-batch path)
+    struct Block { void *p; size_t cap; bool used; };
+    std::vector<Block> pool;
+    struct Staging { void *host; size_t cap; cudaEvent_t done; bool busy; };
+    std::vector<Staging> staging;
 };
+
+static void *pool_get(impop_ctx *ctx, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    int best = -1;
+    for (int k = 0; k < (int)ctx->pool.size(); ++k) {
+        auto &b = ctx->pool[k];
+        if (!b.used && b.cap >= bytes && b.cap <= 2 * bytes + (1u << 20) && (best < 0 || b.cap < ctx->pool[best].cap)) best = k;
+    }
+    if (best >= 0) { ctx->pool[best].used = true; return ctx->pool[best].p; }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        for (auto it = ctx->pool.begin(); it != ctx->pool.end();) {     // give unused blocks back and retry
+            if (!it->used) { cudaFree(it->p); it = ctx->pool.erase(it); } else ++it;
+        }
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    ctx->pool.push_back({p, bytes, true});
+    return p;
+}
+
+static void pool_put(impop_ctx *ctx, void *p) {
+    for (auto &b : ctx->pool)
+        if (b.p == p) { b.used = false; return; }
+}
+
+// A pinned buffer whose previous asynchronous copy has completed.
+static impop_ctx::Staging *staging_get(impop_ctx *ctx, size_t bytes) {
+    for (auto &s : ctx->staging) {
+        if (s.cap < bytes) continue;
+        if (s.busy && cudaEventQuery(s.done) != cudaSuccess) { cudaGetLastError(); continue; }
+        s.busy = false;
+        return &s;
+    }
+    impop_ctx::Staging s{nullptr, bytes + (bytes >> 2) + 4096, nullptr, false};
+    if (cudaMallocHost(&s.host, s.cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(s.host); return nullptr; }
+    ctx->staging.push_back(s);
+    return &ctx->staging.back();
+}
 
 constexpr size_t MAX_TIMING_SLOTS = 1 << 14;
 
@@ -77,7 +124,8 @@ static cudaError_t timed(impop_ctx *ctx, int kid, cudaStream_t st, F fn) {
 
 struct impop_batch {
     WindowTab tab{};
-    std::vector<void *> owned;        // device allocations owned by the batch
+    void *tables = nullptr;           // pooled device blocks: descriptor tables / scratch
+    void *scratch = nullptr;
     std::vector<int64_t> item_off;    // host copy
     std::vector<int32_t> n;
     int64_t items = 0;
@@ -105,28 +153,6 @@ static int64_t items_of(int32_t n) {
     int64_t nb = (n + TILE_M - 1) / TILE_M, t = 0;
     for (int64_t bi = 0; bi < nb; ++bi) t += items_of_rowblock(n, (int)bi);
     return t;
-}
-
-template <typename T>
-static cudaError_t upload(impop_batch *b, const std::vector<T> &host, const T **dev_out) {
-    T *d = nullptr;
-    size_t bytes = sizeof(T) * (host.empty() ? 1 : host.size());
-    cudaError_t e = cudaMalloc(&d, bytes);
-    if (e != cudaSuccess) return e;
-    b->owned.push_back(d);
-    if (!host.empty()) e = cudaMemcpy(d, host.data(), sizeof(T) * host.size(), cudaMemcpyHostToDevice);
-    *dev_out = d;
-    return e;
-}
-
-template <typename T>
-static cudaError_t scratch(impop_batch *b, int64_t count, T **dev_out) {
-    T *d = nullptr;
-    cudaError_t e = cudaMalloc(&d, sizeof(T) * (size_t)(count > 0 ? count : 1));
-    if (e != cudaSuccess) return e;
-    b->owned.push_back(d);
-    *dev_out = d;
-    return cudaSuccess;
 }
 
 extern "C" {
@@ -173,6 +199,8 @@ int impop_destroy(impop_ctx_t *ctx) {
     cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->ri_scratch); cudaFree(ctx->cluster_parent);
     for (auto *v : {&ctx->slots, &ctx->spare})
         for (auto &s : *v) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto &b : ctx->pool) cudaFree(b.p);
+    for (auto &s : ctx->staging) { cudaFreeHost(s.host); cudaEventDestroy(s.done); }
     delete ctx;
     return IMPOP_OK;
 }
@@ -235,11 +263,19 @@ int impop_pack_bits(impop_ctx_t *ctx, const uint8_t *dense_dev, int32_t n, int32
 
 int impop_batch_destroy(impop_ctx_t *ctx, impop_batch_t *batch) {
     if (!ctx || !batch) return IMPOP_ERR_ARG;
-    cudaSetDevice(ctx->device);
-    for (void *p : batch->owned) cudaFree(p);
+    if (batch->tables) pool_put(ctx, batch->tables);     // kernels still in flight on the stream stay valid:
+    if (batch->scratch) pool_put(ctx, batch->scratch);   // a later batch on the same stream is ordered after them
     delete batch;
     return IMPOP_OK;
 }
+
+namespace {
+// Sequential sub-allocation inside one block, 256-byte aligned.
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; }
+};
+}  // namespace
 
 int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batch_t **batch_out) {
     if (!ctx || !d || !batch_out) return IMPOP_ERR_ARG;
@@ -249,18 +285,15 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     if (W > 0 && (!d->n_host || !d->m_host || !d->pitch_words_host || !d->x_off_host || !d->len_off_host ||
                   !d->lab_off_host || !d->length_host))
         return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: null descriptor array");
-    std::vector<int32_t> n(d->n_host, d->n_host + W), m(d->m_host, d->m_host + W),
-        pitch(d->pitch_words_host, d->pitch_words_host + W);
-    std::vector<int64_t> x_off(d->x_off_host, d->x_off_host + W), len_off(d->len_off_host, d->len_off_host + W),
-        lab_off(d->lab_off_host, d->lab_off_host + W), L(d->length_host, d->length_host + W);
-    std::vector<int64_t> row_off(W + 1, 0), w8_off(W + 1, 0), item_off(W + 1, 0), heavy_off(W + 1, 0), xh_off(W + 1, 0);
+    const int32_t *n = d->n_host, *m = d->m_host, *pitch = d->pitch_words_host;
+    std::vector<int64_t> row_off(W + 1, 0), item_off(W + 1, 0);
     bool any_rows = false, any_nodes = false;
     for (int32_t w = 0; w < W; ++w) {
         if (n[w] < 0 || m[w] < 0 || n[w] > (1 << 24) || m[w] > (1 << 24))
             return fail(ctx, IMPOP_ERR_RANGE, "impop_batch_create: n or m out of range (max 2^24)");
-        if (pitch[w] % 4 != 0 || x_off[w] % 4 != 0 || (int64_t)pitch[w] * 32 < m[w])
+        if (pitch[w] % 4 != 0 || d->x_off_host[w] % 4 != 0 || (int64_t)pitch[w] * 32 < m[w])
             return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: pitch_words / x_off must be multiples of 4 and cover m");
-        if (x_off[w] < 0 || len_off[w] < 0 || lab_off[w] < 0)
+        if (d->x_off_host[w] < 0 || d->len_off_host[w] < 0 || d->lab_off_host[w] < 0)
             return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: negative offset");
         row_off[w + 1] = row_off[w] + n[w];
         item_off[w + 1] = item_off[w] + items_of(n[w]);
@@ -270,55 +303,94 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     if ((any_rows && any_nodes && !d->x_dev) || (any_nodes && !d->node_len_dev) || (any_rows && !d->labels_dev))
         return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: null device array");
     CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)d->stream;
     impop_batch *b = new (std::nothrow) impop_batch();
     if (!b) return fail(ctx, IMPOP_ERR_NOMEM, "impop_batch_create: out of host memory");
     WindowTab &t = b->tab;
-    cudaError_t e = cudaSuccess;
-    auto bail = [&](cudaError_t err, const char *where) {
+    auto bail = [&](int code, const std::string &why) {
         impop_batch_destroy(ctx, b);
-        return cuda_fail(ctx, err, where);
+        return fail(ctx, code, why);
     };
-    if ((e = upload(b, n, &t.n)) != cudaSuccess) return bail(e, "upload n");
-    if ((e = upload(b, m, &t.m)) != cudaSuccess) return bail(e, "upload m");
-    if ((e = upload(b, pitch, &t.pitch)) != cudaSuccess) return bail(e, "upload pitch");
-    if ((e = upload(b, x_off, &t.x_off)) != cudaSuccess) return bail(e, "upload x_off");
-    if ((e = upload(b, len_off, &t.len_off)) != cudaSuccess) return bail(e, "upload len_off");
-    if ((e = upload(b, lab_off, &t.lab_off)) != cudaSuccess) return bail(e, "upload lab_off");
-    if ((e = upload(b, L, &t.L)) != cudaSuccess) return bail(e, "upload L");
-    if ((e = upload(b, row_off, &t.row_off)) != cudaSuccess) return bail(e, "upload row_off");
-    if ((e = upload(b, item_off, &t.item_off)) != cudaSuccess) return bail(e, "upload item_off");
+
+    // ---- descriptor tables: one pooled device block, filled by one (two) asynchronous copies from pinned staging
+    const size_t W1 = (size_t)W + 1;
+    Carver ca;
+    const size_t o_n = ca.take(4 * W1), o_m = ca.take(4 * W1), o_pitch = ca.take(4 * W1);
+    const size_t o_xoff = ca.take(8 * W1), o_lenoff = ca.take(8 * W1), o_laboff = ca.take(8 * W1), o_L = ca.take(8 * W1);
+    const size_t o_row = ca.take(8 * W1), o_item = ca.take(8 * W1);
+    const size_t phase1 = ca.off;
+    const size_t o_heavy = ca.take(8 * W1), o_w8 = ca.take(8 * W1), o_xh = ca.take(8 * W1);
+    const size_t o_cnt = ca.take(4 * W1);
+    const size_t tables_bytes = ca.off;
+    b->tables = pool_get(ctx, tables_bytes);
+    impop_ctx::Staging *sg = staging_get(ctx, tables_bytes);
+    if (!b->tables || !sg) return bail(IMPOP_ERR_NOMEM, "impop_batch_create: out of memory (tables)");
+    char *hb = (char *)sg->host, *db = (char *)b->tables;
+    if (W > 0) {
+        memcpy(hb + o_n, n, 4 * (size_t)W); memcpy(hb + o_m, m, 4 * (size_t)W); memcpy(hb + o_pitch, pitch, 4 * (size_t)W);
+        memcpy(hb + o_xoff, d->x_off_host, 8 * (size_t)W); memcpy(hb + o_lenoff, d->len_off_host, 8 * (size_t)W);
+        memcpy(hb + o_laboff, d->lab_off_host, 8 * (size_t)W); memcpy(hb + o_L, d->length_host, 8 * (size_t)W);
+    }
+    memcpy(hb + o_row, row_off.data(), 8 * W1);
+    memcpy(hb + o_item, item_off.data(), 8 * W1);
+    cudaError_t e = cudaMemcpyAsync(db, hb, phase1, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return bail(IMPOP_ERR_CUDA, std::string("upload tables: ") + cudaGetErrorString(e));
+    t.n = (const int32_t *)(db + o_n); t.m = (const int32_t *)(db + o_m); t.pitch = (const int32_t *)(db + o_pitch);
+    t.x_off = (const int64_t *)(db + o_xoff); t.len_off = (const int64_t *)(db + o_lenoff);
+    t.lab_off = (const int64_t *)(db + o_laboff); t.L = (const int64_t *)(db + o_L);
+    t.row_off = (const int64_t *)(db + o_row); t.item_off = (const int64_t *)(db + o_item);
+    t.heavy_off = (const int64_t *)(db + o_heavy); t.w8_off = (const int64_t *)(db + o_w8); t.xh_off = (const int64_t *)(db + o_xh);
     t.x = d->x_dev; t.len = d->node_len_dev; t.labels = d->labels_dev;
     t.W = W; t.err = ctx->err_dev; t.harm = ctx->harm_dev; t.harm_n = HARM_N;
-    // heavy-node table size: count on device, prefix on host
-    {
-        int32_t *cnt_dev = nullptr;
-        if ((e = scratch(b, W, &cnt_dev)) != cudaSuccess) return bail(e, "alloc heavy counts");
-        if ((e = launch_heavy_count(t.len, t.len_off, t.m, W, cnt_dev, 0)) != cudaSuccess) return bail(e, "heavy_count");
-        ctx->launches += (W > 0);
-        std::vector<int32_t> cnt(W, 0);
-        if (W > 0 && (e = cudaMemcpy(cnt.data(), cnt_dev, sizeof(int32_t) * W, cudaMemcpyDeviceToHost)) != cudaSuccess)
-            return bail(e, "read heavy counts");
+
+    // ---- heavy-entry counts: from the caller's host copy of node_len when given (no synchronisation),
+    //      else counted on the device and read back (one stream synchronisation)
+    int32_t *cnt = (int32_t *)(hb + o_cnt);
+    if (W > 0 && d->node_len_host) {
         for (int32_t w = 0; w < W; ++w) {
-            const int64_t hpad = ((int64_t)(cnt[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
-            const int64_t m64 = ((int64_t)(m[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
-            heavy_off[w + 1] = heavy_off[w] + hpad;
-            w8_off[w + 1] = w8_off[w] + m64 + hpad;                 // virtual columns: dense | heavy
-            xh_off[w + 1] = xh_off[w] + (int64_t)n[w] * (hpad / 32);
+            const uint32_t *len = d->node_len_host + d->len_off_host[w];
+            int32_t c = 0;
+            for (int32_t k = 0; k < m[w]; ++k) {
+                const uint32_t q = len[k] / HEAVY_Q;
+                if (q) c += (int32_t)((q + 254u) / 255u);
+            }
+            cnt[w] = c;
         }
+    } else if (W > 0) {
+        if ((e = launch_heavy_count(t.len, t.len_off, t.m, W, (int32_t *)(db + o_cnt), st)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(cnt, db + o_cnt, 4 * (size_t)W, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(st)) != cudaSuccess)
+            return bail(IMPOP_ERR_CUDA, std::string("heavy_count: ") + cudaGetErrorString(e));
+        ctx->launches += 1;
     }
-    if ((e = upload(b, heavy_off, &t.heavy_off)) != cudaSuccess) return bail(e, "upload heavy_off");
-    if ((e = upload(b, w8_off, &t.w8_off)) != cudaSuccess) return bail(e, "upload w8_off");
-    if ((e = upload(b, xh_off, &t.xh_off)) != cudaSuccess) return bail(e, "upload xh_off");
+    int64_t *heavy_off = (int64_t *)(hb + o_heavy), *w8_off = (int64_t *)(hb + o_w8), *xh_off = (int64_t *)(hb + o_xh);
+    heavy_off[0] = w8_off[0] = xh_off[0] = 0;
+    for (int32_t w = 0; w < W; ++w) {
+        const int64_t hpad = ((int64_t)(cnt[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
+        const int64_t m64 = ((int64_t)(m[w] + KCHUNK - 1) / KCHUNK) * KCHUNK;
+        heavy_off[w + 1] = heavy_off[w] + hpad;
+        w8_off[w + 1] = w8_off[w] + m64 + hpad;                 // virtual columns: dense | heavy
+        xh_off[w + 1] = xh_off[w] + (int64_t)n[w] * (hpad / 32);
+    }
+    e = cudaMemcpyAsync(db + o_heavy, hb + o_heavy, o_cnt - o_heavy, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) { e = cudaEventRecord(sg->done, st); sg->busy = true; }
+    if (e != cudaSuccess) return bail(IMPOP_ERR_CUDA, std::string("upload tables: ") + cudaGetErrorString(e));
+
+    // ---- scratch: one pooled block
     b->items = item_off[W];
-    if ((e = scratch(b, row_off[W], &t.A)) != cudaSuccess) return bail(e, "alloc A");
-    if ((e = scratch(b, w8_off[W] + 64, &t.w8)) != cudaSuccess) return bail(e, "alloc w8");
-    if ((e = scratch(b, heavy_off[W] + 64, &t.heavy)) != cudaSuccess) return bail(e, "alloc heavy");
-    if ((e = scratch(b, xh_off[W] + 4, &t.xh)) != cudaSuccess) return bail(e, "alloc heavy bits");
-    if ((e = scratch(b, b->items * PART_STRIDE, &b->partials)) != cudaSuccess) return bail(e, "alloc partials");
-    if ((e = scratch(b, (int64_t)W * 4, &b->sums_tmp)) != cudaSuccess) return bail(e, "alloc sums");
-    if ((e = scratch(b, (int64_t)W * IMPOP_NCOUNTS, &b->counts_tmp)) != cudaSuccess) return bail(e, "alloc counts");
+    Carver cs;
+    const size_t s_A = cs.take(4 * (size_t)(row_off[W] + 1)), s_w8 = cs.take((size_t)w8_off[W] + 64);
+    const size_t s_heavy = cs.take(4 * (size_t)(heavy_off[W] + 64)), s_xh = cs.take(4 * (size_t)(xh_off[W] + 4));
+    const size_t s_part = cs.take(8 * (size_t)(b->items * PART_STRIDE + 1));
+    const size_t s_sums = cs.take(8 * 4 * W1), s_counts = cs.take(8 * IMPOP_NCOUNTS * W1);
+    b->scratch = pool_get(ctx, cs.off);
+    if (!b->scratch) return bail(IMPOP_ERR_NOMEM, "impop_batch_create: out of device memory (scratch)");
+    char *sb = (char *)b->scratch;
+    t.A = (int32_t *)(sb + s_A); t.w8 = (uint8_t *)(sb + s_w8); t.heavy = (uint32_t *)(sb + s_heavy);
+    t.xh = (uint32_t *)(sb + s_xh);
+    b->partials = (double *)(sb + s_part); b->sums_tmp = (double *)(sb + s_sums); b->counts_tmp = (int64_t *)(sb + s_counts);
     b->item_off = item_off;
-    b->n = n;
+    b->n.assign(n, n + W);
     *batch_out = b;
     return IMPOP_OK;
 }

@@ -168,7 +168,7 @@ class WindowBatch:
     """
 
     def __init__(self, ctx: Context, n, m, pitch_words, x_off, len_off, lab_off, length,
-                 x: torch.Tensor, node_len: torch.Tensor, labels: torch.Tensor):
+                 x: torch.Tensor, node_len: torch.Tensor, labels: torch.Tensor, node_len_host=None, stream=None):
         self.ctx = ctx
         self.n = np.ascontiguousarray(n, dtype=np.int32)
         self.m = np.ascontiguousarray(m, dtype=np.int32)
@@ -181,7 +181,7 @@ class WindowBatch:
         self.x, self.node_len, self.labels = x, node_len, labels      # keep the device buffers alive
         d = N.BatchDesc(self.windows, _ptr(self.n), _ptr(self.m), _ptr(self.pitch_words), _ptr(self.x_off),
                         _ptr(self.len_off), _ptr(self.lab_off), _ptr(self.length), _ptr(x), _ptr(node_len),
-                        _ptr(labels))
+                        _ptr(labels), _ptr(node_len_host), _stream_ptr(stream))
         h = C.c_void_p()
         rc = ctx.lib.impop_batch_create(ctx.handle, C.byref(d), C.byref(h))
         if rc != 0:
@@ -190,7 +190,8 @@ class WindowBatch:
 
     # ------------------------------------------------------------------ constructors
     @classmethod
-    def from_uniform(cls, ctx: Context, x_bits, node_len, labels, length, m: int | None = None):
+    def from_uniform(cls, ctx: Context, x_bits, node_len, labels, length, m: int | None = None, node_len_host=None,
+                     stream=None):
         """W same-shape windows: x_bits [W, n, pitch] u32, node_len [W, m_pad] u32, labels [n] or [W, n] u8.
 
         Arguments may be numpy arrays (copied to the device) or device tensors (used in place).
@@ -205,7 +206,8 @@ class WindowBatch:
         ar = np.arange(W, dtype=np.int64)
         L = np.full(W, int(length or 0), dtype=np.int64) if np.isscalar(length) or length is None else np.asarray(length)
         return cls(ctx, np.full(W, n), np.full(W, m_pad if m is None else m), np.full(W, pitch), ar * (n * pitch),
-                   ar * m_pad, ar * n if per_window_labels else np.zeros(W, dtype=np.int64), L, xd, ld, lab)
+                   ar * m_pad, ar * n if per_window_labels else np.zeros(W, dtype=np.int64), L, xd, ld, lab,
+                   node_len_host=node_len_host, stream=stream)
 
     @classmethod
     def from_windows(cls, ctx: Context, windows):

@@ -91,6 +91,10 @@ typedef struct {
     const uint32_t *x_dev;
     const uint32_t *node_len_dev;
     const uint8_t *labels_dev;
+    const uint32_t *node_len_host;   /* optional host copy of node_len (same offsets): lets batch set-up run without
+                                        any device->host read, i.e. fully asynchronously on `stream` */
+    void *stream;                    /* cudaStream_t the set-up copies are enqueued on (NULL = default stream); use the
+                                        stream the kernels will run on */
 } impop_batch_desc_t;
 
 int impop_version(void);
@@ -120,8 +124,10 @@ int impop_timing_read(impop_ctx_t *ctx, int32_t kernel_id, double *total_ms, int
 int impop_pack_bits(impop_ctx_t *ctx, const uint8_t *dense_dev, int32_t n, int32_t m, int64_t dense_pitch,
                     uint32_t *x_dev, int32_t pitch_words, void *stream);
 
-/* Batch set-up: uploads the descriptor tables, sizes the scratch (path lengths, byte weights,
- * heavy-node table and bits, per-item partial sums).  Synchronous (one small device->host read). */
+/* Batch set-up: uploads the descriptor tables (asynchronously, from pinned staging), sizes the scratch (path
+ * lengths, byte weights, heavy-node table and bits, per-item partial sums).  Device blocks come from a pool kept
+ * by the context, so repeated create / destroy does not call cudaMalloc / cudaFree.  With node_len_host given the
+ * call does not synchronise; without it there is one small device->host read. */
 int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *desc, impop_batch_t **batch_out);
 int impop_batch_destroy(impop_ctx_t *ctx, impop_batch_t *batch);
 int64_t impop_batch_items(const impop_batch_t *batch); /* number of 128 x (<= 256) tile work items */
