@@ -318,6 +318,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t o_n = ca.take(4 * W1), o_m = ca.take(4 * W1), o_pitch = ca.take(4 * W1);
     const size_t o_xoff = ca.take(8 * W1), o_lenoff = ca.take(8 * W1), o_laboff = ca.take(8 * W1), o_L = ca.take(8 * W1);
     const size_t o_row = ca.take(8 * W1), o_item = ca.take(8 * W1);
+    const size_t o_items = ca.take(16 * (size_t)(item_off[W] + 1));
     const size_t phase1 = ca.off;
     const size_t o_heavy = ca.take(8 * W1), o_w8 = ca.take(8 * W1), o_xh = ca.take(8 * W1);
     const size_t o_cnt = ca.take(4 * W1);
@@ -333,12 +334,24 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     }
     memcpy(hb + o_row, row_off.data(), 8 * W1);
     memcpy(hb + o_item, item_off.data(), 8 * W1);
+    {   // work-item table: (window, row block, first column, columns)
+        int4 *items = (int4 *)(hb + o_items);
+        int64_t k = 0;
+        for (int32_t w = 0; w < W; ++w) {
+            const int nb = (n[w] + TILE_M - 1) / TILE_M;
+            for (int bi = 0; bi < nb; ++bi) {
+                const int cnt = items_of_rowblock(n[w], bi), width = width_of_rowblock(n[w], bi);
+                for (int r = 0; r < cnt; ++r) items[k++] = make_int4(w, bi, bi * TILE_M + r * width, width);
+            }
+        }
+    }
     cudaError_t e = cudaMemcpyAsync(db, hb, phase1, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return bail(IMPOP_ERR_CUDA, std::string("upload tables: ") + cudaGetErrorString(e));
     t.n = (const int32_t *)(db + o_n); t.m = (const int32_t *)(db + o_m); t.pitch = (const int32_t *)(db + o_pitch);
     t.x_off = (const int64_t *)(db + o_xoff); t.len_off = (const int64_t *)(db + o_lenoff);
     t.lab_off = (const int64_t *)(db + o_laboff); t.L = (const int64_t *)(db + o_L);
     t.row_off = (const int64_t *)(db + o_row); t.item_off = (const int64_t *)(db + o_item);
+    t.items = (const int4 *)(db + o_items);
     t.heavy_off = (const int64_t *)(db + o_heavy); t.w8_off = (const int64_t *)(db + o_w8); t.xh_off = (const int64_t *)(db + o_xh);
     t.x = d->x_dev; t.len = d->node_len_dev; t.labels = d->labels_dev;
     t.W = W; t.err = ctx->err_dev; t.harm = ctx->harm_dev; t.harm_n = HARM_N;

@@ -152,26 +152,10 @@ struct Item {
     int w, bi, col0, ncols;   // window, row block, first column, columns (multiple of 16, <= 256)
 };
 
-__device__ Item decode_item(const WindowTab &tab, int64_t t) {
-    int lo = 0, hi = tab.W - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (tab.item_off[mid] <= t) lo = mid; else hi = mid - 1;
-    }
+__device__ __forceinline__ Item decode_item(const WindowTab &tab, int64_t t) {
+    const int4 v = __ldg(tab.items + t);      // table built on the host at batch creation
     Item it;
-    it.w = lo;
-    int r = (int)(t - tab.item_off[lo]);
-    const int n = tab.n[lo];
-    int bi = 0;
-    while (true) {
-        const int cnt = items_of_rowblock(n, bi);
-        if (r < cnt) break;
-        r -= cnt;
-        ++bi;
-    }
-    it.bi = bi;
-    it.ncols = width_of_rowblock(n, bi);
-    it.col0 = bi * TILE_M + r * it.ncols;
+    it.w = v.x; it.bi = v.y; it.col0 = v.z; it.ncols = v.w;
     return it;
 }
 
@@ -214,14 +198,17 @@ __device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const d
 //   warps 0-11   producers: expand presence bits into the u8 operand tiles of a ring of stages
 //                (warps 0-3: the 128 A rows, warps 4-11: up to 256 B rows; lane = row)
 //   warp  12     MMA issuer (one elected lane): tcgen05.mma kind::i8 into one of two TMEM buffers
-//   warps 13-20  epilogue: tcgen05.ld, exact integer union, fp64 pi_ij, compensated sums
+//                (warps 13-15 only pad the warpgroup so that setmaxnreg applies to whole warpgroups)
+//   warps 16-23  epilogue: tcgen05.ld, exact integer union, fp64 pi_ij, compensated sums
+// Registers are moved from the producer / MMA warpgroups (56 each) to the epilogue warpgroups (128 each).
 // The integer pipes (expansion) and the fp64 pipe (epilogue) so run concurrently on different
 // warps, and items flow through without CTA-wide barriers.
 // ==========================================================================================
 constexpr int WS_PROD_WARPS = 12;
 constexpr int WS_EPI_WARPS = 8;
 constexpr int WS_MMA_WARP = WS_PROD_WARPS;
-constexpr int WS_THREADS = 32 * (WS_PROD_WARPS + 1 + WS_EPI_WARPS);   // 672
+constexpr int WS_EPI_WARP0 = WS_PROD_WARPS + 4;
+constexpr int WS_THREADS = 32 * (WS_EPI_WARP0 + WS_EPI_WARPS);        // 768
 constexpr int WS_STAGES = 6;
 constexpr int A_STAGE_BYTES = TILE_M * KCHUNK;                  // 8 KB
 constexpr int B_STAGE_BYTES = TILE_N * KCHUNK;                  // 16 KB
@@ -232,9 +219,9 @@ constexpr uint32_t SBO_AB = 128;                                // next 8-row gr
 constexpr uint32_t TMEM_COLS = 512;                             // two accumulator buffers of 256 columns
 constexpr int EPI_COLS = 128;                                   // columns one epilogue warp can own
 
-struct __align__(16) ColInfo {
-    uint32_t aj, flags;
-    double fs, fa, fb;       // 1.0 / 0.0: column carries SUBSET / A / B
+struct __align__(16) EpiCols {          // per epilogue warp: its (up to 128) columns of the current item
+    uint32_t aj[EPI_COLS];              // path length A_j
+    double fs[EPI_COLS], fa[EPI_COLS], fb[EPI_COLS];   // 1.0 / 0.0: column carries SUBSET / A / B
 };
 
 struct WsShared {
@@ -242,10 +229,11 @@ struct WsShared {
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    ColInfo col[WS_EPI_WARPS][EPI_COLS];      // 32 KB
+    EpiCols col[WS_EPI_WARPS];          // 28 KB
 };
 constexpr int WS_SMEM_BYTES = WS_STAGES * STAGE_BYTES + (int)sizeof(WsShared);
 
+template <bool DUMP>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_constant__ ItemParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -268,6 +256,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 
     if (warp < WS_PROD_WARPS) {
         // ================================================================ producers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         const bool isA = warp < 4;
         const int rl = (isA ? warp : warp - 4) * 32 + lane;          // row of the operand tile
         const uint32_t lbo = isA ? LBO_A : LBO_B;
@@ -284,15 +273,21 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             const uint32_t *row = tab.x + tab.x_off[it.w] + (size_t)grow * pitch;
             const uint32_t *hrow = tab.xh + tab.xh_off[it.w] + (size_t)grow * hwords;
             const uint8_t *w8 = tab.w8 + tab.w8_off[it.w];
+            auto load_bits = [&](int c) {
+                uint2 v = make_uint2(0u, 0u);
+                if (rvalid && c < nch)
+                    v = (c >= dense_chunks) ? *reinterpret_cast<const uint2 *>(hrow + 2 * (c - dense_chunks))
+                                            : __ldg(reinterpret_cast<const uint2 *>(row + 2 * c));
+                return v;
+            };
+            uint2 next_bits = load_bits(0);
             for (int c = 0; c < nch; ++c, ++g) {
                 const uint32_t s = g % WS_STAGES;
+                const uint2 bits = next_bits;
+                next_bits = load_bits(c + 1);                  // in flight while this chunk is expanded
                 if (alive) alive = mbar_wait(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
                 if (active) {
                     const bool is_heavy = c >= dense_chunks;
-                    uint2 bits = make_uint2(0u, 0u);
-                    if (rvalid)
-                        bits = is_heavy ? *reinterpret_cast<const uint2 *>(hrow + 2 * (c - dense_chunks))
-                                        : __ldg(reinterpret_cast<const uint2 *>(row + 2 * c));
                     uint8_t *dst = smem + s * STAGE_BYTES + (isA ? 0 : A_STAGE_BYTES) + rl * 16;
                     if (isA) {
                         const uint32_t mul = is_heavy ? 255u : 1u;
@@ -326,8 +321,10 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 if (lane == 0) mbar_arrive(&sh.full[s]);
             }
         }
-    } else if (warp == WS_MMA_WARP) {
-        // ================================================================ MMA issuer
+    } else if (warp < WS_EPI_WARP0) {
+        // ================================================================ MMA issuer (warp 12; 13-15 idle)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == WS_MMA_WARP) {
         const uint32_t smem_base_u32 = smem_u32(smem);
         uint32_t g = 0, acc_uses = 0;
         for (int64_t t = first; t < prm.item_end; t += stride) {
@@ -361,13 +358,14 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             }
             ++acc_uses;
         }
+        }
     } else {
         // ================================================================ epilogue
-        const int e = warp - (WS_MMA_WARP + 1);         // 0..7
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        const int e = warp - WS_EPI_WARP0;              // 0..7
         const int q4 = warp & 3;                          // TMEM lane quarter this warp may read
         const int hsel = e >> 2;                          // column half
-        ColInfo *col = sh.col[e];
-        const bool dump = (prm.dumpI != nullptr) || (prm.dumpPi != nullptr);
+        EpiCols &col = sh.col[e];
         uint32_t acc_uses = 0;
         for (int64_t t = first; t < prm.item_end; t += stride) {
             const Item it = decode_item(tab, t);
@@ -377,22 +375,22 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             const uint8_t *lab = tab.labels + tab.lab_off[it.w];
             const int half0 = (((it.ncols >> 4) + 1) >> 1) << 4;        // columns of half 0 (multiple of 16)
             const int cbeg = hsel ? half0 : 0, cend = hsel ? it.ncols : half0;
-            // column table of this warp: path length and class flags of each of its columns
-            uint32_t anyA = 0, anyB = 0;                                 // bit k: 16-column chunk k holds an A / B column
+            // column table of this warp; per 16-column chunk k: bit k of allS (every column valid and in SUBSET),
+            // anyA, anyB (some column in A / B)
+            uint32_t allS = 0, anyA = 0, anyB = 0;
             for (int cc = lane; cc < EPI_COLS; cc += 32) {
                 const int j = it.col0 + cbeg + cc;
                 const bool ok = (cbeg + cc < cend) && j < n;
                 const uint32_t f = ok ? clean_label(__ldg(lab + j)) : 0u;
-                ColInfo ci;
-                ci.aj = ok ? (uint32_t)__ldg(Aw + j) : 0u;
-                ci.flags = f;
-                ci.fs = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
-                ci.fa = (f & IMPOP_LAB_A) ? 1.0 : 0.0;
-                ci.fb = (f & IMPOP_LAB_B) ? 1.0 : 0.0;
-                col[cc] = ci;
+                col.aj[cc] = ok ? (uint32_t)__ldg(Aw + j) : 0u;
+                col.fs[cc] = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
+                col.fa[cc] = (f & IMPOP_LAB_A) ? 1.0 : 0.0;
+                col.fb[cc] = (f & IMPOP_LAB_B) ? 1.0 : 0.0;
+                const uint32_t bs = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_SUBSET) != 0u);
                 const uint32_t ba = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_A) != 0u);
                 const uint32_t bb = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_B) != 0u);
                 const int k0 = (cc - lane) >> 4;
+                allS |= (((bs & 0xFFFFu) == 0xFFFFu ? 1u : 0u) << k0) | (((bs >> 16) == 0xFFFFu ? 1u : 0u) << (k0 + 1));
                 anyA |= (((ba & 0xFFFFu) ? 1u : 0u) << k0) | (((ba >> 16) ? 1u : 0u) << (k0 + 1));
                 anyB |= (((bb & 0xFFFFu) ? 1u : 0u) << k0) | (((bb >> 16) ? 1u : 0u) << (k0 + 1));
             }
@@ -420,24 +418,48 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 #pragma unroll
                     for (int k = 0; k < 16; ++k) r[k] = 0u;
                 }
-                const ColInfo *ck = col + (cc - cbeg);
-                const int kc = (cc - cbeg) >> 4;
-                const bool tri = jbase <= r0 + 31;                 // the chunk touches the diagonal of this warp's rows
-                const bool hasA = (anyA >> kc) & 1u, hasB = (anyB >> kc) & 1u;
-                double cs = 0.0, ca = 0.0, cb = 0.0;
+                const int lc = cc - cbeg, kc = lc >> 4;
+                uint32_t aj[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const ColInfo ci = ck[k];
-                    double p = pi_from_counts_fast(r[k], ai, ci.aj);
-                    if (tri) p = (jbase + k > i) ? p : 0.0;
-                    cs = __fma_rn(p, ci.fs, cs);                   // p * 1.0 or p * 0.0: exact
-                    if (hasA) ca = __fma_rn(p, ci.fa, ca);
-                    if (hasB) cb = __fma_rn(p, ci.fb, cb);
-                    if (dump) pair_dump(prm, n, i, jbase + k, r[k], ai, ci.aj);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(&col.aj[lc + 4 * k4]);
+                    aj[4 * k4] = v.x; aj[4 * k4 + 1] = v.y; aj[4 * k4 + 2] = v.z; aj[4 * k4 + 3] = v.w;
+                }
+                double p[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) p[k] = pi_from_counts_fast(r[k], ai, aj[k]);
+                if (jbase <= r0 + 31) {                            // the chunk touches the diagonal of this warp's rows
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) p[k] = (jbase + k > i) ? p[k] : 0.0;
+                }
+                if (DUMP) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) pair_dump(prm, n, i, jbase + k, r[k], ai, aj[k]);
+                }
+                double cs;
+                if ((allS >> kc) & 1u) {
+                    cs = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])),
+                                             __dadd_rn(__dadd_rn(p[4], p[5]), __dadd_rn(p[6], p[7]))),
+                                   __dadd_rn(__dadd_rn(__dadd_rn(p[8], p[9]), __dadd_rn(p[10], p[11])),
+                                             __dadd_rn(__dadd_rn(p[12], p[13]), __dadd_rn(p[14], p[15]))));
+                } else {
+                    cs = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) cs = __fma_rn(p[k], col.fs[lc + k], cs);   // p * 1.0 or p * 0.0: exact
                 }
                 dd_add(ts, cs);
-                if (hasA) dd_add(ta, ca);
-                if (hasB) dd_add(tb, cb);
+                if ((anyA >> kc) & 1u) {
+                    double ca = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) ca = __fma_rn(p[k], col.fa[lc + k], ca);
+                    dd_add(ta, ca);
+                }
+                if ((anyB >> kc) & 1u) {
+                    double cb = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) cb = __fma_rn(p[k], col.fb[lc + k], cb);
+                    dd_add(tb, cb);
+                }
             }
             if (nch > 0) {
                 tc_fence_before();
@@ -714,7 +736,9 @@ cudaError_t launch_prep(const WindowTab &tab, int sm_count, cudaStream_t st) {
 }
 
 cudaError_t configure_kernels() {
-    return cudaFuncSetAttribute(window_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(window_pairs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(window_pairs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
 }
 
 cudaError_t launch_pairs(const WindowTab &tab, const ItemParams &prm, int algo, int sm_count, cudaStream_t st) {
@@ -723,7 +747,8 @@ cudaError_t launch_pairs(const WindowTab &tab, const ItemParams &prm, int algo, 
     if (items <= 0) return cudaSuccess;
     if (algo == IMPOP_ALGO_TCGEN05) {
         int grid = (int)(items < sm_count ? items : sm_count);
-        window_pairs_tc_kernel<<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(tab, prm);
+        if (prm.dumpI || prm.dumpPi) window_pairs_tc_kernel<true><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(tab, prm);
+        else window_pairs_tc_kernel<false><<<grid, WS_THREADS, WS_SMEM_BYTES, st>>>(tab, prm);
     } else {
         int64_t cap = (int64_t)sm_count * 8;
         int grid = (int)(items < cap ? items : cap);
