@@ -76,22 +76,34 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
             __syncthreads();
             const int w0 = c0 >> 5;                       // first word of this pass
             const int passes = (m - c0 > 1024) ? 2 : 1;   // 32 words (1024 nodes) per warp pass
-            for (int i = warp; i < n; i += PREP_THREADS / 32) {
-                const uint32_t *row = x + (size_t)i * pitch + w0;
-                uint32_t acc = 0;
+            constexpr int RU = 4;                         // rows in flight per warp (memory-level parallelism)
+            for (int i0 = warp * RU; i0 < n; i0 += (PREP_THREADS / 32) * RU) {
+                uint32_t acc[RU];
+#pragma unroll
+                for (int r = 0; r < RU; ++r) acc[r] = 0u;
                 for (int ps = 0; ps < passes; ++ps) {
                     const int wd = ps * 32 + lane;
-                    const uint32_t word = (w0 + wd < pitch) ? __ldg(row + wd) : 0u;
+                    uint32_t word[RU];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t src = __shfl_sync(0xffffffffu, word, q * 4 + (lane >> 3));
-                        const uint32_t nib = (src >> ((lane & 7) * 4)) & 15u;
-                        acc += s_lut[nib][ps * 256 + q * 32 + lane];
+                    for (int r = 0; r < RU; ++r)
+                        word[r] = (i0 + r < n && w0 + wd < pitch) ? __ldg(x + (size_t)(i0 + r) * pitch + w0 + wd) : 0u;
+#pragma unroll
+                    for (int r = 0; r < RU; ++r) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t src = __shfl_sync(0xffffffffu, word[r], q * 4 + (lane >> 3));
+                            const uint32_t nib = (src >> ((lane & 7) * 4)) & 15u;
+                            acc[r] += s_lut[nib][ps * 256 + q * 32 + lane];
+                        }
                     }
                 }
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-                if (lane == 0) A[i] = (int32_t)(acc + (c0 ? (uint32_t)A[i] : 0u));
+                for (int r = 0; r < RU; ++r) {
+                    uint32_t a = acc[r];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+                    if (lane == 0 && i0 + r < n) A[i0 + r] = (int32_t)(a + (c0 ? (uint32_t)A[i0 + r] : 0u));
+                }
             }
             __syncthreads();
         }
@@ -285,7 +297,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 const uint32_t s = g % WS_STAGES;
                 const uint2 bits = next_bits;
                 next_bits = load_bits(c + 1);                  // in flight while this chunk is expanded
-                if (alive) alive = mbar_wait(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
+                if (alive) alive = mbar_wait<200>(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
                 if (active) {
                     const bool is_heavy = c >= dense_chunks;
                     uint8_t *dst = smem + s * STAGE_BYTES + (isA ? 0 : A_STAGE_BYTES) + rl * 16;
@@ -334,13 +346,13 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             const int nch = dense_chunks + (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 6);
             if (nch == 0) continue;
             const uint32_t buf = acc_uses & 1u;
-            if (alive) alive = mbar_wait(&sh.acc_empty[buf], ((acc_uses >> 1) & 1u) ^ 1u, tab.err);
+            if (alive) alive = mbar_wait<0>(&sh.acc_empty[buf], ((acc_uses >> 1) & 1u) ^ 1u, tab.err);
             tc_fence_after();
             const uint32_t idesc = make_idesc_u8(TILE_M, (uint32_t)it.ncols);
             const uint32_t tmem_d = tmem_base + buf * TILE_N;
             for (int c = 0; c < nch; ++c, ++g) {
                 const uint32_t s = g % WS_STAGES;
-                if (alive) alive = mbar_wait(&sh.full[s], (g / WS_STAGES) & 1u, tab.err);
+                if (alive) alive = mbar_wait<0>(&sh.full[s], (g / WS_STAGES) & 1u, tab.err);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
@@ -402,7 +414,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             const uint32_t fi = rvalid ? clean_label(__ldg(lab + i)) : 0u;
             const uint32_t buf = acc_uses & 1u;
             if (nch > 0) {
-                if (alive) alive = mbar_wait(&sh.acc_full[buf], (acc_uses >> 1) & 1u, tab.err);
+                if (alive) alive = mbar_wait<100>(&sh.acc_full[buf], (acc_uses >> 1) & 1u, tab.err);
                 tc_fence_after();
             }
             dd ts = {0.0, 0.0}, ta = {0.0, 0.0}, tb = {0.0, 0.0};
@@ -584,10 +596,12 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const _
 // ==========================================================================================
 // Segregating nodes + label counts: one CTA per window.  counts row = nS nA nB pS pAA pBB pAB S.
 // ==========================================================================================
-constexpr int COL_THREADS = 128;
+constexpr int COL_THREADS = 256;
 
 __global__ void __launch_bounds__(COL_THREADS) colstat_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
     __shared__ int s_cnt[4];
+    __shared__ uint32_t s_any[64], s_all[64];     // one pass covers 64 words = 2048 nodes
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int w = blockIdx.x; w < tab.W; w += gridDim.x) {
         const int n = tab.n[w], m = tab.m[w], pitch = tab.pitch[w];
         const uint32_t *x = tab.x + tab.x_off[w];
@@ -595,30 +609,50 @@ __global__ void __launch_bounds__(COL_THREADS) colstat_kernel(const __grid_const
         const uint8_t *lab = tab.labels + tab.lab_off[w];
         if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
         __syncthreads();
-        int c0 = 0, c1 = 0, c2 = 0;
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
         for (int i = threadIdx.x; i < n; i += COL_THREADS) {
             uint32_t f = clean_label(lab[i]);
             c0 += (f & IMPOP_LAB_SUBSET) != 0; c1 += (f & IMPOP_LAB_A) != 0; c2 += (f & IMPOP_LAB_B) != 0;
+            c3 += (f & IMPOP_LAB_SEG) != 0;
         }
         if (c0) atomicAdd(&s_cnt[0], c0);
         if (c1) atomicAdd(&s_cnt[1], c1);
         if (c2) atomicAdd(&s_cnt[2], c2);
+        if (c3) atomicAdd(&s_cnt[3], c3);
+        __syncthreads();
+        const int seg_rows = s_cnt[3];
+        __syncthreads();
+        if (threadIdx.x == 0) s_cnt[3] = 0;           // reused as the segregating-node counter
         const int words = (m + 31) >> 5;
         int seg = 0;
-        for (int wd = threadIdx.x; wd < words; wd += COL_THREADS) {
-            uint32_t any = 0u, all = 0xffffffffu;
-            int rows = 0;
-            for (int i = 0; i < n; ++i) {
-                if (!(lab[i] & IMPOP_LAB_SEG)) continue;   // uniform across the CTA
-                uint32_t v = __ldg(x + (size_t)i * pitch + wd);
-                any |= v; all &= v; ++rows;
+        for (int w0 = 0; w0 < words; w0 += 64) {
+            if (threadIdx.x < 64) { s_any[threadIdx.x] = 0u; s_all[threadIdx.x] = 0xffffffffu; }
+            __syncthreads();
+            // warp -> rows warp, warp + 8, ...; lane -> words lane, lane + 32 of this pass (coalesced row reads)
+            uint32_t any0 = 0u, all0 = 0xffffffffu, any1 = 0u, all1 = 0xffffffffu;
+            const bool has1 = w0 + 32 < words;
+            for (int i = warp; i < n; i += COL_THREADS / 32) {
+                if (!(lab[i] & IMPOP_LAB_SEG)) continue;
+                const uint32_t *row = x + (size_t)i * pitch + w0;
+                const uint32_t v0 = (w0 + lane < words) ? __ldg(row + lane) : 0u;
+                any0 |= v0; all0 &= v0;
+                if (has1) {
+                    const uint32_t v1 = (w0 + 32 + lane < words) ? __ldg(row + 32 + lane) : 0u;
+                    any1 |= v1; all1 &= v1;
+                }
             }
-            uint32_t sg = rows ? (any & ~all) : 0u;
-            while (sg) {
-                int k = wd * 32 + (__ffs(sg) - 1);
-                if (k < m && __ldg(len + k) > 0u) ++seg;
-                sg &= sg - 1;
+            atomicOr(&s_any[lane], any0); atomicAnd(&s_all[lane], all0);
+            if (has1) { atomicOr(&s_any[32 + lane], any1); atomicAnd(&s_all[32 + lane], all1); }
+            __syncthreads();
+            if (threadIdx.x < 64 && w0 + threadIdx.x < words && seg_rows > 0) {
+                uint32_t sg = s_any[threadIdx.x] & ~s_all[threadIdx.x];
+                while (sg) {
+                    int k = (w0 + threadIdx.x) * 32 + (__ffs(sg) - 1);
+                    if (k < m && __ldg(len + k) > 0u) ++seg;
+                    sg &= sg - 1;
+                }
             }
+            __syncthreads();
         }
         if (seg) atomicAdd(&s_cnt[3], seg);
         __syncthreads();
@@ -759,7 +793,7 @@ cudaError_t launch_pairs(const WindowTab &tab, const ItemParams &prm, int algo, 
 
 cudaError_t launch_colstat(const WindowTab &tab, int64_t *counts, cudaStream_t st) {
     if (tab.W == 0) return cudaSuccess;
-    colstat_kernel<<<min(tab.W, 148 * 16), COL_THREADS, 0, st>>>(tab, counts);
+    colstat_kernel<<<min(tab.W, 148 * 8), COL_THREADS, 0, st>>>(tab, counts);
     return cudaGetLastError();
 }
 
