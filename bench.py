@@ -245,7 +245,7 @@ def run_ours(args):
     ms_step = ev0.elapsed_time(ev1) / args.steps
     launches = ctx.launches - launches0
     pairs_ms, pairs_n = ctx.timing_read("pairs")
-    per_kernel = {k: ctx.timing_read(k)[0] / max(args.steps, 1) for k in ("prep", "pairs", "sums", "colstat", "finalize")}
+    per_kernel = {k: ctx.timing_read(k)[0] / max(args.steps, 1) for k in ("prep", "pairs", "sums", "finalize")}
     ctx.timing(False)
     ctx.check()
     clocks = sampler.stop() if rank == 0 else None

@@ -13,11 +13,10 @@
 namespace impop {
 cudaError_t launch_heavy_count(const uint32_t *, const int64_t *, const int32_t *, int32_t, int32_t *, cudaStream_t);
 cudaError_t launch_harmonic_table(double2 *, int32_t, cudaStream_t);
-cudaError_t launch_prep(const WindowTab &, int, cudaStream_t);
+cudaError_t launch_prep(const WindowTab &, int64_t *, int, cudaStream_t);
 cudaError_t launch_division_selftest(uint64_t, int64_t, unsigned long long *, cudaStream_t);
 cudaError_t configure_kernels();
 cudaError_t launch_pairs(const WindowTab &, const ItemParams &, int, int, cudaStream_t);
-cudaError_t launch_colstat(const WindowTab &, int64_t *, cudaStream_t);
 cudaError_t launch_window_sums(const WindowTab &, const double *, int, int, double *, cudaStream_t);
 cudaError_t launch_finalize(const WindowTab &, const double *, int, const int64_t *, double *, cudaStream_t);
 cudaError_t launch_export_a(const int32_t *, int32_t, int64_t *, cudaStream_t);
@@ -415,7 +414,7 @@ static int run_sums(impop_ctx_t *ctx, impop_batch_t *b, int32_t algo, int32_t ra
     if (algo != IMPOP_ALGO_TCGEN05 && algo != IMPOP_ALGO_SIMT) return fail(ctx, IMPOP_ERR_ARG, "unknown algo");
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, IMPOP_ERR_ARG, "bad rank/world");
     if (b->tab.W == 0) return IMPOP_OK;
-    CU(timed(ctx, IMPOP_KERNEL_PREP, st, [&] { return launch_prep(b->tab, ctx->sm_count, st); }));
+    CU(timed(ctx, IMPOP_KERNEL_PREP, st, [&] { return launch_prep(b->tab, b->counts_tmp, ctx->sm_count, st); }));
     ItemParams prm{};
     prm.partials = b->partials;
     prm.item_begin = 0; prm.item_end = b->items; prm.rank = rank; prm.world = world;
@@ -440,10 +439,12 @@ int impop_window_finalize(impop_ctx_t *ctx, impop_batch_t *batch, const double *
     if (!sums_dev || !stats_dev || parts < 1) return fail(ctx, IMPOP_ERR_ARG, "impop_window_finalize: bad argument");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    int64_t *counts = counts_dev ? counts_dev : batch->counts_tmp;
-    CU(timed(ctx, IMPOP_KERNEL_COLSTAT, st, [&] { return launch_colstat(batch->tab, counts, st); }));
-    CU(timed(ctx, IMPOP_KERNEL_FINALIZE, st, [&] { return launch_finalize(batch->tab, sums_dev, parts, counts, stats_dev, st); }));
-    ctx->launches += 2;
+    // label counts and segregating nodes were formed by the prep pass of the preceding impop_window_sums / _stats
+    CU(timed(ctx, IMPOP_KERNEL_FINALIZE, st, [&] { return launch_finalize(batch->tab, sums_dev, parts, batch->counts_tmp, stats_dev, st); }));
+    if (counts_dev)
+        CU(cudaMemcpyAsync(counts_dev, batch->counts_tmp, sizeof(int64_t) * IMPOP_NCOUNTS * (size_t)batch->tab.W,
+                           cudaMemcpyDeviceToDevice, st));
+    ctx->launches += 1;
     return IMPOP_OK;
 }
 
@@ -465,7 +466,7 @@ int impop_pairwise(impop_ctx_t *ctx, impop_batch_t *batch, int32_t window, int32
     if (algo != IMPOP_ALGO_TCGEN05 && algo != IMPOP_ALGO_SIMT) return fail(ctx, IMPOP_ERR_ARG, "unknown algo");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CU(launch_prep(batch->tab, ctx->sm_count, st));
+    CU(launch_prep(batch->tab, batch->counts_tmp, ctx->sm_count, st));
     ctx->launches += 1;
     if (I_dev || pi_dev) {
         ItemParams prm{};

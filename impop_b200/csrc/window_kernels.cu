@@ -16,31 +16,51 @@
 namespace impop {
 
 // ==========================================================================================
-// Prep: one CTA per window.
+// Prep: one CTA per window, one pass over the window's presence matrix.
 //   (a) byte weights of the dense columns, heavy-node table, range check sum(len) < 2^31
 //   (b) path lengths A_i through a nibble look-up table of node lengths held in shared memory
 //       (lane l of a warp looks up nibble position 32 q + l, so the 32 look-ups of a warp hit 32
-//       different banks)
-//   (c) presence bits of the heavy columns, gathered once per row (ballot)
+//       different banks), with four rows in flight per warp
+//   (c) presence bits of the heavy columns (warp shuffle of the row words already in registers + ballot)
+//   (d) label counts and segregating nodes S = #{k : 0 < sum_{i in SEG} x_ik < |SEG|, len_k > 0}
+//       (replaces `povu gfa2vcf | wc -l`, run_tajd.sh:126-148) -> counts row nS nA nB pS pAA pBB pAB S
 // ==========================================================================================
 constexpr int PREP_THREADS = 256;
 constexpr int LUT_POS = 512;                 // nibble positions per table pass = 2048 nodes = 64 words
 
-__global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constant__ WindowTab tab) {
+__global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
     __shared__ uint32_t s_lut[16][LUT_POS];   // 32 KB
-    __shared__ int s_heavy;
+    __shared__ uint32_t s_any[64], s_all[64];
+    __shared__ int s_heavy, s_cnt[5];
     __shared__ unsigned long long s_total;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int w = blockIdx.x; w < tab.W; w += gridDim.x) {
         const int n = tab.n[w], m = tab.m[w], pitch = tab.pitch[w];
         const uint32_t *len = tab.len + tab.len_off[w];
         const uint32_t *x = tab.x + tab.x_off[w];
+        const uint8_t *lab = tab.labels + tab.lab_off[w];
         uint8_t *w8 = tab.w8 + tab.w8_off[w];
         uint32_t *heavy = tab.heavy + tab.heavy_off[w];
         const int m64 = ((m + KCHUNK - 1) / KCHUNK) * KCHUNK;
         const int hpad = (int)(tab.heavy_off[w + 1] - tab.heavy_off[w]);
+        const int hwords = hpad >> 5;
+        uint32_t *xh = tab.xh + tab.xh_off[w];
         if (threadIdx.x == 0) { s_heavy = 0; s_total = 0ull; }
+        if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
         __syncthreads();
+        // ---- (d) label counts
+        {
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            for (int i = threadIdx.x; i < n; i += PREP_THREADS) {
+                const uint32_t f = clean_label(lab[i]);
+                c0 += (f & IMPOP_LAB_SUBSET) != 0; c1 += (f & IMPOP_LAB_A) != 0; c2 += (f & IMPOP_LAB_B) != 0;
+                c3 += (f & IMPOP_LAB_SEG) != 0;
+            }
+            if (c0) atomicAdd(&s_cnt[0], c0);
+            if (c1) atomicAdd(&s_cnt[1], c1);
+            if (c2) atomicAdd(&s_cnt[2], c2);
+            if (c3) atomicAdd(&s_cnt[3], c3);
+        }
         // ---- (a)
         unsigned long long tot = 0;
         for (int k = threadIdx.x; k < m64; k += PREP_THREADS) {
@@ -56,14 +76,18 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
             }
         }
         if (tot) atomicAdd(&s_total, tot);
+        for (size_t s = threadIdx.x; s < (size_t)n * hwords; s += PREP_THREADS) xh[s] = 0u;
         __syncthreads();
         if (threadIdx.x == 0 && (s_total >= (1ull << 31) || s_heavy > hpad)) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);
         const int nh = s_heavy < hpad ? s_heavy : hpad;
         for (int s = nh + threadIdx.x; s < hpad; s += PREP_THREADS) heavy[s] = 0u;
         __syncthreads();
         for (int s = threadIdx.x; s < hpad; s += PREP_THREADS) w8[m64 + s] = (uint8_t)(heavy[s] & 255u);
-        // ---- (b)
+        // ---- (b) + (c) + (d): one sweep over the rows per 2048-node slice
         int32_t *A = tab.A + tab.row_off[w];
+        const int words = (m + 31) >> 5;
+        const int seg_rows = s_cnt[3];
+        int seg = 0;
         for (int c0 = 0; c0 < m || c0 == 0; c0 += 4 * LUT_POS) {
             for (int p = threadIdx.x; p < LUT_POS; p += PREP_THREADS) {
                 const int k = c0 + 4 * p;
@@ -73,15 +97,23 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
                 for (int v = 0; v < 16; ++v)
                     s_lut[v][p] = ((v & 1) ? l0 : 0u) + ((v & 2) ? l1 : 0u) + ((v & 4) ? l2 : 0u) + ((v & 8) ? l3 : 0u);
             }
+            if (threadIdx.x < 64) { s_any[threadIdx.x] = 0u; s_all[threadIdx.x] = 0xffffffffu; }
             __syncthreads();
-            const int w0 = c0 >> 5;                       // first word of this pass
+            const int w0 = c0 >> 5;                       // first word of this slice
             const int passes = (m - c0 > 1024) ? 2 : 1;   // 32 words (1024 nodes) per warp pass
             constexpr int RU = 4;                         // rows in flight per warp (memory-level parallelism)
+            uint32_t any[2] = {0u, 0u}, all[2] = {0xffffffffu, 0xffffffffu};
             for (int i0 = warp * RU; i0 < n; i0 += (PREP_THREADS / 32) * RU) {
                 uint32_t acc[RU];
+                bool segrow[RU];
 #pragma unroll
-                for (int r = 0; r < RU; ++r) acc[r] = 0u;
-                for (int ps = 0; ps < passes; ++ps) {
+                for (int r = 0; r < RU; ++r) {
+                    acc[r] = 0u;
+                    segrow[r] = (i0 + r < n) && (lab[i0 + r] & IMPOP_LAB_SEG);
+                }
+#pragma unroll
+                for (int ps = 0; ps < 2; ++ps) {
+                    if (ps >= passes) break;
                     const int wd = ps * 32 + lane;
                     uint32_t word[RU];
 #pragma unroll
@@ -95,6 +127,20 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
                             const uint32_t nib = (src >> ((lane & 7) * 4)) & 15u;
                             acc[r] += s_lut[nib][ps * 256 + q * 32 + lane];
                         }
+                        if (segrow[r]) { any[ps] |= word[r]; all[ps] &= word[r]; }
+                    }
+                    for (int hw = 0; hw < hwords; ++hw) {            // heavy columns whose node lies in these 32 words
+                        const uint32_t ent = heavy[hw * 32 + lane];
+                        const uint32_t col = ent >> 8;
+                        const int rel = (int)(col >> 5) - (w0 + ps * 32);
+                        const bool in = (ent & 255u) && rel >= 0 && rel < 32;
+                        if (!__any_sync(0xffffffffu, in)) continue;
+#pragma unroll
+                        for (int r = 0; r < RU; ++r) {
+                            const uint32_t wsrc = __shfl_sync(0xffffffffu, word[r], rel & 31);
+                            const uint32_t bw = __ballot_sync(0xffffffffu, in && ((wsrc >> (col & 31u)) & 1u));
+                            if (lane == 0 && bw && i0 + r < n) xh[(size_t)(i0 + r) * hwords + hw] |= bw;
+                        }
                     }
                 }
 #pragma unroll
@@ -105,20 +151,27 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
                     if (lane == 0 && i0 + r < n) A[i0 + r] = (int32_t)(a + (c0 ? (uint32_t)A[i0 + r] : 0u));
                 }
             }
+            atomicOr(&s_any[lane], any[0]); atomicAnd(&s_all[lane], all[0]);
+            if (passes > 1) { atomicOr(&s_any[32 + lane], any[1]); atomicAnd(&s_all[32 + lane], all[1]); }
+            __syncthreads();
+            if (threadIdx.x < 64 && w0 + threadIdx.x < words && seg_rows > 0) {
+                uint32_t sg = s_any[threadIdx.x] & ~s_all[threadIdx.x];
+                while (sg) {
+                    const int k = (w0 + threadIdx.x) * 32 + (__ffs(sg) - 1);
+                    if (k < m && __ldg(len + k) > 0u) ++seg;
+                    sg &= sg - 1;
+                }
+            }
             __syncthreads();
         }
-        // ---- (c)
-        const int hwords = hpad >> 5;
-        uint32_t *xh = tab.xh + tab.xh_off[w];
-        for (int i = warp; i < n; i += PREP_THREADS / 32) {
-            const uint32_t *row = x + (size_t)i * pitch;
-            for (int hw = 0; hw < hwords; ++hw) {
-                const uint32_t ent = heavy[hw * 32 + lane];
-                const uint32_t col = ent >> 8;
-                const bool bit = (ent & 255u) && ((__ldg(row + (col >> 5)) >> (col & 31u)) & 1u);
-                const uint32_t word = __ballot_sync(0xffffffffu, bit);
-                if (lane == 0) xh[(size_t)i * hwords + hw] = word;
-            }
+        if (seg) atomicAdd(&s_cnt[4], seg);
+        __syncthreads();
+        if (threadIdx.x == 0 && counts) {
+            const int64_t nS = s_cnt[0], nA = s_cnt[1], nB = s_cnt[2];
+            int64_t *row = counts + (size_t)w * IMPOP_NCOUNTS;
+            row[0] = nS; row[1] = nA; row[2] = nB;
+            row[3] = nS * (nS - 1) / 2; row[4] = nA * (nA - 1) / 2; row[5] = nB * (nB - 1) / 2; row[6] = nA * nB;
+            row[7] = s_cnt[4];
         }
         __syncthreads();
     }
@@ -594,80 +647,6 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const _
 }
 
 // ==========================================================================================
-// Segregating nodes + label counts: one CTA per window.  counts row = nS nA nB pS pAA pBB pAB S.
-// ==========================================================================================
-constexpr int COL_THREADS = 256;
-
-__global__ void __launch_bounds__(COL_THREADS) colstat_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
-    __shared__ int s_cnt[4];
-    __shared__ uint32_t s_any[64], s_all[64];     // one pass covers 64 words = 2048 nodes
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int w = blockIdx.x; w < tab.W; w += gridDim.x) {
-        const int n = tab.n[w], m = tab.m[w], pitch = tab.pitch[w];
-        const uint32_t *x = tab.x + tab.x_off[w];
-        const uint32_t *len = tab.len + tab.len_off[w];
-        const uint8_t *lab = tab.labels + tab.lab_off[w];
-        if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-        __syncthreads();
-        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        for (int i = threadIdx.x; i < n; i += COL_THREADS) {
-            uint32_t f = clean_label(lab[i]);
-            c0 += (f & IMPOP_LAB_SUBSET) != 0; c1 += (f & IMPOP_LAB_A) != 0; c2 += (f & IMPOP_LAB_B) != 0;
-            c3 += (f & IMPOP_LAB_SEG) != 0;
-        }
-        if (c0) atomicAdd(&s_cnt[0], c0);
-        if (c1) atomicAdd(&s_cnt[1], c1);
-        if (c2) atomicAdd(&s_cnt[2], c2);
-        if (c3) atomicAdd(&s_cnt[3], c3);
-        __syncthreads();
-        const int seg_rows = s_cnt[3];
-        __syncthreads();
-        if (threadIdx.x == 0) s_cnt[3] = 0;           // reused as the segregating-node counter
-        const int words = (m + 31) >> 5;
-        int seg = 0;
-        for (int w0 = 0; w0 < words; w0 += 64) {
-            if (threadIdx.x < 64) { s_any[threadIdx.x] = 0u; s_all[threadIdx.x] = 0xffffffffu; }
-            __syncthreads();
-            // warp -> rows warp, warp + 8, ...; lane -> words lane, lane + 32 of this pass (coalesced row reads)
-            uint32_t any0 = 0u, all0 = 0xffffffffu, any1 = 0u, all1 = 0xffffffffu;
-            const bool has1 = w0 + 32 < words;
-            for (int i = warp; i < n; i += COL_THREADS / 32) {
-                if (!(lab[i] & IMPOP_LAB_SEG)) continue;
-                const uint32_t *row = x + (size_t)i * pitch + w0;
-                const uint32_t v0 = (w0 + lane < words) ? __ldg(row + lane) : 0u;
-                any0 |= v0; all0 &= v0;
-                if (has1) {
-                    const uint32_t v1 = (w0 + 32 + lane < words) ? __ldg(row + 32 + lane) : 0u;
-                    any1 |= v1; all1 &= v1;
-                }
-            }
-            atomicOr(&s_any[lane], any0); atomicAnd(&s_all[lane], all0);
-            if (has1) { atomicOr(&s_any[32 + lane], any1); atomicAnd(&s_all[32 + lane], all1); }
-            __syncthreads();
-            if (threadIdx.x < 64 && w0 + threadIdx.x < words && seg_rows > 0) {
-                uint32_t sg = s_any[threadIdx.x] & ~s_all[threadIdx.x];
-                while (sg) {
-                    int k = (w0 + threadIdx.x) * 32 + (__ffs(sg) - 1);
-                    if (k < m && __ldg(len + k) > 0u) ++seg;
-                    sg &= sg - 1;
-                }
-            }
-            __syncthreads();
-        }
-        if (seg) atomicAdd(&s_cnt[3], seg);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int64_t nS = s_cnt[0], nA = s_cnt[1], nB = s_cnt[2];
-            int64_t *row = counts + (size_t)w * IMPOP_NCOUNTS;
-            row[0] = nS; row[1] = nA; row[2] = nB;
-            row[3] = nS * (nS - 1) / 2; row[4] = nA * (nA - 1) / 2; row[5] = nB * (nB - 1) / 2; row[6] = nA * nB;
-            row[7] = s_cnt[3];
-        }
-        __syncthreads();
-    }
-}
-
-// ==========================================================================================
 // Window sums (fixed-order reduction of the items' partial records) and finalize.
 // ==========================================================================================
 __global__ void window_sums_kernel(const __grid_constant__ WindowTab tab, const double *partials, int32_t rank,
@@ -764,8 +743,8 @@ cudaError_t launch_harmonic_table(double2 *harm, int32_t nmax, cudaStream_t st) 
     return cudaGetLastError();
 }
 
-cudaError_t launch_prep(const WindowTab &tab, int sm_count, cudaStream_t st) {
-    prep_kernel<<<max(1, min(tab.W, sm_count * 6)), PREP_THREADS, 0, st>>>(tab);
+cudaError_t launch_prep(const WindowTab &tab, int64_t *counts, int sm_count, cudaStream_t st) {
+    prep_kernel<<<max(1, min(tab.W, sm_count * 6)), PREP_THREADS, 0, st>>>(tab, counts);
     return cudaGetLastError();
 }
 
@@ -788,12 +767,6 @@ cudaError_t launch_pairs(const WindowTab &tab, const ItemParams &prm, int algo, 
         int grid = (int)(items < cap ? items : cap);
         window_pairs_simt_kernel<<<grid, SIMT_THREADS, 0, st>>>(tab, prm);
     }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_colstat(const WindowTab &tab, int64_t *counts, cudaStream_t st) {
-    if (tab.W == 0) return cudaSuccess;
-    colstat_kernel<<<min(tab.W, 148 * 8), COL_THREADS, 0, st>>>(tab, counts);
     return cudaGetLastError();
 }
 

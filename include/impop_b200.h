@@ -110,10 +110,10 @@ int64_t impop_launch_count(impop_ctx_t *ctx);
  * kernels below is bracketed by CUDA events on the caller's stream (no synchronisation added).
  * impop_timing_read sums the elapsed time of the launches of one kernel recorded since the last
  * impop_timing_enable call (which also clears the record). */
-#define IMPOP_KERNEL_PREP 0      /* path lengths, byte weights, heavy-node table */
+#define IMPOP_KERNEL_PREP 0      /* path lengths, byte weights, heavy-node table and bits, S, label counts */
 #define IMPOP_KERNEL_PAIRS 1     /* fused pairwise + fp64 reduction (tcgen05 or SIMT) */
 #define IMPOP_KERNEL_SUMS 2      /* per-window fixed-order sum of tile partials */
-#define IMPOP_KERNEL_COLSTAT 3   /* segregating nodes + label counts */
+#define IMPOP_KERNEL_COLSTAT 3   /* (unused since the prep pass forms S and the label counts) */
 #define IMPOP_KERNEL_FINALIZE 4  /* derived statistics */
 #define IMPOP_KERNEL_SITES 5     /* per-site allele counts */
 int impop_timing_enable(impop_ctx_t *ctx, int32_t enable);
@@ -142,7 +142,8 @@ int impop_window_stats(impop_ctx_t *ctx, impop_batch_t *batch, int32_t algo, dou
 /* The same in two steps, for splitting one batch's tile grid over several GPUs (SURVEY.md 8 e):
  * rank r of `world` processes work items t with t % world == r and writes raw sums
  * (W x 4: S, AA, BB, AB).  After an all-gather, impop_window_finalize adds `parts` such arrays
- * ([parts][W][4], fixed order => run-to-run reproducible) and derives the statistics. */
+ * ([parts][W][4], fixed order => run-to-run reproducible) and derives the statistics; the label counts and
+ * segregating-node counts it uses were formed by the preceding impop_window_sums call on this batch. */
 int impop_window_sums(impop_ctx_t *ctx, impop_batch_t *batch, int32_t algo, int32_t rank, int32_t world,
                       double *sums_dev, void *stream);
 int impop_window_finalize(impop_ctx_t *ctx, impop_batch_t *batch, const double *sums_dev, int32_t parts,
