@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
                 q -= c;
             }
         }
-        if (tot) atomicAdd(&s_total, tot);
-        for (size_t s = threadIdx.x; s < (size_t)n * hwords; s += PREP_THREADS) xh[s] = 0u;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+        if (lane == 0 && tot) atomicAdd(&s_total, tot);
         __syncthreads();
         if (threadIdx.x == 0 && (s_total >= (1ull << 31) || s_heavy > hpad)) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);
         const int nh = s_heavy < hpad ? s_heavy : hpad;
@@ -104,42 +105,49 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
             constexpr int RU = 4;                         // rows in flight per warp (memory-level parallelism)
             uint32_t any[2] = {0u, 0u}, all[2] = {0xffffffffu, 0xffffffffu};
             for (int i0 = warp * RU; i0 < n; i0 += (PREP_THREADS / 32) * RU) {
-                uint32_t acc[RU];
+                uint32_t acc[RU], word[2][RU];
                 bool segrow[RU];
 #pragma unroll
                 for (int r = 0; r < RU; ++r) {
                     acc[r] = 0u;
                     segrow[r] = (i0 + r < n) && (lab[i0 + r] & IMPOP_LAB_SEG);
+#pragma unroll
+                    for (int ps = 0; ps < 2; ++ps) {
+                        const int wd = ps * 32 + lane;
+                        word[ps][r] = (ps < passes && i0 + r < n && w0 + wd < pitch)
+                                          ? __ldg(x + (size_t)(i0 + r) * pitch + w0 + wd) : 0u;
+                    }
                 }
 #pragma unroll
                 for (int ps = 0; ps < 2; ++ps) {
                     if (ps >= passes) break;
-                    const int wd = ps * 32 + lane;
-                    uint32_t word[RU];
-#pragma unroll
-                    for (int r = 0; r < RU; ++r)
-                        word[r] = (i0 + r < n && w0 + wd < pitch) ? __ldg(x + (size_t)(i0 + r) * pitch + w0 + wd) : 0u;
 #pragma unroll
                     for (int r = 0; r < RU; ++r) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            const uint32_t src = __shfl_sync(0xffffffffu, word[r], q * 4 + (lane >> 3));
+                            const uint32_t src = __shfl_sync(0xffffffffu, word[ps][r], q * 4 + (lane >> 3));
                             const uint32_t nib = (src >> ((lane & 7) * 4)) & 15u;
                             acc[r] += s_lut[nib][ps * 256 + q * 32 + lane];
                         }
-                        if (segrow[r]) { any[ps] |= word[r]; all[ps] &= word[r]; }
+                        if (segrow[r]) { any[ps] |= word[ps][r]; all[ps] &= word[ps][r]; }
                     }
-                    for (int hw = 0; hw < hwords; ++hw) {            // heavy columns whose node lies in these 32 words
-                        const uint32_t ent = heavy[hw * 32 + lane];
-                        const uint32_t col = ent >> 8;
-                        const int rel = (int)(col >> 5) - (w0 + ps * 32);
-                        const bool in = (ent & 255u) && rel >= 0 && rel < 32;
-                        if (!__any_sync(0xffffffffu, in)) continue;
+                }
+                for (int hw = 0; hw < hwords; ++hw) {                // heavy columns: one table entry per lane
+                    const uint32_t ent = heavy[hw * 32 + lane];
+                    const uint32_t col = ent >> 8;
+                    const int rel = (int)(col >> 5) - w0;            // word of the node within this slice
+                    const bool in = (ent & 255u) && rel >= 0 && rel < 32 * passes;
+                    if (c0 > 0 && !__any_sync(0xffffffffu, in)) continue;
 #pragma unroll
-                        for (int r = 0; r < RU; ++r) {
-                            const uint32_t wsrc = __shfl_sync(0xffffffffu, word[r], rel & 31);
-                            const uint32_t bw = __ballot_sync(0xffffffffu, in && ((wsrc >> (col & 31u)) & 1u));
-                            if (lane == 0 && bw && i0 + r < n) xh[(size_t)(i0 + r) * hwords + hw] |= bw;
+                    for (int r = 0; r < RU; ++r) {
+                        const uint32_t w_lo = __shfl_sync(0xffffffffu, word[0][r], rel & 31);
+                        const uint32_t w_hi = __shfl_sync(0xffffffffu, word[1][r], rel & 31);
+                        const uint32_t wsrc = (rel >= 32) ? w_hi : w_lo;
+                        const uint32_t bw = __ballot_sync(0xffffffffu, in && ((wsrc >> (col & 31u)) & 1u));
+                        if (lane == 0 && i0 + r < n) {
+                            uint32_t *dst = xh + (size_t)(i0 + r) * hwords + hw;
+                            if (c0 == 0) *dst = bw;                  // first slice defines the word, later ones add bits
+                            else if (bw) *dst |= bw;
                         }
                     }
                 }
@@ -744,7 +752,13 @@ cudaError_t launch_harmonic_table(double2 *harm, int32_t nmax, cudaStream_t st) 
 }
 
 cudaError_t launch_prep(const WindowTab &tab, int64_t *counts, int sm_count, cudaStream_t st) {
-    prep_kernel<<<max(1, min(tab.W, sm_count * 6)), PREP_THREADS, 0, st>>>(tab, counts);
+    static int per_sm = 0;                         // resident CTAs per SM (registers / shared memory), queried once
+    if (per_sm == 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, prep_kernel, PREP_THREADS, 0) != cudaSuccess || v < 1) v = 2;
+        per_sm = v;
+    }
+    prep_kernel<<<max(1, min(tab.W, sm_count * per_sm)), PREP_THREADS, 0, st>>>(tab, counts);
     return cudaGetLastError();
 }
 
