@@ -303,3 +303,37 @@ def test_range_error_is_reported(ctx):
         ctx.check()
     assert err.value.code == -4
     batch.close()
+
+
+def test_wrapper_tsv_rows(ctx, tmp_path):
+    """Matrix mode end to end: batch -> stats -> the wrappers' TSV columns (run_h-fst.sh:148, run_tajd.sh:101)."""
+    import io
+    from impop_b200 import windows
+    from impop_b200.engine import WindowBatch
+    ws = synth.make_windows(90, 100000, 3, seed=0xB200 + 1, n_sites_override=40)
+    lab = _labels(90, range(0, 30), range(30, 70))
+    batch = WindowBatch.from_uniform(ctx, ws.x_bits, ws.node_len, lab, ws.length)
+    stats, counts = batch.stats(0)
+    ctx.check()
+    st, ct = stats.cpu().numpy(), counts.cpu().numpy()
+    regions = [windows.region_name("chr2", 100000 * k, 100000 * (k + 1)) for k in range(3)]
+    buf = io.StringIO()
+    windows.write_tsv(buf, "fst", windows.fst_rows(regions, [ws.length] * 3, st))
+    lines = buf.getvalue().splitlines()
+    assert lines[0].split("\t") == ["REGION", "LENGTH", "FST", "PI_A", "PI_B", "PI_XY", "DXY", "DA"]
+    want_s, want_c = clib.window_stats(ws.x_bits[1], ws.m_pad, ws.node_len[1], lab, ws.length)
+    f = lines[2].split("\t")
+    assert f[0] == "CHM13#0#chr2:100000-200000" and f[1] == "100000"
+    assert f[2:] == [f"{want_s[k]:.8f}" for k in (7, 2, 3, 4, 5, 6)]
+    buf = io.StringIO()
+    windows.write_tsv(buf, "tajd", windows.tajd_rows(regions, [ws.length] * 3, st, ct))
+    t = buf.getvalue().splitlines()[2].split("\t")
+    assert t[2] == "90" and t[3] == str(int(want_c[7])) and t[4] == f"{want_s[1]:.8f}"
+    assert t[5] == ("NA" if np.isnan(want_s[9]) else repr(float(st[1][9])))
+    pi = list(windows.pi_rows(regions, [ws.length] * 3, st))
+    assert pi[0][-1] == f"{want_s_first(ws, lab):.8f} (sequence length: 100000)"
+    batch.close()
+
+
+def want_s_first(ws, lab):
+    return clib.window_stats(ws.x_bits[0], ws.m_pad, ws.node_len[0], lab, ws.length)[0][1]
