@@ -32,7 +32,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get("IMPOP_NVCC_DEFS", "").split()      # experiment switches, e.g. -DIMPOP_EPI_I2F=1
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -290,11 +290,12 @@ constexpr uint32_t LBO_A = TILE_M * 16;                         // next 16-byte 
 constexpr uint32_t LBO_B = TILE_N * 16;
 constexpr uint32_t SBO_AB = 128;                                // next 8-row group
 constexpr uint32_t TMEM_COLS = 512;                             // two accumulator buffers of 256 columns
-constexpr int EPI_COLS = 128;                                   // columns one epilogue warp can own
+constexpr int EPI_COLS = TILE_N;                                // columns of one item
 
-struct __align__(16) EpiCols {          // per epilogue warp: its (up to 128) columns of the current item
+struct __align__(16) EpiCols {          // per epilogue team: the columns of its current item
     uint32_t aj[EPI_COLS];              // path length A_j
     double fs[EPI_COLS], fa[EPI_COLS], fb[EPI_COLS];   // 1.0 / 0.0: column carries SUBSET / A / B
+    uint32_t cmask[EPI_COLS / 16];      // per 16-column chunk: bit 0 all columns valid and in SUBSET, bit 1 any A, bit 2 any B
 };
 
 struct WsShared {
@@ -302,10 +303,17 @@ struct WsShared {
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    EpiCols col[WS_EPI_WARPS];          // 28 KB
+    EpiCols col[2];                     // 2 x 7.2 KB
 };
 constexpr int WS_SMEM_BYTES = WS_STAGES * STAGE_BYTES + (int)sizeof(WsShared);
 
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Items are dealt to CTAs as CONTIGUOUS ranges (consecutive items of a CTA mostly belong to the same window:
+// its rows stay in L1/L2, and the per-row sums can be carried across items and reduced once per window).
+// Local item u of this launch is global item item_begin + u * world + rank.
 template <bool DUMP>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_constant__ ItemParams prm) {
@@ -315,7 +323,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 
     if (tid == 0) {
         for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&sh.full[s], WS_PROD_WARPS); mbar_init(&sh.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&sh.acc_full[b], 1); mbar_init(&sh.acc_empty[b], WS_EPI_WARPS); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sh.acc_full[b], 1); mbar_init(&sh.acc_empty[b], WS_EPI_WARPS / 2); }
         fence_mbar_init();
     }
     if (warp == WS_MMA_WARP) tmem_alloc(&sh.tmem_base, TMEM_COLS);
@@ -323,8 +331,9 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sh.tmem_base;
-    const int64_t stride = (int64_t)gridDim.x * prm.world;
-    const int64_t first = prm.item_begin + (int64_t)blockIdx.x * prm.world + prm.rank;
+    const int64_t u_total = (prm.item_end - prm.item_begin - prm.rank + prm.world - 1) / prm.world;
+    const int64_t u_lo = u_total * blockIdx.x / gridDim.x, u_hi = u_total * (blockIdx.x + 1) / gridDim.x;
+    auto item_of = [&](int64_t u) { return prm.item_begin + u * prm.world + prm.rank; };
     bool alive = true;
 
     if (warp < WS_PROD_WARPS) {
@@ -334,8 +343,8 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
         const int rl = (isA ? warp : warp - 4) * 32 + lane;          // row of the operand tile
         const uint32_t lbo = isA ? LBO_A : LBO_B;
         uint32_t g = 0;                                               // chunks produced so far
-        for (int64_t t = first; t < prm.item_end; t += stride) {
-            const Item it = decode_item(tab, t);
+        for (int64_t u = u_lo; u < u_hi; ++u) {
+            const Item it = decode_item(tab, item_of(u));
             const int n = tab.n[it.w], pitch = tab.pitch[it.w], m = tab.m[it.w];
             const int dense_chunks = (m + KCHUNK - 1) / KCHUNK;
             const int hwords = (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 5);
@@ -359,7 +368,11 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 const uint2 bits = next_bits;
                 next_bits = load_bits(c + 1);                  // in flight while this chunk is expanded
                 if (alive) alive = mbar_wait<200>(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
+#ifdef IMPOP_DBG_NO_EXPAND   // timing experiment only: skip the operand expansion
+                if (false) {
+#else
                 if (active) {
+#endif
                     const bool is_heavy = c >= dense_chunks;
                     uint8_t *dst = smem + s * STAGE_BYTES + (isA ? 0 : A_STAGE_BYTES) + rl * 16;
                     if (isA) {
@@ -398,62 +411,64 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
         // ================================================================ MMA issuer (warp 12; 13-15 idle)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == WS_MMA_WARP) {
-        const uint32_t smem_base_u32 = smem_u32(smem);
-        uint32_t g = 0, acc_uses = 0;
-        for (int64_t t = first; t < prm.item_end; t += stride) {
-            const Item it = decode_item(tab, t);
-            const int m = tab.m[it.w];
-            const int dense_chunks = (m + KCHUNK - 1) / KCHUNK;
-            const int nch = dense_chunks + (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 6);
-            if (nch == 0) continue;
-            const uint32_t buf = acc_uses & 1u;
-            if (alive) alive = mbar_wait<0>(&sh.acc_empty[buf], ((acc_uses >> 1) & 1u) ^ 1u, tab.err);
-            tc_fence_after();
-            const uint32_t idesc = make_idesc_u8(TILE_M, (uint32_t)it.ncols);
-            const uint32_t tmem_d = tmem_base + buf * TILE_N;
-            for (int c = 0; c < nch; ++c, ++g) {
-                const uint32_t s = g % WS_STAGES;
-                if (alive) alive = mbar_wait<0>(&sh.full[s], (g / WS_STAGES) & 1u, tab.err);
+            const uint32_t smem_base_u32 = smem_u32(smem);
+            uint32_t g = 0, uses[2] = {0u, 0u};
+            for (int64_t u = u_lo; u < u_hi; ++u) {
+                const Item it = decode_item(tab, item_of(u));
+                const int m = tab.m[it.w];
+                const int dense_chunks = (m + KCHUNK - 1) / KCHUNK;
+                const int nch = dense_chunks + (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 6);
+                if (nch == 0) continue;
+                const uint32_t buf = (uint32_t)(u - u_lo) & 1u;           // item parity = TMEM buffer = epilogue team
+                if (alive) alive = mbar_wait<0>(&sh.acc_empty[buf], (uses[buf] & 1u) ^ 1u, tab.err);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
-                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                const uint32_t idesc = make_idesc_u8(TILE_M, (uint32_t)it.ncols);
+                const uint32_t tmem_d = tmem_base + buf * TILE_N;
+                for (int c = 0; c < nch; ++c, ++g) {
+                    const uint32_t s = g % WS_STAGES;
+                    if (alive) alive = mbar_wait<0>(&sh.full[s], (g / WS_STAGES) & 1u, tab.err);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
+                        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
-                    for (int k32 = 0; k32 < KCHUNK / 32; ++k32) {
-                        uint64_t da = make_smem_desc(a_addr + k32 * 2 * LBO_A, LBO_A, SBO_AB);
-                        uint64_t db = make_smem_desc(b_addr + k32 * 2 * LBO_B, LBO_B, SBO_AB);
-                        tc_mma_i8(tmem_d, da, db, idesc, (c > 0 || k32 > 0) ? 1u : 0u);
+                        for (int k32 = 0; k32 < KCHUNK / 32; ++k32) {
+                            uint64_t da = make_smem_desc(a_addr + k32 * 2 * LBO_A, LBO_A, SBO_AB);
+                            uint64_t db = make_smem_desc(b_addr + k32 * 2 * LBO_B, LBO_B, SBO_AB);
+                            tc_mma_i8(tmem_d, da, db, idesc, (c > 0 || k32 > 0) ? 1u : 0u);
+                        }
+                        tc_commit(&sh.empty[s]);
+                        if (c == nch - 1) tc_commit(&sh.acc_full[buf]);
                     }
-                    tc_commit(&sh.empty[s]);
-                    if (c == nch - 1) tc_commit(&sh.acc_full[buf]);
+                    __syncwarp();
                 }
-                __syncwarp();
+                ++uses[buf];
             }
-            ++acc_uses;
-        }
         }
     } else {
-        // ================================================================ epilogue
+        // ================================================================ epilogue: two teams of four warps;
+        // team = item parity = TMEM buffer, so each team has two item periods to drain its accumulator
         asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
         const int e = warp - WS_EPI_WARP0;              // 0..7
         const int q4 = warp & 3;                          // TMEM lane quarter this warp may read
-        const int hsel = e >> 2;                          // column half
-        EpiCols &col = sh.col[e];
-        uint32_t acc_uses = 0;
-        for (int64_t t = first; t < prm.item_end; t += stride) {
+        const int team = e >> 2;
+        EpiCols &col = sh.col[team];
+        uint32_t uses = 0;
+        dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // this lane's S, AA, BB, AB sums of the current window
+        for (int64_t u = u_lo + team; u < u_hi; u += 2) {
+            const int64_t t = item_of(u);
             const Item it = decode_item(tab, t);
             const int n = tab.n[it.w], m = tab.m[it.w];
             const int nch = (m + KCHUNK - 1) / KCHUNK + (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 6);
             const int32_t *Aw = tab.A + tab.row_off[it.w];
             const uint8_t *lab = tab.labels + tab.lab_off[it.w];
-            const int half0 = (((it.ncols >> 4) + 1) >> 1) << 4;        // columns of half 0 (multiple of 16)
-            const int cbeg = hsel ? half0 : 0, cend = hsel ? it.ncols : half0;
-            // column table of this warp; per 16-column chunk k: bit k of allS (every column valid and in SUBSET),
-            // anyA, anyB (some column in A / B)
-            uint32_t allS = 0, anyA = 0, anyB = 0;
-            for (int cc = lane; cc < EPI_COLS; cc += 32) {
-                const int j = it.col0 + cbeg + cc;
-                const bool ok = (cbeg + cc < cend) && j < n;
+            // column table of the team's item: warp q4 fills columns [64 q4, 64 q4 + 64)
+            named_bar_sync(1 + team, 128);                 // the team is done reading the previous table
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cc = q4 * 64 + h * 32 + lane;
+                const int j = it.col0 + cc;
+                const bool ok = cc < it.ncols && j < n;
                 const uint32_t f = ok ? clean_label(__ldg(lab + j)) : 0u;
                 col.aj[cc] = ok ? (uint32_t)__ldg(Aw + j) : 0u;
                 col.fs[cc] = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
@@ -462,45 +477,50 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 const uint32_t bs = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_SUBSET) != 0u);
                 const uint32_t ba = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_A) != 0u);
                 const uint32_t bb = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_B) != 0u);
-                const int k0 = (cc - lane) >> 4;
-                allS |= (((bs & 0xFFFFu) == 0xFFFFu ? 1u : 0u) << k0) | (((bs >> 16) == 0xFFFFu ? 1u : 0u) << (k0 + 1));
-                anyA |= (((ba & 0xFFFFu) ? 1u : 0u) << k0) | (((ba >> 16) ? 1u : 0u) << (k0 + 1));
-                anyB |= (((bb & 0xFFFFu) ? 1u : 0u) << k0) | (((bb >> 16) ? 1u : 0u) << (k0 + 1));
+                if (lane < 2) {
+                    const uint32_t hs = lane ? (bs >> 16) : (bs & 0xFFFFu), ha = lane ? (ba >> 16) : (ba & 0xFFFFu),
+                                   hb = lane ? (bb >> 16) : (bb & 0xFFFFu);
+                    col.cmask[(q4 * 64 + h * 32) / 16 + lane] = (hs == 0xFFFFu ? 1u : 0u) | (ha ? 2u : 0u) | (hb ? 4u : 0u);
+                }
             }
-            __syncwarp();
+            named_bar_sync(1 + team, 128);                 // table complete
             const int r0 = it.bi * TILE_M + q4 * 32;
             const int i = r0 + lane;
             const bool rvalid = i < n;
             const uint32_t ai = rvalid ? (uint32_t)__ldg(Aw + i) : 0u;
             const uint32_t fi = rvalid ? clean_label(__ldg(lab + i)) : 0u;
-            const uint32_t buf = acc_uses & 1u;
             if (nch > 0) {
-                if (alive) alive = mbar_wait<100>(&sh.acc_full[buf], (acc_uses >> 1) & 1u, tab.err);
+                if (alive) alive = mbar_wait<100>(&sh.acc_full[team], uses & 1u, tab.err);
                 tc_fence_after();
             }
             dd ts = {0.0, 0.0}, ta = {0.0, 0.0}, tb = {0.0, 0.0};
-            for (int cc = cbeg; cc < cend; cc += 16) {
+            for (int cc = 0; cc < it.ncols; cc += 16) {
                 const int jbase = it.col0 + cc;
                 if (jbase >= n) break;
                 if (jbase + 15 < r0) continue;                     // every j below every i of this warp
                 uint32_t r[16];
                 if (nch > 0) {
-                    tmem_ld16(tmem_base + buf * TILE_N + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cc, r);
+                    tmem_ld16(tmem_base + team * TILE_N + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cc, r);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
                     for (int k = 0; k < 16; ++k) r[k] = 0u;
                 }
-                const int lc = cc - cbeg, kc = lc >> 4;
+                const uint32_t cm = col.cmask[cc >> 4];
                 uint32_t aj[16];
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(&col.aj[lc + 4 * k4]);
-                    aj[4 * k4] = v.x; aj[4 * k4 + 1] = v.y; aj[4 * k4 + 2] = v.z; aj[4 * k4 + 3] = v.w;
+                    const uint4 q = *reinterpret_cast<const uint4 *>(&col.aj[cc + 4 * k4]);
+                    aj[4 * k4] = q.x; aj[4 * k4 + 1] = q.y; aj[4 * k4 + 2] = q.z; aj[4 * k4 + 3] = q.w;
                 }
                 double p[16];
+#ifdef IMPOP_DBG_NO_EPI      // timing experiment only: skip the fp64 math
 #pragma unroll
-                for (int k = 0; k < 16; ++k) p[k] = pi_from_counts_fast(r[k], ai, aj[k]);
+                for (int k = 0; k < 16; ++k) p[k] = __hiloint2double(r[k] + aj[k], ai);
+#else
+                pi_batch<8>(r, ai, aj, p);
+                pi_batch<8>(r + 8, ai, aj + 8, p + 8);
+#endif
                 if (jbase <= r0 + 31) {                            // the chunk touches the diagonal of this warp's rows
 #pragma unroll
                     for (int k = 0; k < 16; ++k) p[k] = (jbase + k > i) ? p[k] : 0.0;
@@ -510,7 +530,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     for (int k = 0; k < 16; ++k) pair_dump(prm, n, i, jbase + k, r[k], ai, aj[k]);
                 }
                 double cs;
-                if ((allS >> kc) & 1u) {
+                if (cm & 1u) {
                     cs = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])),
                                              __dadd_rn(__dadd_rn(p[4], p[5]), __dadd_rn(p[6], p[7]))),
                                    __dadd_rn(__dadd_rn(__dadd_rn(p[8], p[9]), __dadd_rn(p[10], p[11])),
@@ -518,29 +538,44 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 } else {
                     cs = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) cs = __fma_rn(p[k], col.fs[lc + k], cs);   // p * 1.0 or p * 0.0: exact
+                    for (int k = 0; k < 16; ++k) cs = __fma_rn(p[k], col.fs[cc + k], cs);   // p * 1.0 or p * 0.0: exact
                 }
                 dd_add(ts, cs);
-                if ((anyA >> kc) & 1u) {
+                if (cm & 2u) {
                     double ca = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) ca = __fma_rn(p[k], col.fa[lc + k], ca);
+                    for (int k = 0; k < 16; ++k) ca = __fma_rn(p[k], col.fa[cc + k], ca);
                     dd_add(ta, ca);
                 }
-                if ((anyB >> kc) & 1u) {
+                if (cm & 4u) {
                     double cb = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) cb = __fma_rn(p[k], col.fb[lc + k], cb);
+                    for (int k = 0; k < 16; ++k) cb = __fma_rn(p[k], col.fb[cc + k], cb);
                     dd_add(tb, cb);
                 }
             }
             if (nch > 0) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.acc_empty[buf]);
-                ++acc_uses;
+                if (lane == 0) mbar_arrive(&sh.acc_empty[team]);
+                ++uses;
             }
-            warp_partial(ts, ta, tb, fi, prm.partials + t * PART_STRIDE + e * 8);
+            // row-side class combination, carried in this lane across the team's items of the same window
+            if (fi & IMPOP_LAB_SUBSET) dd_merge(v[0], ts);
+            if (fi & IMPOP_LAB_A) { dd_merge(v[1], ta); dd_merge(v[3], tb); }
+            if (fi & IMPOP_LAB_B) { dd_merge(v[2], tb); dd_merge(v[3], ta); }
+            const bool last = (u + 2 >= u_hi) || (__ldg(&tab.items[item_of(u + 2)].x) != it.w);
+            double *rec = prm.partials + t * PART_STRIDE + q4 * 8;
+            if (last) {                                        // reduce over the warp's 32 lanes, once per window visit
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const dd tot = warp_sum_dd(v[k]);
+                    if (lane == 0) { rec[k] = tot.hi; rec[4 + k] = tot.lo; }
+                    v[k].hi = 0.0; v[k].lo = 0.0;
+                }
+            } else if (lane < 8) {
+                rec[lane] = 0.0;                               // the sums travel on to the next item's record
+            }
         }
     }
 
@@ -649,8 +684,6 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const _
         }
         __syncthreads();
         warp_partial(ts, ta, tb, fi, prm.partials + t * PART_STRIDE + warp * 8);
-        if (tid < (PART_SLOTS - SIMT_THREADS / 32) * 8)             // unused partial slots of this item
-            prm.partials[t * PART_STRIDE + (SIMT_THREADS / 32) * 8 + tid] = 0.0;
     }
 }
 
