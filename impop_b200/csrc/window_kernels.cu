@@ -277,15 +277,18 @@ __device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const d
 // The integer pipes (expansion) and the fp64 pipe (epilogue) so run concurrently on different
 // warps, and items flow through without CTA-wide barriers.
 // ==========================================================================================
+#ifndef IMPOP_PROD_SLEEP
+#define IMPOP_PROD_SLEEP 200
+#endif
 constexpr int WS_PROD_WARPS = 12;
 constexpr int WS_EPI_WARPS = 8;
 constexpr int WS_MMA_WARP = WS_PROD_WARPS;
 constexpr int WS_EPI_WARP0 = WS_PROD_WARPS + 4;
 constexpr int WS_THREADS = 32 * (WS_EPI_WARP0 + WS_EPI_WARPS);        // 768
-constexpr int WS_STAGES = 6;
-constexpr int A_STAGE_BYTES = TILE_M * KCHUNK;                  // 8 KB
-constexpr int B_STAGE_BYTES = TILE_N * KCHUNK;                  // 16 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;      // 24 KB
+constexpr int WS_STAGES = 4;
+constexpr int A_STAGE_BYTES = TILE_M * KCHUNK;                  // 16 KB
+constexpr int B_STAGE_BYTES = TILE_N * KCHUNK;                  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;      // 48 KB
 constexpr uint32_t LBO_A = TILE_M * 16;                         // next 16-byte K slab of the A tile
 constexpr uint32_t LBO_B = TILE_N * 16;
 constexpr uint32_t SBO_AB = 128;                                // next 8-row group
@@ -336,38 +339,60 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
     auto item_of = [&](int64_t u) { return prm.item_begin + u * prm.world + prm.rank; };
     bool alive = true;
 
+    // Per-window values every role needs; re-read only when a CTA's next item belongs to another window
+    // (a CTA's items are contiguous, so that is once per ~6 items at n = 466), the item table entry of the
+    // next item is prefetched one item ahead.
+    struct Win {
+        int w = -1, n = 0, m = 0, pitch = 0, dense_chunks = 0, hwords = 0, nch = 0;
+        int64_t x_off = 0, w8_off = 0, xh_off = 0, row_off = 0, lab_off = 0;
+    };
+    auto load_win = [&](Win &wi, int w) {
+        if (w == wi.w) return;
+        wi.w = w;
+        wi.n = tab.n[w]; wi.m = tab.m[w]; wi.pitch = tab.pitch[w];
+        const int64_t h0 = tab.heavy_off[w], h1 = tab.heavy_off[w + 1];
+        wi.x_off = tab.x_off[w]; wi.w8_off = tab.w8_off[w]; wi.xh_off = tab.xh_off[w];
+        wi.row_off = tab.row_off[w]; wi.lab_off = tab.lab_off[w];
+        wi.dense_chunks = (wi.m + KCHUNK - 1) / KCHUNK;
+        wi.hwords = (int)((h1 - h0) >> 5);
+        wi.nch = wi.dense_chunks + wi.hwords / (KCHUNK / 32);
+    };
+    auto raw_item = [&](int64_t u) { return (u < u_hi) ? __ldg(tab.items + item_of(u)) : make_int4(-1, 0, 0, 0); };
+
     if (warp < WS_PROD_WARPS) {
         // ================================================================ producers
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         const bool isA = warp < 4;
         const int rl = (isA ? warp : warp - 4) * 32 + lane;          // row of the operand tile
         const uint32_t lbo = isA ? LBO_A : LBO_B;
         uint32_t g = 0;                                               // chunks produced so far
+        Win wi;
+        int4 nxt = raw_item(u_lo);
         for (int64_t u = u_lo; u < u_hi; ++u) {
-            const Item it = decode_item(tab, item_of(u));
-            const int n = tab.n[it.w], pitch = tab.pitch[it.w], m = tab.m[it.w];
-            const int dense_chunks = (m + KCHUNK - 1) / KCHUNK;
-            const int hwords = (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 5);
-            const int nch = dense_chunks + (hwords >> 1);
-            const int grow = (isA ? it.bi * TILE_M : it.col0) + rl;
-            const bool active = isA || rl < it.ncols;
-            const bool rvalid = active && grow < n;
-            const uint32_t *row = tab.x + tab.x_off[it.w] + (size_t)grow * pitch;
-            const uint32_t *hrow = tab.xh + tab.xh_off[it.w] + (size_t)grow * hwords;
-            const uint8_t *w8 = tab.w8 + tab.w8_off[it.w];
+            const int4 cur = nxt;
+            nxt = raw_item(u + 1);
+            load_win(wi, cur.x);
+            const int bi = cur.y, col0 = cur.z, ncols = cur.w;
+            const int nch = wi.nch, dense_chunks = wi.dense_chunks, hwords = wi.hwords;
+            const int grow = (isA ? bi * TILE_M : col0) + rl;
+            const bool active = isA || rl < ncols;
+            const bool rvalid = active && grow < wi.n;
+            const uint32_t *row = tab.x + wi.x_off + (size_t)grow * wi.pitch;
+            const uint32_t *hrow = tab.xh + wi.xh_off + (size_t)grow * hwords;
+            const uint8_t *w8 = tab.w8 + wi.w8_off;
             auto load_bits = [&](int c) {
-                uint2 v = make_uint2(0u, 0u);
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (rvalid && c < nch)
-                    v = (c >= dense_chunks) ? *reinterpret_cast<const uint2 *>(hrow + 2 * (c - dense_chunks))
-                                            : __ldg(reinterpret_cast<const uint2 *>(row + 2 * c));
+                    v = (c >= dense_chunks) ? *reinterpret_cast<const uint4 *>(hrow + 4 * (c - dense_chunks))
+                                            : __ldg(reinterpret_cast<const uint4 *>(row + 4 * c));
                 return v;
             };
-            uint2 next_bits = load_bits(0);
+            uint4 next_bits = load_bits(0);
             for (int c = 0; c < nch; ++c, ++g) {
                 const uint32_t s = g % WS_STAGES;
-                const uint2 bits = next_bits;
+                const uint4 bits = next_bits;
                 next_bits = load_bits(c + 1);                  // in flight while this chunk is expanded
-                if (alive) alive = mbar_wait<200>(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
+                if (alive) alive = mbar_wait<IMPOP_PROD_SLEEP>(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
 #ifdef IMPOP_DBG_NO_EXPAND   // timing experiment only: skip the operand expansion
                 if (false) {
 #else
@@ -375,11 +400,12 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 #endif
                     const bool is_heavy = c >= dense_chunks;
                     uint8_t *dst = smem + s * STAGE_BYTES + (isA ? 0 : A_STAGE_BYTES) + rl * 16;
+                    const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
                     if (isA) {
                         const uint32_t mul = is_heavy ? 255u : 1u;
 #pragma unroll
-                        for (int slab = 0; slab < 4; ++slab) {
-                            const uint32_t b16 = ((slab & 2) ? bits.y : bits.x) >> ((slab & 1) * 16);
+                        for (int slab = 0; slab < KCHUNK / 16; ++slab) {
+                            const uint32_t b16 = bw[slab >> 1] >> ((slab & 1) * 16);
                             uint4 o;
                             o.x = nibble_to_bytes01(b16 & 0xFu) * mul;
                             o.y = nibble_to_bytes01((b16 >> 4) & 0xFu) * mul;
@@ -390,8 +416,8 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     } else {
                         const uint4 *wp = reinterpret_cast<const uint4 *>(w8 + (size_t)c * KCHUNK);
 #pragma unroll
-                        for (int slab = 0; slab < 4; ++slab) {
-                            const uint32_t b16 = ((slab & 2) ? bits.y : bits.x) >> ((slab & 1) * 16);
+                        for (int slab = 0; slab < KCHUNK / 16; ++slab) {
+                            const uint32_t b16 = bw[slab >> 1] >> ((slab & 1) * 16);
                             const uint4 wv = __ldg(wp + slab);
                             uint4 o;
                             o.x = (nibble_to_bytes01(b16 & 0xFu) * 255u) & wv.x;
@@ -408,39 +434,42 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             }
         }
     } else if (warp < WS_EPI_WARP0) {
-        // ================================================================ MMA issuer (warp 12; 13-15 idle)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (warp == WS_MMA_WARP) {
+        // ================================================================ MMA issuer (one lane of warp 12; 13-15 idle)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (warp == WS_MMA_WARP && lane == 0) {
             const uint32_t smem_base_u32 = smem_u32(smem);
             uint32_t g = 0, uses[2] = {0u, 0u};
+            Win wi;
+            int4 nxt = raw_item(u_lo);
             for (int64_t u = u_lo; u < u_hi; ++u) {
-                const Item it = decode_item(tab, item_of(u));
-                const int m = tab.m[it.w];
-                const int dense_chunks = (m + KCHUNK - 1) / KCHUNK;
-                const int nch = dense_chunks + (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 6);
+                const int4 cur = nxt;
+                nxt = raw_item(u + 1);
+                load_win(wi, cur.x);
+                const int nch = wi.nch;
                 if (nch == 0) continue;
                 const uint32_t buf = (uint32_t)(u - u_lo) & 1u;           // item parity = TMEM buffer = epilogue team
                 if (alive) alive = mbar_wait<0>(&sh.acc_empty[buf], (uses[buf] & 1u) ^ 1u, tab.err);
                 tc_fence_after();
-                const uint32_t idesc = make_idesc_u8(TILE_M, (uint32_t)it.ncols);
+                const uint32_t idesc = make_idesc_u8(TILE_M, (uint32_t)cur.w);
                 const uint32_t tmem_d = tmem_base + buf * TILE_N;
                 for (int c = 0; c < nch; ++c, ++g) {
                     const uint32_t s = g % WS_STAGES;
                     if (alive) alive = mbar_wait<0>(&sh.full[s], (g / WS_STAGES) & 1u, tab.err);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
-                        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                    const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                    uint64_t da = make_smem_desc(a_addr, LBO_A, SBO_AB);
+                    uint64_t db = make_smem_desc(b_addr, LBO_B, SBO_AB);
 #pragma unroll
-                        for (int k32 = 0; k32 < KCHUNK / 32; ++k32) {
-                            uint64_t da = make_smem_desc(a_addr + k32 * 2 * LBO_A, LBO_A, SBO_AB);
-                            uint64_t db = make_smem_desc(b_addr + k32 * 2 * LBO_B, LBO_B, SBO_AB);
-                            tc_mma_i8(tmem_d, da, db, idesc, (c > 0 || k32 > 0) ? 1u : 0u);
-                        }
-                        tc_commit(&sh.empty[s]);
-                        if (c == nch - 1) tc_commit(&sh.acc_full[buf]);
+                    for (int k32 = 0; k32 < KCHUNK / 32; ++k32) {
+#ifndef IMPOP_DBG_NO_MMA      // timing experiment only
+                        tc_mma_i8(tmem_d, da, db, idesc, (c > 0 || k32 > 0) ? 1u : 0u);
+#endif
+                        da += (uint64_t)((2 * LBO_A) >> 4);                // start-address field advances by 2 K slabs
+                        db += (uint64_t)((2 * LBO_B) >> 4);
                     }
-                    __syncwarp();
+                    tc_commit(&sh.empty[s]);
+                    if (c == nch - 1) tc_commit(&sh.acc_full[buf]);
                 }
                 ++uses[buf];
             }
@@ -455,13 +484,18 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
         EpiCols &col = sh.col[team];
         uint32_t uses = 0;
         dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // this lane's S, AA, BB, AB sums of the current window
+        Win wi;
+        int4 nxt = raw_item(u_lo + team);
         for (int64_t u = u_lo + team; u < u_hi; u += 2) {
             const int64_t t = item_of(u);
-            const Item it = decode_item(tab, t);
-            const int n = tab.n[it.w], m = tab.m[it.w];
-            const int nch = (m + KCHUNK - 1) / KCHUNK + (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 6);
-            const int32_t *Aw = tab.A + tab.row_off[it.w];
-            const uint8_t *lab = tab.labels + tab.lab_off[it.w];
+            const int4 cur = nxt;
+            nxt = raw_item(u + 2);
+            load_win(wi, cur.x);
+            Item it;
+            it.w = cur.x; it.bi = cur.y; it.col0 = cur.z; it.ncols = cur.w;
+            const int n = wi.n, nch = wi.nch;
+            const int32_t *Aw = tab.A + wi.row_off;
+            const uint8_t *lab = tab.labels + wi.lab_off;
             // column table of the team's item: warp q4 fills columns [64 q4, 64 q4 + 64)
             named_bar_sync(1 + team, 128);                 // the team is done reading the previous table
 #pragma unroll
@@ -564,7 +598,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             if (fi & IMPOP_LAB_SUBSET) dd_merge(v[0], ts);
             if (fi & IMPOP_LAB_A) { dd_merge(v[1], ta); dd_merge(v[3], tb); }
             if (fi & IMPOP_LAB_B) { dd_merge(v[2], tb); dd_merge(v[3], ta); }
-            const bool last = (u + 2 >= u_hi) || (__ldg(&tab.items[item_of(u + 2)].x) != it.w);
+            const bool last = nxt.x != it.w;                   // (-1 past the end of this CTA's range)
             double *rec = prm.partials + t * PART_STRIDE + q4 * 8;
             if (last) {                                        // reduce over the warp's 32 lanes, once per window visit
 #pragma unroll
@@ -591,17 +625,18 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 // ==========================================================================================
 constexpr int SIMT_THREADS = 128;
 constexpr int SIMT_COLS = 16;
+constexpr int SIMT_K = 64;       // virtual columns per staging step
 
 __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const __grid_constant__ WindowTab tab,
                                                                          const __grid_constant__ ItemParams prm) {
-    __shared__ __align__(16) uint32_t s_b[SIMT_COLS][KCHUNK / 4 + 4];  // +4 words: rows stay 16-byte aligned
+    __shared__ __align__(16) uint32_t s_b[SIMT_COLS][SIMT_K / 4 + 4];  // +4 words: rows stay 16-byte aligned
     const int tid = threadIdx.x, warp = tid >> 5;
     const int64_t stride = (int64_t)gridDim.x * prm.world;
     for (int64_t t = prm.item_begin + (int64_t)blockIdx.x * prm.world + prm.rank; t < prm.item_end; t += stride) {
         const Item it = decode_item(tab, t);
         const int n = tab.n[it.w], pitch = tab.pitch[it.w], m = tab.m[it.w];
         const uint32_t *x = tab.x + tab.x_off[it.w];
-        const int dense_chunks = (m + KCHUNK - 1) / KCHUNK;
+        const int dense_chunks = ((m + KCHUNK - 1) / KCHUNK) * (KCHUNK / SIMT_K);   // in 64-column sub-chunks
         const int hwords = (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 5);
         const int nch = dense_chunks + (hwords >> 1);
         const uint32_t *xh = tab.xh + tab.xh_off[it.w];
@@ -633,13 +668,13 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const _
                         word = is_heavy ? xh[(size_t)gj * hwords + 2 * (c - dense_chunks) + (slab >> 2)]
                                         : __ldg(x + (size_t)gj * pitch + 2 * c + (slab >> 2));
                     const uint32_t b8 = (word >> ((slab & 3) * 8)) & 0xFFu;
-                    const uint2 wv = *reinterpret_cast<const uint2 *>(w8 + (size_t)c * KCHUNK + slab * 8);
+                    const uint2 wv = *reinterpret_cast<const uint2 *>(w8 + (size_t)c * SIMT_K + slab * 8);
                     uint2 o;
                     o.x = (nibble_to_bytes01(b8 & 0xFu) * 255u) & wv.x;
                     o.y = (nibble_to_bytes01(b8 >> 4) * 255u) & wv.y;
                     *reinterpret_cast<uint2 *>(&s_b[jr][slab * 2]) = o;
                 }
-                uint32_t a[KCHUNK / 4];
+                uint32_t a[SIMT_K / 4];
                 {
                     uint2 bits = make_uint2(0u, 0u);
                     if (rvalid)
@@ -656,7 +691,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const _
 #pragma unroll
                 for (int j = 0; j < SIMT_COLS; ++j) {
 #pragma unroll
-                    for (int q4 = 0; q4 < KCHUNK / 16; ++q4) {
+                    for (int q4 = 0; q4 < SIMT_K / 16; ++q4) {
                         uint4 b = *reinterpret_cast<const uint4 *>(&s_b[j][q4 * 4]);
                         cnt[j] = __dp4a(a[q4 * 4 + 0], b.x, cnt[j]);
                         cnt[j] = __dp4a(a[q4 * 4 + 1], b.y, cnt[j]);
