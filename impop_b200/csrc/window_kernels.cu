@@ -273,7 +273,9 @@ __device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const d
 //   warp  12     MMA issuer (one elected lane): tcgen05.mma kind::i8 into one of two TMEM buffers
 //                (warps 13-15 only pad the warpgroup so that setmaxnreg applies to whole warpgroups)
 //   warps 16-23  epilogue: tcgen05.ld, exact integer union, fp64 pi_ij, compensated sums
-// Registers are moved from the producer / MMA warpgroups (56 each) to the epilogue warpgroups (128 each).
+// Registers are moved from the producer / MMA warpgroups (56 each) to the epilogue warpgroups (128 each):
+// 16 x 32 x 56 + 8 x 32 x 128 = 61 440 = the 768 x 80 registers the CTA owns (a larger sum makes
+// setmaxnreg.inc wait forever).
 // The integer pipes (expansion) and the fp64 pipe (epilogue) so run concurrently on different
 // warps, and items flow through without CTA-wide barriers.
 // ==========================================================================================
@@ -361,7 +363,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 
     if (warp < WS_PROD_WARPS) {
         // ================================================================ producers
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         const bool isA = warp < 4;
         const int rl = (isA ? warp : warp - 4) * 32 + lane;          // row of the operand tile
         const uint32_t lbo = isA ? LBO_A : LBO_B;
@@ -434,9 +436,9 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             }
         }
     } else if (warp < WS_EPI_WARP0) {
-        // ================================================================ MMA issuer (one lane of warp 12; 13-15 idle)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        if (warp == WS_MMA_WARP && lane == 0) {
+        // ================================================================ MMA issuer (warp 12, one lane issues; 13-15 idle)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == WS_MMA_WARP) {
             const uint32_t smem_base_u32 = smem_u32(smem);
             uint32_t g = 0, uses[2] = {0u, 0u};
             Win wi;
@@ -456,20 +458,23 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     const uint32_t s = g % WS_STAGES;
                     if (alive) alive = mbar_wait<0>(&sh.full[s], (g / WS_STAGES) & 1u, tab.err);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
-                    const uint32_t b_addr = a_addr + A_STAGE_BYTES;
-                    uint64_t da = make_smem_desc(a_addr, LBO_A, SBO_AB);
-                    uint64_t db = make_smem_desc(b_addr, LBO_B, SBO_AB);
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
+                        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+                        uint64_t da = make_smem_desc(a_addr, LBO_A, SBO_AB);
+                        uint64_t db = make_smem_desc(b_addr, LBO_B, SBO_AB);
 #pragma unroll
-                    for (int k32 = 0; k32 < KCHUNK / 32; ++k32) {
+                        for (int k32 = 0; k32 < KCHUNK / 32; ++k32) {
 #ifndef IMPOP_DBG_NO_MMA      // timing experiment only
-                        tc_mma_i8(tmem_d, da, db, idesc, (c > 0 || k32 > 0) ? 1u : 0u);
+                            tc_mma_i8(tmem_d, da, db, idesc, (c > 0 || k32 > 0) ? 1u : 0u);
 #endif
-                        da += (uint64_t)((2 * LBO_A) >> 4);                // start-address field advances by 2 K slabs
-                        db += (uint64_t)((2 * LBO_B) >> 4);
+                            da += (uint64_t)((2 * LBO_A) >> 4);            // start-address field advances by 2 K slabs
+                            db += (uint64_t)((2 * LBO_B) >> 4);
+                        }
+                        tc_commit(&sh.empty[s]);
+                        if (c == nch - 1) tc_commit(&sh.acc_full[buf]);
                     }
-                    tc_commit(&sh.empty[s]);
-                    if (c == nch - 1) tc_commit(&sh.acc_full[buf]);
+                    __syncwarp();
                 }
                 ++uses[buf];
             }

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for defs in "$@"; do
   echo "=== variant: [$defs]" >> gpurun_out/exp.log
   IMPOP_NVCC_DEFS="$defs" python -c "from impop_b200 import build; build.build(force=True)" >> gpurun_out/exp.log 2>&1 || { echo "build failed" >> gpurun_out/exp.log; continue; }
-  timeout 300 python - >> gpurun_out/exp.log 2>&1 <<'PY'
+  timeout 90 python - >> gpurun_out/exp.log 2>&1 <<'PY'
 import json, subprocess, sys
 from impop_b200.engine import Context
 ctx = Context(0)
