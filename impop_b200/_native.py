@@ -55,6 +55,7 @@ SIGNATURES = {
     "impop_site_counts": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p, _p, _p]),
     "impop_cluster": (C.c_int, [_p, _p, _i32, _i64, _f64, _p, _p]),
     "impop_selftest_division": (C.c_int, [_p, C.c_uint64, _i64, C.POINTER(_i64), _p]),
+    "impop_debug_role_times": (C.c_int, [_p, _p, _i32]),
     "impop_greedy_groups": (C.c_int, [_p, _p, _i32, _i64, _f64, _p, _p, _p]),
 }
 

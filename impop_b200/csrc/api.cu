@@ -41,6 +41,7 @@ struct impop_ctx {
     int32_t *err_dev = nullptr;
     double2 *harm_dev = nullptr;
     double *ri_scratch = nullptr;     // reduce_identity partials
+    long long *prof_dev = nullptr;    // role-time counters of the last pairs launch (IMPOP_PROFILE_ROLES builds)
     int32_t *cluster_parent = nullptr;
     int32_t cluster_cap = 0;
     int64_t launches = 0;
@@ -180,6 +181,8 @@ int impop_create(int device, impop_ctx_t **ctx_out) {
               cudaMemset(ctx->err_dev, 0, sizeof(int32_t)) == cudaSuccess &&
               cudaMalloc(&ctx->harm_dev, sizeof(double2) * (HARM_N + 1)) == cudaSuccess &&
               cudaMalloc(&ctx->ri_scratch, sizeof(double) * 16 * 148 * 4) == cudaSuccess &&
+              cudaMalloc(&ctx->prof_dev, sizeof(long long) * 16 * 1024) == cudaSuccess &&
+              cudaMemset(ctx->prof_dev, 0, sizeof(long long) * 16 * 1024) == cudaSuccess &&
               configure_kernels() == cudaSuccess && launch_harmonic_table(ctx->harm_dev, HARM_N, 0) == cudaSuccess &&
               cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
@@ -418,7 +421,7 @@ static int run_sums(impop_ctx_t *ctx, impop_batch_t *b, int32_t algo, int32_t ra
     ItemParams prm{};
     prm.partials = b->partials;
     prm.item_begin = 0; prm.item_end = b->items; prm.rank = rank; prm.world = world;
-    prm.dumpI = nullptr; prm.dumpPi = nullptr;
+    prm.dumpI = nullptr; prm.dumpPi = nullptr; prm.prof = ctx->prof_dev;
     CU(timed(ctx, IMPOP_KERNEL_PAIRS, st, [&] { return launch_pairs(b->tab, prm, algo, ctx->sm_count, st); }));
     CU(timed(ctx, IMPOP_KERNEL_SUMS, st, [&] { return launch_window_sums(b->tab, b->partials, rank, world, sums_dev, st); }));
     ctx->launches += 3;
@@ -566,6 +569,13 @@ int impop_selftest_division(impop_ctx_t *ctx, uint64_t seed, int64_t count, int6
     if (e != cudaSuccess) return cuda_fail(ctx, e, "impop_selftest_division");
     ctx->launches += 1;
     *mismatches_host = (int64_t)host;
+    return IMPOP_OK;
+}
+
+int impop_debug_role_times(impop_ctx_t *ctx, int64_t *out_host, int32_t ctas) {
+    if (!ctx || !out_host || ctas < 0 || ctas > 1024) return IMPOP_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpy(out_host, ctx->prof_dev, sizeof(long long) * 16 * (size_t)ctas, cudaMemcpyDeviceToHost));
     return IMPOP_OK;
 }
 

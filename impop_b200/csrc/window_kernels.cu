@@ -319,6 +319,20 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // Items are dealt to CTAs as CONTIGUOUS ranges (consecutive items of a CTA mostly belong to the same window:
 // its rows stay in L1/L2, and the per-row sums can be carried across items and reduced once per window).
 // Local item u of this launch is global item item_begin + u * world + rank.
+#ifdef IMPOP_PROFILE_ROLES
+#define PROF_DECL long long pf_wait = 0, pf_work = 0, pf_t = clock64(), pf_aux = 0;
+#define PROF_WAIT_END { long long n_ = clock64(); pf_wait += n_ - pf_t; pf_t = n_; }
+#define PROF_WORK_END { long long n_ = clock64(); pf_work += n_ - pf_t; pf_t = n_; }
+#define PROF_AUX_END { long long n_ = clock64(); pf_aux += n_ - pf_t; pf_t = n_; }
+#define PROF_STORE(slot) if (prm.prof && lane == 0) { long long *o_ = prm.prof + (size_t)blockIdx.x * 16 + (slot) * 3; o_[0] = pf_wait; o_[1] = pf_work; o_[2] = pf_aux; }
+#else
+#define PROF_DECL
+#define PROF_WAIT_END
+#define PROF_WORK_END
+#define PROF_AUX_END
+#define PROF_STORE(slot) {}
+#endif
+
 template <bool DUMP>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_constant__ ItemParams prm) {
@@ -328,7 +342,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 
     if (tid == 0) {
         for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&sh.full[s], WS_PROD_WARPS); mbar_init(&sh.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&sh.acc_full[b], 1); mbar_init(&sh.acc_empty[b], WS_EPI_WARPS / 2); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&sh.acc_full[b], 1); mbar_init(&sh.acc_empty[b], WS_EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == WS_MMA_WARP) tmem_alloc(&sh.tmem_base, TMEM_COLS);
@@ -370,10 +384,12 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
         uint32_t g = 0;                                               // chunks produced so far
         Win wi;
         int4 nxt = raw_item(u_lo);
+        PROF_DECL
         for (int64_t u = u_lo; u < u_hi; ++u) {
             const int4 cur = nxt;
             nxt = raw_item(u + 1);
             load_win(wi, cur.x);
+            PROF_AUX_END
             const int bi = cur.y, col0 = cur.z, ncols = cur.w;
             const int nch = wi.nch, dense_chunks = wi.dense_chunks, hwords = wi.hwords;
             const int grow = (isA ? bi * TILE_M : col0) + rl;
@@ -395,6 +411,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 const uint4 bits = next_bits;
                 next_bits = load_bits(c + 1);                  // in flight while this chunk is expanded
                 if (alive) alive = mbar_wait<IMPOP_PROD_SLEEP>(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
+                PROF_WAIT_END
 #ifdef IMPOP_DBG_NO_EXPAND   // timing experiment only: skip the operand expansion
                 if (false) {
 #else
@@ -433,8 +450,11 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.full[s]);
+                PROF_WORK_END
             }
         }
+        if (warp == 0) PROF_STORE(0)
+        if (warp == 4) PROF_STORE(1)
     } else if (warp < WS_EPI_WARP0) {
         // ================================================================ MMA issuer (warp 12, one lane issues; 13-15 idle)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -443,20 +463,24 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             uint32_t g = 0, uses[2] = {0u, 0u};
             Win wi;
             int4 nxt = raw_item(u_lo);
+            PROF_DECL
             for (int64_t u = u_lo; u < u_hi; ++u) {
                 const int4 cur = nxt;
                 nxt = raw_item(u + 1);
                 load_win(wi, cur.x);
                 const int nch = wi.nch;
                 if (nch == 0) continue;
+                PROF_WORK_END
                 const uint32_t buf = (uint32_t)(u - u_lo) & 1u;           // item parity = TMEM buffer = epilogue team
                 if (alive) alive = mbar_wait<0>(&sh.acc_empty[buf], (uses[buf] & 1u) ^ 1u, tab.err);
+                PROF_AUX_END
                 tc_fence_after();
                 const uint32_t idesc = make_idesc_u8(TILE_M, (uint32_t)cur.w);
                 const uint32_t tmem_d = tmem_base + buf * TILE_N;
                 for (int c = 0; c < nch; ++c, ++g) {
                     const uint32_t s = g % WS_STAGES;
                     if (alive) alive = mbar_wait<0>(&sh.full[s], (g / WS_STAGES) & 1u, tab.err);
+                    PROF_WAIT_END
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t a_addr = smem_base_u32 + s * STAGE_BYTES;
@@ -475,37 +499,39 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                         if (c == nch - 1) tc_commit(&sh.acc_full[buf]);
                     }
                     __syncwarp();
+                    PROF_WORK_END
                 }
                 ++uses[buf];
             }
+            PROF_STORE(2)
         }
     } else {
-        // ================================================================ epilogue: two teams of four warps;
-        // team = item parity = TMEM buffer, so each team has two item periods to drain its accumulator
+        // ================================================================ epilogue: all eight warps work on the same
+        // item (warp -> 32-row quarter x column half) while the MMA of the next item fills the other TMEM buffer
         asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
         const int e = warp - WS_EPI_WARP0;              // 0..7
         const int q4 = warp & 3;                          // TMEM lane quarter this warp may read
-        const int team = e >> 2;
-        EpiCols &col = sh.col[team];
-        uint32_t uses = 0;
+        const int hsel = e >> 2;                          // column half
+        uint32_t uses[2] = {0u, 0u};
         dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // this lane's S, AA, BB, AB sums of the current window
         Win wi;
-        int4 nxt = raw_item(u_lo + team);
-        for (int64_t u = u_lo + team; u < u_hi; u += 2) {
+        int4 nxt = raw_item(u_lo);
+        PROF_DECL
+        for (int64_t u = u_lo; u < u_hi; ++u) {
             const int64_t t = item_of(u);
             const int4 cur = nxt;
-            nxt = raw_item(u + 2);
+            nxt = raw_item(u + 1);
             load_win(wi, cur.x);
             Item it;
             it.w = cur.x; it.bi = cur.y; it.col0 = cur.z; it.ncols = cur.w;
             const int n = wi.n, nch = wi.nch;
             const int32_t *Aw = tab.A + wi.row_off;
             const uint8_t *lab = tab.labels + wi.lab_off;
-            // column table of the team's item: warp q4 fills columns [64 q4, 64 q4 + 64)
-            named_bar_sync(1 + team, 128);                 // the team is done reading the previous table
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int cc = q4 * 64 + h * 32 + lane;
+            const uint32_t buf = (uint32_t)(u - u_lo) & 1u;           // item parity = TMEM buffer = column table
+            EpiCols &col = sh.col[buf];
+            {   // column table of the item: warp e fills columns [32 e, 32 e + 32).  The table of parity `buf` was last
+                // read two items ago; every warp has passed the barrier of the previous item since, so it is free.
+                const int cc = e * 32 + lane;
                 const int j = it.col0 + cc;
                 const bool ok = cc < it.ncols && j < n;
                 const uint32_t f = ok ? clean_label(__ldg(lab + j)) : 0u;
@@ -519,27 +545,31 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 if (lane < 2) {
                     const uint32_t hs = lane ? (bs >> 16) : (bs & 0xFFFFu), ha = lane ? (ba >> 16) : (ba & 0xFFFFu),
                                    hb = lane ? (bb >> 16) : (bb & 0xFFFFu);
-                    col.cmask[(q4 * 64 + h * 32) / 16 + lane] = (hs == 0xFFFFu ? 1u : 0u) | (ha ? 2u : 0u) | (hb ? 4u : 0u);
+                    col.cmask[e * 2 + lane] = (hs == 0xFFFFu ? 1u : 0u) | (ha ? 2u : 0u) | (hb ? 4u : 0u);
                 }
             }
-            named_bar_sync(1 + team, 128);                 // table complete
+            named_bar_sync(1, WS_EPI_WARPS * 32);          // table complete
             const int r0 = it.bi * TILE_M + q4 * 32;
             const int i = r0 + lane;
             const bool rvalid = i < n;
             const uint32_t ai = rvalid ? (uint32_t)__ldg(Aw + i) : 0u;
             const uint32_t fi = rvalid ? clean_label(__ldg(lab + i)) : 0u;
+            const int half0 = (((it.ncols >> 4) + 1) >> 1) << 4;        // columns of half 0 (multiple of 16)
+            const int cbeg = hsel ? half0 : 0, cend = hsel ? it.ncols : half0;
+            PROF_AUX_END
             if (nch > 0) {
-                if (alive) alive = mbar_wait<100>(&sh.acc_full[team], uses & 1u, tab.err);
+                if (alive) alive = mbar_wait<100>(&sh.acc_full[buf], uses[buf] & 1u, tab.err);
                 tc_fence_after();
             }
+            PROF_WAIT_END
             dd ts = {0.0, 0.0}, ta = {0.0, 0.0}, tb = {0.0, 0.0};
-            for (int cc = 0; cc < it.ncols; cc += 16) {
+            for (int cc = cbeg; cc < cend && r0 < n; cc += 16) {
                 const int jbase = it.col0 + cc;
                 if (jbase >= n) break;
                 if (jbase + 15 < r0) continue;                     // every j below every i of this warp
                 uint32_t r[16];
                 if (nch > 0) {
-                    tmem_ld16(tmem_base + team * TILE_N + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cc, r);
+                    tmem_ld16(tmem_base + buf * TILE_N + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cc, r);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
@@ -596,15 +626,16 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             if (nch > 0) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.acc_empty[team]);
-                ++uses;
+                if (lane == 0) mbar_arrive(&sh.acc_empty[buf]);
+                ++uses[buf];
             }
-            // row-side class combination, carried in this lane across the team's items of the same window
+            PROF_WORK_END
+            // row-side class combination, carried in this lane across the CTA's items of the same window
             if (fi & IMPOP_LAB_SUBSET) dd_merge(v[0], ts);
             if (fi & IMPOP_LAB_A) { dd_merge(v[1], ta); dd_merge(v[3], tb); }
             if (fi & IMPOP_LAB_B) { dd_merge(v[2], tb); dd_merge(v[3], ta); }
             const bool last = nxt.x != it.w;                   // (-1 past the end of this CTA's range)
-            double *rec = prm.partials + t * PART_STRIDE + q4 * 8;
+            double *rec = prm.partials + t * PART_STRIDE + e * 8;
             if (last) {                                        // reduce over the warp's 32 lanes, once per window visit
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -616,6 +647,8 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 rec[lane] = 0.0;                               // the sums travel on to the next item's record
             }
         }
+        if (e == 0) PROF_STORE(3)
+        if (e == 4) PROF_STORE(4)
     }
 
     tc_fence_before();
@@ -724,6 +757,8 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const _
         }
         __syncthreads();
         warp_partial(ts, ta, tb, fi, prm.partials + t * PART_STRIDE + warp * 8);
+        if (tid < (PART_SLOTS - SIMT_THREADS / 32) * 8)             // unused partial slots of this item
+            prm.partials[t * PART_STRIDE + (SIMT_THREADS / 32) * 8 + tid] = 0.0;
     }
 }
 

@@ -194,6 +194,10 @@ int impop_greedy_groups(impop_ctx_t *ctx, const double *ident_dev, int32_t n, in
  * in-range operand triples (I, A_i, A_j).  *mismatches_host must come back 0.  Synchronous. */
 int impop_selftest_division(impop_ctx_t *ctx, uint64_t seed, int64_t count, int64_t *mismatches_host, void *stream);
 
+/* Development aid: cycle counters (wait / work / other) of the pairs kernel's warp roles in the last launch, 16
+ * int64 per CTA; all zero unless the library was built with -DIMPOP_PROFILE_ROLES.  Synchronous. */
+int impop_debug_role_times(impop_ctx_t *ctx, int64_t *out_host, int32_t ctas);
+
 #ifdef __cplusplus
 }
 #endif
