@@ -163,30 +163,41 @@ int impop_create(int device, impop_ctx_t **ctx_out) {
     if (!ctx_out) return IMPOP_ERR_ARG;
     *ctx_out = nullptr;
     int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return IMPOP_ERR_CUDA;
+    cudaError_t e0 = cudaGetDeviceCount(&count);
+    if (e0 != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        fprintf(stderr, "impop_create: no usable CUDA device (%s, %d devices)\n", cudaGetErrorString(e0), count);
+        return IMPOP_ERR_CUDA;
+    }
     impop_ctx *ctx = new (std::nothrow) impop_ctx();
     if (!ctx) return IMPOP_ERR_NOMEM;
     ctx->device = device;
     cudaDeviceProp prop;
-    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    if ((e0 = cudaSetDevice(device)) != cudaSuccess || (e0 = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        fprintf(stderr, "impop_create: %s\n", cudaGetErrorString(e0));
         delete ctx;
         return IMPOP_ERR_CUDA;
     }
     if (prop.major != 10) {   // sm_100a cubin only: fail loudly rather than fall back
+        fprintf(stderr, "impop_create: device %d is sm_%d%d, this library is built for sm_100a only\n", device, prop.major, prop.minor);
         delete ctx;
         return IMPOP_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
-    bool ok = cudaMalloc(&ctx->err_dev, sizeof(int32_t)) == cudaSuccess &&
-              cudaMemset(ctx->err_dev, 0, sizeof(int32_t)) == cudaSuccess &&
-              cudaMalloc(&ctx->harm_dev, sizeof(double2) * (HARM_N + 1)) == cudaSuccess &&
-              cudaMalloc(&ctx->ri_scratch, sizeof(double) * 16 * 148 * 4) == cudaSuccess &&
-              cudaMalloc(&ctx->prof_dev, sizeof(long long) * 16 * 1024) == cudaSuccess &&
-              cudaMemset(ctx->prof_dev, 0, sizeof(long long) * 16 * 1024) == cudaSuccess &&
-              configure_kernels() == cudaSuccess && launch_harmonic_table(ctx->harm_dev, HARM_N, 0) == cudaSuccess &&
-              cudaDeviceSynchronize() == cudaSuccess;
+    const char *step = "";
+    cudaError_t es = cudaSuccess;
+    auto run = [&](const char *what, cudaError_t r) { if (es == cudaSuccess && r != cudaSuccess) { es = r; step = what; } return es == cudaSuccess; };
+    bool ok = run("alloc err flag", cudaMalloc(&ctx->err_dev, sizeof(int32_t))) &&
+              run("memset", cudaMemset(ctx->err_dev, 0, sizeof(int32_t))) &&
+              run("alloc harmonic table", cudaMalloc(&ctx->harm_dev, sizeof(double2) * (HARM_N + 1))) &&
+              run("alloc scratch", cudaMalloc(&ctx->ri_scratch, sizeof(double) * 16 * 148 * 4)) &&
+              run("alloc counters", cudaMalloc(&ctx->prof_dev, sizeof(long long) * 16 * 1024)) &&
+              run("memset", cudaMemset(ctx->prof_dev, 0, sizeof(long long) * 16 * 1024)) &&
+              run("shared-memory attribute of the pairs kernel", configure_kernels()) &&
+              run("harmonic table launch", launch_harmonic_table(ctx->harm_dev, HARM_N, 0)) &&
+              run("synchronize", cudaDeviceSynchronize());
     if (!ok) {
-        cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->ri_scratch);
+        fprintf(stderr, "impop_create: CUDA set-up failed at '%s': %s\n", step, cudaGetErrorString(es));
+        cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->ri_scratch); cudaFree(ctx->prof_dev);
         delete ctx;
         return IMPOP_ERR_CUDA;
     }

@@ -11,6 +11,8 @@
 // and, when len_k >= 255, ceil(q / 255) "heavy" columns (a = x_ik * c, b = 255 * x_jk) with the c's
 // summing to q = len_k / 255, so a * b summed over a node's columns is exactly len_k.  The weights sit on
 // the A operand because the A tile has at most half the rows of the B tile (fewer weighted expansions).
+#include <stdio.h>
+
 #include "common.cuh"
 #include "stats_math.cuh"
 
@@ -296,12 +298,11 @@ constexpr uint32_t LBO_A = TILE_M * 16;                         // next 16-byte 
 constexpr uint32_t LBO_B = TILE_N * 16;
 constexpr uint32_t SBO_AB = 128;                                // next 8-row group
 constexpr uint32_t TMEM_COLS = 512;                             // two accumulator buffers of 256 columns
-constexpr int EPI_COLS = TILE_N;                                // columns of one item
+constexpr int EPI_COLS = 128;                                   // columns one epilogue warp can own
 
-struct __align__(16) EpiCols {          // per epilogue team: the columns of its current item
+struct __align__(16) EpiCols {          // private to one epilogue warp: its columns of the current item
     uint32_t aj[EPI_COLS];              // path length A_j
     double fs[EPI_COLS], fa[EPI_COLS], fb[EPI_COLS];   // 1.0 / 0.0: column carries SUBSET / A / B
-    uint32_t cmask[EPI_COLS / 16];      // per 16-column chunk: bit 0 all columns valid and in SUBSET, bit 1 any A, bit 2 any B
 };
 
 struct WsShared {
@@ -312,6 +313,7 @@ struct WsShared {
     EpiCols col[WS_EPI_WARPS];          // 8 x 3.6 KB
 };
 constexpr int WS_SMEM_BYTES = WS_STAGES * STAGE_BYTES + (int)sizeof(WsShared);
+static_assert(WS_SMEM_BYTES <= 232448, "pairs kernel exceeds the 227 KB of shared memory a CTA can have");
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -909,7 +911,13 @@ cudaError_t launch_prep(const WindowTab &tab, int64_t *counts, int sm_count, cud
 
 cudaError_t configure_kernels() {
     cudaError_t e = cudaFuncSetAttribute(window_pairs_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, window_pairs_tc_kernel<false>) == cudaSuccess)
+            fprintf(stderr, "pairs kernel: dynamic shared memory %d B requested, static %zu B, max dynamic %d B\n",
+                    WS_SMEM_BYTES, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
+        return e;
+    }
     return cudaFuncSetAttribute(window_pairs_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES);
 }
 
