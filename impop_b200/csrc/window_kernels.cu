@@ -298,11 +298,12 @@ constexpr uint32_t LBO_A = TILE_M * 16;                         // next 16-byte 
 constexpr uint32_t LBO_B = TILE_N * 16;
 constexpr uint32_t SBO_AB = 128;                                // next 8-row group
 constexpr uint32_t TMEM_COLS = 512;                             // two accumulator buffers of 256 columns
-constexpr int EPI_COLS = 128;                                   // columns one epilogue warp can own
+constexpr int EPI_COLS = TILE_N;                                // columns of one item
 
-struct __align__(16) EpiCols {          // private to one epilogue warp: its columns of the current item
+struct __align__(16) EpiCols {          // per epilogue team: the columns of its current item
     uint32_t aj[EPI_COLS];              // path length A_j
     double fs[EPI_COLS], fa[EPI_COLS], fb[EPI_COLS];   // 1.0 / 0.0: column carries SUBSET / A / B
+    uint32_t cmask[EPI_COLS / 16];      // per 16-column chunk: bit 0 all columns valid and in SUBSET, bit 1 any A, bit 2 any B
 };
 
 struct WsShared {
@@ -310,7 +311,7 @@ struct WsShared {
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
-    EpiCols col[WS_EPI_WARPS];          // 8 x 3.6 KB
+    EpiCols col[2];                     // 2 x 7.2 KB
 };
 constexpr int WS_SMEM_BYTES = WS_STAGES * STAGE_BYTES + (int)sizeof(WsShared);
 static_assert(WS_SMEM_BYTES <= 232448, "pairs kernel exceeds the 227 KB of shared memory a CTA can have");
@@ -517,83 +518,48 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
         const int hsel = e >> 2;                          // column half
         uint32_t uses[2] = {0u, 0u};
         dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // this lane's S, AA, BB, AB sums of the current window
-        EpiCols &col = sh.col[e];
         Win wi;
         int4 nxt = raw_item(u_lo);
         PROF_DECL
-        // The two warps of a row quarter split the quarter's VALID 16-column chunks (those not entirely below the
-        // diagonal) evenly, so both warps of an SM sub-partition carry the same fp64 load.
-        auto my_range = [&](const int4 &item, int n, int &cbeg, int &cend) {
-            const int r0 = item.y * TILE_M + q4 * 32;
-            int first = (r0 - item.z) >> 4;                 // first chunk with some j >= r0 ...
-            if (first < 0) first = 0;
-            int last = (min(item.z + item.w, n) - item.z + 15) >> 4;   // ... up to the last chunk with some j < n
-            if (last < first) last = first;
-            const int mid = first + ((last - first + 1) >> 1);
-            cbeg = (hsel ? mid : first) << 4;
-            cend = (hsel ? last : mid) << 4;
-        };
-        // column data of the next item, fetched while the current one is processed (same window only)
-        uint32_t pre_a[4], pre_f[4], pre_ai = 0u, pre_fi = 0u;
-        bool have_pre = false;
         for (int64_t u = u_lo; u < u_hi; ++u) {
             const int64_t t = item_of(u);
             const int4 cur = nxt;
             nxt = raw_item(u + 1);
-            const bool same_win = cur.x == wi.w;
             load_win(wi, cur.x);
             Item it;
             it.w = cur.x; it.bi = cur.y; it.col0 = cur.z; it.ncols = cur.w;
             const int n = wi.n, nch = wi.nch;
             const int32_t *Aw = tab.A + wi.row_off;
             const uint8_t *lab = tab.labels + wi.lab_off;
-            const uint32_t buf = (uint32_t)(u - u_lo) & 1u;           // item parity = TMEM buffer
-            int cbeg, cend;
-            my_range(cur, n, cbeg, cend);
+            const uint32_t buf = (uint32_t)(u - u_lo) & 1u;           // item parity = TMEM buffer = column table
+            EpiCols &col = sh.col[buf];
+            {   // column table of the item: warp e fills columns [32 e, 32 e + 32).  The table of parity `buf` was last
+                // read two items ago; every warp has passed the barrier of the previous item since, so it is free.
+                const int cc = e * 32 + lane;
+                const int j = it.col0 + cc;
+                const bool ok = cc < it.ncols && j < n;
+                const uint32_t f = ok ? clean_label(__ldg(lab + j)) : 0u;
+                col.aj[cc] = ok ? (uint32_t)__ldg(Aw + j) : 0u;
+                col.fs[cc] = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
+                col.fa[cc] = (f & IMPOP_LAB_A) ? 1.0 : 0.0;
+                col.fb[cc] = (f & IMPOP_LAB_B) ? 1.0 : 0.0;
+                const uint32_t bs = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_SUBSET) != 0u);
+                const uint32_t ba = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_A) != 0u);
+                const uint32_t bb = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_B) != 0u);
+                if (lane < 2) {
+                    const uint32_t hs = lane ? (bs >> 16) : (bs & 0xFFFFu), ha = lane ? (ba >> 16) : (ba & 0xFFFFu),
+                                   hb = lane ? (bb >> 16) : (bb & 0xFFFFu);
+                    col.cmask[e * 2 + lane] = (hs == 0xFFFFu ? 1u : 0u) | (ha ? 2u : 0u) | (hb ? 4u : 0u);
+                }
+            }
+            named_bar_sync(1, WS_EPI_WARPS * 32);          // table complete
             const int r0 = it.bi * TILE_M + q4 * 32;
             const int i = r0 + lane;
             const bool rvalid = i < n;
-            uint32_t ai, fi;
-            uint32_t allS = 0u, anyA = 0u, anyB = 0u;                  // bit k: property of the warp's k-th chunk
-            {
-                const bool use_pre = have_pre && same_win;
-                ai = use_pre ? pre_ai : (rvalid ? (uint32_t)__ldg(Aw + i) : 0u);
-                fi = use_pre ? pre_fi : (rvalid ? clean_label(__ldg(lab + i)) : 0u);
-#pragma unroll
-                for (int h = 0; h < EPI_COLS / 32; ++h) {
-                    const int cc = h * 32 + lane;                      // column within the warp's range
-                    const int j = it.col0 + cbeg + cc;
-                    const bool ok = cbeg + cc < cend && j < n;
-                    const uint32_t f = use_pre ? pre_f[h] : (ok ? clean_label(__ldg(lab + j)) : 0u);
-                    col.aj[cc] = use_pre ? pre_a[h] : (ok ? (uint32_t)__ldg(Aw + j) : 0u);
-                    col.fs[cc] = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
-                    col.fa[cc] = (f & IMPOP_LAB_A) ? 1.0 : 0.0;
-                    col.fb[cc] = (f & IMPOP_LAB_B) ? 1.0 : 0.0;
-                    const uint32_t bs = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_SUBSET) != 0u);
-                    const uint32_t ba = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_A) != 0u);
-                    const uint32_t bb = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_B) != 0u);
-                    allS |= (((bs & 0xFFFFu) == 0xFFFFu ? 1u : 0u) << (2 * h)) | (((bs >> 16) == 0xFFFFu ? 1u : 0u) << (2 * h + 1));
-                    anyA |= (((ba & 0xFFFFu) ? 1u : 0u) << (2 * h)) | (((ba >> 16) ? 1u : 0u) << (2 * h + 1));
-                    anyB |= (((bb & 0xFFFFu) ? 1u : 0u) << (2 * h)) | (((bb >> 16) ? 1u : 0u) << (2 * h + 1));
-                }
-                __syncwarp();
-            }
-            have_pre = nxt.x == wi.w;
-            if (have_pre) {                                            // issue the next item's loads now
-                int nb, ne;
-                my_range(nxt, n, nb, ne);
-                const int ni = nxt.y * TILE_M + q4 * 32 + lane;
-                pre_ai = (ni < n) ? (uint32_t)__ldg(Aw + ni) : 0u;
-                pre_fi = (ni < n) ? clean_label(__ldg(lab + ni)) : 0u;
-#pragma unroll
-                for (int h = 0; h < EPI_COLS / 32; ++h) {
-                    const int cc = h * 32 + lane;
-                    const int j = nxt.z + nb + cc;
-                    const bool ok = nb + cc < ne && j < n;
-                    pre_f[h] = ok ? clean_label(__ldg(lab + j)) : 0u;
-                    pre_a[h] = ok ? (uint32_t)__ldg(Aw + j) : 0u;
-                }
-            }
+            const uint32_t ai = rvalid ? (uint32_t)__ldg(Aw + i) : 0u;
+            const uint32_t fi = rvalid ? clean_label(__ldg(lab + i)) : 0u;
+            const int half0 = (((it.ncols >> 4) + 1) >> 1) << 4;        // columns of half 0 (multiple of 16)
+            const int cbeg = hsel ? half0 : 0, cend = hsel ? it.ncols : half0;
             PROF_AUX_END
             if (nch > 0) {
                 if (alive) alive = mbar_wait<100>(&sh.acc_full[buf], uses[buf] & 1u, tab.err);
@@ -613,12 +579,11 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 #pragma unroll
                     for (int k = 0; k < 16; ++k) r[k] = 0u;
                 }
-                const int lc = cc - cbeg, kc = lc >> 4;
-                const uint32_t cm = ((allS >> kc) & 1u) | (((anyA >> kc) & 1u) << 1) | (((anyB >> kc) & 1u) << 2);
+                const uint32_t cm = col.cmask[cc >> 4];
                 uint32_t aj[16];
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(&col.aj[lc + 4 * k4]);
+                    const uint4 q = *reinterpret_cast<const uint4 *>(&col.aj[cc + 4 * k4]);
                     aj[4 * k4] = q.x; aj[4 * k4 + 1] = q.y; aj[4 * k4 + 2] = q.z; aj[4 * k4 + 3] = q.w;
                 }
                 double p[16];
@@ -646,19 +611,19 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 } else {
                     cs = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) cs = __fma_rn(p[k], col.fs[lc + k], cs);   // p * 1.0 or p * 0.0: exact
+                    for (int k = 0; k < 16; ++k) cs = __fma_rn(p[k], col.fs[cc + k], cs);   // p * 1.0 or p * 0.0: exact
                 }
                 dd_add(ts, cs);
                 if (cm & 2u) {
                     double ca = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) ca = __fma_rn(p[k], col.fa[lc + k], ca);
+                    for (int k = 0; k < 16; ++k) ca = __fma_rn(p[k], col.fa[cc + k], ca);
                     dd_add(ta, ca);
                 }
                 if (cm & 4u) {
                     double cb = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) cb = __fma_rn(p[k], col.fb[lc + k], cb);
+                    for (int k = 0; k < 16; ++k) cb = __fma_rn(p[k], col.fb[cc + k], cb);
                     dd_add(tb, cb);
                 }
             }
