@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -299,7 +300,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
                   !d->lab_off_host || !d->length_host))
         return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: null descriptor array");
     const int32_t *n = d->n_host, *m = d->m_host, *pitch = d->pitch_words_host;
-    std::vector<int64_t> row_off(W + 1, 0), item_off(W + 1, 0);
+    std::vector<int64_t> row_off(W + 1, 0), item_off(W + 1, 0), word_off(W + 1, 0);
     bool any_rows = false, any_nodes = false;
     for (int32_t w = 0; w < W; ++w) {
         if (n[w] < 0 || m[w] < 0 || n[w] > (1 << 24) || m[w] > (1 << 24))
@@ -310,6 +311,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
             return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: negative offset");
         row_off[w + 1] = row_off[w] + n[w];
         item_off[w + 1] = item_off[w] + items_of(n[w]);
+        word_off[w + 1] = word_off[w] + (m[w] + 31) / 32;
         any_rows |= n[w] > 0;
         any_nodes |= m[w] > 0;
     }
@@ -317,6 +319,19 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
         return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: null device array");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)d->stream;
+    // prep row slices: one per window when the batch has enough windows to fill the GPU, else windows are cut
+    // into slices of >= 32 rows so that about 4 CTAs per SM have work
+    std::vector<int4> slices;
+    {
+        const int64_t target = (int64_t)ctx->sm_count * 4;
+        const int per_window = (W > 0 && W < target) ? (int)((target + W - 1) / W) : 1;
+        for (int32_t w = 0; w < W; ++w) {
+            int cnt = std::min(per_window, std::max(1, (n[w] + 31) / 32));
+            int rows = (((n[w] + cnt - 1) / std::max(cnt, 1)) + 31) & ~31;
+            if (rows < 32) rows = 32;
+            for (int lo = 0; lo < n[w] || lo == 0; lo += rows) slices.push_back(make_int4(w, lo, std::min(lo + rows, n[w]), 0));
+        }
+    }
     impop_batch *b = new (std::nothrow) impop_batch();
     if (!b) return fail(ctx, IMPOP_ERR_NOMEM, "impop_batch_create: out of host memory");
     WindowTab &t = b->tab;
@@ -332,6 +347,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t o_xoff = ca.take(8 * W1), o_lenoff = ca.take(8 * W1), o_laboff = ca.take(8 * W1), o_L = ca.take(8 * W1);
     const size_t o_row = ca.take(8 * W1), o_item = ca.take(8 * W1);
     const size_t o_items = ca.take(16 * (size_t)(item_off[W] + 1));
+    const size_t o_slices = ca.take(16 * (slices.size() + 1)), o_word = ca.take(8 * W1);
     const size_t phase1 = ca.off;
     const size_t o_heavy = ca.take(8 * W1), o_w8 = ca.take(8 * W1), o_xh = ca.take(8 * W1);
     const size_t o_cnt = ca.take(4 * W1);
@@ -347,6 +363,8 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     }
     memcpy(hb + o_row, row_off.data(), 8 * W1);
     memcpy(hb + o_item, item_off.data(), 8 * W1);
+    memcpy(hb + o_word, word_off.data(), 8 * W1);
+    if (!slices.empty()) memcpy(hb + o_slices, slices.data(), 16 * slices.size());
     {   // work-item table: (window, row block, first column, columns)
         int4 *items = (int4 *)(hb + o_items);
         int64_t k = 0;
@@ -365,6 +383,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     t.lab_off = (const int64_t *)(db + o_laboff); t.L = (const int64_t *)(db + o_L);
     t.row_off = (const int64_t *)(db + o_row); t.item_off = (const int64_t *)(db + o_item);
     t.items = (const int4 *)(db + o_items);
+    t.slices = (const int4 *)(db + o_slices); t.word_off = (const int64_t *)(db + o_word); t.n_slices = (int32_t)slices.size();
     t.heavy_off = (const int64_t *)(db + o_heavy); t.w8_off = (const int64_t *)(db + o_w8); t.xh_off = (const int64_t *)(db + o_xh);
     t.x = d->x_dev; t.len = d->node_len_dev; t.labels = d->labels_dev;
     t.W = W; t.err = ctx->err_dev; t.harm = ctx->harm_dev; t.harm_n = HARM_N;
@@ -409,11 +428,12 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t s_heavy = cs.take(4 * (size_t)(heavy_off[W] + 64)), s_xh = cs.take(4 * (size_t)(xh_off[W] + 4));
     const size_t s_part = cs.take(8 * (size_t)(b->items * PART_STRIDE + 1));
     const size_t s_sums = cs.take(8 * 4 * W1), s_counts = cs.take(8 * IMPOP_NCOUNTS * W1);
+    const size_t s_any = cs.take(4 * (size_t)(word_off[W] + 1)), s_all = cs.take(4 * (size_t)(word_off[W] + 1));
     b->scratch = pool_get(ctx, cs.off);
     if (!b->scratch) return bail(IMPOP_ERR_NOMEM, "impop_batch_create: out of device memory (scratch)");
     char *sb = (char *)b->scratch;
     t.A = (int32_t *)(sb + s_A); t.w8 = (uint8_t *)(sb + s_w8); t.heavy = (uint32_t *)(sb + s_heavy);
-    t.xh = (uint32_t *)(sb + s_xh);
+    t.xh = (uint32_t *)(sb + s_xh); t.seg_any = (uint32_t *)(sb + s_any); t.seg_all = (uint32_t *)(sb + s_all);
     b->partials = (double *)(sb + s_part); b->sums_tmp = (double *)(sb + s_sums); b->counts_tmp = (int64_t *)(sb + s_counts);
     b->item_off = item_off;
     b->n.assign(n, n + W);
@@ -435,7 +455,7 @@ static int run_sums(impop_ctx_t *ctx, impop_batch_t *b, int32_t algo, int32_t ra
     prm.dumpI = nullptr; prm.dumpPi = nullptr; prm.prof = ctx->prof_dev;
     CU(timed(ctx, IMPOP_KERNEL_PAIRS, st, [&] { return launch_pairs(b->tab, prm, algo, ctx->sm_count, st); }));
     CU(timed(ctx, IMPOP_KERNEL_SUMS, st, [&] { return launch_window_sums(b->tab, b->partials, rank, world, sums_dev, st); }));
-    ctx->launches += 3;
+    ctx->launches += 5;
     return IMPOP_OK;
 }
 
@@ -481,7 +501,7 @@ int impop_pairwise(impop_ctx_t *ctx, impop_batch_t *batch, int32_t window, int32
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     CU(launch_prep(batch->tab, batch->counts_tmp, ctx->sm_count, st));
-    ctx->launches += 1;
+    ctx->launches += 3;
     if (I_dev || pi_dev) {
         ItemParams prm{};
         prm.partials = batch->partials;

@@ -183,13 +183,16 @@ __global__ void __launch_bounds__(SITE_THREADS) site_counts_kernel(const uint64_
 }
 
 // Fast path for words == 8 (up to 512 haplotypes, the HPRC panel): the 64-byte site row is read
-// once as four 16-byte loads and every population is counted from registers.
+// once as four 16-byte loads and every population is counted from registers.  Results are transposed
+// through shared memory so that a warp's 32 x P counts (and frequencies) leave as fully coalesced stores.
 template <int P>
 __global__ void __launch_bounds__(SITE_THREADS) site_counts_w8_kernel(const uint64_t *sites, int64_t M,
                                                                       const uint64_t *masks, int32_t *counts,
                                                                       double *freq) {
     __shared__ uint64_t s_mask[P * 8];
     __shared__ double s_size[P];
+    __shared__ int32_t s_cnt[SITE_THREADS / 32][32 * P];
+    __shared__ double s_frq[SITE_THREADS / 32][32 * P];
     for (int k = threadIdx.x; k < P * 8; k += SITE_THREADS) s_mask[k] = masks[k];
     __syncthreads();
     if (threadIdx.x < P) {
@@ -198,18 +201,35 @@ __global__ void __launch_bounds__(SITE_THREADS) site_counts_w8_kernel(const uint
         s_size[threadIdx.x] = (double)c;
     }
     __syncthreads();
-    for (int64_t s = (int64_t)blockIdx.x * SITE_THREADS + threadIdx.x; s < M; s += (int64_t)gridDim.x * SITE_THREADS) {
-        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(sites + (size_t)s * 8);
-        ulonglong2 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2), r3 = __ldg(row + 3);
-        uint64_t v[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (SITE_THREADS / 32);
+    for (int64_t s0 = ((int64_t)blockIdx.x * (SITE_THREADS / 32) + warp) * 32; s0 < M; s0 += warps_total * 32) {
+        const int64_t s = s0 + lane;
+        uint64_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (s < M) {
+            const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(sites + (size_t)s * 8);
+            ulonglong2 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2), r3 = __ldg(row + 3);
+            v[0] = r0.x; v[1] = r0.y; v[2] = r1.x; v[3] = r1.y; v[4] = r2.x; v[5] = r2.y; v[6] = r3.x; v[7] = r3.y;
+        }
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             int c = 0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) c += __popcll(v[w] & s_mask[p * 8 + w]);
-            counts[(size_t)s * P + p] = c;
-            if (freq) freq[(size_t)s * P + p] = s_size[p] > 0.0 ? __ddiv_rn((double)c, s_size[p]) : 0.0;
+            s_cnt[warp][lane * P + p] = c;                       // stride P words: conflict-free for odd P
+            if (freq) s_frq[warp][lane * P + p] = s_size[p] > 0.0 ? __ddiv_rn((double)c, s_size[p]) : 0.0;
         }
+        __syncwarp();
+        const int64_t valid = (M - s0 < 32 ? M - s0 : 32) * P;  // entries of this warp's 32 sites
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const int k = q * 32 + lane;
+            if (k < valid) {
+                counts[(size_t)s0 * P + k] = s_cnt[warp][k];
+                if (freq) freq[(size_t)s0 * P + k] = s_frq[warp][k];
+            }
+        }
+        __syncwarp();
     }
 }
 

@@ -19,39 +19,35 @@
 namespace impop {
 
 // ==========================================================================================
-// Prep: one CTA per window, one pass over the window's presence matrix.
-//   (a) byte weights of the dense columns, heavy-node table, range check sum(len) < 2^31
-//   (b) path lengths A_i through a nibble look-up table of node lengths held in shared memory
-//       (lane l of a warp looks up nibble position 32 q + l, so the 32 look-ups of a warp hit 32
-//       different banks), with four rows in flight per warp
-//   (c) presence bits of the heavy columns (warp shuffle of the row words already in registers + ballot)
-//   (d) label counts and segregating nodes S = #{k : 0 < sum_{i in SEG} x_ik < |SEG|, len_k > 0}
-//       (replaces `povu gfa2vcf | wc -l`, run_tajd.sh:126-148) -> counts row nS nA nB pS pAA pBB pAB S
+// Prep, three small kernels (the second is the only one that touches the presence matrix):
+//   prep_cols   one CTA per window: byte weights of the dense columns, heavy-node table, range check
+//               sum(len) < 2^31, label counts, reset of the any / all words
+//   prep_rows   one CTA per (window, row slice) -- a window with many haplotypes is cut into slices so that a
+//               batch of few large windows still fills the GPU: path lengths A_i through a nibble look-up table
+//               of node lengths in shared memory (lane l looks up nibble position 32 q + l: 32 distinct banks;
+//               four rows in flight per warp), presence bits of the heavy columns (shuffle of the row words
+//               already in registers + ballot), any / all masks over the SEG rows
+//   seg_count   S = #{k : 0 < sum_{i in SEG} x_ik < |SEG|, len_k > 0} (replaces `povu gfa2vcf | wc -l`,
+//               run_tajd.sh:126-148) -> counts row nS nA nB pS pAA pBB pAB S
 // ==========================================================================================
 constexpr int PREP_THREADS = 256;
 constexpr int LUT_POS = 512;                 // nibble positions per table pass = 2048 nodes = 64 words
 
-__global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
-    __shared__ uint32_t s_lut[16][LUT_POS];   // 32 KB
-    __shared__ uint32_t s_any[64], s_all[64];
-    __shared__ int s_heavy, s_cnt[5];
+__global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
+    __shared__ int s_heavy, s_cnt[4];
     __shared__ unsigned long long s_total;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     for (int w = blockIdx.x; w < tab.W; w += gridDim.x) {
-        const int n = tab.n[w], m = tab.m[w], pitch = tab.pitch[w];
+        const int n = tab.n[w], m = tab.m[w];
         const uint32_t *len = tab.len + tab.len_off[w];
-        const uint32_t *x = tab.x + tab.x_off[w];
         const uint8_t *lab = tab.labels + tab.lab_off[w];
         uint8_t *w8 = tab.w8 + tab.w8_off[w];
         uint32_t *heavy = tab.heavy + tab.heavy_off[w];
         const int m64 = ((m + KCHUNK - 1) / KCHUNK) * KCHUNK;
         const int hpad = (int)(tab.heavy_off[w + 1] - tab.heavy_off[w]);
-        const int hwords = hpad >> 5;
-        uint32_t *xh = tab.xh + tab.xh_off[w];
         if (threadIdx.x == 0) { s_heavy = 0; s_total = 0ull; }
-        if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
+        if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
         __syncthreads();
-        // ---- (d) label counts
         {
             int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             for (int i = threadIdx.x; i < n; i += PREP_THREADS) {
@@ -64,7 +60,6 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
             if (c2) atomicAdd(&s_cnt[2], c2);
             if (c3) atomicAdd(&s_cnt[3], c3);
         }
-        // ---- (a)
         unsigned long long tot = 0;
         for (int k = threadIdx.x; k < m64; k += PREP_THREADS) {
             uint32_t l = (k < m) ? __ldg(len + k) : 0u;
@@ -81,17 +76,41 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
         if (lane == 0 && tot) atomicAdd(&s_total, tot);
+        const int64_t wo = tab.word_off[w], words = tab.word_off[w + 1] - wo;
+        for (int64_t k = threadIdx.x; k < words; k += PREP_THREADS) { tab.seg_any[wo + k] = 0u; tab.seg_all[wo + k] = 0xffffffffu; }
         __syncthreads();
         if (threadIdx.x == 0 && (s_total >= (1ull << 31) || s_heavy > hpad)) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);
         const int nh = s_heavy < hpad ? s_heavy : hpad;
         for (int s = nh + threadIdx.x; s < hpad; s += PREP_THREADS) heavy[s] = 0u;
         __syncthreads();
         for (int s = threadIdx.x; s < hpad; s += PREP_THREADS) w8[m64 + s] = (uint8_t)(heavy[s] & 255u);
-        // ---- (b) + (c) + (d): one sweep over the rows per 2048-node slice
+        if (threadIdx.x == 0 && counts) {
+            const int64_t nS = s_cnt[0], nA = s_cnt[1], nB = s_cnt[2];
+            int64_t *row = counts + (size_t)w * IMPOP_NCOUNTS;
+            row[0] = nS; row[1] = nA; row[2] = nB;
+            row[3] = nS * (nS - 1) / 2; row[4] = nA * (nA - 1) / 2; row[5] = nB * (nB - 1) / 2; row[6] = nA * nB;
+            row[7] = s_cnt[3];                  // number of SEG rows for now; seg_count_kernel replaces it by S
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(PREP_THREADS, 4) prep_rows_kernel(const __grid_constant__ WindowTab tab) {
+    __shared__ uint32_t s_lut[16][LUT_POS];   // 32 KB
+    __shared__ uint32_t s_any[64], s_all[64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int sidx = blockIdx.x; sidx < tab.n_slices; sidx += gridDim.x) {
+        const int4 sl = __ldg(tab.slices + sidx);
+        const int w = sl.x, row_lo = sl.y, row_hi = sl.z;
+        const int m = tab.m[w], pitch = tab.pitch[w];
+        const uint32_t *len = tab.len + tab.len_off[w];
+        const uint32_t *x = tab.x + tab.x_off[w];
+        const uint8_t *lab = tab.labels + tab.lab_off[w];
+        const uint32_t *heavy = tab.heavy + tab.heavy_off[w];
+        const int hwords = (int)((tab.heavy_off[w + 1] - tab.heavy_off[w]) >> 5);
+        uint32_t *xh = tab.xh + tab.xh_off[w];
         int32_t *A = tab.A + tab.row_off[w];
-        const int words = (m + 31) >> 5;
-        const int seg_rows = s_cnt[3];
-        int seg = 0;
+        const int64_t wo = tab.word_off[w];
         for (int c0 = 0; c0 < m || c0 == 0; c0 += 4 * LUT_POS) {
             for (int p = threadIdx.x; p < LUT_POS; p += PREP_THREADS) {
                 const int k = c0 + 4 * p;
@@ -103,21 +122,21 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
             }
             if (threadIdx.x < 64) { s_any[threadIdx.x] = 0u; s_all[threadIdx.x] = 0xffffffffu; }
             __syncthreads();
-            const int w0 = c0 >> 5;                       // first word of this slice
+            const int w0 = c0 >> 5;                       // first word of this slice of nodes
             const int passes = (m - c0 > 1024) ? 2 : 1;   // 32 words (1024 nodes) per warp pass
             constexpr int RU = 4;                         // rows in flight per warp (memory-level parallelism)
             uint32_t any[2] = {0u, 0u}, all[2] = {0xffffffffu, 0xffffffffu};
-            for (int i0 = warp * RU; i0 < n; i0 += (PREP_THREADS / 32) * RU) {
+            for (int i0 = row_lo + warp * RU; i0 < row_hi; i0 += (PREP_THREADS / 32) * RU) {
                 uint32_t acc[RU], word[2][RU];
                 bool segrow[RU];
 #pragma unroll
                 for (int r = 0; r < RU; ++r) {
                     acc[r] = 0u;
-                    segrow[r] = (i0 + r < n) && (lab[i0 + r] & IMPOP_LAB_SEG);
+                    segrow[r] = (i0 + r < row_hi) && (lab[i0 + r] & IMPOP_LAB_SEG);
 #pragma unroll
                     for (int ps = 0; ps < 2; ++ps) {
                         const int wd = ps * 32 + lane;
-                        word[ps][r] = (ps < passes && i0 + r < n && w0 + wd < pitch)
+                        word[ps][r] = (ps < passes && i0 + r < row_hi && w0 + wd < pitch)
                                           ? __ldg(x + (size_t)(i0 + r) * pitch + w0 + wd) : 0u;
                     }
                 }
@@ -138,7 +157,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
                 for (int hw = 0; hw < hwords; ++hw) {                // heavy columns: one table entry per lane
                     const uint32_t ent = heavy[hw * 32 + lane];
                     const uint32_t col = ent >> 8;
-                    const int rel = (int)(col >> 5) - w0;            // word of the node within this slice
+                    const int rel = (int)(col >> 5) - w0;            // word of the node within this slice of nodes
                     const bool in = (ent & 255u) && rel >= 0 && rel < 32 * passes;
                     if (c0 > 0 && !__any_sync(0xffffffffu, in)) continue;
 #pragma unroll
@@ -147,7 +166,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
                         const uint32_t w_hi = __shfl_sync(0xffffffffu, word[1][r], rel & 31);
                         const uint32_t wsrc = (rel >= 32) ? w_hi : w_lo;
                         const uint32_t bw = __ballot_sync(0xffffffffu, in && ((wsrc >> (col & 31u)) & 1u));
-                        if (lane == 0 && i0 + r < n) {
+                        if (lane == 0 && i0 + r < row_hi) {
                             uint32_t *dst = xh + (size_t)(i0 + r) * hwords + hw;
                             if (c0 == 0) *dst = bw;                  // first slice defines the word, later ones add bits
                             else if (bw) *dst |= bw;
@@ -159,32 +178,44 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const __grid_constan
                     uint32_t a = acc[r];
 #pragma unroll
                     for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-                    if (lane == 0 && i0 + r < n) A[i0 + r] = (int32_t)(a + (c0 ? (uint32_t)A[i0 + r] : 0u));
+                    if (lane == 0 && i0 + r < row_hi) A[i0 + r] = (int32_t)(a + (c0 ? (uint32_t)A[i0 + r] : 0u));
                 }
             }
             atomicOr(&s_any[lane], any[0]); atomicAnd(&s_all[lane], all[0]);
             if (passes > 1) { atomicOr(&s_any[32 + lane], any[1]); atomicAnd(&s_all[32 + lane], all[1]); }
             __syncthreads();
-            if (threadIdx.x < 64 && w0 + threadIdx.x < words && seg_rows > 0) {
-                uint32_t sg = s_any[threadIdx.x] & ~s_all[threadIdx.x];
-                while (sg) {
-                    const int k = (w0 + threadIdx.x) * 32 + (__ffs(sg) - 1);
-                    if (k < m && __ldg(len + k) > 0u) ++seg;
-                    sg &= sg - 1;
-                }
+            if (threadIdx.x < 64 && w0 + threadIdx.x < ((m + 31) >> 5)) {
+                atomicOr(&tab.seg_any[wo + w0 + threadIdx.x], s_any[threadIdx.x]);
+                atomicAnd(&tab.seg_all[wo + w0 + threadIdx.x], s_all[threadIdx.x]);
             }
             __syncthreads();
         }
-        if (seg) atomicAdd(&s_cnt[4], seg);
-        __syncthreads();
-        if (threadIdx.x == 0 && counts) {
-            const int64_t nS = s_cnt[0], nA = s_cnt[1], nB = s_cnt[2];
-            int64_t *row = counts + (size_t)w * IMPOP_NCOUNTS;
-            row[0] = nS; row[1] = nA; row[2] = nB;
-            row[3] = nS * (nS - 1) / 2; row[4] = nA * (nA - 1) / 2; row[5] = nB * (nB - 1) / 2; row[6] = nA * nB;
-            row[7] = s_cnt[4];
+    }
+}
+
+__global__ void seg_count_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    for (int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < tab.W; w += gridDim.x * warps_per_block) {
+        const int m = tab.m[w];
+        const uint32_t *len = tab.len + tab.len_off[w];
+        const int64_t wo = tab.word_off[w];
+        const int words = (m + 31) >> 5;
+        int64_t *row = counts + (size_t)w * IMPOP_NCOUNTS;
+        const bool have_rows = row[7] > 0;                       // prep_cols left the number of SEG rows here
+        int seg = 0;
+        for (int wd = lane; wd < words && have_rows; wd += 32) {
+            uint32_t sg = tab.seg_any[wo + wd] & ~tab.seg_all[wo + wd];
+            while (sg) {
+                const int k = wd * 32 + (__ffs(sg) - 1);
+                if (k < m && __ldg(len + k) > 0u) ++seg;
+                sg &= sg - 1;
+            }
         }
-        __syncthreads();
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) seg += __shfl_xor_sync(0xffffffffu, seg, off);
+        __syncwarp();
+        if (lane == 0) row[7] = seg;
     }
 }
 
@@ -864,13 +895,20 @@ cudaError_t launch_harmonic_table(double2 *harm, int32_t nmax, cudaStream_t st) 
 }
 
 cudaError_t launch_prep(const WindowTab &tab, int64_t *counts, int sm_count, cudaStream_t st) {
-    static int per_sm = 0;                         // resident CTAs per SM (registers / shared memory), queried once
+    if (tab.W == 0) return cudaSuccess;
+    static int per_sm = 0;                         // resident prep_rows CTAs per SM (registers / shared memory), queried once
     if (per_sm == 0) {
         int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, prep_kernel, PREP_THREADS, 0) != cudaSuccess || v < 1) v = 2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, prep_rows_kernel, PREP_THREADS, 0) != cudaSuccess || v < 1) v = 2;
         per_sm = v;
     }
-    prep_kernel<<<max(1, min(tab.W, sm_count * per_sm)), PREP_THREADS, 0, st>>>(tab, counts);
+    prep_cols_kernel<<<min(tab.W, sm_count * 8), PREP_THREADS, 0, st>>>(tab, counts);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    prep_rows_kernel<<<max(1, min(tab.n_slices, sm_count * per_sm)), PREP_THREADS, 0, st>>>(tab);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    seg_count_kernel<<<min((tab.W + 3) / 4, sm_count * 8), 128, 0, st>>>(tab, counts);
     return cudaGetLastError();
 }
 
