@@ -280,10 +280,12 @@ def run_ours(args):
                 continue
             st = streams[k % 2]
             with torch.cuda.stream(st):
-                dx[lo:hi].copy_(hx[lo:hi], non_blocking=True)
-                dl[lo:hi].copy_(hl[lo:hi], non_blocking=True)
-                dlabs[k].copy_(hlab, non_blocking=True)
+                # set-up first (its small table upload), the big copy last: a small copy enqueued after the big one would
+                # wait on the copy engine behind the OTHER stream's big copy and delay this sub-batch's kernels
                 b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], WINDOW_BP, node_len_host=hl[lo:hi], stream=st)
+                dlabs[k].copy_(hlab, non_blocking=True)
+                dl[lo:hi].copy_(hl[lo:hi], non_blocking=True)
+                dx[lo:hi].copy_(hx[lo:hi], non_blocking=True)
                 b.stats(algo, stream=st, out_stats=ds[lo:hi], out_counts=dc[lo:hi])
                 hs[lo:hi].copy_(ds[lo:hi], non_blocking=True)
                 hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)

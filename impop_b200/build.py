@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libimpop_b200.so")
 SOURCES = ("api.cu", "window_kernels.cu", "aux_kernels.cu")
 HEADERS = ("common.cuh", "stats_math.cuh", os.path.join("..", "..", "include", "impop_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC,-O3,-pthread", "-shared"]
 
 
 def _nvcc() -> str:

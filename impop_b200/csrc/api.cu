@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -392,14 +393,25 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     //      else counted on the device and read back (one stream synchronisation)
     int32_t *cnt = (int32_t *)(hb + o_cnt);
     if (W > 0 && d->node_len_host) {
-        for (int32_t w = 0; w < W; ++w) {
-            const uint32_t *len = d->node_len_host + d->len_off_host[w];
-            int32_t c = 0;
-            for (int32_t k = 0; k < m[w]; ++k) {
-                const uint32_t q = len[k] / HEAVY_Q;
-                if (q) c += (int32_t)((q + 254u) / 255u);
+        // branch-free so that the compiler vectorises it; a few host threads for large batches
+        auto count_range = [&](int32_t w0, int32_t w1) {
+            for (int32_t w = w0; w < w1; ++w) {
+                const uint32_t *len = d->node_len_host + d->len_off_host[w];
+                uint32_t c = 0;
+                const int32_t mm = m[w];
+                for (int32_t k = 0; k < mm; ++k) c += (len[k] / HEAVY_Q + 254u) / 255u;
+                cnt[w] = (int32_t)c;
             }
-            cnt[w] = c;
+        };
+        int64_t nodes = 0;
+        for (int32_t w = 0; w < W; ++w) nodes += m[w];
+        const int threads = nodes > (1 << 18) ? 4 : 1;
+        if (threads == 1) count_range(0, W);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; ++t)
+                pool.emplace_back(count_range, (int32_t)((int64_t)W * t / threads), (int32_t)((int64_t)W * (t + 1) / threads));
+            for (auto &th : pool) th.join();
         }
     } else if (W > 0) {
         if ((e = launch_heavy_count(t.len, t.len_off, t.m, W, (int32_t *)(db + o_cnt), st)) != cudaSuccess ||
