@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
         if (threadIdx.x == 0 && (s_total >= (1ull << 31) || s_heavy > hpad)) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);
         const int nh = s_heavy < hpad ? s_heavy : hpad;
         for (int s = nh + threadIdx.x; s < hpad; s += PREP_THREADS) heavy[s] = 0u;
+        if (threadIdx.x == 0) tab.heavy_n[w] = nh;
         __syncthreads();
         for (int s = threadIdx.x; s < hpad; s += PREP_THREADS) w8[m64 + s] = (uint8_t)(heavy[s] & 255u);
         if (threadIdx.x == 0 && counts) {
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(PREP_THREADS, 4) prep_rows_kernel(const __grid
         const uint8_t *lab = tab.labels + tab.lab_off[w];
         const uint32_t *heavy = tab.heavy + tab.heavy_off[w];
         const int hwords = (int)((tab.heavy_off[w + 1] - tab.heavy_off[w]) >> 5);
+        const int hw_used = (tab.heavy_n[w] + 31) >> 5;      // words of the heavy table that hold real entries
         uint32_t *xh = tab.xh + tab.xh_off[w];
         int32_t *A = tab.A + tab.row_off[w];
         const int64_t wo = tab.word_off[w];
@@ -154,7 +156,12 @@ __global__ void __launch_bounds__(PREP_THREADS, 4) prep_rows_kernel(const __grid
                         if (segrow[r]) { any[ps] |= word[ps][r]; all[ps] &= word[ps][r]; }
                     }
                 }
-                for (int hw = 0; hw < hwords; ++hw) {                // heavy columns: one table entry per lane
+                if (c0 == 0) {                                       // padding words of the heavy bits: zero
+#pragma unroll
+                    for (int r = 0; r < RU; ++r)
+                        for (int hw = hw_used + lane; hw < hwords && i0 + r < row_hi; hw += 32) xh[(size_t)(i0 + r) * hwords + hw] = 0u;
+                }
+                for (int hw = 0; hw < hw_used; ++hw) {               // heavy columns: one table entry per lane
                     const uint32_t ent = heavy[hw * 32 + lane];
                     const uint32_t col = ent >> 8;
                     const int rel = (int)(col >> 5) - w0;            // word of the node within this slice of nodes
