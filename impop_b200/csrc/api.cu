@@ -310,6 +310,8 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
             return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: pitch_words / x_off must be multiples of 4 and cover m");
         if (d->x_off_host[w] < 0 || d->len_off_host[w] < 0 || d->lab_off_host[w] < 0)
             return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: negative offset");
+        if (d->lab_off_host[w] > 0x7FFFFFFFll || row_off[w] + n[w] > 0x7FFFFFFFll)
+            return fail(ctx, IMPOP_ERR_RANGE, "impop_batch_create: more than 2^31 haplotype rows / label bytes in one batch");
         row_off[w + 1] = row_off[w] + n[w];
         item_off[w + 1] = item_off[w] + items_of(n[w]);
         word_off[w + 1] = word_off[w] + (m[w] + 31) / 32;
@@ -347,7 +349,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t o_n = ca.take(4 * W1), o_m = ca.take(4 * W1), o_pitch = ca.take(4 * W1);
     const size_t o_xoff = ca.take(8 * W1), o_lenoff = ca.take(8 * W1), o_laboff = ca.take(8 * W1), o_L = ca.take(8 * W1);
     const size_t o_row = ca.take(8 * W1), o_item = ca.take(8 * W1);
-    const size_t o_items = ca.take(16 * (size_t)(item_off[W] + 1));
+    const size_t o_items = ca.take(16 * (size_t)(item_off[W] + 1)), o_iext = ca.take(16 * (size_t)(item_off[W] + 1));
     const size_t o_slices = ca.take(16 * (slices.size() + 1)), o_word = ca.take(8 * W1);
     const size_t phase1 = ca.off;
     const size_t o_heavy = ca.take(8 * W1), o_w8 = ca.take(8 * W1), o_xh = ca.take(8 * W1);
@@ -367,13 +369,15 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     memcpy(hb + o_word, word_off.data(), 8 * W1);
     if (!slices.empty()) memcpy(hb + o_slices, slices.data(), 16 * slices.size());
     {   // work-item table: (window, row block, first column, columns)
-        int4 *items = (int4 *)(hb + o_items);
+        //      and what the epilogue needs of the item's window in one load: (n, m, row_off, lab_off)
+        int4 *items = (int4 *)(hb + o_items), *iext = (int4 *)(hb + o_iext);
         int64_t k = 0;
         for (int32_t w = 0; w < W; ++w) {
             const int nb = (n[w] + TILE_M - 1) / TILE_M;
+            const int4 ext = make_int4(n[w], m[w], (int)row_off[w], (int)d->lab_off_host[w]);
             for (int bi = 0; bi < nb; ++bi) {
                 const int cnt = items_of_rowblock(n[w], bi), width = width_of_rowblock(n[w], bi);
-                for (int r = 0; r < cnt; ++r) items[k++] = make_int4(w, bi, bi * TILE_M + r * width, width);
+                for (int r = 0; r < cnt; ++r) { iext[k] = ext; items[k++] = make_int4(w, bi, bi * TILE_M + r * width, width); }
             }
         }
     }
@@ -383,7 +387,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     t.x_off = (const int64_t *)(db + o_xoff); t.len_off = (const int64_t *)(db + o_lenoff);
     t.lab_off = (const int64_t *)(db + o_laboff); t.L = (const int64_t *)(db + o_L);
     t.row_off = (const int64_t *)(db + o_row); t.item_off = (const int64_t *)(db + o_item);
-    t.items = (const int4 *)(db + o_items);
+    t.items = (const int4 *)(db + o_items); t.items_ext = (const int4 *)(db + o_iext);
     t.slices = (const int4 *)(db + o_slices); t.word_off = (const int64_t *)(db + o_word); t.n_slices = (int32_t)slices.size();
     t.heavy_off = (const int64_t *)(db + o_heavy); t.w8_off = (const int64_t *)(db + o_w8); t.xh_off = (const int64_t *)(db + o_xh);
     t.x = d->x_dev; t.len = d->node_len_dev; t.labels = d->labels_dev;
@@ -436,7 +440,8 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     // ---- scratch: one pooled block
     b->items = item_off[W];
     Carver cs;
-    const size_t s_A = cs.take(4 * (size_t)(row_off[W] + 1)), s_w8 = cs.take((size_t)w8_off[W] + 64);
+    const size_t s_A = cs.take(4 * (size_t)(row_off[W] + 1)), s_w8 = cs.take((size_t)w8_off[W] + 64),
+                 s_w8n = cs.take((size_t)w8_off[W] + 64);
     const size_t s_heavy = cs.take(4 * (size_t)(heavy_off[W] + 64)), s_xh = cs.take(4 * (size_t)(xh_off[W] + 4));
     const size_t s_part = cs.take(8 * (size_t)(b->items * PART_STRIDE + 1));
     const size_t s_sums = cs.take(8 * 4 * W1), s_counts = cs.take(8 * IMPOP_NCOUNTS * W1);
@@ -445,7 +450,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     b->scratch = pool_get(ctx, cs.off);
     if (!b->scratch) return bail(IMPOP_ERR_NOMEM, "impop_batch_create: out of device memory (scratch)");
     char *sb = (char *)b->scratch;
-    t.A = (int32_t *)(sb + s_A); t.w8 = (uint8_t *)(sb + s_w8); t.heavy = (uint32_t *)(sb + s_heavy);
+    t.A = (int32_t *)(sb + s_A); t.w8 = (uint8_t *)(sb + s_w8); t.w8n = (uint8_t *)(sb + s_w8n); t.heavy = (uint32_t *)(sb + s_heavy);
     t.xh = (uint32_t *)(sb + s_xh); t.seg_any = (uint32_t *)(sb + s_any); t.seg_all = (uint32_t *)(sb + s_all);
     t.heavy_n = (int32_t *)(sb + s_hn);
     b->partials = (double *)(sb + s_part); b->sums_tmp = (double *)(sb + s_sums); b->counts_tmp = (int64_t *)(sb + s_counts);

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
         const int n = tab.n[w], m = tab.m[w];
         const uint32_t *len = tab.len + tab.len_off[w];
         const uint8_t *lab = tab.labels + tab.lab_off[w];
-        uint8_t *w8 = tab.w8 + tab.w8_off[w];
+        uint8_t *w8 = tab.w8 + tab.w8_off[w], *w8n = tab.w8n + tab.w8_off[w];
         uint32_t *heavy = tab.heavy + tab.heavy_off[w];
         const int m64 = ((m + KCHUNK - 1) / KCHUNK) * KCHUNK;
         const int hpad = (int)(tab.heavy_off[w + 1] - tab.heavy_off[w]);
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
         for (int k = threadIdx.x; k < m64; k += PREP_THREADS) {
             uint32_t l = (k < m) ? __ldg(len + k) : 0u;
             tot += l;
-            w8[k] = (uint8_t)(l % HEAVY_Q);
+            w8[kperm(k)] = w8n[k] = (uint8_t)(l % HEAVY_Q);
             uint32_t q = l / HEAVY_Q;
             while (q > 0) {
                 uint32_t c = q < 255u ? q : 255u;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
         for (int s = nh + threadIdx.x; s < hpad; s += PREP_THREADS) heavy[s] = 0u;
         if (threadIdx.x == 0) tab.heavy_n[w] = nh;
         __syncthreads();
-        for (int s = threadIdx.x; s < hpad; s += PREP_THREADS) w8[m64 + s] = (uint8_t)(heavy[s] & 255u);
+        for (int s = threadIdx.x; s < hpad; s += PREP_THREADS) w8[m64 + kperm(s)] = w8n[m64 + s] = (uint8_t)(heavy[s] & 255u);
         if (threadIdx.x == 0 && counts) {
             const int64_t nS = s_cnt[0], nA = s_cnt[1], nB = s_cnt[2];
             int64_t *row = counts + (size_t)w * IMPOP_NCOUNTS;
@@ -309,13 +309,15 @@ __device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const d
 
 // ==========================================================================================
 // tcgen05 implementation, warp specialised.  One CTA per SM:
-//   warps 0-11   producers: expand presence bits into the u8 operand tiles of a ring of stages
-//                (warps 0-3: the 128 A rows, warps 4-11: up to 256 B rows; lane = row)
+//   warps 0-11   producers: expand the presence bits of a raw slot into the u8 operand tiles of a ring of stages
+//                (warps 0-3: the 128 A rows, warps 4-11: up to 256 B rows; lane = row); shared memory only
 //   warp  12     MMA issuer (one elected lane): tcgen05.mma kind::i8 into one of two TMEM buffers
-//                (warps 13-15 only pad the warpgroup so that setmaxnreg applies to whole warpgroups)
+//   warp  13     table warp: per item, the column / row values and geometry the epilogue needs, into one of
+//                three tables in shared memory, up to three items ahead
+//   warps 14-15  loaders: cp.async of each chunk's packed presence bits and byte weights into a ring of raw slots
 //   warps 16-23  epilogue: tcgen05.ld, exact integer union, fp64 pi_ij, compensated sums
-// Registers are moved from the producer / MMA warpgroups (56 each) to the epilogue warpgroups (128 each):
-// 16 x 32 x 56 + 8 x 32 x 128 = 61 440 = the 768 x 80 registers the CTA owns (a larger sum makes
+// Registers are moved from the producer / MMA / table warpgroups (48 each) to the epilogue warpgroups (144 each):
+// 16 x 32 x 48 + 8 x 32 x 144 = 61 440 = the 768 x 80 registers the CTA owns (a larger sum makes
 // setmaxnreg.inc wait forever).
 // The integer pipes (expansion) and the fp64 pipe (epilogue) so run concurrently on different
 // warps, and items flow through without CTA-wide barriers.
@@ -323,12 +325,35 @@ __device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const d
 #ifndef IMPOP_PROD_SLEEP
 #define IMPOP_PROD_SLEEP 200
 #endif
-constexpr int WS_PROD_WARPS = 12;
-constexpr int WS_EPI_WARPS = 8;
+#ifndef IMPOP_PROD_WARPS
+#define IMPOP_PROD_WARPS 12      // 4 for the A tile (lane = row) + 8 or 4 for the B tile (1 or 2 rows per lane)
+#endif
+#ifndef IMPOP_EPI_WARPS
+#define IMPOP_EPI_WARPS 12       // a multiple of 4: IMPOP_EPI_WARPS / 4 warps share each TMEM lane quarter
+#endif
+constexpr int WS_PROD_WARPS = IMPOP_PROD_WARPS;
+constexpr int WS_EPI_WARPS = IMPOP_EPI_WARPS;
+constexpr int WS_B_RPL = TILE_N / (32 * (WS_PROD_WARPS - 4));   // B rows per producer lane
+static_assert(WS_PROD_WARPS % 4 == 0 && WS_EPI_WARPS % 4 == 0 && WS_B_RPL * 32 * (WS_PROD_WARPS - 4) == TILE_N, "warp roles");
+static_assert(WS_EPI_WARPS == PART_SLOTS, "one partial record per epilogue warp");
 constexpr int WS_MMA_WARP = WS_PROD_WARPS;
 constexpr int WS_EPI_WARP0 = WS_PROD_WARPS + 4;
 constexpr int WS_THREADS = 32 * (WS_EPI_WARP0 + WS_EPI_WARPS);        // 768
-constexpr int WS_STAGES = 4;
+constexpr int WS_STAGES = 3;                                    // operand stages (expanded u8 tiles)
+constexpr int WS_RAW = 8;                                       // raw ring: packed presence bits + byte weights of a chunk
+constexpr int WS_LOADER_LANES = 64;                             // warps 14-15
+constexpr int RAW_ROWS = TILE_M + TILE_N;                       // 384 operand rows per chunk
+constexpr int WS_TABLES = 3;                                    // item tables in flight (see the table warps)
+constexpr int WS_TBL_WARPS = 1;                                 // warp 13
+#ifndef IMPOP_REGS_LOW
+#define IMPOP_REGS_LOW 48        // producer / MMA / table / loader warps
+#define IMPOP_REGS_EPI 104       // epilogue warps: 16 x 32 x 48 + 12 x 32 x 104 = 64 512 = the 896 x 72 registers the CTA owns
+#endif
+#ifndef IMPOP_EPI_PREFETCH
+#define IMPOP_EPI_PREFETCH (IMPOP_EPI_WARPS <= 8)   // second TMEM register buffer: worth its 16 registers only with few warps
+#endif
+#define IMPOP_STR2(x) #x
+#define IMPOP_STR(x) IMPOP_STR2(x)
 constexpr int A_STAGE_BYTES = TILE_M * KCHUNK;                  // 16 KB
 constexpr int B_STAGE_BYTES = TILE_N * KCHUNK;                  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;      // 48 KB
@@ -338,25 +363,33 @@ constexpr uint32_t SBO_AB = 128;                                // next 8-row gr
 constexpr uint32_t TMEM_COLS = 512;                             // two accumulator buffers of 256 columns
 constexpr int EPI_COLS = TILE_N;                                // columns of one item
 
-struct __align__(16) EpiCols {          // per epilogue team: the columns of its current item
+struct __align__(16) EpiCols {          // everything the epilogue needs of one item, built by the table warps
+    int32_t n, r0, col0, ncols;         // haplotypes of the window, first row, first column, columns of the item
+    int32_t have_acc, last, pad0, pad1; // m > 0 (an accumulator exists); last item of this CTA's visit to the window
     uint32_t aj[EPI_COLS];              // path length A_j
     double fs[EPI_COLS], fa[EPI_COLS], fb[EPI_COLS];   // 1.0 / 0.0: column carries SUBSET / A / B
     uint32_t cmask[EPI_COLS / 16];      // per 16-column chunk: bit 0 all columns valid and in SUBSET, bit 1 any A, bit 2 any B
+    uint32_t ai[TILE_M];                // path length A_i of the item's rows
+    uint32_t fi[TILE_M];                // cleaned labels of the item's rows
 };
 
 struct WsShared {
     uint64_t full[WS_STAGES], empty[WS_STAGES];
     uint64_t acc_full[2], acc_empty[2];
+    uint64_t tbl_full[WS_TABLES], tbl_empty[WS_TABLES];
     uint32_t tmem_base;
     uint32_t pad;
-    EpiCols col[2];                     // 2 x 7.2 KB
+    uint64_t raw_full[WS_RAW], raw_empty[WS_RAW];
+    EpiCols col[WS_TABLES];             // 3 x 7.2 KB
 };
-constexpr int WS_SMEM_BYTES = WS_STAGES * STAGE_BYTES + (int)sizeof(WsShared);
+struct __align__(16) RawSlot {          // one chunk as it lies in global memory: 16 bytes of presence bits per operand row
+    uint4 bits[RAW_ROWS];               // rows 0-127: A tile, 128-383: B tile
+    uint4 w[KCHUNK / 16];               // the chunk's 128 byte weights (kperm order)
+};
+constexpr int WS_RAW_OFF = WS_STAGES * STAGE_BYTES;
+constexpr int WS_SH_OFF = WS_RAW_OFF + WS_RAW * (int)sizeof(RawSlot);
+constexpr int WS_SMEM_BYTES = WS_SH_OFF + (int)sizeof(WsShared);
 static_assert(WS_SMEM_BYTES <= 232448, "pairs kernel exceeds the 227 KB of shared memory a CTA can have");
-
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 // Items are dealt to CTAs as CONTIGUOUS ranges (consecutive items of a CTA mostly belong to the same window:
 // its rows stay in L1/L2, and the per-row sums can be carried across items and reduced once per window).
@@ -375,16 +408,49 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 #define PROF_STORE(slot) {}
 #endif
 
+// Byte s of the result = 0xFF if bit 8 s + 7 of v is set, else 0 (PRMT with the sign-replicating selector).
+// (inline PTX: the __byte_perm intrinsic masks the replicate bit of the selector nibbles away)
+__device__ __forceinline__ uint32_t msb_to_bytes(uint32_t v) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+// One 16-byte K slab (half h of presence word `word`) of an operand row, in kperm order.
+//   MODE 0: bytes 0 / 1       (B operand, dense chunk)
+//   MODE 1: bytes 0 / 255     (B operand, heavy chunk)
+//   MODE 2: bytes 0 / weight  (A operand)
+template <int MODE>
+__device__ __forceinline__ uint4 expand_slab(uint32_t word, int h, const uint4 &wv) {
+    uint4 o;
+    if (MODE == 0) {
+        o.x = (word >> (4 * h)) & 0x01010101u;
+        o.y = (word >> (4 * h + 1)) & 0x01010101u;
+        o.z = (word >> (4 * h + 2)) & 0x01010101u;
+        o.w = (word >> (4 * h + 3)) & 0x01010101u;
+    } else {
+        o.x = msb_to_bytes(word << (7 - 4 * h));
+        o.y = msb_to_bytes(word << (6 - 4 * h));
+        o.z = msb_to_bytes(word << (5 - 4 * h));
+        o.w = msb_to_bytes(word << (4 - 4 * h));
+        if (MODE == 2) { o.x &= wv.x; o.y &= wv.y; o.z &= wv.z; o.w &= wv.w; }
+    }
+    return o;
+}
+
 template <bool DUMP>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_constant__ ItemParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
-    WsShared &sh = *reinterpret_cast<WsShared *>(smem + WS_STAGES * STAGE_BYTES);
+    WsShared &sh = *reinterpret_cast<WsShared *>(smem + WS_SH_OFF);
+    RawSlot *raw = reinterpret_cast<RawSlot *>(smem + WS_RAW_OFF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&sh.full[s], WS_PROD_WARPS); mbar_init(&sh.empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&sh.acc_full[b], 1); mbar_init(&sh.acc_empty[b], WS_EPI_WARPS); }
+        for (int b = 0; b < WS_TABLES; ++b) { mbar_init(&sh.tbl_full[b], WS_TBL_WARPS); mbar_init(&sh.tbl_empty[b], WS_EPI_WARPS); }
+        for (int b = 0; b < WS_RAW; ++b) { mbar_init(&sh.raw_full[b], WS_LOADER_LANES); mbar_init(&sh.raw_empty[b], WS_PROD_WARPS); }
         fence_mbar_init();
     }
     if (warp == WS_MMA_WARP) tmem_alloc(&sh.tmem_base, TMEM_COLS);
@@ -397,12 +463,12 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
     auto item_of = [&](int64_t u) { return prm.item_begin + u * prm.world + prm.rank; };
     bool alive = true;
 
-    // Per-window values every role needs; re-read only when a CTA's next item belongs to another window
-    // (a CTA's items are contiguous, so that is once per ~6 items at n = 466), the item table entry of the
-    // next item is prefetched one item ahead.
+    // Per-window values the producer / MMA roles need; re-read only when a CTA's next item belongs to another
+    // window (a CTA's items are contiguous, so that is once per ~6 items at n = 466); the item table entry of
+    // the next item is prefetched one item ahead.
     struct Win {
         int w = -1, n = 0, m = 0, pitch = 0, dense_chunks = 0, hwords = 0, nch = 0;
-        int64_t x_off = 0, w8_off = 0, xh_off = 0, row_off = 0, lab_off = 0;
+        int64_t x_off = 0, w8_off = 0, xh_off = 0;
     };
     auto load_win = [&](Win &wi, int w) {
         if (w == wi.w) return;
@@ -410,19 +476,20 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
         wi.n = tab.n[w]; wi.m = tab.m[w]; wi.pitch = tab.pitch[w];
         const int64_t h0 = tab.heavy_off[w], h1 = tab.heavy_off[w + 1];
         wi.x_off = tab.x_off[w]; wi.w8_off = tab.w8_off[w]; wi.xh_off = tab.xh_off[w];
-        wi.row_off = tab.row_off[w]; wi.lab_off = tab.lab_off[w];
         wi.dense_chunks = (wi.m + KCHUNK - 1) / KCHUNK;
         wi.hwords = (int)((h1 - h0) >> 5);
         wi.nch = wi.dense_chunks + wi.hwords / (KCHUNK / 32);
     };
     auto raw_item = [&](int64_t u) { return (u < u_hi) ? __ldg(tab.items + item_of(u)) : make_int4(-1, 0, 0, 0); };
+    auto raw_ext = [&](int64_t u) { return (u < u_hi) ? __ldg(tab.items_ext + item_of(u)) : make_int4(0, 0, 0, 0); };
 
     if (warp < WS_PROD_WARPS) {
         // ================================================================ producers
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " IMPOP_STR(IMPOP_REGS_LOW) ";");
         const bool isA = warp < 4;
-        const int rl = (isA ? warp : warp - 4) * 32 + lane;          // row of the operand tile
+        const int rl = (isA ? warp : warp - 4) * 32 + lane;          // (first) row of the operand tile
         const uint32_t lbo = isA ? LBO_A : LBO_B;
+        const int nrows = isA ? 1 : WS_B_RPL;                         // B warps: rows rl, rl + 128 when there are only four
         uint32_t g = 0;                                               // chunks produced so far
         Win wi;
         int4 nxt = raw_item(u_lo);
@@ -432,66 +499,52 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             nxt = raw_item(u + 1);
             load_win(wi, cur.x);
             PROF_AUX_END
-            const int bi = cur.y, col0 = cur.z, ncols = cur.w;
-            const int nch = wi.nch, dense_chunks = wi.dense_chunks, hwords = wi.hwords;
-            const int grow = (isA ? bi * TILE_M : col0) + rl;
-            const bool active = isA || rl < ncols;
-            const bool rvalid = active && grow < wi.n;
-            const uint32_t *row = tab.x + wi.x_off + (size_t)grow * wi.pitch;
-            const uint32_t *hrow = tab.xh + wi.xh_off + (size_t)grow * hwords;
-            const uint8_t *w8 = tab.w8 + wi.w8_off;
-            auto load_bits = [&](int c) {
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (rvalid && c < nch)
-                    v = (c >= dense_chunks) ? *reinterpret_cast<const uint4 *>(hrow + 4 * (c - dense_chunks))
-                                            : __ldg(reinterpret_cast<const uint4 *>(row + 4 * c));
-                return v;
-            };
-            uint4 next_bits = load_bits(0);
+            const int ncols = cur.w;
+            const int nch = wi.nch, dense_chunks = wi.dense_chunks;
+            // Presence bits and byte weights arrive through the raw ring (loader warps, cp.async): the producers touch
+            // shared memory only, so the proxy fence after the expansion has no global load to wait for.
             for (int c = 0; c < nch; ++c, ++g) {
-                const uint32_t s = g % WS_STAGES;
-                const uint4 bits = next_bits;
-                next_bits = load_bits(c + 1);                  // in flight while this chunk is expanded
+                const uint32_t s = g % WS_STAGES, rs = g % WS_RAW;
+                if (alive) alive = mbar_wait<IMPOP_PROD_SLEEP>(&sh.raw_full[rs], (g / WS_RAW) & 1u, tab.err);
+                const RawSlot &slot = raw[rs];
+                uint4 bits[WS_B_RPL];
+#pragma unroll
+                for (int q = 0; q < WS_B_RPL; ++q) {
+                    const int r = rl + q * (TILE_N / WS_B_RPL);
+                    bits[q] = (q < nrows && (isA || r < ncols)) ? slot.bits[isA ? r : TILE_M + r] : make_uint4(0u, 0u, 0u, 0u);
+                }
                 if (alive) alive = mbar_wait<IMPOP_PROD_SLEEP>(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
                 PROF_WAIT_END
-#ifdef IMPOP_DBG_NO_EXPAND   // timing experiment only: skip the operand expansion
-                if (false) {
-#else
-                if (active) {
-#endif
-                    const bool is_heavy = c >= dense_chunks;
-                    uint8_t *dst = smem + s * STAGE_BYTES + (isA ? 0 : A_STAGE_BYTES) + rl * 16;
-                    const uint32_t bw[4] = {bits.x, bits.y, bits.z, bits.w};
-                    if (!isA) {
-                        const uint32_t mul = is_heavy ? 255u : 1u;
+#ifndef IMPOP_DBG_NO_EXPAND   // (timing experiment: skip the operand expansion)
+                const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+                if (isA) {
+                    uint8_t *dst = smem + s * STAGE_BYTES + rl * 16;
+                    const uint32_t bw[4] = {bits[0].x, bits[0].y, bits[0].z, bits[0].w};
 #pragma unroll
-                        for (int slab = 0; slab < KCHUNK / 16; ++slab) {
-                            const uint32_t b16 = bw[slab >> 1] >> ((slab & 1) * 16);
-                            uint4 o;
-                            o.x = nibble_to_bytes01(b16 & 0xFu) * mul;
-                            o.y = nibble_to_bytes01((b16 >> 4) & 0xFu) * mul;
-                            o.z = nibble_to_bytes01((b16 >> 8) & 0xFu) * mul;
-                            o.w = nibble_to_bytes01((b16 >> 12) & 0xFu) * mul;
-                            *reinterpret_cast<uint4 *>(dst + slab * lbo) = o;
-                        }
-                    } else {
-                        const uint4 *wp = reinterpret_cast<const uint4 *>(w8 + (size_t)c * KCHUNK);
+                    for (int slab = 0; slab < KCHUNK / 16; ++slab)
+                        *reinterpret_cast<uint4 *>(dst + slab * lbo) = expand_slab<2>(bw[slab >> 1], slab & 1, slot.w[slab]);
+                } else {
 #pragma unroll
-                        for (int slab = 0; slab < KCHUNK / 16; ++slab) {
-                            const uint32_t b16 = bw[slab >> 1] >> ((slab & 1) * 16);
-                            const uint4 wv = __ldg(wp + slab);
-                            uint4 o;
-                            o.x = (nibble_to_bytes01(b16 & 0xFu) * 255u) & wv.x;
-                            o.y = (nibble_to_bytes01((b16 >> 4) & 0xFu) * 255u) & wv.y;
-                            o.z = (nibble_to_bytes01((b16 >> 8) & 0xFu) * 255u) & wv.z;
-                            o.w = (nibble_to_bytes01((b16 >> 12) & 0xFu) * 255u) & wv.w;
-                            *reinterpret_cast<uint4 *>(dst + slab * lbo) = o;
+                    for (int q = 0; q < WS_B_RPL; ++q) {
+                        const int r = rl + q * (TILE_N / WS_B_RPL);
+                        if (r >= ncols) continue;
+                        uint8_t *dst = smem + s * STAGE_BYTES + A_STAGE_BYTES + r * 16;
+                        const uint32_t bw[4] = {bits[q].x, bits[q].y, bits[q].z, bits[q].w};
+                        if (c < dense_chunks) {
+#pragma unroll
+                            for (int slab = 0; slab < KCHUNK / 16; ++slab)
+                                *reinterpret_cast<uint4 *>(dst + slab * lbo) = expand_slab<0>(bw[slab >> 1], slab & 1, none);
+                        } else {
+#pragma unroll
+                            for (int slab = 0; slab < KCHUNK / 16; ++slab)
+                                *reinterpret_cast<uint4 *>(dst + slab * lbo) = expand_slab<1>(bw[slab >> 1], slab & 1, none);
                         }
                     }
-                    fence_proxy_async_smem();
                 }
+                fence_proxy_async_smem();
+#endif
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.full[s]);
+                if (lane == 0) { mbar_arrive(&sh.full[s]); mbar_arrive(&sh.raw_empty[rs]); }
                 PROF_WORK_END
             }
         }
@@ -499,10 +552,10 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
         if (warp == 4) PROF_STORE(1)
     } else if (warp < WS_EPI_WARP0) {
         // ================================================================ MMA issuer (warp 12, one lane issues; 13-15 idle)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " IMPOP_STR(IMPOP_REGS_LOW) ";");
         if (warp == WS_MMA_WARP) {
             const uint32_t smem_base_u32 = smem_u32(smem);
-            uint32_t g = 0, uses[2] = {0u, 0u};
+            uint32_t g = 0, uses0 = 0u, uses1 = 0u;
             Win wi;
             int4 nxt = raw_item(u_lo);
             PROF_DECL
@@ -513,8 +566,9 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 const int nch = wi.nch;
                 if (nch == 0) continue;
                 PROF_WORK_END
-                const uint32_t buf = (uint32_t)(u - u_lo) & 1u;           // item parity = TMEM buffer = epilogue team
-                if (alive) alive = mbar_wait<100>(&sh.acc_empty[buf], (uses[buf] & 1u) ^ 1u, tab.err);
+                const uint32_t buf = (uint32_t)(u - u_lo) & 1u;           // item parity = TMEM buffer
+                const uint32_t used = buf ? uses1 : uses0;
+                if (alive) alive = mbar_wait<100>(&sh.acc_empty[buf], (used & 1u) ^ 1u, tab.err);
                 PROF_AUX_END
                 tc_fence_after();
                 const uint32_t idesc = make_idesc_u8(TILE_M, (uint32_t)cur.w);
@@ -543,81 +597,161 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     __syncwarp();
                     PROF_WORK_END
                 }
-                ++uses[buf];
+                if (buf) ++uses1; else ++uses0;
             }
             PROF_STORE(2)
-        }
-    } else {
-        // ================================================================ epilogue: all eight warps work on the same
-        // item (warp -> 32-row quarter x column half) while the MMA of the next item fills the other TMEM buffer
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-        const int e = warp - WS_EPI_WARP0;              // 0..7
-        const int q4 = warp & 3;                          // TMEM lane quarter this warp may read
-        const int hsel = e >> 2;                          // column half
-        uint32_t uses[2] = {0u, 0u};
-        dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // this lane's S, AA, BB, AB sums of the current window
-        Win wi;
-        int4 nxt = raw_item(u_lo);
-        PROF_DECL
-        for (int64_t u = u_lo; u < u_hi; ++u) {
-            const int64_t t = item_of(u);
-            const int4 cur = nxt;
-            nxt = raw_item(u + 1);
-            load_win(wi, cur.x);
-            Item it;
-            it.w = cur.x; it.bi = cur.y; it.col0 = cur.z; it.ncols = cur.w;
-            const int n = wi.n, nch = wi.nch;
-            const int32_t *Aw = tab.A + wi.row_off;
-            const uint8_t *lab = tab.labels + wi.lab_off;
-            const uint32_t buf = (uint32_t)(u - u_lo) & 1u;           // item parity = TMEM buffer = column table
-            EpiCols &col = sh.col[buf];
-            {   // column table of the item: warp e fills columns [32 e, 32 e + 32).  The table of parity `buf` was last
-                // read two items ago; every warp has passed the barrier of the previous item since, so it is free.
-                const int cc = e * 32 + lane;
-                const int j = it.col0 + cc;
-                const bool ok = cc < it.ncols && j < n;
-                const uint32_t f = ok ? clean_label(__ldg(lab + j)) : 0u;
-                col.aj[cc] = ok ? (uint32_t)__ldg(Aw + j) : 0u;
-                col.fs[cc] = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
-                col.fa[cc] = (f & IMPOP_LAB_A) ? 1.0 : 0.0;
-                col.fb[cc] = (f & IMPOP_LAB_B) ? 1.0 : 0.0;
-                const uint32_t bs = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_SUBSET) != 0u);
-                const uint32_t ba = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_A) != 0u);
-                const uint32_t bb = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_B) != 0u);
-                if (lane < 2) {
-                    const uint32_t hs = lane ? (bs >> 16) : (bs & 0xFFFFu), ha = lane ? (ba >> 16) : (ba & 0xFFFFu),
-                                   hb = lane ? (bb >> 16) : (bb & 0xFFFFu);
-                    col.cmask[e * 2 + lane] = (hs == 0xFFFFu ? 1u : 0u) | (ha ? 2u : 0u) | (hb ? 4u : 0u);
+        } else if (warp == WS_MMA_WARP + 1) {
+            // ============================================================ table warp (13): builds, up to three items ahead of
+            // the epilogue, everything it needs of an item -- A_j and class flags of the columns, A_i and labels of the
+            // rows, the item's geometry -- so that no epilogue warp ever waits for global memory or for another
+            // epilogue warp between two items.  tbl_full[slot]: 1 arrival (this warp); tbl_empty[slot]: 8 (epilogue).
+            int4 nxt = raw_item(u_lo), nxt_x = raw_ext(u_lo);
+            for (int64_t u = u_lo; u < u_hi; ++u) {
+                const int k = (int)(u - u_lo), slot = k % WS_TABLES;
+                const int4 cur = nxt, ext = nxt_x;
+                nxt = raw_item(u + 1); nxt_x = raw_ext(u + 1);
+                const int n = ext.x, col0 = cur.z, ncols = cur.w;
+                const uint8_t *lab = tab.labels + (size_t)ext.w;
+                const int32_t *Aw = tab.A + (size_t)ext.z;
+                // issue the global loads before waiting for the slot
+                uint32_t cf[EPI_COLS / 32], ca[EPI_COLS / 32], rf[TILE_M / 32], ra_[TILE_M / 32];
+#pragma unroll
+                for (int ps = 0; ps < EPI_COLS / 32; ++ps) {
+                    const int cc = ps * 32 + lane, j = col0 + cc;
+                    const bool ok = cc < ncols && j < n;
+                    cf[ps] = ok ? clean_label(__ldg(lab + j)) : 0u;
+                    ca[ps] = ok ? (uint32_t)__ldg(Aw + j) : 0u;
+                }
+#pragma unroll
+                for (int ps = 0; ps < TILE_M / 32; ++ps) {
+                    const int i = cur.y * TILE_M + ps * 32 + lane;
+                    rf[ps] = i < n ? clean_label(__ldg(lab + i)) : 0u;
+                    ra_[ps] = i < n ? (uint32_t)__ldg(Aw + i) : 0u;
+                }
+                if (alive) alive = mbar_wait<100>(&sh.tbl_empty[slot], ((uint32_t)(k / WS_TABLES) & 1u) ^ 1u, tab.err);
+                EpiCols &col = sh.col[slot];
+#pragma unroll
+                for (int ps = 0; ps < EPI_COLS / 32; ++ps) {
+                    const int cc = ps * 32 + lane;
+                    const uint32_t f = cf[ps];
+                    col.aj[cc] = ca[ps];
+                    col.fs[cc] = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
+                    col.fa[cc] = (f & IMPOP_LAB_A) ? 1.0 : 0.0;
+                    col.fb[cc] = (f & IMPOP_LAB_B) ? 1.0 : 0.0;
+                    const uint32_t bs = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_SUBSET) != 0u);
+                    const uint32_t ba = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_A) != 0u);
+                    const uint32_t bb = __ballot_sync(0xffffffffu, (f & IMPOP_LAB_B) != 0u);
+                    if (lane < 2) {
+                        const uint32_t hs = lane ? (bs >> 16) : (bs & 0xFFFFu), ha = lane ? (ba >> 16) : (ba & 0xFFFFu),
+                                       hb = lane ? (bb >> 16) : (bb & 0xFFFFu);
+                        col.cmask[ps * 2 + lane] = (hs == 0xFFFFu ? 1u : 0u) | (ha ? 2u : 0u) | (hb ? 4u : 0u);
+                    }
+                }
+#pragma unroll
+                for (int ps = 0; ps < TILE_M / 32; ++ps) { col.ai[ps * 32 + lane] = ra_[ps]; col.fi[ps * 32 + lane] = rf[ps]; }
+                if (lane == 0) {
+                    col.n = n; col.r0 = cur.y * TILE_M; col.col0 = col0; col.ncols = ncols;
+                    col.have_acc = ext.y > 0 ? 1 : 0; col.last = (nxt.x != cur.x) ? 1 : 0;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.tbl_full[slot]);
+            }
+        } else {
+            // ============================================================ loader warps (14-15): copy every chunk as it lies in
+            // global memory -- 16 bytes of presence bits per operand row, the 128 byte weights -- into the raw ring with
+            // cp.async (no registers, no waiting: up to WS_RAW chunks in flight), completion counted by the slot's mbarrier.
+            const int ll = (warp - WS_MMA_WARP - 2) * 32 + lane;     // 0..63
+            constexpr int ROWS_PER_LANE = RAW_ROWS / WS_LOADER_LANES;   // 6
+            uint32_t g = 0;
+            Win wi;
+            int4 nxt = raw_item(u_lo);
+            const uint32_t raw_u32 = smem_u32(raw);
+            for (int64_t u = u_lo; u < u_hi; ++u) {
+                const int4 cur = nxt;
+                nxt = raw_item(u + 1);
+                load_win(wi, cur.x);
+                const int nch = wi.nch, dense_chunks = wi.dense_chunks, hwords = wi.hwords;
+                int growv[ROWS_PER_LANE];                               // global row per slot row of this lane, -1: none
+#pragma unroll
+                for (int r = 0; r < ROWS_PER_LANE; ++r) {
+                    const int tr = ll + r * WS_LOADER_LANES;            // 0..383: row of the raw slot
+                    const bool isArow = tr < TILE_M;
+                    const int grow = isArow ? cur.y * TILE_M + tr : cur.z + (tr - TILE_M);
+                    growv[r] = ((isArow || tr - TILE_M < cur.w) && grow < wi.n) ? grow : -1;
+                }
+                const uint32_t *xw = tab.x + wi.x_off, *xhw = tab.xh + wi.xh_off;
+                const uint8_t *w8 = tab.w8 + wi.w8_off;
+                const int pitch = wi.pitch;
+                for (int c = 0; c < nch; ++c, ++g) {
+                    const uint32_t rs = g % WS_RAW;
+                    if (alive) alive = mbar_wait<100>(&sh.raw_empty[rs], ((g / WS_RAW) & 1u) ^ 1u, tab.err);
+                    const uint32_t slot_u32 = raw_u32 + rs * (uint32_t)sizeof(RawSlot) + (uint32_t)ll * 16u;
+                    const bool heavy_chunk = c >= dense_chunks;
+                    const uint32_t *base = heavy_chunk ? xhw + 4 * (c - dense_chunks) : xw + 4 * c;
+                    const int stride = heavy_chunk ? hwords : pitch;
+#pragma unroll
+                    for (int r = 0; r < ROWS_PER_LANE; ++r) {
+                        const bool ok = growv[r] >= 0;
+                        cp_async16(slot_u32 + (uint32_t)(r * WS_LOADER_LANES) * 16u,
+                                   ok ? (const void *)(base + (size_t)growv[r] * stride) : (const void *)w8, ok ? 16u : 0u);
+                    }
+                    if (ll < KCHUNK / 16)
+                        cp_async16(slot_u32 + (uint32_t)RAW_ROWS * 16u, w8 + (size_t)c * KCHUNK + ll * 16, 16u);
+                    cp_async_arrive_noinc(&sh.raw_full[rs]);
                 }
             }
-            named_bar_sync(1, WS_EPI_WARPS * 32);          // table complete
-            const int r0 = it.bi * TILE_M + q4 * 32;
+        }
+    } else {
+        // ================================================================ epilogue.  All eight warps work on the same item
+        // (warp -> 32-row quarter q4 of the TMEM lanes x one half of that quarter's valid 16-column chunks) while the
+        // MMA of the next item fills the other TMEM buffer.  Everything else an item needs comes from its table in
+        // shared memory (table warps above): a warp that finishes its chunks early moves on to the next item as soon
+        // as the MMA has filled that accumulator -- no barrier couples the eight warps.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " IMPOP_STR(IMPOP_REGS_EPI) ";");
+        const int e = warp - WS_EPI_WARP0;              // 0..7
+        const int q4 = warp & 3;                          // TMEM lane quarter this warp may read
+        constexpr int H = WS_EPI_WARPS / 4;               // warps per TMEM lane quarter
+        const int hsel = e >> 2;                          // which share of the quarter's chunks
+        uint32_t uses0 = 0u, uses1 = 0u;
+        dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // this lane's S, AA, BB, AB sums of the current window
+        PROF_DECL
+        for (int64_t u = u_lo; u < u_hi; ++u) {
+            const int k = (int)(u - u_lo);
+            const int slot = k % WS_TABLES;
+            const int64_t t = item_of(u);
+            const uint32_t buf = (uint32_t)k & 1u;                        // item parity = TMEM buffer
+            if (alive) alive = mbar_wait<20>(&sh.tbl_full[slot], (uint32_t)(k / WS_TABLES) & 1u, tab.err);
+            const EpiCols &col = sh.col[slot];
+            const int4 geo = *reinterpret_cast<const int4 *>(&col.n);     // n, first row, first column, columns
+            const int n = geo.x, col0 = geo.z;
+            const bool have_acc = col.have_acc != 0, last = col.last != 0;
+            const int r0 = geo.y + q4 * 32;
             const int i = r0 + lane;
-            const bool rvalid = i < n;
-            const uint32_t ai = rvalid ? (uint32_t)__ldg(Aw + i) : 0u;
-            const uint32_t fi = rvalid ? clean_label(__ldg(lab + i)) : 0u;
-            const int half0 = (((it.ncols >> 4) + 1) >> 1) << 4;        // columns of half 0 (multiple of 16)
-            const int cbeg = hsel ? half0 : 0, cend = hsel ? it.ncols : half0;
+            const uint32_t ai = col.ai[q4 * 32 + lane];
+            const uint32_t fi = col.fi[q4 * 32 + lane];
+            // this quarter's valid chunks [c_lo, c_hi): columns below n, not entirely left of the diagonal; split in two
+            int c_lo = 0, c_hi = 0;
+            if (r0 < n) {
+                const int width = min(geo.w, n - col0);
+                c_hi = (width + 15) >> 4;
+                c_lo = max(0, (r0 - col0) >> 4);
+                if (c_lo > c_hi) c_lo = c_hi;
+            }
+            const int hh = (hsel + k) % H, cnt = c_hi - c_lo;          // shares rotate with the item: remainders even out
+            const int cbeg = c_lo + cnt * hh / H, cend = c_lo + cnt * (hh + 1) / H;
             PROF_AUX_END
-            if (nch > 0) {
-                if (alive) alive = mbar_wait<100>(&sh.acc_full[buf], uses[buf] & 1u, tab.err);
+            if (have_acc) {
+                if (alive) alive = mbar_wait<20>(&sh.acc_full[buf], (buf ? uses1 : uses0) & 1u, tab.err);
                 tc_fence_after();
             }
             PROF_WAIT_END
             dd ts = {0.0, 0.0}, ta = {0.0, 0.0}, tb = {0.0, 0.0};
-            for (int cc = cbeg; cc < cend && r0 < n; cc += 16) {
-                const int jbase = it.col0 + cc;
-                if (jbase >= n) break;
-                if (jbase + 15 < r0) continue;                     // every j below every i of this warp
-                uint32_t r[16];
-                if (nch > 0) {
-                    tmem_ld16(tmem_base + buf * TILE_N + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cc, r);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) r[k] = 0u;
-                }
-                const uint32_t cm = col.cmask[cc >> 4];
+            const uint32_t tm0 = tmem_base + buf * TILE_N + ((uint32_t)(q4 * 32) << 16);
+            uint32_t ra[16];
+            auto chunk = [&](const uint32_t (&r)[16], int c) {
+                const int cc = c << 4;
+                const int jbase = col0 + cc;
+                const uint32_t cm = col.cmask[c];
                 uint32_t aj[16];
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
@@ -627,18 +761,18 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 double p[16];
 #ifdef IMPOP_DBG_NO_EPI      // timing experiment only: skip the fp64 math
 #pragma unroll
-                for (int k = 0; k < 16; ++k) p[k] = __hiloint2double(r[k] + aj[k], ai);
+                for (int q = 0; q < 16; ++q) p[q] = __hiloint2double(r[q] + aj[q], ai);
 #else
                 pi_batch<8>(r, ai, aj, p);
                 pi_batch<8>(r + 8, ai, aj + 8, p + 8);
 #endif
                 if (jbase <= r0 + 31) {                            // the chunk touches the diagonal of this warp's rows
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) p[k] = (jbase + k > i) ? p[k] : 0.0;
+                    for (int q = 0; q < 16; ++q) p[q] = (jbase + q > i) ? p[q] : 0.0;
                 }
                 if (DUMP) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) pair_dump(prm, n, i, jbase + k, r[k], ai, aj[k]);
+                    for (int q = 0; q < 16; ++q) pair_dump(prm, n, i, jbase + q, r[q], ai, aj[q]);
                 }
                 double cs;
                 if (cm & 1u) {
@@ -649,41 +783,67 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 } else {
                     cs = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) cs = __fma_rn(p[k], col.fs[cc + k], cs);   // p * 1.0 or p * 0.0: exact
+                    for (int q = 0; q < 16; ++q) cs = __fma_rn(p[q], col.fs[cc + q], cs);   // p * 1.0 or p * 0.0: exact
                 }
                 dd_add(ts, cs);
                 if (cm & 2u) {
                     double ca = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) ca = __fma_rn(p[k], col.fa[cc + k], ca);
+                    for (int q = 0; q < 16; ++q) ca = __fma_rn(p[q], col.fa[cc + q], ca);
                     dd_add(ta, ca);
                 }
                 if (cm & 4u) {
                     double cb = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) cb = __fma_rn(p[k], col.fb[cc + k], cb);
+                    for (int q = 0; q < 16; ++q) cb = __fma_rn(p[q], col.fb[cc + q], cb);
                     dd_add(tb, cb);
                 }
-            }
-            if (nch > 0) {
+            };
+            if (have_acc) {
+#if IMPOP_EPI_PREFETCH
+                // two chunks per trip: the TMEM load of the next chunk is in flight while this one is computed
+                uint32_t rb[16];
+                if (cbeg < cend) tmem_ld16(tm0 + (uint32_t)(cbeg << 4), ra);
+                for (int c = cbeg; c < cend; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < cend) tmem_ld16(tm0 + (uint32_t)((c + 1) << 4), rb);
+                    chunk(ra, c);
+                    if (c + 1 < cend) {
+                        tmem_ld_wait();
+                        if (c + 2 < cend) tmem_ld16(tm0 + (uint32_t)((c + 2) << 4), ra);
+                        chunk(rb, c + 1);
+                    }
+                }
+#else
+                for (int c = cbeg; c < cend; ++c) {
+                    tmem_ld16(tm0 + (uint32_t)(c << 4), ra);
+                    tmem_ld_wait();
+                    chunk(ra, c);
+                }
+#endif
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.acc_empty[buf]);
-                ++uses[buf];
+                if (lane == 0) { mbar_arrive(&sh.acc_empty[buf]); mbar_arrive(&sh.tbl_empty[slot]); }
+                if (buf) ++uses1; else ++uses0;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) ra[q] = 0u;
+                for (int c = cbeg; c < cend; ++c) chunk(ra, c);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.tbl_empty[slot]);
             }
             PROF_WORK_END
             // row-side class combination, carried in this lane across the CTA's items of the same window
             if (fi & IMPOP_LAB_SUBSET) dd_merge(v[0], ts);
             if (fi & IMPOP_LAB_A) { dd_merge(v[1], ta); dd_merge(v[3], tb); }
             if (fi & IMPOP_LAB_B) { dd_merge(v[2], tb); dd_merge(v[3], ta); }
-            const bool last = nxt.x != it.w;                   // (-1 past the end of this CTA's range)
             double *rec = prm.partials + t * PART_STRIDE + e * 8;
             if (last) {                                        // reduce over the warp's 32 lanes, once per window visit
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const dd tot = warp_sum_dd(v[k]);
-                    if (lane == 0) { rec[k] = tot.hi; rec[4 + k] = tot.lo; }
-                    v[k].hi = 0.0; v[k].lo = 0.0;
+                for (int q = 0; q < 4; ++q) {
+                    const dd tot = warp_sum_dd(v[q]);
+                    if (lane == 0) { rec[q] = tot.hi; rec[4 + q] = tot.lo; }
+                    v[q].hi = 0.0; v[q].lo = 0.0;
                 }
             } else if (lane < 8) {
                 rec[lane] = 0.0;                               // the sums travel on to the next item's record
@@ -720,7 +880,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const _
         const int hwords = (int)((tab.heavy_off[it.w + 1] - tab.heavy_off[it.w]) >> 5);
         const int nch = dense_chunks + (hwords >> 1);
         const uint32_t *xh = tab.xh + tab.xh_off[it.w];
-        const uint8_t *w8 = tab.w8 + tab.w8_off[it.w];
+        const uint8_t *w8 = tab.w8n + tab.w8_off[it.w];
         const int32_t *Aw = tab.A + tab.row_off[it.w];
         const uint8_t *lab = tab.labels + tab.lab_off[it.w];
         const int i = it.bi * TILE_M + tid;
@@ -882,6 +1042,16 @@ __global__ void division_selftest_kernel(uint64_t seed, int64_t count, unsigned 
         const uint32_t uni = ai + aj - inter;
         const double a = u32_to_double(inter), b = u32_to_double(uni ? uni : 1u);
         if (__double_as_longlong(__ddiv_rn(a, b)) != __double_as_longlong(div_rn_inrange(a, b))) ++bad;
+        if (__double_as_longlong(__ddiv_rn(a, b)) != __double_as_longlong(div_rn_int31(a, b))) ++bad;
+        {   // ratios of arbitrary 31-bit integers (not only I <= U), small denominators, near-equal operands
+            const uint32_t a2 = (uint32_t)(z2 >> 13) & 0x7FFFFFFFu;
+            uint32_t b2 = (uint32_t)(z >> 7) & 0x7FFFFFFFu;
+            if ((z2 & 3u) == 2u) b2 >>= (sh2 % 31u);
+            if ((z2 & 31u) == 3u) b2 = a2 + 1u - (uint32_t)((z2 >> 5) & 3u);
+            b2 = (b2 & 0x7FFFFFFFu) ? (b2 & 0x7FFFFFFFu) : 1u;
+            const double da = u32_to_double(a2), db = u32_to_double(b2);
+            if (__double_as_longlong(__ddiv_rn(da, db)) != __double_as_longlong(div_rn_int31(da, db))) ++bad;
+        }
     }
     if (bad) atomicAdd(out, bad);
 }

@@ -43,7 +43,58 @@ void run(const char *name, int warps) {
     cudaFree(out);
 }
 
+// Dependent chain of DFMAs in one warp: cycles per instruction = latency of the fp64 pipe.
+__global__ void dfma_latency(double *out, long long *cyc, int iters) {
+    double x = 1.0 + threadIdx.x * 1e-9, y = 0.999999;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x = __fma_rn(x, y, 1e-12);
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cyc[0] = t1 - t0;
+    if (x == 12345.0) out[0] = x;
+}
+// ILP independent chains in one warp: cycles per instruction -> issue interval of the pipe.
+template <int ILP>
+__global__ void dfma_ilp(double *out, long long *cyc, int iters) {
+    double x[ILP];
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) x[k] = 1.0 + threadIdx.x * 1e-9 + k;
+    const double y = 0.999999;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) x[k] = __fma_rn(x[k], y, 1e-12);
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+    double s = 0; for (int k = 0; k < ILP; ++k) s += x[k];
+    if (s == 12345.0) out[0] = s;
+}
+template <int ILP>
+void run_ilp(int warps) {
+    double *out; long long *cyc; cudaMalloc(&out, 8); cudaMalloc(&cyc, 8 * 148);
+    const int iters = 1000;
+    dfma_ilp<ILP><<<1, warps * 32>>>(out, cyc, iters);
+    long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("dfma ILP %2d, %2d warps on one SM: %.2f cycles per warp-DFMA per SMSP-slot (total %lld)\n", ILP, warps,
+           (double)h / (iters * 4.0 * ILP) / ((warps + 3) / 4), h);
+    cudaFree(out); cudaFree(cyc);
+}
+
 int main() {
+    {
+        double *out; long long *cyc; cudaMalloc(&out, 8); cudaMalloc(&cyc, 8);
+        dfma_latency<<<1, 32>>>(out, cyc, 1000);
+        long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("dependent DFMA latency: %.2f cycles\n", (double)h / 16000.0);
+        cudaFree(out); cudaFree(cyc);
+    }
+    run_ilp<1>(4); run_ilp<2>(4); run_ilp<4>(4); run_ilp<8>(4); run_ilp<16>(4);
+    run_ilp<4>(8); run_ilp<8>(8); run_ilp<8>(16); run_ilp<4>(16);
     for (int w : {4, 8, 16, 32}) run<8, 0>("layered NP=8", w);
     for (int w : {4, 8, 16, 32}) run<4, 0>("layered NP=4", w);
     for (int w : {4, 8, 16, 32}) run<16, 0>("layered NP=16", w);
