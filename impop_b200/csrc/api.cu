@@ -377,7 +377,11 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
             const int4 ext = make_int4(n[w], m[w], (int)row_off[w], (int)d->lab_off_host[w]);
             for (int bi = 0; bi < nb; ++bi) {
                 const int cnt = items_of_rowblock(n[w], bi), width = width_of_rowblock(n[w], bi);
-                for (int r = 0; r < cnt; ++r) { iext[k] = ext; items[k++] = make_int4(w, bi, bi * TILE_M + r * width, width); }
+                for (int r = 0; r < cnt; ++r) {
+                    const int rev = (r == 0 && (bi & 1)) ? ITEM_REV : 0;      // every other diagonal block (common.cuh)
+                    iext[k] = ext;
+                    items[k++] = make_int4(w, bi | rev, bi * TILE_M + r * width, width);
+                }
             }
         }
     }

@@ -269,7 +269,7 @@ struct Item {
 __device__ __forceinline__ Item decode_item(const WindowTab &tab, int64_t t) {
     const int4 v = __ldg(tab.items + t);      // table built on the host at batch creation
     Item it;
-    it.w = v.x; it.bi = v.y; it.col0 = v.z; it.ncols = v.w;
+    it.w = v.x; it.bi = v.y & ITEM_BI_MASK; it.col0 = v.z; it.ncols = v.w;
     return it;
 }
 
@@ -349,6 +349,9 @@ constexpr int WS_TBL_WARPS = 1;                                 // warp 13
 #define IMPOP_REGS_LOW 48        // producer / MMA / table / loader warps
 #define IMPOP_REGS_EPI 104       // epilogue warps: 16 x 32 x 48 + 12 x 32 x 104 = 64 512 = the 896 x 72 registers the CTA owns
 #endif
+#ifndef IMPOP_EPI_NP
+#define IMPOP_EPI_NP 8           // pairs whose division chains advance together
+#endif
 #ifndef IMPOP_EPI_PREFETCH
 #define IMPOP_EPI_PREFETCH (IMPOP_EPI_WARPS <= 8)   // second TMEM register buffer: worth its 16 registers only with few warps
 #endif
@@ -365,7 +368,8 @@ constexpr int EPI_COLS = TILE_N;                                // columns of on
 
 struct __align__(16) EpiCols {          // everything the epilogue needs of one item, built by the table warps
     int32_t n, r0, col0, ncols;         // haplotypes of the window, first row, first column, columns of the item
-    int32_t have_acc, last, pad0, pad1; // m > 0 (an accumulator exists); last item of this CTA's visit to the window
+    int32_t have_acc, last, rev, pad1;  // m > 0 (an accumulator exists); last item of this CTA's visit to the window;
+                                        // rev: TMEM lane quarter q holds row quarter 3 - q (see ITEM_REV)
     uint32_t aj[EPI_COLS];              // path length A_j
     double fs[EPI_COLS], fa[EPI_COLS], fb[EPI_COLS];   // 1.0 / 0.0: column carries SUBSET / A / B
     uint32_t cmask[EPI_COLS / 16];      // per 16-column chunk: bit 0 all columns valid and in SUBSET, bit 1 any A, bit 2 any B
@@ -501,17 +505,21 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             PROF_AUX_END
             const int ncols = cur.w;
             const int nch = wi.nch, dense_chunks = wi.dense_chunks;
+            const int a_src = (((cur.y & ITEM_REV) ? 3 - warp : warp) & 3) * 32 + lane;   // A warps: block row behind tile row rl
             // Presence bits and byte weights arrive through the raw ring (loader warps, cp.async): the producers touch
             // shared memory only, so the proxy fence after the expansion has no global load to wait for.
             for (int c = 0; c < nch; ++c, ++g) {
                 const uint32_t s = g % WS_STAGES, rs = g % WS_RAW;
                 if (alive) alive = mbar_wait<IMPOP_PROD_SLEEP>(&sh.raw_full[rs], (g / WS_RAW) & 1u, tab.err);
+#ifdef IMPOP_PROFILE_ROLES2
+                PROF_AUX_END          // aux = wait for the raw slot (+ item setup)
+#endif
                 const RawSlot &slot = raw[rs];
                 uint4 bits[WS_B_RPL];
 #pragma unroll
                 for (int q = 0; q < WS_B_RPL; ++q) {
                     const int r = rl + q * (TILE_N / WS_B_RPL);
-                    bits[q] = (q < nrows && (isA || r < ncols)) ? slot.bits[isA ? r : TILE_M + r] : make_uint4(0u, 0u, 0u, 0u);
+                    bits[q] = (q < nrows && (isA || r < ncols)) ? slot.bits[isA ? a_src : TILE_M + r] : make_uint4(0u, 0u, 0u, 0u);
                 }
                 if (alive) alive = mbar_wait<IMPOP_PROD_SLEEP>(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
                 PROF_WAIT_END
@@ -624,7 +632,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 }
 #pragma unroll
                 for (int ps = 0; ps < TILE_M / 32; ++ps) {
-                    const int i = cur.y * TILE_M + ps * 32 + lane;
+                    const int i = (cur.y & ITEM_BI_MASK) * TILE_M + ps * 32 + lane;
                     rf[ps] = i < n ? clean_label(__ldg(lab + i)) : 0u;
                     ra_[ps] = i < n ? (uint32_t)__ldg(Aw + i) : 0u;
                 }
@@ -650,8 +658,8 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 #pragma unroll
                 for (int ps = 0; ps < TILE_M / 32; ++ps) { col.ai[ps * 32 + lane] = ra_[ps]; col.fi[ps * 32 + lane] = rf[ps]; }
                 if (lane == 0) {
-                    col.n = n; col.r0 = cur.y * TILE_M; col.col0 = col0; col.ncols = ncols;
-                    col.have_acc = ext.y > 0 ? 1 : 0; col.last = (nxt.x != cur.x) ? 1 : 0;
+                    col.n = n; col.r0 = (cur.y & ITEM_BI_MASK) * TILE_M; col.col0 = col0; col.ncols = ncols;
+                    col.have_acc = ext.y > 0 ? 1 : 0; col.last = (nxt.x != cur.x) ? 1 : 0; col.rev = (cur.y & ITEM_REV) ? 1 : 0;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.tbl_full[slot]);
@@ -666,17 +674,19 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             Win wi;
             int4 nxt = raw_item(u_lo);
             const uint32_t raw_u32 = smem_u32(raw);
+            PROF_DECL
             for (int64_t u = u_lo; u < u_hi; ++u) {
                 const int4 cur = nxt;
                 nxt = raw_item(u + 1);
                 load_win(wi, cur.x);
+                PROF_AUX_END
                 const int nch = wi.nch, dense_chunks = wi.dense_chunks, hwords = wi.hwords;
                 int growv[ROWS_PER_LANE];                               // global row per slot row of this lane, -1: none
 #pragma unroll
                 for (int r = 0; r < ROWS_PER_LANE; ++r) {
                     const int tr = ll + r * WS_LOADER_LANES;            // 0..383: row of the raw slot
                     const bool isArow = tr < TILE_M;
-                    const int grow = isArow ? cur.y * TILE_M + tr : cur.z + (tr - TILE_M);
+                    const int grow = isArow ? (cur.y & ITEM_BI_MASK) * TILE_M + tr : cur.z + (tr - TILE_M);
                     growv[r] = ((isArow || tr - TILE_M < cur.w) && grow < wi.n) ? grow : -1;
                 }
                 const uint32_t *xw = tab.x + wi.x_off, *xhw = tab.xh + wi.xh_off;
@@ -685,6 +695,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 for (int c = 0; c < nch; ++c, ++g) {
                     const uint32_t rs = g % WS_RAW;
                     if (alive) alive = mbar_wait<100>(&sh.raw_empty[rs], ((g / WS_RAW) & 1u) ^ 1u, tab.err);
+                    PROF_WAIT_END
                     const uint32_t slot_u32 = raw_u32 + rs * (uint32_t)sizeof(RawSlot) + (uint32_t)ll * 16u;
                     const bool heavy_chunk = c >= dense_chunks;
                     const uint32_t *base = heavy_chunk ? xhw + 4 * (c - dense_chunks) : xw + 4 * c;
@@ -698,8 +709,12 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     if (ll < KCHUNK / 16)
                         cp_async16(slot_u32 + (uint32_t)RAW_ROWS * 16u, w8 + (size_t)c * KCHUNK + ll * 16, 16u);
                     cp_async_arrive_noinc(&sh.raw_full[rs]);
+                    PROF_WORK_END
                 }
             }
+#ifdef IMPOP_PROFILE_ROLES2
+            if (ll == 0) PROF_STORE(4)     // replaces epilogue team 1 in the report
+#endif
         }
     } else {
         // ================================================================ epilogue.  All eight warps work on the same item
@@ -725,10 +740,11 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             const int4 geo = *reinterpret_cast<const int4 *>(&col.n);     // n, first row, first column, columns
             const int n = geo.x, col0 = geo.z;
             const bool have_acc = col.have_acc != 0, last = col.last != 0;
-            const int r0 = geo.y + q4 * 32;
+            const int rq = col.rev ? 3 - q4 : q4;                         // row quarter behind this warp's TMEM lanes
+            const int r0 = geo.y + rq * 32;
             const int i = r0 + lane;
-            const uint32_t ai = col.ai[q4 * 32 + lane];
-            const uint32_t fi = col.fi[q4 * 32 + lane];
+            const uint32_t ai = col.ai[rq * 32 + lane];
+            const uint32_t fi = col.fi[rq * 32 + lane];
             // this quarter's valid chunks [c_lo, c_hi): columns below n, not entirely left of the diagonal; split in two
             int c_lo = 0, c_hi = 0;
             if (r0 < n) {
@@ -763,8 +779,8 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 #pragma unroll
                 for (int q = 0; q < 16; ++q) p[q] = __hiloint2double(r[q] + aj[q], ai);
 #else
-                pi_batch<8>(r, ai, aj, p);
-                pi_batch<8>(r + 8, ai, aj + 8, p + 8);
+#pragma unroll
+                for (int q = 0; q < 16; q += IMPOP_EPI_NP) pi_batch<IMPOP_EPI_NP>(r + q, ai, aj + q, p + q);
 #endif
                 if (jbase <= r0 + 31) {                            // the chunk touches the diagonal of this warp's rows
 #pragma unroll
@@ -850,7 +866,9 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             }
         }
         if (e == 0) PROF_STORE(3)
+#ifndef IMPOP_PROFILE_ROLES2
         if (e == 4) PROF_STORE(4)
+#endif
     }
 
     tc_fence_before();
