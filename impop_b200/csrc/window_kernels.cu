@@ -23,15 +23,16 @@ namespace impop {
 //   prep_cols   one CTA per window: byte weights of the dense columns, heavy-node table, range check
 //               sum(len) < 2^31, label counts, reset of the any / all words
 //   prep_rows   one CTA per (window, row slice) -- a window with many haplotypes is cut into slices so that a
-//               batch of few large windows still fills the GPU: path lengths A_i through a nibble look-up table
-//               of node lengths in shared memory (lane l looks up nibble position 32 q + l: 32 distinct banks;
-//               four rows in flight per warp), presence bits of the heavy columns (shuffle of the row words
-//               already in registers + ballot), any / all masks over the SEG rows
+//               batch of few large windows still fills the GPU: path lengths A_i as the sum over the eight bit
+//               planes of the dense byte weights of 2^p popc(row word & plane word) (lane = presence word, planes
+//               in registers, four rows in flight per warp) plus 255 c per present heavy column, presence bits of
+//               the heavy columns (shuffle of the row words already in registers + ballot), any / all masks over
+//               the SEG rows
 //   seg_count   S = #{k : 0 < sum_{i in SEG} x_ik < |SEG|, len_k > 0} (replaces `povu gfa2vcf | wc -l`,
 //               run_tajd.sh:126-148) -> counts row nS nA nB pS pAA pBB pAB S
 // ==========================================================================================
 constexpr int PREP_THREADS = 256;
-constexpr int LUT_POS = 512;                 // nibble positions per table pass = 2048 nodes = 64 words
+constexpr int PM_WORDS = 64;                 // presence words per node group of prep_rows = 2048 nodes
 
 __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
     __shared__ int s_heavy, s_cnt[4];
@@ -78,6 +79,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
         if (lane == 0 && tot) atomicAdd(&s_total, tot);
         const int64_t wo = tab.word_off[w], words = tab.word_off[w + 1] - wo;
         for (int64_t k = threadIdx.x; k < words; k += PREP_THREADS) { tab.seg_any[wo + k] = 0u; tab.seg_all[wo + k] = 0xffffffffu; }
+        {   // heavy presence bits start out empty (prep_rows sets the words that hold entries)
+            const int64_t h0 = tab.xh_off[w], h1 = tab.xh_off[w + 1];
+            for (int64_t k = h0 + threadIdx.x; k < h1; k += PREP_THREADS) tab.xh[k] = 0u;
+        }
         __syncthreads();
         if (threadIdx.x == 0 && (s_total >= (1ull << 31) || s_heavy > hpad)) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);
         const int nh = s_heavy < hpad ? s_heavy : hpad;
@@ -96,15 +101,115 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
     }
 }
 
-__global__ void __launch_bounds__(PREP_THREADS, 4) prep_rows_kernel(const __grid_constant__ WindowTab tab) {
-    __shared__ uint32_t s_lut[16][LUT_POS];   // 32 KB
-    __shared__ uint32_t s_any[64], s_all[64];
+// Rows [row_lo, row_hi) of one window against one group of <= 2048 nodes (PASSES x 32 presence words per row).
+// FIRST: the group starts at node 0 (defines A_i and the heavy words; later groups add to them).
+template <int PASSES, bool FIRST>
+__device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS], uint32_t *s_any, uint32_t *s_all,
+                                                const uint32_t *x, int pitch, const uint8_t *lab, int row_lo, int row_hi,
+                                                int w0, const uint32_t *heavy, int hwords, int hw_used, uint32_t *xh,
+                                                int32_t *A) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t pm[PASSES][8];
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps)
+#pragma unroll
+        for (int p = 0; p < 8; ++p) pm[ps][p] = s_pm[p][ps * 32 + lane];
+    // the first heavy word (32 entries) is kept in registers: lane = entry
+    const uint32_t ent0 = hw_used > 0 ? heavy[lane] : 0u;
+    const int rel0 = (int)(ent0 >> 13) - w0;                        // word of the entry's node within this group
+    const bool in0 = (ent0 & 255u) && rel0 >= 0 && rel0 < 32 * PASSES;
+    const uint32_t add0 = HEAVY_Q * (ent0 & 255u), bit0 = (ent0 >> 8) & 31u;
+    const bool any_in0 = __any_sync(0xffffffffu, in0);
+    constexpr int RU = 4;                                           // rows in flight per warp (memory-level parallelism)
+    uint32_t any[PASSES], all[PASSES];
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) { any[ps] = 0u; all[ps] = 0xffffffffu; }
+    for (int i0 = row_lo + warp * RU; i0 < row_hi; i0 += (PREP_THREADS / 32) * RU) {
+        uint32_t word[PASSES][RU], acc[RU];
+        uint32_t labv[RU];
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+            const bool rv = i0 + r < row_hi;
+            labv[r] = rv ? (uint32_t)lab[i0 + r] : 0u;
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) {
+                const int wd = w0 + ps * 32 + lane;
+                word[ps][r] = (rv && wd < pitch) ? __ldg(x + (size_t)(i0 + r) * pitch + wd) : 0u;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+            uint32_t a = 0u;
+#pragma unroll
+            for (int ps = 0; ps < PASSES; ++ps) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) a += (uint32_t)__popc(word[ps][r] & pm[ps][p]) << p;
+                if (labv[r] & IMPOP_LAB_SEG) { any[ps] |= word[ps][r]; all[ps] &= word[ps][r]; }
+            }
+            acc[r] = a;
+        }
+        if (FIRST || any_in0) {
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+                uint32_t wsrc = __shfl_sync(0xffffffffu, word[0][r], rel0 & 31);
+                if (PASSES > 1) {
+                    const uint32_t w_hi = __shfl_sync(0xffffffffu, word[PASSES - 1][r], rel0 & 31);
+                    wsrc = (rel0 >= 32) ? w_hi : wsrc;
+                }
+                const bool on = in0 && ((wsrc >> bit0) & 1u);
+                const uint32_t bw = __ballot_sync(0xffffffffu, on);
+                if (on) acc[r] += add0;
+                if (lane == 0 && i0 + r < row_hi && hw_used > 0) {
+                    uint32_t *dst = xh + (size_t)(i0 + r) * hwords;
+                    if (FIRST) *dst = bw; else if (bw) *dst |= bw;     // (xh was zeroed by prep_cols)
+                }
+            }
+        }
+        for (int hw = 1; hw < hw_used; ++hw) {                      // further heavy words: rare
+            const uint32_t ent = heavy[hw * 32 + lane];
+            const int rel = (int)(ent >> 13) - w0;
+            const bool in = (ent & 255u) && rel >= 0 && rel < 32 * PASSES;
+            if (!FIRST && !__any_sync(0xffffffffu, in)) continue;
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+                uint32_t wsrc = __shfl_sync(0xffffffffu, word[0][r], rel & 31);
+                if (PASSES > 1) {
+                    const uint32_t w_hi = __shfl_sync(0xffffffffu, word[PASSES - 1][r], rel & 31);
+                    wsrc = (rel >= 32) ? w_hi : wsrc;
+                }
+                const bool on = in && ((wsrc >> ((ent >> 8) & 31u)) & 1u);
+                const uint32_t bw = __ballot_sync(0xffffffffu, on);
+                if (on) acc[r] += HEAVY_Q * (ent & 255u);
+                if (lane == 0 && i0 + r < row_hi) {
+                    uint32_t *dst = xh + (size_t)(i0 + r) * hwords + hw;
+                    if (FIRST) *dst = bw; else if (bw) *dst |= bw;
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RU; ++r) {
+            uint32_t a = acc[r];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+            if (lane == 0 && i0 + r < row_hi) A[i0 + r] = (int32_t)(a + (FIRST ? 0u : (uint32_t)A[i0 + r]));
+        }
+    }
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) { atomicOr(&s_any[ps * 32 + lane], any[ps]); atomicAnd(&s_all[ps * 32 + lane], all[ps]); }
+}
+
+#ifndef IMPOP_PREP_OCC
+#define IMPOP_PREP_OCC 4
+#endif
+__global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel(const __grid_constant__ WindowTab tab) {
+    __shared__ uint32_t s_pm[8][PM_WORDS];    // bit planes of the dense byte weights, per presence word of the node group
+    __shared__ uint32_t s_any[PM_WORDS], s_all[PM_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int sidx = blockIdx.x; sidx < tab.n_slices; sidx += gridDim.x) {
         const int4 sl = __ldg(tab.slices + sidx);
         const int w = sl.x, row_lo = sl.y, row_hi = sl.z;
         const int m = tab.m[w], pitch = tab.pitch[w];
-        const uint32_t *len = tab.len + tab.len_off[w];
+        const uint8_t *w8n = tab.w8n + tab.w8_off[w];            // natural order; prep_cols ran before this kernel
         const uint32_t *x = tab.x + tab.x_off[w];
         const uint8_t *lab = tab.labels + tab.lab_off[w];
         const uint32_t *heavy = tab.heavy + tab.heavy_off[w];
@@ -113,85 +218,30 @@ __global__ void __launch_bounds__(PREP_THREADS, 4) prep_rows_kernel(const __grid
         uint32_t *xh = tab.xh + tab.xh_off[w];
         int32_t *A = tab.A + tab.row_off[w];
         const int64_t wo = tab.word_off[w];
-        for (int c0 = 0; c0 < m || c0 == 0; c0 += 4 * LUT_POS) {
-            for (int p = threadIdx.x; p < LUT_POS; p += PREP_THREADS) {
-                const int k = c0 + 4 * p;
-                const uint32_t l0 = (k < m) ? __ldg(len + k) : 0u, l1 = (k + 1 < m) ? __ldg(len + k + 1) : 0u;
-                const uint32_t l2 = (k + 2 < m) ? __ldg(len + k + 2) : 0u, l3 = (k + 3 < m) ? __ldg(len + k + 3) : 0u;
+        for (int c0 = 0; c0 < m || c0 == 0; c0 += 32 * PM_WORDS) {   // groups of 2048 nodes = 64 presence words
+            // plane p of word wv: bit j = bit p of the byte weight of node c0 + 32 wv + j (ballot over the 32 nodes)
+            for (int wv = warp; wv < PM_WORDS; wv += PREP_THREADS / 32) {
+                const int k = c0 + wv * 32 + lane;
+                const uint32_t b = (k < m) ? (uint32_t)w8n[k] : 0u;
 #pragma unroll
-                for (int v = 0; v < 16; ++v)
-                    s_lut[v][p] = ((v & 1) ? l0 : 0u) + ((v & 2) ? l1 : 0u) + ((v & 4) ? l2 : 0u) + ((v & 8) ? l3 : 0u);
-            }
-            if (threadIdx.x < 64) { s_any[threadIdx.x] = 0u; s_all[threadIdx.x] = 0xffffffffu; }
-            __syncthreads();
-            const int w0 = c0 >> 5;                       // first word of this slice of nodes
-            const int passes = (m - c0 > 1024) ? 2 : 1;   // 32 words (1024 nodes) per warp pass
-            constexpr int RU = 4;                         // rows in flight per warp (memory-level parallelism)
-            uint32_t any[2] = {0u, 0u}, all[2] = {0xffffffffu, 0xffffffffu};
-            for (int i0 = row_lo + warp * RU; i0 < row_hi; i0 += (PREP_THREADS / 32) * RU) {
-                uint32_t acc[RU], word[2][RU];
-                bool segrow[RU];
-#pragma unroll
-                for (int r = 0; r < RU; ++r) {
-                    acc[r] = 0u;
-                    segrow[r] = (i0 + r < row_hi) && (lab[i0 + r] & IMPOP_LAB_SEG);
-#pragma unroll
-                    for (int ps = 0; ps < 2; ++ps) {
-                        const int wd = ps * 32 + lane;
-                        word[ps][r] = (ps < passes && i0 + r < row_hi && w0 + wd < pitch)
-                                          ? __ldg(x + (size_t)(i0 + r) * pitch + w0 + wd) : 0u;
-                    }
-                }
-#pragma unroll
-                for (int ps = 0; ps < 2; ++ps) {
-                    if (ps >= passes) break;
-#pragma unroll
-                    for (int r = 0; r < RU; ++r) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const uint32_t src = __shfl_sync(0xffffffffu, word[ps][r], q * 4 + (lane >> 3));
-                            const uint32_t nib = (src >> ((lane & 7) * 4)) & 15u;
-                            acc[r] += s_lut[nib][ps * 256 + q * 32 + lane];
-                        }
-                        if (segrow[r]) { any[ps] |= word[ps][r]; all[ps] &= word[ps][r]; }
-                    }
-                }
-                if (c0 == 0) {                                       // padding words of the heavy bits: zero
-#pragma unroll
-                    for (int r = 0; r < RU; ++r)
-                        for (int hw = hw_used + lane; hw < hwords && i0 + r < row_hi; hw += 32) xh[(size_t)(i0 + r) * hwords + hw] = 0u;
-                }
-                for (int hw = 0; hw < hw_used; ++hw) {               // heavy columns: one table entry per lane
-                    const uint32_t ent = heavy[hw * 32 + lane];
-                    const uint32_t col = ent >> 8;
-                    const int rel = (int)(col >> 5) - w0;            // word of the node within this slice of nodes
-                    const bool in = (ent & 255u) && rel >= 0 && rel < 32 * passes;
-                    if (c0 > 0 && !__any_sync(0xffffffffu, in)) continue;
-#pragma unroll
-                    for (int r = 0; r < RU; ++r) {
-                        const uint32_t w_lo = __shfl_sync(0xffffffffu, word[0][r], rel & 31);
-                        const uint32_t w_hi = __shfl_sync(0xffffffffu, word[1][r], rel & 31);
-                        const uint32_t wsrc = (rel >= 32) ? w_hi : w_lo;
-                        const uint32_t bw = __ballot_sync(0xffffffffu, in && ((wsrc >> (col & 31u)) & 1u));
-                        if (lane == 0 && i0 + r < row_hi) {
-                            uint32_t *dst = xh + (size_t)(i0 + r) * hwords + hw;
-                            if (c0 == 0) *dst = bw;                  // first slice defines the word, later ones add bits
-                            else if (bw) *dst |= bw;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < RU; ++r) {
-                    uint32_t a = acc[r];
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-                    if (lane == 0 && i0 + r < row_hi) A[i0 + r] = (int32_t)(a + (c0 ? (uint32_t)A[i0 + r] : 0u));
+                for (int p = 0; p < 8; ++p) {
+                    const uint32_t msk = __ballot_sync(0xffffffffu, (b >> p) & 1u);
+                    if (lane == p) s_pm[p][wv] = msk;
                 }
             }
-            atomicOr(&s_any[lane], any[0]); atomicAnd(&s_all[lane], all[0]);
-            if (passes > 1) { atomicOr(&s_any[32 + lane], any[1]); atomicAnd(&s_all[32 + lane], all[1]); }
+            if (threadIdx.x < PM_WORDS) { s_any[threadIdx.x] = 0u; s_all[threadIdx.x] = 0xffffffffu; }
             __syncthreads();
-            if (threadIdx.x < 64 && w0 + threadIdx.x < ((m + 31) >> 5)) {
+            const int w0 = c0 >> 5;                       // first word of this group of nodes
+            const bool two = m - c0 > 1024;               // 32 words (1024 nodes) per warp pass
+            if (c0 == 0) {
+                if (two) prep_rows_group<2, true>(s_pm, s_any, s_all, x, pitch, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+                else prep_rows_group<1, true>(s_pm, s_any, s_all, x, pitch, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+            } else {
+                if (two) prep_rows_group<2, false>(s_pm, s_any, s_all, x, pitch, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+                else prep_rows_group<1, false>(s_pm, s_any, s_all, x, pitch, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+            }
+            __syncthreads();
+            if (threadIdx.x < PM_WORDS && w0 + threadIdx.x < ((m + 31) >> 5)) {
                 atomicOr(&tab.seg_any[wo + w0 + threadIdx.x], s_any[threadIdx.x]);
                 atomicAnd(&tab.seg_all[wo + w0 + threadIdx.x], s_all[threadIdx.x]);
             }
