@@ -280,12 +280,13 @@ def run_ours(args):
                 continue
             st = streams[k % 2]
             with torch.cuda.stream(st):
-                # set-up first (its small table upload), the big copy last: a small copy enqueued after the big one would
-                # wait on the copy engine behind the OTHER stream's big copy and delay this sub-batch's kernels
-                b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], WINDOW_BP, node_len_host=hl[lo:hi], stream=st)
+                # this sub-batch's copies first, its set-up (host-side tables + their small upload) while they run: the copy
+                # engine is the bottleneck of the step and must never wait for the host; the table upload lands in the
+                # engine's FIFO right behind this sub-batch's own big copy, ahead of the OTHER stream's next one
                 dlabs[k].copy_(hlab, non_blocking=True)
                 dl[lo:hi].copy_(hl[lo:hi], non_blocking=True)
                 dx[lo:hi].copy_(hx[lo:hi], non_blocking=True)
+                b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], WINDOW_BP, node_len_host=hl[lo:hi], stream=st)
                 b.stats(algo, stream=st, out_stats=ds[lo:hi], out_counts=dc[lo:hi])
                 hs[lo:hi].copy_(ds[lo:hi], non_blocking=True)
                 hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)
