@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libimpop_b200.so")
-SOURCES = ("api.cu", "window_kernels.cu", "aux_kernels.cu")
+SOURCES = ("api.cu", "window_kernels.cu", "aux_kernels.cu", "ingest.cpp")
 HEADERS = ("common.cuh", "stats_math.cuh", os.path.join("..", "..", "include", "impop_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-pthread", "-shared"]

@@ -1,0 +1,255 @@
+// Host-side ingest of the C ABI (include/impop_b200.h, "Ingest"): GFA v1 text of one window -> bit-packed
+// haplotype x node presence matrix, node lengths, path names (and optional multiset coverage counts).
+//
+// Replaces the text hand-off in front of the similarity tool: the reference extracts a window graph and lets
+// `odgi similarity -i tmp.gfa` walk its paths (run_pica2_odgi.sh:60-96); `impg similarity -r REGION` does the
+// same from alignments (run_h-fst.sh:65-67).  One matrix row per path line (P or W), as `odgi similarity` with
+// no grouping flags makes one group per path; node k = k-th S line.  Plain C++ on the host: no CUDA in here.
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/impop_b200.h"
+
+namespace {
+
+struct Line {
+    const char *p, *e;   // [p, e): one line without its terminator
+};
+
+// Next line of [cur, end); false at the end.  Strips a trailing '\r'.
+inline bool next_line(const char *&cur, const char *end, Line &ln) {
+    if (cur >= end) return false;
+    const char *nl = (const char *)memchr(cur, '\n', (size_t)(end - cur));
+    const char *e = nl ? nl : end;
+    ln.p = cur;
+    ln.e = (e > cur && e[-1] == '\r') ? e - 1 : e;
+    cur = nl ? nl + 1 : end;
+    return true;
+}
+
+// k-th tab-separated field of a line (0-based); false if the line has fewer fields.
+inline bool field(const Line &ln, int k, const char *&fp, const char *&fe) {
+    const char *p = ln.p;
+    for (int i = 0; i < k; ++i) {
+        const char *t = (const char *)memchr(p, '\t', (size_t)(ln.e - p));
+        if (!t) return false;
+        p = t + 1;
+    }
+    const char *t = (const char *)memchr(p, '\t', (size_t)(ln.e - p));
+    fp = p;
+    fe = t ? t : ln.e;
+    return true;
+}
+
+inline uint64_t hash_bytes(const char *p, size_t n) {   // FNV-1a, finalised
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    return h;
+}
+
+// Open-addressing map segment name -> node index (names are slices of the caller's text).
+struct SegMap {
+    struct Slot { const char *p; uint32_t len; int32_t idx; };
+    std::vector<Slot> slots;
+    uint64_t mask = 0;
+    void init(size_t n) {
+        size_t cap = 16;
+        while (cap < 2 * n + 2) cap <<= 1;
+        slots.assign(cap, Slot{nullptr, 0u, -1});
+        mask = cap - 1;
+    }
+    bool insert(const char *p, size_t len, int32_t idx) {       // false: duplicate name
+        uint64_t h = hash_bytes(p, len) & mask;
+        while (slots[h].p) {
+            if (slots[h].len == len && memcmp(slots[h].p, p, len) == 0) return false;
+            h = (h + 1) & mask;
+        }
+        slots[h] = Slot{p, (uint32_t)len, idx};
+        return true;
+    }
+    int32_t find(const char *p, size_t len) const {
+        uint64_t h = hash_bytes(p, len) & mask;
+        while (slots[h].p) {
+            if (slots[h].len == len && memcmp(slots[h].p, p, len) == 0) return slots[h].idx;
+            h = (h + 1) & mask;
+        }
+        return -1;
+    }
+};
+
+// Length of a segment: its sequence, or the LN:i: tag when the sequence is '*'.
+inline bool segment_length(const Line &ln, uint64_t &len) {
+    const char *sp, *se;
+    if (!field(ln, 2, sp, se)) return false;
+    if (!(se - sp == 1 && *sp == '*')) { len = (uint64_t)(se - sp); return true; }
+    for (int k = 3;; ++k) {
+        const char *tp, *te;
+        if (!field(ln, k, tp, te)) break;
+        if (te - tp > 5 && memcmp(tp, "LN:i:", 5) == 0) {
+            uint64_t v = 0;
+            for (const char *q = tp + 5; q < te; ++q) {
+                if (*q < '0' || *q > '9') return false;
+                v = v * 10 + (uint64_t)(*q - '0');
+                if (v > 0xFFFFFFFFull) return false;
+            }
+            len = v;
+            return true;
+        }
+    }
+    len = 0;      // '*' without LN: length unknown, counts as 0 (contributes nothing to any statistic)
+    return true;
+}
+
+// Calls f(name_begin, name_end) for every step of a P line's segment list ("11+,12-,...") or a W line's walk
+// (">11<12..."); false on a malformed step.
+template <typename F>
+inline bool for_each_step(char kind, const char *p, const char *e, F f) {
+    if (kind == 'P') {
+        if (e - p == 1 && *p == '*') return true;
+        while (p < e) {
+            const char *c = (const char *)memchr(p, ',', (size_t)(e - p));
+            const char *se = c ? c : e;
+            if (se - p < 2 || (se[-1] != '+' && se[-1] != '-')) return false;
+            if (!f(p, se - 1)) return false;
+            p = c ? c + 1 : e;
+        }
+        return true;
+    }
+    if (e - p == 1 && *p == '*') return true;
+    while (p < e) {
+        if (*p != '>' && *p != '<') return false;
+        const char *q = p + 1;
+        while (q < e && *q != '>' && *q != '<') ++q;
+        if (q == p + 1) return false;
+        if (!f(p + 1, q)) return false;
+        p = q;
+    }
+    return true;
+}
+
+// The row name of a path line.  P: the path name as it stands.  W: sample#hap#seqid[:start-end] (PanSN).
+inline bool path_name(char kind, const Line &ln, std::string &out) {
+    const char *a, *b;
+    out.clear();
+    if (kind == 'P') {
+        if (!field(ln, 1, a, b)) return false;
+        out.assign(a, b);
+        return true;
+    }
+    for (int k = 1; k <= 3; ++k) {
+        if (!field(ln, k, a, b)) return false;
+        if (k > 1) out.push_back('#');
+        out.append(a, b);
+    }
+    const char *s0, *s1, *e0, *e1;
+    if (!field(ln, 4, s0, s1) || !field(ln, 5, e0, e1)) return false;
+    if (!(s1 - s0 == 1 && *s0 == '*') && !(e1 - e0 == 1 && *e0 == '*')) {
+        out.push_back(':'); out.append(s0, s1); out.push_back('-'); out.append(e0, e1);
+    }
+    return true;
+}
+
+inline int steps_field(char kind) { return kind == 'P' ? 2 : 6; }
+
+}  // namespace
+
+extern "C" {
+
+int impop_gfa_scan(const char *text, int64_t bytes, impop_gfa_info_t *info) {
+    if (!text || bytes < 0 || !info) return IMPOP_ERR_ARG;
+    impop_gfa_info_t out = {0, 0, 0, 0, 0};
+    const char *cur = text, *end = text + bytes;
+    Line ln;
+    std::string name;
+    int64_t lineno = 0;
+    while (next_line(cur, end, ln)) {
+        ++lineno;
+        if (ln.e - ln.p < 2 || ln.p[1] != '\t') continue;
+        const char kind = ln.p[0];
+        if (kind == 'S') {
+            ++out.segments;
+        } else if (kind == 'P' || kind == 'W') {
+            if (!path_name(kind, ln, name)) { out.error_line = lineno; *info = out; return IMPOP_ERR_ARG; }
+            const char *sp, *se;
+            if (!field(ln, steps_field(kind), sp, se)) { out.error_line = lineno; *info = out; return IMPOP_ERR_ARG; }
+            int64_t steps = 0;
+            if (!for_each_step(kind, sp, se, [&](const char *, const char *) { ++steps; return true; })) {
+                out.error_line = lineno; *info = out; return IMPOP_ERR_ARG;
+            }
+            ++out.paths;
+            out.name_bytes += (int64_t)name.size() + 1;
+            out.steps += steps;
+        }
+    }
+    *info = out;
+    return IMPOP_OK;
+}
+
+int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_t *x_bits_host, uint32_t *node_len_host,
+                   uint16_t *counts_host, char *names_host, int64_t *name_off_host, int64_t *error_line) {
+    if (error_line) *error_line = 0;
+    if (!text || bytes < 0 || pitch_words < 0 || pitch_words % 4 != 0) return IMPOP_ERR_ARG;
+    impop_gfa_info_t info;
+    int rc = impop_gfa_scan(text, bytes, &info);
+    if (rc != IMPOP_OK) { if (error_line) *error_line = info.error_line; return rc; }
+    if ((int64_t)pitch_words * 32 < info.segments) return IMPOP_ERR_ARG;
+    if ((info.paths && (!x_bits_host || !names_host || !name_off_host)) || (info.segments && !node_len_host)) return IMPOP_ERR_ARG;
+    if (info.segments > 0x7FFFFFFFll || info.paths > 0x7FFFFFFFll) return IMPOP_ERR_RANGE;
+
+    // pass 1: segments in file order
+    SegMap map;
+    map.init((size_t)info.segments);
+    const char *cur = text, *end = text + bytes;
+    Line ln;
+    int64_t lineno = 0;
+    int32_t seg = 0;
+    while (next_line(cur, end, ln)) {
+        ++lineno;
+        if (ln.e - ln.p < 2 || ln.p[1] != '\t' || ln.p[0] != 'S') continue;
+        const char *np, *ne;
+        uint64_t len = 0;
+        if (!field(ln, 1, np, ne) || ne == np || !segment_length(ln, len) || len > 0xFFFFFFFFull ||
+            !map.insert(np, (size_t)(ne - np), seg)) {
+            if (error_line) *error_line = lineno;
+            return IMPOP_ERR_ARG;
+        }
+        node_len_host[seg++] = (uint32_t)len;
+    }
+    // pass 2: path lines in file order
+    if (info.paths) memset(x_bits_host, 0, sizeof(uint32_t) * (size_t)info.paths * (size_t)pitch_words);
+    if (counts_host && info.paths) memset(counts_host, 0, sizeof(uint16_t) * (size_t)info.paths * (size_t)info.segments);
+    cur = text; lineno = 0;
+    int64_t row = 0, off = 0;
+    std::string name;
+    while (next_line(cur, end, ln)) {
+        ++lineno;
+        if (ln.e - ln.p < 2 || ln.p[1] != '\t') continue;
+        const char kind = ln.p[0];
+        if (kind != 'P' && kind != 'W') continue;
+        path_name(kind, ln, name);
+        name_off_host[row] = off;
+        memcpy(names_host + off, name.c_str(), name.size() + 1);
+        off += (int64_t)name.size() + 1;
+        uint32_t *xr = x_bits_host + (size_t)row * (size_t)pitch_words;
+        uint16_t *cr = counts_host ? counts_host + (size_t)row * (size_t)info.segments : nullptr;
+        const char *sp, *se;
+        field(ln, steps_field(kind), sp, se);
+        const bool ok = for_each_step(kind, sp, se, [&](const char *a, const char *b) {
+            const int32_t k = map.find(a, (size_t)(b - a));
+            if (k < 0) return false;                      // step over a segment the file does not define
+            xr[k >> 5] |= 1u << (k & 31);
+            if (cr && cr[k] != 0xFFFFu) ++cr[k];
+            return true;
+        });
+        if (!ok) { if (error_line) *error_line = lineno; return IMPOP_ERR_ARG; }
+        ++row;
+    }
+    if (info.paths) name_off_host[row] = off;
+    return IMPOP_OK;
+}
+
+}  // extern "C"

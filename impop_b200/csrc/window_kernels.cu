@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
 // FIRST: the group starts at node 0 (defines A_i and the heavy words; later groups add to them).
 template <int PASSES, bool FIRST>
 __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS], uint32_t *s_any, uint32_t *s_all,
-                                                const uint32_t *x, int pitch, const uint8_t *lab, int row_lo, int row_hi,
+                                                const uint32_t *x, int pitch, int wlim, const uint8_t *lab, int row_lo, int row_hi,
                                                 int w0, const uint32_t *heavy, int hwords, int hw_used, uint32_t *xh,
                                                 int32_t *A) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,7 +134,7 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
 #pragma unroll
             for (int ps = 0; ps < PASSES; ++ps) {
                 const int wd = w0 + ps * 32 + lane;
-                word[ps][r] = (rv && wd < pitch) ? __ldg(x + (size_t)(i0 + r) * pitch + wd) : 0u;
+                word[ps][r] = (rv && wd < wlim) ? __ldg(x + (size_t)(i0 + r) * pitch + wd) : 0u;
             }
         }
 #pragma unroll
@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
         const int4 sl = __ldg(tab.slices + sidx);
         const int w = sl.x, row_lo = sl.y, row_hi = sl.z;
         const int m = tab.m[w], pitch = tab.pitch[w];
+        const int wlim = min(pitch, ((m + 127) >> 7) << 2);      // words of a row that can hold nodes < m (16-byte groups):
+                                                                 // a window may be a column range of a wider matrix
         const uint8_t *w8n = tab.w8n + tab.w8_off[w];            // natural order; prep_cols ran before this kernel
         const uint32_t *x = tab.x + tab.x_off[w];
         const uint8_t *lab = tab.labels + tab.lab_off[w];
@@ -234,11 +236,11 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
             const int w0 = c0 >> 5;                       // first word of this group of nodes
             const bool two = m - c0 > 1024;               // 32 words (1024 nodes) per warp pass
             if (c0 == 0) {
-                if (two) prep_rows_group<2, true>(s_pm, s_any, s_all, x, pitch, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
-                else prep_rows_group<1, true>(s_pm, s_any, s_all, x, pitch, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+                if (two) prep_rows_group<2, true>(s_pm, s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+                else prep_rows_group<1, true>(s_pm, s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
             } else {
-                if (two) prep_rows_group<2, false>(s_pm, s_any, s_all, x, pitch, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
-                else prep_rows_group<1, false>(s_pm, s_any, s_all, x, pitch, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+                if (two) prep_rows_group<2, false>(s_pm, s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+                else prep_rows_group<1, false>(s_pm, s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
             }
             __syncthreads();
             if (threadIdx.x < PM_WORDS && w0 + threadIdx.x < ((m + 31) >> 5)) {
@@ -373,7 +375,10 @@ __device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const d
 // warps, and items flow through without CTA-wide barriers.
 // ==========================================================================================
 #ifndef IMPOP_PROD_SLEEP
-#define IMPOP_PROD_SLEEP 200
+#define IMPOP_PROD_SLEEP 200     // ns between polls of a waiting producer warp
+#endif
+#ifndef IMPOP_EPI_SLEEP
+#define IMPOP_EPI_SLEEP 20       // ns between polls of a waiting epilogue warp
 #endif
 #ifndef IMPOP_PROD_WARPS
 #define IMPOP_PROD_WARPS 12      // 4 for the A tile (lane = row) + 8 or 4 for the B tile (1 or 2 rows per lane)
@@ -785,7 +790,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             const int slot = k % WS_TABLES;
             const int64_t t = item_of(u);
             const uint32_t buf = (uint32_t)k & 1u;                        // item parity = TMEM buffer
-            if (alive) alive = mbar_wait<20>(&sh.tbl_full[slot], (uint32_t)(k / WS_TABLES) & 1u, tab.err);
+            if (alive) alive = mbar_wait<IMPOP_EPI_SLEEP>(&sh.tbl_full[slot], (uint32_t)(k / WS_TABLES) & 1u, tab.err);
             const EpiCols &col = sh.col[slot];
             const int4 geo = *reinterpret_cast<const int4 *>(&col.n);     // n, first row, first column, columns
             const int n = geo.x, col0 = geo.z;
@@ -807,7 +812,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             const int cbeg = c_lo + cnt * hh / H, cend = c_lo + cnt * (hh + 1) / H;
             PROF_AUX_END
             if (have_acc) {
-                if (alive) alive = mbar_wait<20>(&sh.acc_full[buf], (buf ? uses1 : uses0) & 1u, tab.err);
+                if (alive) alive = mbar_wait<IMPOP_EPI_SLEEP>(&sh.acc_full[buf], (buf ? uses1 : uses0) & 1u, tab.err);
                 tc_fence_after();
             }
             PROF_WAIT_END

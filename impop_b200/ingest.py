@@ -1,0 +1,149 @@
+"""Ingest for matrix mode: window graphs (GFA v1) -> bit-packed haplotype x node matrices + node lengths + names.
+
+The reference never holds a matrix: per window it extracts a graph and hands *text* to the similarity tool
+(`odgi similarity -i tmp.gfa`, run_pica2_odgi.sh:60-96; `impg similarity -r REGION`, run_h-fst.sh:65-67), whose
+all-pairs TSV the scripts parse again.  Here the window graph is parsed once by libimpop_b200's host-side reader
+(`impop_gfa_scan` / `impop_gfa_fill`, include/impop_b200.h) into exactly the arrays `WindowBatch.from_windows`
+uploads, and a set of windows can be kept in one compact binary container so that nothing round-trips through
+text between extraction and the GPU.  Only parsing and name handling happen on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native
+from ._native import GfaInfo, NativeError, lib
+
+
+@dataclass
+class GraphWindow:
+    """One window: rows = paths (file order), columns = segments (file order)."""
+    names: list            # row names, e.g. 'HG00097#1#CM094061.1:109468899-109469099'
+    x_bits: np.ndarray     # [n, pitch_words] uint32, bit k & 31 of word k >> 5 = node k present
+    node_len: np.ndarray   # [m] uint32
+    counts: np.ndarray | None = None   # [n, m] uint16 visit counts (multiset coverage), when requested
+    region: str | None = None
+    length: int = 0        # window length L in bp (BED end - start); 0 = unknown
+
+    @property
+    def n(self) -> int:
+        return self.x_bits.shape[0]
+
+    @property
+    def m(self) -> int:
+        return self.node_len.shape[0]
+
+
+def _pitch_for(m: int) -> int:
+    return max(4, ((m + 127) // 128) * 4)
+
+
+def parse_gfa(text, want_counts: bool = False, region: str | None = None, length: int = 0) -> GraphWindow:
+    """GFA v1 text (bytes / str / path-like object with .read) -> GraphWindow.  Raises NativeError with the
+    offending line number on malformed input."""
+    if hasattr(text, "read"):
+        text = text.read()
+    if isinstance(text, str):
+        text = text.encode()
+    L = lib()
+    info = GfaInfo()
+    rc = L.impop_gfa_scan(text, len(text), C.byref(info))
+    if rc:
+        raise NativeError(rc, "impop_gfa_scan", f"malformed GFA at line {info.error_line}")
+    n, m = int(info.paths), int(info.segments)
+    pitch = _pitch_for(m)
+    x = np.zeros((n, pitch), dtype=np.uint32)
+    node_len = np.zeros(m, dtype=np.uint32)
+    counts = np.zeros((n, m), dtype=np.uint16) if want_counts else None
+    names_buf = np.zeros(max(int(info.name_bytes), 1), dtype=np.uint8)
+    name_off = np.zeros(n + 1, dtype=np.int64)
+    err_line = C.c_int64(0)
+    rc = L.impop_gfa_fill(text, len(text), pitch, x.ctypes.data, node_len.ctypes.data,
+                          counts.ctypes.data if counts is not None else None, names_buf.ctypes.data,
+                          name_off.ctypes.data, C.byref(err_line))
+    if rc:
+        raise NativeError(rc, "impop_gfa_fill", f"malformed GFA at line {err_line.value}")
+    raw = names_buf.tobytes()
+    names = [raw[name_off[i]:name_off[i + 1] - 1].decode() for i in range(n)]
+    return GraphWindow(names, x, node_len, counts, region, int(length))
+
+
+def read_gfa(path, want_counts: bool = False, region: str | None = None, length: int = 0) -> GraphWindow:
+    with open(path, "rb") as fh:
+        return parse_gfa(fh.read(), want_counts, region, length)
+
+
+def write_gfa(handle, names, x: np.ndarray, node_len: np.ndarray, walks: bool = False) -> None:
+    """Emit a window as GFA v1 (what the synthetic generator hands to the text path and to tests): one S line per
+    node (sequence 'N' * len up to 64 bp, else '*' + LN:i:), one P (or W) line per haplotype listing its nodes."""
+    x = np.asarray(x).astype(bool)
+    handle.write("H\tVN:Z:1.0\n")
+    for k, ln in enumerate(np.asarray(node_len).tolist()):
+        if 0 < ln <= 64:
+            handle.write(f"S\t{k + 1}\t{'N' * ln}\n")
+        else:
+            handle.write(f"S\t{k + 1}\t*\tLN:i:{ln}\n")
+    for name, row in zip(names, x):
+        idx = np.flatnonzero(row) + 1
+        if walks:
+            sample, hap, rest = name.split("#", 2)
+            seqid, _, rng = rest.partition(":")
+            s, _, e = rng.partition("-")
+            handle.write(f"W\t{sample}\t{hap}\t{seqid}\t{s or '*'}\t{e or '*'}\t" + "".join(f">{v}" for v in idx) + "\n")
+        else:
+            handle.write(f"P\t{name}\t" + (",".join(f"{v}+" for v in idx) if len(idx) else "*") + "\t*\n")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Compact container for a set of windows (one .npz: every array concatenated, offsets per window)
+# ------------------------------------------------------------------------------------------------------------
+def save_batch(path, windows) -> None:
+    """Write windows (GraphWindow list) as one binary file: bit matrices, node lengths, names, regions, lengths."""
+    n = np.array([w.n for w in windows], dtype=np.int32)
+    m = np.array([w.m for w in windows], dtype=np.int32)
+    pitch = np.array([w.x_bits.shape[1] for w in windows], dtype=np.int32)
+    x = np.concatenate([w.x_bits.reshape(-1) for w in windows]) if windows else np.zeros(0, np.uint32)
+    nl = np.concatenate([w.node_len for w in windows]) if windows else np.zeros(0, np.uint32)
+    names = "\n".join("\t".join(w.names) for w in windows)
+    regions = "\n".join(w.region or "" for w in windows)
+    L = np.array([w.length for w in windows], dtype=np.int64)
+    np.savez(path, format=np.array([1]), n=n, m=m, pitch=pitch, x=x.astype(np.uint32), node_len=nl.astype(np.uint32),
+             names=np.frombuffer(names.encode(), dtype=np.uint8), regions=np.frombuffer(regions.encode(), dtype=np.uint8),
+             length=L)
+
+
+def load_batch(path) -> list:
+    z = np.load(path)
+    n, m, pitch = z["n"], z["m"], z["pitch"]
+    names = z["names"].tobytes().decode().split("\n") if len(n) else []
+    regions = z["regions"].tobytes().decode().split("\n") if len(n) else []
+    out, xo, lo = [], 0, 0
+    for w in range(len(n)):
+        xs = int(n[w]) * int(pitch[w])
+        out.append(GraphWindow(names[w].split("\t") if names[w] else [],
+                               z["x"][xo:xo + xs].reshape(int(n[w]), int(pitch[w])).copy(),
+                               z["node_len"][lo:lo + int(m[w])].copy(), None, regions[w] or None, int(z["length"][w])))
+        xo += xs
+        lo += int(m[w])
+    return out
+
+
+def labels_from_names(names, pop_a=None, pop_b=None, subset=None, seg=None) -> np.ndarray:
+    """Label byte per row from name sets (after h-fst.py:64-82 expansion / run_tajd.sh -l subsetting):
+    SUBSET / SEG default to every row."""
+    lab = np.zeros(len(names), dtype=np.uint8)
+    for i, s in enumerate(names):
+        f = 0
+        if subset is None or s in subset:
+            f |= _native.LAB_SUBSET
+        if seg is None or s in seg:
+            f |= _native.LAB_SEG
+        if pop_a is not None and s in pop_a:
+            f |= _native.LAB_A
+        if pop_b is not None and s in pop_b:
+            f |= _native.LAB_B
+        lab[i] = f
+    return lab

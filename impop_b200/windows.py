@@ -54,3 +54,88 @@ def write_tsv(handle, kind: str, rows):
     handle.write("\t".join(HEADERS[kind]) + "\n")
     for row in rows:
         handle.write("\t".join(row) + "\n")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Matrix-mode driver: window graphs in, the wrappers' TSVs out (replaces the per-window loops of
+# run_pica2_impg.sh:126-192, run_h-fst.sh:155-194 and run_tajd.sh:103-198 -- one batch on the GPU instead of
+# 3-6 process spawns per BED row)
+# ------------------------------------------------------------------------------------------------------------
+def batch_from_graphs(ctx, graphs, pop_a_ids=None, pop_b_ids=None, subset_ids=None):
+    """GraphWindow list (impop_b200.ingest) -> WindowBatch with per-window labels.  Population / subset identifiers are
+    assembly names or PanSN prefixes, expanded per window against its row names exactly as h-fst.py:64-82 does."""
+    from . import ingest
+    from .engine import WindowBatch
+    from .hfst import expand_population
+    wins = []
+    for g in graphs:
+        pa = expand_population(pop_a_ids, g.names)[0] if pop_a_ids else None
+        pb = expand_population(pop_b_ids, g.names)[0] if pop_b_ids else None
+        sub = expand_population(subset_ids, g.names)[0] if subset_ids else None
+        lab = ingest.labels_from_names(g.names, pa, pb, sub, sub)
+        wins.append((g.x_bits, g.node_len, lab, g.length))
+    return WindowBatch.from_windows(ctx, wins)
+
+
+def main(argv=None):
+    """impop-windows: windowed pi / Hudson Fst / Tajima's D straight from window graphs.
+
+        impop-windows.py --gfa-list windows.tsv [-a popA.txt -b popB.txt] [-s subset.txt]
+                         [--pi-out pi.tsv] [--fst-out fst.tsv] [--tajd-out tajd.tsv] [--save-batch windows.npz]
+        impop-windows.py --batch windows.npz ...
+
+    windows.tsv: one line per window, `REGION<TAB>path/to/window.gfa` with REGION like CHM13#0#chr2:100000-150000
+    (its end - start is the window length L the wrappers pass as -l)."""
+    import argparse
+    import re
+    import sys
+
+    from . import ingest
+    from .engine import Context
+    from .hfst import read_subset_file
+
+    ap = argparse.ArgumentParser(prog="impop-windows", description=main.__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    src = ap.add_mutually_exclusive_group(required=True)
+    src.add_argument("--gfa-list", help="TSV: REGION <tab> GFA file of that window")
+    src.add_argument("--batch", help="binary container written by --save-batch")
+    ap.add_argument("-a", "--pop-a", help="file listing population A (h-fst.py -a)")
+    ap.add_argument("-b", "--pop-b", help="file listing population B (h-fst.py -b)")
+    ap.add_argument("-s", "--subset", help="file listing the samples pi / S / Tajima's D are computed over (run_tajd.sh -l)")
+    ap.add_argument("--pi-out"), ap.add_argument("--fst-out"), ap.add_argument("--tajd-out")
+    ap.add_argument("--save-batch", help="also write the parsed windows as one binary container")
+    ap.add_argument("--device", type=int, default=0)
+    args = ap.parse_args(argv)
+
+    if args.batch:
+        graphs = ingest.load_batch(args.batch)
+    else:
+        graphs = []
+        with open(args.gfa_list) as fh:
+            for line in fh:
+                if not line.strip() or line.startswith("#"):
+                    continue
+                region, path = line.rstrip("\n").split("\t")[:2]
+                mt = re.search(r":(\d+)-(\d+)$", region)
+                graphs.append(ingest.read_gfa(path, region=region, length=int(mt.group(2)) - int(mt.group(1)) if mt else 0))
+    if args.save_batch:
+        ingest.save_batch(args.save_batch, graphs)
+    if (args.fst_out is None) != (args.pop_a is None or args.pop_b is None):
+        ap.error("--fst-out needs both -a and -b (and vice versa)")
+    pop_a = read_subset_file(args.pop_a) if args.pop_a else None
+    pop_b = read_subset_file(args.pop_b) if args.pop_b else None
+    subset = read_subset_file(args.subset) if args.subset else None
+    ctx = Context(args.device)
+    batch = batch_from_graphs(ctx, graphs, pop_a, pop_b, subset)
+    stats, counts = batch.stats()
+    ctx.check()
+    stats, counts = stats.cpu().numpy(), counts.cpu().numpy()
+    batch.close()
+    regions = [g.region or f"window{i}" for i, g in enumerate(graphs)]
+    lengths = [g.length for g in graphs]
+    for path, kind, rows in ((args.pi_out, "pi", pi_rows(regions, lengths, stats)),
+                             (args.fst_out, "fst", fst_rows(regions, lengths, stats)),
+                             (args.tajd_out, "tajd", tajd_rows(regions, lengths, stats, counts))):
+        if path:
+            with (sys.stdout if path == "-" else open(path, "w")) as out:
+                write_tsv(out, kind, rows)
+    return 0

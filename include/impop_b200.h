@@ -15,7 +15,9 @@
  *    the stream and reports device-side errors (bad input, barrier time-out).
  *  - Bit layout of a window's presence matrix: haplotype i, node k -> bit (k & 31) of the
  *    32-bit word x[x_off + i * pitch_words + (k >> 5)].  pitch_words and x_off must be
- *    multiples of 4 (16-byte rows); bits at k >= m must be zero.
+ *    multiples of 4 (16-byte rows).  Bits at k >= m are ignored (their weight is zero), so a window may be a
+ *    column range of a wider matrix: x_off = its first 128-node group, pitch_words = the wide matrix's pitch,
+ *    node_len = 0 for the nodes of that group that precede the window (impop_b200/chromosome.py).
  *  - Exactness: intersections, path lengths and unions are exact integers; a window must
  *    satisfy sum(node_len) < 2^31 (checked on device -> IMPOP_ERR_RANGE at impop_check).
  *  - There is no CPU fallback anywhere: without a CUDA device impop_create fails.
@@ -189,6 +191,30 @@ int impop_cluster(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t 
  * member, the representative pica2.py:128 uses); weight_dev (nullable, n fp64) = |G|/n on seeds, 0 elsewhere. */
 int impop_greedy_groups(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t ld, double threshold,
                         int32_t *group_dev, double *weight_dev, void *stream);
+
+/* ---- Ingest (host side, no device work): GFA v1 text of one window -> presence matrix ------------------------
+ * Replaces the text hand-off in front of the similarity tool: `odgi similarity -i tmp.gfa` walks the paths of the
+ * extracted window graph (run_pica2_odgi.sh:60-96; `impg similarity -r REGION`, run_h-fst.sh:65-67, does the same
+ * from alignments).  Node k = the k-th S line (length = its sequence, or LN:i: when the sequence is '*'); one
+ * matrix row per P or W line in file order, as odgi similarity without grouping flags makes one group per path.
+ * Row names: the P line's path name as it stands (e.g. `HG00097#1#CM094061.1:109468899-109469099`, h-fst.py:21-22),
+ * or `sample#hap#seqid[:start-end]` for a W line.  Orientations are ignored (presence of the node, as the
+ * similarity tools count it).  A malformed line or a step over an undefined segment -> IMPOP_ERR_ARG with its
+ * 1-based line number. */
+typedef struct {
+    int64_t segments;    /* S lines = nodes m */
+    int64_t paths;       /* P + W lines = matrix rows n */
+    int64_t name_bytes;  /* bytes of all row names, each NUL-terminated */
+    int64_t steps;       /* path steps in total */
+    int64_t error_line;  /* 0, or the line impop_gfa_scan stopped at */
+} impop_gfa_info_t;
+int impop_gfa_scan(const char *text, int64_t bytes, impop_gfa_info_t *info);
+/* Caller-owned host buffers sized from impop_gfa_scan: x_bits [paths x pitch_words] u32 (pitch_words a multiple of 4,
+ * 32 * pitch_words >= segments; zeroed here), node_len [segments], names [name_bytes] with name_off [paths + 1],
+ * counts (optional, may be NULL) [paths x segments] u16 = how often the path visits the node (saturating; the
+ * multiset coverage a cyclic graph needs). */
+int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_t *x_bits_host, uint32_t *node_len_host,
+                   uint16_t *counts_host, char *names_host, int64_t *name_off_host, int64_t *error_line);
 
 /* Device self-test: the epilogue's range-restricted division against __ddiv_rn on `count` pseudo-random
  * in-range operand triples (I, A_i, A_j).  *mismatches_host must come back 0.  Synchronous. */

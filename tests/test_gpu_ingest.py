@@ -1,0 +1,66 @@
+"""Matrix mode from window graphs: GFA text -> libimpop_b200 reader -> fused GPU pass -> the
+wrappers' TSVs, against the CPU oracle run on the generator's own matrices."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from impop_b200 import ingest, synth, windows  # noqa: E402
+from oracle import clib  # noqa: E402
+from oracle.compare import row_mismatches  # noqa: E402
+
+
+def test_gfa_windows_through_the_driver(tmp_path):
+    n, L, W = 60, 50000, 4
+    ws = synth.make_windows(n, L, W, seed=0xB200 + 7, n_sites_override=60)
+    idx = np.arange(n)
+    names = synth.haplotype_names(n, "chr2", 0, L)
+    asm = synth.assembly_names(idx)
+    pop_a, pop_b = [asm[i] for i in range(0, 20)], [asm[i] for i in range(20, 45)]
+    (tmp_path / "a.txt").write_text("\n".join(pop_a) + "\n")
+    (tmp_path / "b.txt").write_text("# population B\n" + "\n".join(pop_b) + "\n")
+    listing = []
+    for w in range(W):
+        region = windows.region_name("chr2", w * L, (w + 1) * L)
+        path = tmp_path / f"w{w}.gfa"
+        with open(path, "w") as fh:
+            ingest.write_gfa(fh, names, ws.dense(w)[:, :ws.m], ws.node_len[w, :ws.m], walks=bool(w & 1))
+        listing.append(f"{region}\t{path}")
+    (tmp_path / "windows.tsv").write_text("\n".join(listing) + "\n")
+    rc = windows.main(["--gfa-list", str(tmp_path / "windows.tsv"), "-a", str(tmp_path / "a.txt"), "-b", str(tmp_path / "b.txt"),
+                       "--fst-out", str(tmp_path / "fst.tsv"), "--tajd-out", str(tmp_path / "tajd.tsv"),
+                       "--pi-out", str(tmp_path / "pi.tsv"), "--save-batch", str(tmp_path / "batch.npz")])
+    assert rc == 0
+    # the rows the reference-side restatement gives on the generator's matrices
+    lab = np.full(n, 1 | 8, dtype=np.uint8)
+    lab[0:20] |= 2            # asm[i] is the assembly-name spelling of names[i]
+    lab[20:45] |= 4
+    fst = (tmp_path / "fst.tsv").read_text().splitlines()
+    taj = (tmp_path / "tajd.tsv").read_text().splitlines()
+    pi = (tmp_path / "pi.tsv").read_text().splitlines()
+    assert fst[0].split("\t") == windows.HEADERS["fst"] and taj[0].split("\t") == windows.HEADERS["tajd"]
+    for w in range(W):
+        want_s, want_c = clib.window_stats(ws.x_bits[w], ws.m_pad, ws.node_len[w], lab, L)
+        f = fst[1 + w].split("\t")
+        assert f[0] == windows.region_name("chr2", w * L, (w + 1) * L) and f[1] == str(L)
+        got = np.array([float(v) for v in f[2:]])
+        assert np.allclose(got, [want_s[k] for k in (7, 2, 3, 4, 5, 6)], rtol=0, atol=6e-9)      # %.8f text
+        t = taj[1 + w].split("\t")
+        assert t[2] == str(n) and t[3] == str(int(want_c[7]))
+        assert pi[1 + w].split("\t")[-1] == f"{want_s[1]:.8f} (sequence length: {L})"
+    # the binary container reproduces the same statistics bit for bit
+    from impop_b200.engine import Context
+    ctx = Context(0)
+    graphs = ingest.load_batch(tmp_path / "batch.npz")
+    batch = windows.batch_from_graphs(ctx, graphs, set(pop_a), set(pop_b))
+    st, ct = batch.stats()
+    ctx.check()
+    st, ct = st.cpu().numpy(), ct.cpu().numpy()
+    for w in range(W):
+        want_s, want_c = clib.window_stats(ws.x_bits[w], ws.m_pad, ws.node_len[w], lab, L)
+        assert not row_mismatches(st[w], want_s, 1e-12)
+        assert (ct[w] == want_c).all()
+    batch.close()
+    ctx.close()

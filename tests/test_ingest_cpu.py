@@ -1,0 +1,81 @@
+"""Host-side ingest: the C reader of libimpop_b200 against the pure-Python restatement
+(oracle/gfa.py) on GFA v1 text with P and W lines, '*' sequences, repeated visits, CRLF, foreign record types."""
+import io
+
+import numpy as np
+import pytest
+
+from impop_b200 import ingest, synth
+from impop_b200._native import NativeError
+from oracle import gfa as ogfa
+from oracle import similarity
+
+HAND = ("H\tVN:Z:1.0\n"
+        "S\ts1\tACGT\n"
+        "S\t2\t*\tLN:i:300\n"
+        "S\tnode_3\tA\tRC:i:5\n"
+        "S\t44\t*\n"
+        "L\ts1\t+\t2\t+\t0M\n"
+        "P\tHG00097#1#CM094061.1:100-200\ts1+,2-,node_3+\t*\n"
+        "P\tHG00097#2#CM094062.1:100-200\ts1+,node_3+,s1+,s1-\t4M,1M\n"
+        "W\tHG002\t1\tchr2\t10\t90\t>2<44>2\n"
+        "W\tCHM13\t0\tchr2\t*\t*\t>s1\n"
+        "P\tempty#1#ctg\t*\t*\r\n"
+        "# trailing comment\n")
+
+
+def check(text):
+    names, x, counts, node_len = ogfa.parse(text)
+    win = ingest.parse_gfa(text, want_counts=True)
+    assert win.names == names
+    assert np.array_equal(win.node_len.astype(np.int64), node_len)
+    assert np.array_equal(similarity.unpack_bits(win.x_bits, len(node_len)), x)
+    assert np.array_equal(win.counts.astype(np.int64), np.minimum(counts, 65535))
+    assert win.x_bits.shape[1] % 4 == 0
+    return win
+
+
+def test_hand_written_gfa():
+    win = check(HAND)
+    assert win.names[2] == "HG002#1#chr2:10-90" and win.names[3] == "CHM13#0#chr2"
+    assert win.node_len.tolist() == [4, 300, 1, 0]
+    assert win.counts[1].tolist() == [3, 0, 1, 0]
+
+
+@pytest.mark.parametrize("walks", [False, True])
+def test_synthetic_window_round_trip(walks):
+    ws = synth.make_windows(40, 20000, 1, seed=77)
+    names = synth.haplotype_names(40, "chr2", 1000, 21000)
+    buf = io.StringIO()
+    ingest.write_gfa(buf, names, ws.dense(0)[:, :ws.m], ws.node_len[0, :ws.m], walks=walks)
+    win = check(buf.getvalue())
+    assert win.names == names and win.m == ws.m
+    assert np.array_equal(similarity.unpack_bits(win.x_bits, win.m), ws.dense(0)[:, :ws.m])
+    assert np.array_equal(win.node_len, ws.node_len[0, :ws.m])
+
+
+def test_empty_and_errors():
+    win = ingest.parse_gfa("H\tVN:Z:1.0\n")
+    assert win.n == 0 and win.m == 0
+    with pytest.raises(NativeError):
+        ingest.parse_gfa("S\t1\tA\nP\tp\t1+,9+\t*\n")          # step over an undefined segment
+    with pytest.raises(NativeError):
+        ingest.parse_gfa("S\t1\tA\nS\t1\tC\n")                  # duplicate segment name
+    with pytest.raises(NativeError):
+        ingest.parse_gfa("S\t1\tA\nP\tp\t1\t*\n")               # step without orientation
+
+
+def test_batch_container(tmp_path):
+    ws = synth.make_windows(12, 5000, 3, seed=5)
+    wins = []
+    for w in range(3):
+        names = synth.haplotype_names(12, "chr2", w * 5000, (w + 1) * 5000)
+        wins.append(ingest.GraphWindow(names, ws.x_bits[w].copy(), ws.node_len[w, :ws.m].copy(),
+                                       None, f"CHM13#0#chr2:{w * 5000}-{(w + 1) * 5000}", 5000))
+    path = tmp_path / "batch.npz"
+    ingest.save_batch(path, wins)
+    back = ingest.load_batch(path)
+    assert len(back) == 3
+    for a, b in zip(wins, back):
+        assert a.names == b.names and a.region == b.region and a.length == b.length
+        assert np.array_equal(a.x_bits, b.x_bits) and np.array_equal(a.node_len, b.node_len)

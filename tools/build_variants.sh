@@ -8,7 +8,7 @@ for spec in "$@"; do
   name="${spec%%=*}"; defs="${spec#*=}"
   [ "$name" = "$spec" ] && defs=""
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O3,-pthread -shared $defs \
-    -o "variants/$name.so" impop_b200/csrc/api.cu impop_b200/csrc/window_kernels.cu impop_b200/csrc/aux_kernels.cu &
+    -o "variants/$name.so" impop_b200/csrc/api.cu impop_b200/csrc/window_kernels.cu impop_b200/csrc/aux_kernels.cu impop_b200/csrc/ingest.cpp &
 done
 wait
 ls -la variants/
