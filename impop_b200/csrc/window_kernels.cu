@@ -120,7 +120,7 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
     const bool in0 = (ent0 & 255u) && rel0 >= 0 && rel0 < 32 * PASSES;
     const uint32_t add0 = HEAVY_Q * (ent0 & 255u), bit0 = (ent0 >> 8) & 31u;
     const bool any_in0 = __any_sync(0xffffffffu, in0);
-    constexpr int RU = 4;                                           // rows in flight per warp (memory-level parallelism)
+    constexpr int RU = PASSES == 1 ? 8 : 4;                         // rows in flight per warp (memory-level parallelism)
     uint32_t any[PASSES], all[PASSES];
 #pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) { any[ps] = 0u; all[ps] = 0xffffffffu; }
@@ -148,7 +148,12 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
             }
             acc[r] = a;
         }
+        // lane 4 g (g = 0..7) ends up owning row i0 + g: it holds the row's total after the transposed reduction below
+        // and stores the row's path length and heavy word -- two store instructions per eight rows
+        const int g = RU == 8 ? lane >> 2 : lane >> 3;
+        const bool owner = (lane & (RU == 8 ? 3 : 7)) == 0 && i0 + g < row_hi;
         if (FIRST || any_in0) {
+            uint32_t bw[RU];
 #pragma unroll
             for (int r = 0; r < RU; ++r) {
                 uint32_t wsrc = __shfl_sync(0xffffffffu, word[0][r], rel0 & 31);
@@ -157,12 +162,15 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
                     wsrc = (rel0 >= 32) ? w_hi : wsrc;
                 }
                 const bool on = in0 && ((wsrc >> bit0) & 1u);
-                const uint32_t bw = __ballot_sync(0xffffffffu, on);
+                bw[r] = __ballot_sync(0xffffffffu, on);
                 if (on) acc[r] += add0;
-                if (lane == 0 && i0 + r < row_hi && hw_used > 0) {
-                    uint32_t *dst = xh + (size_t)(i0 + r) * hwords;
-                    if (FIRST) *dst = bw; else if (bw) *dst |= bw;     // (xh was zeroed by prep_cols)
-                }
+            }
+            if (owner && hw_used > 0) {
+                uint32_t mine = bw[0];
+#pragma unroll
+                for (int r = 1; r < RU; ++r) mine = (g == r) ? bw[r] : mine;
+                uint32_t *dst = xh + (size_t)(i0 + g) * hwords;
+                if (FIRST) *dst = mine; else if (mine) *dst |= mine;   // (xh was zeroed by prep_cols)
             }
         }
         for (int hw = 1; hw < hw_used; ++hw) {                      // further heavy words: rare
@@ -186,12 +194,27 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
                 }
             }
         }
+        {   // transposed warp reduction of the RU row totals: 9 shuffles for eight rows instead of 40
+            const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+            uint32_t t;
+            if constexpr (RU == 8) {
+                uint32_t v[4], u[2];
 #pragma unroll
-        for (int r = 0; r < RU; ++r) {
-            uint32_t a = acc[r];
+                for (int r = 0; r < 4; ++r)      // rows r | r + 4
+                    v[r] = (up16 ? acc[r + 4] : acc[r]) + __shfl_xor_sync(0xffffffffu, up16 ? acc[r] : acc[r + 4], 16);
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-            if (lane == 0 && i0 + r < row_hi) A[i0 + r] = (int32_t)(a + (FIRST ? 0u : (uint32_t)A[i0 + r]));
+                for (int r = 0; r < 2; ++r)      // rows r | r + 2 (+ 4)
+                    u[r] = (up8 ? v[r + 2] : v[r]) + __shfl_xor_sync(0xffffffffu, up8 ? v[r] : v[r + 2], 8);
+                t = (up4 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, up4 ? u[0] : u[1], 4);              // row g = lane >> 2
+            } else {
+                const uint32_t v0 = (up16 ? acc[2] : acc[0]) + __shfl_xor_sync(0xffffffffu, up16 ? acc[0] : acc[2], 16);   // rows 0 | 2
+                const uint32_t v1 = (up16 ? acc[3] : acc[1]) + __shfl_xor_sync(0xffffffffu, up16 ? acc[1] : acc[3], 16);   // rows 1 | 3
+                t = (up8 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, up8 ? v0 : v1, 8);                       // row g = lane >> 3
+                t += __shfl_xor_sync(0xffffffffu, t, 4);
+            }
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            if (owner) A[i0 + g] = (int32_t)(t + (FIRST ? 0u : (uint32_t)A[i0 + g]));
         }
     }
 #pragma unroll
