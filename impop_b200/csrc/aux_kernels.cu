@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(RI_THREADS) reduce_identity_stage1(const doubl
             }
             if (weight) {
                 const double wj = weight[j];
-                if (wi != 0.0 && wj != 0.0) {
+                // labels given as well: only pairs with one row in A and the other in B (hud.py:235-263, grouped Dxy)
+                const bool counted = !labels || ((fi & IMPOP_LAB_A) && (fj & IMPOP_LAB_B)) || ((fi & IMPOP_LAB_B) && (fj & IMPOP_LAB_A));
+                if (counted && wi != 0.0 && wj != 0.0) {
                     dd_add(v[4], __dmul_rn(__dmul_rn(p, wi), wj));  // pica2.py:139
                     c[4] += 1.0;
                 }

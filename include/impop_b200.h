@@ -163,6 +163,8 @@ int impop_pairwise(impop_ctx_t *ctx, impop_batch_t *batch, int32_t window, int32
  * when given, wsum_dev[0] = sum_{i<j} (1 - s_ij) * w_i * w_j over present pairs (pica2.py:137-139),
  * wsum_dev[1] = number of such pairs with w_i * w_j != 0, wsum_dev[2] = pica2's grouped
  * pi = n/(n-1) * 2 * wsum_dev[0] (pica2.py:154; 0 when no pair) and wsum_dev[3] = pi / length (NaN when length == 0).
+ * With BOTH labels_dev and weight_dev the weighted sum runs over the pairs with one row in A and the other in B only
+ * (hudson/hud.py:235-263: grouped Dxy, weights |G_a|/n_A and |G_b|/n_B on the group representatives).
  * wsum_dev holds 4 doubles.  stats_dev: IMPOP_NSTATS, counts_dev: IMPOP_NCOUNTS (S and Tajima columns use seg_sites as S). */
 int impop_reduce_identity(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t ld,
                           const uint8_t *labels_dev, const double *weight_dev, int64_t length, double seg_sites,

@@ -344,3 +344,52 @@ def site_allele_counts(site_bits: np.ndarray, pop_masks: np.ndarray, pop_sizes=N
         freq = counts.astype(np.float64) / sizes[None, :]
     freq = np.where(sizes[None, :] > 0, freq, 0.0)
     return counts, freq
+
+
+# ----------------------------------------------------------------------------
+# f-3 : hudson/hud.py, grouped method (deterministic seeds)
+# ----------------------------------------------------------------------------
+def hud_grouped_diversity(mat: np.ndarray, idx, threshold: float = 0.999):
+    """(diversity, groups, missing) of hud.calculate_diversity_grouped (hud.py:99-128) over the rows `idx` (sorted by
+    name), with group_sequences (hud.py:64-84) seeded by the smallest remaining name instead of set.pop().
+    `mat` is already rounded.  The representative similarity is that of the groups' first members, which is what
+    hud.get_group_similarity (hud.py:86-97) finds first on a complete table."""
+    idx = list(idx)
+    sub = mat[np.ix_(idx, idx)] if idx else np.zeros((0, 0))
+    groups = greedy_groups(sub, idx, threshold)
+    n_total = len(idx)
+    if n_total <= 1:
+        return 0.0, len(groups), 0, groups
+    total, missing = 0.0, 0                                     # sequential float accumulation as hud.py:108-121
+    for i in range(len(groups)):
+        for j in range(i + 1, len(groups)):
+            s = float(sub[groups[i][0], groups[j][0]])
+            if s != s:
+                missing += 1
+                continue
+            total += 2 * (len(groups[i]) / n_total) * (len(groups[j]) / n_total) * (1 - s)
+    return total * n_total / (n_total - 1), len(groups), missing, groups
+
+
+def hud_fst_grouped(mat, names, pop_a, pop_b, sequence_length=None, round_digits=None, threshold: float = 0.999):
+    """hud.calculate_fst(method='grouped') (hud.py:172-300)."""
+    mat = py_round_matrix(mat, round_digits)
+    both = set(pop_a) & set(pop_b)
+    where = {s: i for i, s in enumerate(names)}
+    ia = [where[s] for s in sorted(set(pop_a) - both) if s in where]
+    ib = [where[s] for s in sorted(set(pop_b) - both) if s in where]
+    pi_a, _, _, ga = hud_grouped_diversity(mat, ia, threshold)
+    pi_b, _, _, gb = hud_grouped_diversity(mat, ib, threshold)
+    pi_xy = 0.5 * (pi_a + pi_b)
+    dxy = 0.0
+    for g1 in ga:
+        for g2 in gb:
+            s = float(mat[ia[g1[0]], ib[g2[0]]])
+            if s != s:
+                continue
+            dxy += (len(g1) * len(g2)) / (len(ia) * len(ib)) * (1 - s)
+    fst = (dxy - pi_xy) / dxy if dxy > 0 else 0.0
+    if sequence_length and sequence_length > 0:
+        L = sequence_length
+        return dict(fst=fst, pi_a=pi_a / L, pi_b=pi_b / L, pi_xy=pi_xy / L, dxy=dxy / L, da=(dxy - pi_xy) / L)
+    return dict(fst=fst, pi_a=pi_a, pi_b=pi_b, pi_xy=pi_xy, dxy=dxy, da=dxy - pi_xy)
