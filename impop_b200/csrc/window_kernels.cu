@@ -118,7 +118,9 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
     const uint32_t ent0 = hw_used > 0 ? heavy[lane] : 0u;
     const int rel0 = (int)(ent0 >> 13) - w0;                        // word of the entry's node within this group
     const bool in0 = (ent0 & 255u) && rel0 >= 0 && rel0 < 32 * PASSES;
-    const uint32_t add0 = HEAVY_Q * (ent0 & 255u), bit0 = (ent0 >> 8) & 31u;
+    const uint32_t add0 = in0 ? HEAVY_Q * (ent0 & 255u) : 0u;
+    const uint32_t sh0 = in0 ? ((ent0 >> 8) & 31u) : 32u;           // funnel shift by 32 yields 0: entry not in this group
+    const int src0 = rel0 & 31;
     const bool any_in0 = __any_sync(0xffffffffu, in0);
     constexpr int RU = PASSES == 1 ? 8 : 4;                         // rows in flight per warp (memory-level parallelism)
     uint32_t any[PASSES], all[PASSES];
@@ -126,11 +128,10 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
     for (int ps = 0; ps < PASSES; ++ps) { any[ps] = 0u; all[ps] = 0xffffffffu; }
     for (int i0 = row_lo + warp * RU; i0 < row_hi; i0 += (PREP_THREADS / 32) * RU) {
         uint32_t word[PASSES][RU], acc[RU];
-        uint32_t labv[RU];
+        const uint32_t segrows = __ballot_sync(0xffffffffu, lane < RU && i0 + lane < row_hi && (lab[i0 + lane] & IMPOP_LAB_SEG));
 #pragma unroll
         for (int r = 0; r < RU; ++r) {
             const bool rv = i0 + r < row_hi;
-            labv[r] = rv ? (uint32_t)lab[i0 + r] : 0u;
 #pragma unroll
             for (int ps = 0; ps < PASSES; ++ps) {
                 const int wd = w0 + ps * 32 + lane;
@@ -144,7 +145,7 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
             for (int ps = 0; ps < PASSES; ++ps) {
 #pragma unroll
                 for (int p = 0; p < 8; ++p) a += (uint32_t)__popc(word[ps][r] & pm[ps][p]) << p;
-                if (labv[r] & IMPOP_LAB_SEG) { any[ps] |= word[ps][r]; all[ps] &= word[ps][r]; }
+                if ((segrows >> r) & 1u) { any[ps] |= word[ps][r]; all[ps] &= word[ps][r]; }
             }
             acc[r] = a;
         }
@@ -156,14 +157,14 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
             uint32_t bw[RU];
 #pragma unroll
             for (int r = 0; r < RU; ++r) {
-                uint32_t wsrc = __shfl_sync(0xffffffffu, word[0][r], rel0 & 31);
+                uint32_t wsrc = __shfl_sync(0xffffffffu, word[0][r], src0);
                 if (PASSES > 1) {
-                    const uint32_t w_hi = __shfl_sync(0xffffffffu, word[PASSES - 1][r], rel0 & 31);
+                    const uint32_t w_hi = __shfl_sync(0xffffffffu, word[PASSES - 1][r], src0);
                     wsrc = (rel0 >= 32) ? w_hi : wsrc;
                 }
-                const bool on = in0 && ((wsrc >> bit0) & 1u);
-                bw[r] = __ballot_sync(0xffffffffu, on);
-                if (on) acc[r] += add0;
+                const uint32_t on = __funnelshift_rc(wsrc, 0u, sh0) & 1u;        // clamped: a shift of 32 gives 0
+                bw[r] = __ballot_sync(0xffffffffu, on != 0u);
+                acc[r] += on * add0;
             }
             if (owner && hw_used > 0) {
                 uint32_t mine = bw[0];

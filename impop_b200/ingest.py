@@ -147,3 +147,29 @@ def labels_from_names(names, pop_a=None, pop_b=None, subset=None, seg=None) -> n
             f |= _native.LAB_B
         lab[i] = f
     return lab
+
+
+def multiset_expand(win: GraphWindow, max_copies: int = 255) -> GraphWindow:
+    """Multiset (visit-count) coverage as a presence matrix the set kernels take unchanged.
+
+    With c_ik = how often path i visits node k, the multiset intersection is sum_k len_k min(c_ik, c_jk)
+    [UPSTREAM-UNVERIFIED: what `odgi similarity` computes on graphs whose paths revisit nodes].  Because
+    min(a, b) = sum_{t >= 1} [a >= t][b >= t], it equals the SET intersection over "copy" nodes (k, t), t = 1 ..
+    max_i c_ik, each of length len_k and present in path i iff c_ik >= t.  Path lengths become sum_k len_k c_ik and
+    the union A_i + A_j - I_ij follows; every kernel and statistic downstream is untouched.  Needs `win.counts`
+    (parse_gfa(..., want_counts=True)); copies beyond `max_copies` are dropped (the reader saturates at 65 535)."""
+    if win.counts is None:
+        raise ValueError("multiset_expand needs visit counts: parse the GFA with want_counts=True")
+    c = np.minimum(win.counts.astype(np.int64), max_copies)
+    tmax = c.max(axis=0) if c.size else np.zeros(win.m, dtype=np.int64)
+    tmax = np.maximum(tmax, 1)                                   # a node nobody visits stays as one empty column
+    node = np.repeat(np.arange(win.m), tmax)                     # copy column -> node
+    first = np.cumsum(tmax) - tmax
+    t = np.arange(node.shape[0]) - first[node] + 1               # copy index 1 .. tmax
+    dense = (c[:, node] >= t[None, :]).astype(np.uint8)
+    m2 = node.shape[0]
+    pitch = _pitch_for(m2)
+    padded = np.zeros((win.n, pitch * 32), dtype=np.uint8)
+    padded[:, :m2] = dense
+    bits = np.packbits(padded, axis=1, bitorder="little").view("<u4").reshape(win.n, pitch).copy()
+    return GraphWindow(list(win.names), bits, win.node_len[node].astype(np.uint32), None, win.region, win.length)

@@ -64,3 +64,36 @@ def test_gfa_windows_through_the_driver(tmp_path):
         assert (ct[w] == want_c).all()
     batch.close()
     ctx.close()
+
+
+def test_multiset_coverage_window_on_the_gpu():
+    """f-4: a window whose paths revisit nodes, expanded to copy nodes, through the fused pass; expected values from the
+    min-count definition directly (oracle.similarity.identity_from_counts on I = sum len min(c_i, c_j), A = sum len c)."""
+    from impop_b200.engine import Context, WindowBatch
+    from oracle import similarity
+    rng = np.random.default_rng(10)
+    n, m = 40, 90
+    counts = rng.integers(0, 3, size=(n, m))
+    counts[:, ::7] = 1
+    node_len = rng.integers(1, 500, size=m)
+    lines = ["H\tVN:Z:1.0"] + [f"S\t{k + 1}\t*\tLN:i:{node_len[k]}" for k in range(m)]
+    for i in range(n):
+        steps = [f"{k + 1}+" for k in range(m) for _ in range(counts[i, k])]
+        lines.append(f"P\tS{i:03d}#1#ctg:0-1000\t" + ",".join(steps) + "\t*")
+    win = ingest.multiset_expand(ingest.parse_gfa("\n".join(lines) + "\n", want_counts=True))
+    inter = np.einsum("k,ijk->ij", node_len.astype(np.int64), np.minimum(counts[:, None, :], counts[None, :, :]))
+    a = counts @ node_len
+    _, _, _, pi = similarity.identity_from_counts(inter, a)
+    ctx = Context(0)
+    batch = WindowBatch.from_windows(ctx, [(win.x_bits, win.node_len, np.full(n, 9, dtype=np.uint8), 1000)])
+    I, A, P = batch.pairwise(0, 0)
+    ctx.check()
+    assert np.array_equal(I.cpu().numpy(), inter) and np.array_equal(A.cpu().numpy(), a)
+    got = P.cpu().numpy()
+    iu = np.triu_indices(n, 1)
+    assert np.array_equal(got[iu], pi[iu])                     # bit-exact pi_ij
+    st, ct = batch.stats(0)
+    ctx.check()
+    want_pi = n / (n - 1) * 2 * float(np.sum(pi[iu])) / (n * n)
+    assert abs(float(st[0, 0]) - want_pi) <= 1e-12 * want_pi
+    batch.close(); ctx.close()

@@ -79,3 +79,27 @@ def test_batch_container(tmp_path):
     for a, b in zip(wins, back):
         assert a.names == b.names and a.region == b.region and a.length == b.length
         assert np.array_equal(a.x_bits, b.x_bits) and np.array_equal(a.node_len, b.node_len)
+
+
+def test_multiset_expansion_is_the_min_count_intersection():
+    """f-4: set intersection over copy nodes == sum len * min(count_i, count_j); path length == sum len * count."""
+    rng = np.random.default_rng(9)
+    n, m = 14, 37
+    counts = rng.integers(0, 4, size=(n, m))
+    counts[:, 5] = 0                                             # a node nobody visits
+    counts[3] = 0                                                # an empty path
+    node_len = rng.integers(0, 400, size=m)
+    lines = ["H\tVN:Z:1.0"] + [f"S\t{k + 1}\t*\tLN:i:{node_len[k]}" for k in range(m)]
+    for i in range(n):
+        steps = [f"{k + 1}+" for k in range(m) for _ in range(counts[i, k])]
+        rng.shuffle(steps)
+        lines.append(f"P\tS{i:03d}#1#ctg:0-100\t" + (",".join(steps) if steps else "*") + "\t*")
+    win = ingest.parse_gfa("\n".join(lines) + "\n", want_counts=True)
+    assert np.array_equal(win.counts.astype(np.int64), counts)
+    ex = ingest.multiset_expand(win)
+    x = similarity.unpack_bits(ex.x_bits, ex.m).astype(np.int64)
+    inter = (x * ex.node_len.astype(np.int64)[None, :]) @ x.T
+    want = np.einsum("k,ijk->ij", node_len.astype(np.int64), np.minimum(counts[:, None, :], counts[None, :, :]))
+    assert np.array_equal(inter, want)
+    assert np.array_equal(np.diag(inter), counts @ node_len)
+    assert ex.m == int(np.maximum(counts.max(axis=0), 1).sum())
