@@ -19,6 +19,7 @@ HEADERS = {
     "pi_subset": ["REGION", "SUBSET", "LENGTH", "THRESHOLD", "R_VALUE", "PICA_OUTPUT"],
     "fst": ["REGION", "LENGTH", "FST", "PI_A", "PI_B", "PI_XY", "DXY", "DA"],
     "tajd": ["REGION", "LENGTH", "SAMPLES", "SEGREGATING_SITES", "PI", "TAJIMAS_D"],
+    "pooled_fst": ["REGION", "LENGTH", "THRESHOLD", "R_VALUE", "PI_A", "PI_B", "PI_C", "PI_AB_AVG", "FST"],
 }
 
 
@@ -48,6 +49,24 @@ def tajd_rows(regions, lengths, stats, counts):
         d = float(row[ST["tajima_d"]])
         pi = row[ST["pi_per_site"]] if L else row[ST["pi"]]
         yield [reg, str(int(L)), str(int(cnt[0])), str(int(cnt[7])), f"{pi:.8f}", "NA" if math.isnan(d) else repr(d)]
+
+
+def pooled_fst_text(pi_a: str, pi_b: str, pi_c: str):
+    """(PI_AB_AVG, FST) from the three 8-decimal per-site pi texts pica2 printed, exactly as the two inline python
+    snippets of run_fst_impg.sh:199-218 form them: `NA` when pi_C == 0."""
+    a, b, c = float(pi_a), float(pi_b), float(pi_c)
+    avg = 0.5 * (a + b)
+    return f"{avg:.8f}", ("NA" if c == 0 else f"{(c - avg) / c:.8f}")
+
+
+def pooled_fst_rows(regions, lengths, stats_a, stats_b, stats_c, threshold="1.0", r_value="NA"):
+    """run_fst_impg.sh:158, :220: pica2's per-site pi over subset A, subset B and their union C (three passes whose SUBSET
+    class is A, B, A + B), then the pooled estimator on the printed values."""
+    for reg, L, ra, rb, rc in zip(regions, lengths, stats_a, stats_b, stats_c):
+        key = ST["pi_per_site"] if L else ST["pi"]
+        pa, pb, pc = (f"{row[key]:.8f}" if L else f"{row[key]:.6f}" for row in (ra, rb, rc))
+        avg, fst = pooled_fst_text(pa, pb, pc)
+        yield [reg, str(int(L)), str(threshold), str(r_value), pa, pb, pc, avg, fst]
 
 
 def write_tsv(handle, kind: str, rows):
@@ -102,6 +121,7 @@ def main(argv=None):
     ap.add_argument("-b", "--pop-b", help="file listing population B (h-fst.py -b)")
     ap.add_argument("-s", "--subset", help="file listing the samples pi / S / Tajima's D are computed over (run_tajd.sh -l)")
     ap.add_argument("--pi-out"), ap.add_argument("--fst-out"), ap.add_argument("--tajd-out")
+    ap.add_argument("--pooled-fst-out", help="run_fst_impg.sh's table: pica2 pi of subset A, B and their union, pooled Fst (needs -a, -b)")
     ap.add_argument("--save-batch", help="also write the parsed windows as one binary container")
     ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args(argv)
@@ -119,8 +139,8 @@ def main(argv=None):
                 graphs.append(ingest.read_gfa(path, region=region, length=int(mt.group(2)) - int(mt.group(1)) if mt else 0))
     if args.save_batch:
         ingest.save_batch(args.save_batch, graphs)
-    if (args.fst_out is None) != (args.pop_a is None or args.pop_b is None):
-        ap.error("--fst-out needs both -a and -b (and vice versa)")
+    if (args.fst_out or args.pooled_fst_out) and (args.pop_a is None or args.pop_b is None):
+        ap.error("--fst-out / --pooled-fst-out need both -a and -b")
     pop_a = read_subset_file(args.pop_a) if args.pop_a else None
     pop_b = read_subset_file(args.pop_b) if args.pop_b else None
     subset = read_subset_file(args.subset) if args.subset else None
@@ -132,6 +152,15 @@ def main(argv=None):
     batch.close()
     regions = [g.region or f"window{i}" for i, g in enumerate(graphs)]
     lengths = [g.length for g in graphs]
+    if args.pooled_fst_out:
+        per_subset = []
+        for ids in (pop_a, pop_b, set(pop_a) | set(pop_b)):           # run_fst_impg.sh:143-147: C = union list
+            b = batch_from_graphs(ctx, graphs, subset_ids=ids)
+            per_subset.append(b.stats()[0].cpu().numpy())
+            ctx.check()
+            b.close()
+        with (sys.stdout if args.pooled_fst_out == "-" else open(args.pooled_fst_out, "w")) as out:
+            write_tsv(out, "pooled_fst", pooled_fst_rows(regions, lengths, *per_subset))
     for path, kind, rows in ((args.pi_out, "pi", pi_rows(regions, lengths, stats)),
                              (args.fst_out, "fst", fst_rows(regions, lengths, stats)),
                              (args.tajd_out, "tajd", tajd_rows(regions, lengths, stats, counts))):

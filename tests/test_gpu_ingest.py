@@ -31,8 +31,21 @@ def test_gfa_windows_through_the_driver(tmp_path):
     (tmp_path / "windows.tsv").write_text("\n".join(listing) + "\n")
     rc = windows.main(["--gfa-list", str(tmp_path / "windows.tsv"), "-a", str(tmp_path / "a.txt"), "-b", str(tmp_path / "b.txt"),
                        "--fst-out", str(tmp_path / "fst.tsv"), "--tajd-out", str(tmp_path / "tajd.tsv"),
-                       "--pi-out", str(tmp_path / "pi.tsv"), "--save-batch", str(tmp_path / "batch.npz")])
+                       "--pi-out", str(tmp_path / "pi.tsv"), "--save-batch", str(tmp_path / "batch.npz"),
+                       "--pooled-fst-out", str(tmp_path / "pooled.tsv")])
     assert rc == 0
+    # row a-10 (run_fst_impg.sh:158-220): pica2's printed per-site pi of A, B, A + B and the pooled estimator on the text
+    from oracle import popstats
+    pooled = (tmp_path / "pooled.tsv").read_text().splitlines()
+    assert pooled[0].split("\t") == ["REGION", "LENGTH", "THRESHOLD", "R_VALUE", "PI_A", "PI_B", "PI_C", "PI_AB_AVG", "FST"]
+    for w in range(W):
+        txt = []
+        for rows in (range(0, 20), range(20, 45), range(0, 45)):
+            sub_lab = np.zeros(n, dtype=np.uint8)
+            sub_lab[list(rows)] = 1 | 8
+            txt.append(f"{clib.window_stats(ws.x_bits[w], ws.m_pad, ws.node_len[w], sub_lab, L)[0][1]:.8f}")
+        avg, fst_txt = popstats.pooled_fst_text(*txt)
+        assert pooled[1 + w].split("\t")[4:] == txt + [avg, fst_txt], (w, pooled[1 + w])
     # the rows the reference-side restatement gives on the generator's matrices
     lab = np.full(n, 1 | 8, dtype=np.uint8)
     lab[0:20] |= 2            # asm[i] is the assembly-name spelling of names[i]

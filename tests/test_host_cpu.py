@@ -180,3 +180,15 @@ def test_gather_world_size_2_gloo(tmp_path):
         out, err = p.communicate(timeout=240)
         assert p.returncode == 0, err[-2000:]
         assert f"ok {r}" in out
+
+
+def test_pooled_fst_text_matches_the_wrapper_snippets():
+    """Row a-10: run_fst_impg.sh:199-218's inline python, outputs stored by tests/golden/make_golden_pooled.py."""
+    import json
+    from impop_b200 import windows
+    from oracle import popstats
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pooled_fst.json")))
+    assert len(cases) > 50
+    for a, b, c, avg, fst in cases:
+        assert windows.pooled_fst_text(a, b, c) == (avg, fst)
+        assert popstats.pooled_fst_text(a, b, c) == (avg, fst)
