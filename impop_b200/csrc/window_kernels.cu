@@ -126,17 +126,20 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
     uint32_t any[PASSES], all[PASSES];
 #pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) { any[ps] = 0u; all[ps] = 0xffffffffu; }
-    for (int i0 = row_lo + warp * RU; i0 < row_hi; i0 += (PREP_THREADS / 32) * RU) {
+    bool lane_ok[PASSES];                                           // this lane's word of pass ps can hold nodes < m
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) lane_ok[ps] = w0 + ps * 32 + lane < wlim;
+    const uint32_t *rowp = x + (size_t)(row_lo + warp * RU) * pitch + w0 + lane;      // first row of this warp, this lane's word
+    const size_t step = (size_t)(PREP_THREADS / 32) * RU * pitch;
+    for (int i0 = row_lo + warp * RU; i0 < row_hi; i0 += (PREP_THREADS / 32) * RU, rowp += step) {
         uint32_t word[PASSES][RU], acc[RU];
         const uint32_t segrows = __ballot_sync(0xffffffffu, lane < RU && i0 + lane < row_hi && (lab[i0 + lane] & IMPOP_LAB_SEG));
+        const int nrows = min(RU, row_hi - i0);
 #pragma unroll
         for (int r = 0; r < RU; ++r) {
-            const bool rv = i0 + r < row_hi;
 #pragma unroll
-            for (int ps = 0; ps < PASSES; ++ps) {
-                const int wd = w0 + ps * 32 + lane;
-                word[ps][r] = (rv && wd < wlim) ? __ldg(x + (size_t)(i0 + r) * pitch + wd) : 0u;
-            }
+            for (int ps = 0; ps < PASSES; ++ps)
+                word[ps][r] = (r < nrows && lane_ok[ps]) ? __ldg(rowp + (size_t)r * pitch + ps * 32) : 0u;
         }
 #pragma unroll
         for (int r = 0; r < RU; ++r) {

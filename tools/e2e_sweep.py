@@ -17,7 +17,7 @@ hs = torch.empty((W, NSTATS), dtype=torch.float64, pin_memory=True); hc = torch.
 dx, dl = torch.empty_like(x), torch.empty_like(nl)
 ds = torch.empty((W, NSTATS), dtype=torch.float64, device=dev); dc = torch.empty((W, NCOUNTS), dtype=torch.int64, device=dev)
 streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-for nsub in (1, 2, 4, 8, 16, 32):
+for nsub in (4, 6, 8, 10, 12, 16, 24):
     cuts = [int(v) for v in np.linspace(0, W, nsub + 1)]
     dlabs = [torch.empty_like(labels) for _ in range(nsub)]
     def step(host_only=False):
