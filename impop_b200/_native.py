@@ -37,6 +37,11 @@ class GfaInfo(C.Structure):
     _fields_ = [("segments", _i64), ("paths", _i64), ("name_bytes", _i64), ("steps", _i64), ("error_line", _i64)]
 
 
+class TsvInfo(C.Structure):
+    """impop_tsv_info_t"""
+    _fields_ = [("rows", _i64), ("names", _i64), ("name_bytes", _i64), ("status", _i32), ("reserved", _i32)]
+
+
 # name -> (restype, argtypes); every symbol include/impop_b200.h declares
 SIGNATURES = {
     "impop_version": (C.c_int, []),
@@ -62,6 +67,8 @@ SIGNATURES = {
     "impop_selftest_division": (C.c_int, [_p, C.c_uint64, _i64, C.POINTER(_i64), _p]),
     "impop_debug_role_times": (C.c_int, [_p, _p, _i32]),
     "impop_greedy_groups": (C.c_int, [_p, _p, _i32, _i64, _f64, _p, _p, _p]),
+    "impop_tsv_scan": (C.c_int, [C.c_char_p, _i64, C.POINTER(TsvInfo)]),
+    "impop_tsv_fill": (C.c_int, [C.c_char_p, _i64, _p, _p, _p]),
     "impop_gfa_scan": (C.c_int, [C.c_char_p, _i64, C.POINTER(GfaInfo)]),
     "impop_gfa_fill": (C.c_int, [C.c_char_p, _i64, _i32, _p, _p, _p, _p, _p, C.POINTER(_i64)]),
 }

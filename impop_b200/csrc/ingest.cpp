@@ -6,7 +6,10 @@
 // same from alignments (run_h-fst.sh:65-67).  One matrix row per path line (P or W), as `odgi similarity` with
 // no grouping flags makes one group per path; node k = k-th S line.  Plain C++ on the host: no CUDA in here.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include <string>
 #include <vector>
@@ -249,6 +252,180 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
         ++row;
     }
     if (info.paths) name_off_host[row] = off;
+    return IMPOP_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// All-pairs similarity table (the TSV `odgi similarity` / `impg similarity` print and pica2.py:6-58,
+// h-fst.py:84-119 parse with csv.DictReader -- 47-92 % of those scripts' run time at 466 haplotypes, SURVEY 8 a-1 /
+// a-4) -> sorted names + dense identity matrix (NaN = pair absent), last row of a repeated pair wins (pica2.py:44).
+// Only MACHINE-CLEAN text is taken here: ASCII, no quote characters, every row as wide as the header needs, numbers
+// in plain decimal / exponent form or nan / inf.  Anything else reports status 1 and the caller uses the general
+// reader, so that the reference's behaviour on odd input (csv quoting, Python's float() grammar, its error
+// messages) is reproduced by the code that mirrors it line by line.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct TsvCols { int a = -1, b = -1, v = -1, need = 0; };
+
+inline bool tsv_header(const Line &ln, TsvCols &c) {
+    int k = 0, na = 0, nb = 0, nv = 0;
+    const char *p = ln.p;
+    while (true) {
+        const char *t = (const char *)memchr(p, '\t', (size_t)(ln.e - p));
+        const char *fe = t ? t : ln.e;
+        const size_t len = (size_t)(fe - p);
+        if (len == 7 && memcmp(p, "group.a", 7) == 0) { c.a = k; ++na; }
+        else if (len == 7 && memcmp(p, "group.b", 7) == 0) { c.b = k; ++nb; }
+        else if (len == 18 && memcmp(p, "estimated.identity", 18) == 0) { c.v = k; ++nv; }
+        ++k;
+        if (!t) break;
+        p = t + 1;
+    }
+    c.need = 1 + (c.a > c.b ? (c.a > c.v ? c.a : c.v) : (c.b > c.v ? c.b : c.v));
+    return na == 1 && nb == 1 && nv == 1;
+}
+
+// Plain decimal / exponent number or [+-]nan / inf / infinity, nothing else (no spaces, no hex, no underscores).
+inline bool tsv_number(const char *p, const char *e, double &out) {
+    if (p == e || e - p > 64) return false;
+    const char *q = p;
+    if (*q == '+' || *q == '-') ++q;
+    if (q == e) return false;
+    auto ieq = [&](const char *w) {
+        size_t n = strlen(w);
+        if ((size_t)(e - q) != n) return false;
+        for (size_t i = 0; i < n; ++i) if ((q[i] | 0x20) != w[i]) return false;
+        return true;
+    };
+    if (!(ieq("nan") || ieq("inf") || ieq("infinity"))) {
+        int digits = 0;
+        while (q < e && *q >= '0' && *q <= '9') { ++q; ++digits; }
+        if (q < e && *q == '.') { ++q; while (q < e && *q >= '0' && *q <= '9') { ++q; ++digits; } }
+        if (digits == 0) return false;
+        if (q < e && (*q == 'e' || *q == 'E')) {
+            ++q;
+            if (q < e && (*q == '+' || *q == '-')) ++q;
+            int ed = 0;
+            while (q < e && *q >= '0' && *q <= '9') { ++q; ++ed; }
+            if (ed == 0) return false;
+        }
+        if (q != e) return false;
+    }
+    char buf[72];
+    memcpy(buf, p, (size_t)(e - p));
+    buf[e - p] = 0;
+    char *end = nullptr;
+    out = strtod(buf, &end);                 // glibc: correctly rounded, as CPython's float()
+    return end == buf + (e - p);
+}
+
+struct NameMap {                              // name -> first-seen index
+    SegMap map;
+    std::vector<Line> names;
+    void init(size_t cap) { map.init(cap); }
+    int32_t get(const char *p, const char *e) {
+        int32_t k = map.find(p, (size_t)(e - p));
+        if (k >= 0) return k;
+        if (2 * (names.size() + 2) > map.slots.size()) {          // grow: rehash everything
+            SegMap bigger;
+            bigger.init(map.slots.size());
+            for (size_t i = 0; i < names.size(); ++i) bigger.insert(names[i].p, (size_t)(names[i].e - names[i].p), (int32_t)i);
+            map = bigger;
+        }
+        k = (int32_t)names.size();
+        map.insert(p, (size_t)(e - p), k);
+        names.push_back(Line{p, e});
+        return k;
+    }
+};
+
+// One pass over a clean table: calls row(ia, ib, value) per data row.  Returns 0 clean, 1 needs the general reader.
+template <typename F>
+int tsv_walk(const char *text, int64_t bytes, NameMap &nm, int64_t &rows, F row) {
+    for (int64_t i = 0; i < bytes; ++i) {
+        const unsigned char ch = (unsigned char)text[i];
+        if (ch == '"' || ch >= 0x80 || ch == 0) return 1;
+    }
+    const char *cur = text, *end = text + bytes;
+    Line ln;
+    if (!next_line(cur, end, ln)) return 1;                       // empty file: the general reader words the error
+    TsvCols c;
+    if (!tsv_header(ln, c)) return 1;
+    rows = 0;
+    while (next_line(cur, end, ln)) {
+        if (ln.e == ln.p) continue;                               // csv.DictReader skips blank lines
+        if (memchr(ln.p, '\r', (size_t)(ln.e - ln.p))) return 1;
+        const char *ap, *ae, *bp, *be, *vp, *ve, *xp, *xe;
+        if (!field(ln, c.need - 1, xp, xe)) return 1;             // row narrower than the header needs
+        field(ln, c.a, ap, ae); field(ln, c.b, bp, be); field(ln, c.v, vp, ve);
+        double v;
+        if (!tsv_number(vp, ve, v)) return 1;
+        ++rows;
+        row(nm.get(ap, ae), nm.get(bp, be), v);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int impop_tsv_scan(const char *text, int64_t bytes, impop_tsv_info_t *info) {
+    if (!text || bytes < 0 || !info) return IMPOP_ERR_ARG;
+    impop_tsv_info_t out = {0, 0, 0, 0, 0};
+    NameMap nm;
+    nm.init(1024);
+    int64_t rows = 0;
+    out.status = tsv_walk(text, bytes, nm, rows, [](int32_t, int32_t, double) {});
+    if (out.status == 0) {
+        out.rows = rows;
+        out.names = (int64_t)nm.names.size();
+        for (const Line &s : nm.names) out.name_bytes += (int64_t)(s.e - s.p) + 1;
+    }
+    *info = out;
+    return IMPOP_OK;
+}
+
+int impop_tsv_fill(const char *text, int64_t bytes, double *matrix_host, char *names_host, int64_t *name_off_host) {
+    if (!text || bytes < 0 || !name_off_host) return IMPOP_ERR_ARG;
+    NameMap nm;
+    nm.init(1024);
+    struct Row { int32_t a, b; double v; };
+    std::vector<Row> rows;
+    int64_t count = 0;
+    if (tsv_walk(text, bytes, nm, count, [&](int32_t a, int32_t b, double v) { rows.push_back(Row{a, b, v}); }) != 0)
+        return IMPOP_ERR_ARG;
+    const size_t n = nm.names.size();
+    if (n && (!matrix_host || !names_host)) return IMPOP_ERR_ARG;
+    // names in byte order (= Python's str order on ASCII), first-seen index -> sorted rank
+    std::vector<int32_t> order(n), rank(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (int32_t)i;
+    std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        const Line &a = nm.names[x], &b = nm.names[y];
+        const size_t la = (size_t)(a.e - a.p), lb = (size_t)(b.e - b.p);
+        const int c = memcmp(a.p, b.p, la < lb ? la : lb);
+        return c != 0 ? c < 0 : la < lb;
+    });
+    int64_t off = 0;
+    for (size_t r = 0; r < n; ++r) {
+        rank[order[r]] = (int32_t)r;
+        const Line &s = nm.names[order[r]];
+        name_off_host[r] = off;
+        memcpy(names_host + off, s.p, (size_t)(s.e - s.p));
+        names_host[off + (s.e - s.p)] = 0;
+        off += (int64_t)(s.e - s.p) + 1;
+    }
+    name_off_host[n] = off;
+    const double nan = __builtin_nan("");
+    for (size_t i = 0; i < n * n; ++i) matrix_host[i] = nan;
+    for (const Row &r : rows) {                                   // file order: the last row of a pair stays
+        const size_t i = (size_t)rank[r.a], j = (size_t)rank[r.b];
+        matrix_host[i * n + j] = r.v;
+        matrix_host[j * n + i] = r.v;
+    }
     return IMPOP_OK;
 }
 

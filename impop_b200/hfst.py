@@ -13,7 +13,7 @@ import os
 import sys
 
 from .runtime import default_context
-from .tables import SimilarityTable, TableFormatError, read_rows
+from .tables import SimilarityTable, TableFormatError, read_rows, read_table_fast
 
 _HAP_TAGS = (("_hap1", "#1#"), ("_hap2", "#2#"), ("_mat", "#1#"), ("_pat", "#2#"))
 
@@ -57,6 +57,9 @@ def expand_population(raw_ids, all_sequences):
 
 def read_similarity_file(filename):
     """(similarity table, set of sequence names) -- h-fst.py:84-119; an unparsable value is skipped with a warning."""
+    fast = read_table_fast(filename)        # machine-clean text: native reader; anything else: the csv path below
+    if fast is not None:
+        return fast[0], set(fast[0].names)
     try:
         with open(filename, newline="") as handle:
             try:

@@ -19,7 +19,7 @@ import os
 import sys
 
 from .runtime import default_context
-from .tables import SimilarityTable, TableFormatError, read_rows
+from .tables import SimilarityTable, TableFormatError, read_rows, read_table_fast
 
 
 def read_similarity_file(filename):
@@ -27,6 +27,12 @@ def read_similarity_file(filename):
 
     The first item is a `SimilarityTable`: a Mapping keyed by (name_a, name_b) like the
     reference's dict, backed by the dense matrix the device reduces."""
+    fast = read_table_fast(filename)        # machine-clean text: native reader; anything else: the csv path below
+    if fast is not None:
+        table, pair_count = fast
+        if pair_count == 0:
+            print(f"Warning: No similarity entries found in {filename}")
+        return table, set(table.names), pair_count
     try:
         with open(filename, newline="") as handle:
             try:

@@ -126,6 +126,33 @@ class SimilarityTable(Mapping):
         return torch.from_numpy(lab).to(ctx.torch_device)
 
 
+def read_table_fast(path):
+    """(SimilarityTable, data rows) through libimpop_b200's native reader (impop_tsv_scan / impop_tsv_fill), or None
+    when the text is not machine-clean (quotes, non-ASCII, short rows, unusual numbers, missing columns, empty
+    file ...) -- the caller then runs `read_rows`, which mirrors the reference's handling of such input."""
+    import ctypes as C
+
+    from . import _native
+    try:
+        with open(path, "rb") as fh:
+            text = fh.read()
+    except OSError:
+        return None
+    lib = _native.lib()
+    info = _native.TsvInfo()
+    if lib.impop_tsv_scan(text, len(text), C.byref(info)) != 0 or info.status != 0:
+        return None
+    n = int(info.names)
+    mat = np.empty((n, n), dtype=np.float64)
+    names_buf = np.zeros(max(int(info.name_bytes), 1), dtype=np.uint8)
+    name_off = np.zeros(n + 1, dtype=np.int64)
+    if lib.impop_tsv_fill(text, len(text), mat.ctypes.data, names_buf.ctypes.data, name_off.ctypes.data) != 0:
+        return None
+    raw = names_buf.tobytes()
+    names = [raw[name_off[i]:name_off[i + 1] - 1].decode("ascii") for i in range(n)]
+    return SimilarityTable(names, mat), int(info.rows)
+
+
 class TableFormatError(Exception):
     """A similarity table the reference scripts would refuse (message mirrors theirs)."""
 

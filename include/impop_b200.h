@@ -218,6 +218,23 @@ int impop_gfa_scan(const char *text, int64_t bytes, impop_gfa_info_t *info);
 int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_t *x_bits_host, uint32_t *node_len_host,
                    uint16_t *counts_host, char *names_host, int64_t *name_off_host, int64_t *error_line);
 
+/* All-pairs similarity table (the TSV the similarity tools print; pica2.py:6-58 and h-fst.py:84-119 parse it with
+ * csv.DictReader, 47-92 % of those scripts' run time at 466 haplotypes) -> names in sorted order + dense n x n identity
+ * matrix (NaN = pair absent; a repeated pair keeps its last row, pica2.py:44), the form impop_reduce_identity takes.
+ * Columns `group.a`, `group.b`, `estimated.identity` are located by name, extras ignored.  Only machine-clean text is
+ * accepted (ASCII, no quote characters, every row wide enough, plain decimal / exponent numbers or nan / inf):
+ * otherwise status = 1 and the caller falls back to its general reader, which mirrors the reference's handling of
+ * odd input line by line.  impop_tsv_fill returns IMPOP_ERR_ARG on text impop_tsv_scan did not report clean. */
+typedef struct {
+    int64_t rows;        /* data rows */
+    int64_t names;       /* distinct names n */
+    int64_t name_bytes;  /* bytes of all names, each NUL-terminated */
+    int32_t status;      /* 0 clean, 1 use the general reader */
+    int32_t reserved;
+} impop_tsv_info_t;
+int impop_tsv_scan(const char *text, int64_t bytes, impop_tsv_info_t *info);
+int impop_tsv_fill(const char *text, int64_t bytes, double *matrix_host, char *names_host, int64_t *name_off_host);
+
 /* Device self-test: the epilogue's range-restricted division against __ddiv_rn on `count` pseudo-random
  * in-range operand triples (I, A_i, A_j).  *mismatches_host must come back 0.  Synchronous. */
 int impop_selftest_division(impop_ctx_t *ctx, uint64_t seed, int64_t count, int64_t *mismatches_host, void *stream);
