@@ -329,6 +329,10 @@ def run_ours(args):
                 "hbm": {"achieved_gbs": bytes_launch / pairs_avg_s / 1e9, "peak_gbs": peaks["hbm_gbs"],
                         "frac": bytes_launch / pairs_avg_s / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_src"]},
                 "fp64_pair_epilogues_per_s": W * N_HAP * (N_HAP - 1) / 2.0 / pairs_avg_s,
+                # the co-limit DESIGN.md 4.2 derives: 20 fp64 instructions per haplotype pair (2 correctly rounded divisions
+                # + adds) on a pipe of 64 lanes / clk / SM; clock = the SM clock sampled during the timed region
+                "fp64": {"instr_per_pair": 20, "lanes_per_clk_per_sm": 64, "sms": int(torch.cuda.get_device_properties(local).multi_processor_count),
+                         "frac": None},
                 "step_share": {k: v / ms_step for k, v in per_kernel.items()}}
     traffic_file = os.path.join(ROOT, "profiles", "pairs_traffic.json")
     if os.path.exists(traffic_file):
@@ -354,6 +358,9 @@ def run_ours(args):
                "gpu_matches_oracle_on_sample": {"counts_exact": ok_counts, "stats_within_1e-12": ok_stats, "detail": why}}
 
     if rank == 0:
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        f64 = roofline["fp64"]
+        f64["frac"] = roofline["fp64_pair_epilogues_per_s"] * f64["instr_per_pair"] / (f64["lanes_per_clk_per_sm"] * f64["sms"] * mhz * 1e6)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
