@@ -268,9 +268,19 @@ def run_ours(args):
     dx, dl = torch.empty_like(x_bits), torch.empty_like(node_len)
     ds, dc = torch.empty_like(stats), torch.empty_like(counts)
     nsub = max(1, min(args.sub_batches, W))
-    cuts = [int(v) for v in np.linspace(0, W, nsub + 1)]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    if args.e2e_plain or nsub < 4:
+        cuts = [int(v) for v in np.linspace(0, W, nsub + 1)]
+    else:
+        # the last two sub-batches are smaller: what is left to compute after the final copy lands is the step's tail
+        wts = np.ones(nsub); wts[-2], wts[-1] = 0.6, 0.3
+        cuts = [0] + [int(v) for v in np.round(np.cumsum(wts) / wts.sum() * W)]
+        cuts[-1] = W
+    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.e2e_streams))]
     dlabs = [torch.empty_like(labels) for _ in range(nsub)]
+
+    pending = []          # batches of the previous step: closed while this step's copies and kernels run
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(nsub)]
 
     def e2e_step():
         live = []
@@ -278,7 +288,24 @@ def run_ours(args):
             lo, hi = cuts[k], cuts[k + 1]
             if hi <= lo:
                 continue
-            st = streams[k % 2]
+            st = streams[k % len(streams)]
+            if args.e2e_copy_stream:
+                # every host -> device copy goes through ONE stream, in sub-batch order, so the copy engine (the bottleneck
+                # of the step) never waits for a kernel; the set-up's small table upload follows its sub-batch's big copy in
+                # the same stream; the kernels run on the two compute streams behind an event
+                with torch.cuda.stream(copy_stream):
+                    dlabs[k].copy_(hlab, non_blocking=True)
+                    dl[lo:hi].copy_(hl[lo:hi], non_blocking=True)
+                    dx[lo:hi].copy_(hx[lo:hi], non_blocking=True)
+                    b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], WINDOW_BP, node_len_host=hl[lo:hi], stream=copy_stream)
+                    copied[k].record(copy_stream)
+                with torch.cuda.stream(st):
+                    st.wait_event(copied[k])
+                    b.stats(algo, stream=st, out_stats=ds[lo:hi], out_counts=dc[lo:hi])
+                    hs[lo:hi].copy_(ds[lo:hi], non_blocking=True)
+                    hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)
+                live.append(b)
+                continue
             with torch.cuda.stream(st):
                 # this sub-batch's copies first, its set-up (host-side tables + their small upload) while they run: the copy
                 # engine is the bottleneck of the step and must never wait for the host; the table upload lands in the
@@ -291,10 +318,17 @@ def run_ours(args):
                 hs[lo:hi].copy_(ds[lo:hi], non_blocking=True)
                 hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)
             live.append(b)
+        if args.e2e_plain:
+            for st in streams:
+                st.synchronize()
+            for b in live:
+                b.close()
+            return
+        while pending:                      # host work hidden behind the copies just enqueued
+            pending.pop().close()
         for st in streams:
             st.synchronize()
-        for b in live:
-            b.close()
+        pending.extend(live)
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(3):
@@ -303,6 +337,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
+    while pending:                          # inside the timed region: every batch of the timed steps is closed
+        pending.pop().close()
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -395,6 +431,9 @@ def main():
     ap.add_argument("--windows", type=int, default=WINDOWS, help="windows per GPU (default: chr2 / 50 kb = 4854)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sub-batches", type=int, default=8, help="e2e leg: sub-batches alternating between two streams")
+    ap.add_argument("--e2e-streams", type=int, default=2, help="e2e leg: streams the sub-batches rotate over")
+    ap.add_argument("--e2e-copy-stream", type=int, default=0, help="e2e leg: 1 = all host->device copies on one stream, kernels behind events")
+    ap.add_argument("--e2e-plain", action="store_true", help="e2e leg: equal sub-batches, batches closed at the end of their own step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

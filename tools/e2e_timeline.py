@@ -17,7 +17,10 @@ hs = torch.empty((W, NSTATS), dtype=torch.float64, pin_memory=True); hc = torch.
 dx, dl = torch.empty_like(x), torch.empty_like(nl)
 ds = torch.empty((W, NSTATS), dtype=torch.float64, device=dev); dc = torch.empty((W, NCOUNTS), dtype=torch.int64, device=dev)
 streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-cuts = [int(v) for v in np.linspace(0, W, nsub + 1)]
+wts = np.ones(nsub)
+if nsub >= 4 and "--plain" not in sys.argv:
+    wts[-2], wts[-1] = 0.6, 0.3                                  # as bench.py: small last sub-batches, short tail
+cuts = [0] + [int(v) for v in np.round(np.cumsum(wts) / wts.sum() * W)]; cuts[-1] = W
 dlabs = [torch.empty_like(labels) for _ in range(nsub)]
 def step(record=False):
     live = []; evs = []; host = []
@@ -26,12 +29,12 @@ def step(record=False):
         lo, hi = cuts[k], cuts[k + 1]; st = streams[k % 2]
         with torch.cuda.stream(st):
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            h0 = time.perf_counter()
-            b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], 50000, node_len_host=hl[lo:hi], stream=st)
-            h1 = time.perf_counter()
             e[0].record()
             dlabs[k].copy_(hlab, non_blocking=True); dl[lo:hi].copy_(hl[lo:hi], non_blocking=True); dx[lo:hi].copy_(hx[lo:hi], non_blocking=True)
             e[1].record()
+            h0 = time.perf_counter()
+            b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], 50000, node_len_host=hl[lo:hi], stream=st)
+            h1 = time.perf_counter()
             b.stats(0, stream=st, out_stats=ds[lo:hi], out_counts=dc[lo:hi])
             e[2].record()
             hs[lo:hi].copy_(ds[lo:hi], non_blocking=True); hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)
