@@ -177,11 +177,14 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
                 if (FIRST) *dst = mine; else if (mine) *dst |= mine;   // (xh was zeroed by prep_cols)
             }
         }
-        for (int hw = 1; hw < hw_used; ++hw) {                      // further heavy words: rare
-            const uint32_t ent = heavy[hw * 32 + lane];
+        for (int hw = 1; hw < hw_used; ++hw) {                      // further heavy words (windows with > 32 nodes of >= 255 bp):
+            const uint32_t ent = heavy[hw * 32 + lane];             // same scheme as the first word, entry values re-read per word
             const int rel = (int)(ent >> 13) - w0;
             const bool in = (ent & 255u) && rel >= 0 && rel < 32 * PASSES;
             if (!FIRST && !__any_sync(0xffffffffu, in)) continue;
+            const uint32_t add = in ? HEAVY_Q * (ent & 255u) : 0u;
+            const uint32_t sh = in ? ((ent >> 8) & 31u) : 32u;
+            uint32_t mine = 0u;
 #pragma unroll
             for (int r = 0; r < RU; ++r) {
                 uint32_t wsrc = __shfl_sync(0xffffffffu, word[0][r], rel & 31);
@@ -189,13 +192,14 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
                     const uint32_t w_hi = __shfl_sync(0xffffffffu, word[PASSES - 1][r], rel & 31);
                     wsrc = (rel >= 32) ? w_hi : wsrc;
                 }
-                const bool on = in && ((wsrc >> ((ent >> 8) & 31u)) & 1u);
-                const uint32_t bw = __ballot_sync(0xffffffffu, on);
-                if (on) acc[r] += HEAVY_Q * (ent & 255u);
-                if (lane == 0 && i0 + r < row_hi) {
-                    uint32_t *dst = xh + (size_t)(i0 + r) * hwords + hw;
-                    if (FIRST) *dst = bw; else if (bw) *dst |= bw;
-                }
+                const uint32_t on = __funnelshift_rc(wsrc, 0u, sh) & 1u;
+                const uint32_t bw = __ballot_sync(0xffffffffu, on != 0u);
+                acc[r] += on * add;
+                mine = (g == r) ? bw : mine;
+            }
+            if (owner) {                                            // one store instruction per group of rows and word
+                uint32_t *dst = xh + (size_t)(i0 + g) * hwords + hw;
+                if (FIRST) *dst = mine; else if (mine) *dst |= mine;
             }
         }
         {   // transposed warp reduction of the RU row totals: 9 shuffles for eight rows instead of 40
