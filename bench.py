@@ -365,9 +365,9 @@ def run_ours(args):
                 "hbm": {"achieved_gbs": bytes_launch / pairs_avg_s / 1e9, "peak_gbs": peaks["hbm_gbs"],
                         "frac": bytes_launch / pairs_avg_s / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_src"]},
                 "fp64_pair_epilogues_per_s": W * N_HAP * (N_HAP - 1) / 2.0 / pairs_avg_s,
-                # the co-limit DESIGN.md 4.2 derives: 20 fp64 instructions per haplotype pair (2 correctly rounded divisions
-                # + adds) on a pipe of 64 lanes / clk / SM; clock = the SM clock sampled during the timed region
-                "fp64": {"instr_per_pair": 20, "lanes_per_clk_per_sm": 64, "sms": int(torch.cuda.get_device_properties(local).multi_processor_count),
+                # the co-limit DESIGN.md 4.2 derives: 18 fp64 instructions per haplotype pair (2 correctly rounded divisions:
+                # 16, + sums) on a pipe of 64 lanes / clk / SM; clock = the SM clock sampled during the timed region
+                "fp64": {"instr_per_pair": 18, "lanes_per_clk_per_sm": 64, "sms": int(torch.cuda.get_device_properties(local).multi_processor_count),
                          "frac": None},
                 "step_share": {k: v / ms_step for k, v in per_kernel.items()}}
     traffic_file = os.path.join(ROOT, "profiles", "pairs_traffic.json")

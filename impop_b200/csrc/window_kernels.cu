@@ -936,11 +936,19 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             }
             PROF_WORK_END
             // row-side class combination, carried in this lane across the CTA's items of the same window
+#ifdef IMPOP_DBG_NO_REDUCE      // timing experiment only: skip the per-item merges and the per-window warp reduction
+            v[0].hi += ts.hi + ta.hi + tb.hi;
+            double *rec = prm.partials + t * PART_STRIDE + e * 8;
+            if (last) { if (lane < 8) rec[lane] = v[0].hi; v[0].hi = 0.0; }
+            if (true) {
+            } else if (last) {
+#else
             if (fi & IMPOP_LAB_SUBSET) dd_merge(v[0], ts);
             if (fi & IMPOP_LAB_A) { dd_merge(v[1], ta); dd_merge(v[3], tb); }
             if (fi & IMPOP_LAB_B) { dd_merge(v[2], tb); dd_merge(v[3], ta); }
             double *rec = prm.partials + t * PART_STRIDE + e * 8;
-            if (last) {                                        // reduce over the warp's 32 lanes, once per window visit
+            if (last) {
+#endif                                        // reduce over the warp's 32 lanes, once per window visit
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const dd tot = warp_sum_dd(v[q]);
