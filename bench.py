@@ -347,8 +347,8 @@ def run_ours(args):
     e2e_s = float(t.item())
     ctx.check()
     same = bool(torch.equal(hs.nan_to_num(7.0), stats.cpu().nan_to_num(7.0)))
-    h2d = hx.numel() * 4 + hl.numel() * 4 + hlab.numel() * nsub
-    d2h = hs.numel() * 8 + hc.numel() * 8
+    h2d = world * (hx.numel() * 4 + hl.numel() * 4 + hlab.numel() * nsub)      # whole job: every rank copies its own batch
+    d2h = world * (hs.numel() * 8 + hc.numel() * 8)
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
     peaks = load_peaks()
