@@ -346,7 +346,16 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     ctx.check()
-    same = bool(torch.equal(hs.nan_to_num(7.0), stats.cpu().nan_to_num(7.0)))
+    # the sub-batched run must reproduce the resident run: same NaN pattern, every statistic within 1e-12 of the column's scale
+    # (the per-lane sums of the pairs kernel are plain fp64, so the last bits depend on how a batch is dealt to the CTAs)
+    ha, hb = hs.numpy(), stats.cpu().numpy()
+    scale = np.nanmax(np.abs(hb), axis=0, keepdims=True)
+    scale = np.where(np.isfinite(scale), scale, 0.0)
+    with np.errstate(invalid="ignore"):
+        close = np.abs(ha - hb) <= 1e-12 * np.maximum(scale, np.maximum(np.abs(ha), np.abs(hb)))
+    same = bool(np.array_equal(np.isnan(ha), np.isnan(hb)) and bool(np.all(close | np.isnan(hb)))
+                and torch.equal(hc, counts.cpu()))
+    bitwise = bool(torch.equal(hs.nan_to_num(7.0), stats.cpu().nan_to_num(7.0)))
     h2d = world * (hx.numel() * 4 + hl.numel() * 4 + hlab.numel() * nsub)      # whole job: every rank copies its own batch
     d2h = world * (hs.numel() * 8 + hc.numel() * 8)
 
@@ -408,7 +417,7 @@ def run_ours(args):
                        "l2": f"inputs larger than L2 ({(x_bits.numel() * 4 + node_len.numel() * 4) / 1e6:.0f} MB per GPU read every step)",
                        "algo": args.algo},
             "e2e": {"value": units_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": nsub, "matches_resident_run": same},
+                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": nsub, "matches_resident_run": same, "bitwise_equal_to_resident_run": bitwise},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

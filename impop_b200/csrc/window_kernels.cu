@@ -528,6 +528,33 @@ __device__ __forceinline__ uint4 expand_slab(uint32_t word, int h, const uint4 &
     return o;
 }
 
+// Per-lane sums of the epilogue.  IMPOP_EPI_PLAIN = 1: plain fp64 (every term is a non-negative pi_ij and a lane adds at
+// most a few dozen chunk sums per window, so the relative error is bounded by (terms + tree depth) x 2^-53 ~ 1e-14, far
+// inside the 1e-12 contract; the cross-item / cross-warp sums of window_sums_kernel and finalize stay compensated).
+// IMPOP_EPI_PLAIN = 0: two-sum compensated (hi, lo) as in the other kernels.
+#ifndef IMPOP_EPI_PLAIN
+#define IMPOP_EPI_PLAIN 1
+#endif
+#if IMPOP_EPI_PLAIN
+struct esum { double hi; };
+__device__ __forceinline__ esum esum_zero() { return esum{0.0}; }
+__device__ __forceinline__ void esum_add(esum &a, double x) { a.hi = __dadd_rn(a.hi, x); }
+__device__ __forceinline__ void esum_merge(esum &a, const esum &b) { a.hi = __dadd_rn(a.hi, b.hi); }
+__device__ __forceinline__ double esum_lo(const esum &) { return 0.0; }
+__device__ __forceinline__ esum esum_warp(esum v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v.hi = __dadd_rn(v.hi, __shfl_xor_sync(0xffffffffu, v.hi, off));
+    return v;
+}
+#else
+typedef dd esum;
+__device__ __forceinline__ esum esum_zero() { return esum{0.0, 0.0}; }
+__device__ __forceinline__ void esum_add(esum &a, double x) { dd_add(a, x); }
+__device__ __forceinline__ void esum_merge(esum &a, const esum &b) { dd_merge(a, b); }
+__device__ __forceinline__ double esum_lo(const esum &a) { return a.lo; }
+__device__ __forceinline__ esum esum_warp(esum v) { return warp_sum_dd(v); }
+#endif
+
 template <bool DUMP>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_constant__ ItemParams prm) {
@@ -814,7 +841,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
         constexpr int H = WS_EPI_WARPS / 4;               // warps per TMEM lane quarter
         const int hsel = e >> 2;                          // which share of the quarter's chunks
         uint32_t uses0 = 0u, uses1 = 0u;
-        dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};   // this lane's S, AA, BB, AB sums of the current window
+        esum v[4] = {esum_zero(), esum_zero(), esum_zero(), esum_zero()};   // this lane's S, AA, BB, AB sums of the current window
         PROF_DECL
         for (int64_t u = u_lo; u < u_hi; ++u) {
             const int k = (int)(u - u_lo);
@@ -847,7 +874,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 tc_fence_after();
             }
             PROF_WAIT_END
-            dd ts = {0.0, 0.0}, ta = {0.0, 0.0}, tb = {0.0, 0.0};
+            esum ts = esum_zero(), ta = esum_zero(), tb = esum_zero();
             const uint32_t tm0 = tmem_base + buf * TILE_N + ((uint32_t)(q4 * 32) << 16);
             uint32_t ra[16];
             auto chunk = [&](const uint32_t (&r)[16], int c) {
@@ -887,18 +914,18 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 #pragma unroll
                     for (int q = 0; q < 16; ++q) cs = __fma_rn(p[q], col.fs[cc + q], cs);   // p * 1.0 or p * 0.0: exact
                 }
-                dd_add(ts, cs);
+                esum_add(ts, cs);
                 if (cm & 2u) {
                     double ca = 0.0;
 #pragma unroll
                     for (int q = 0; q < 16; ++q) ca = __fma_rn(p[q], col.fa[cc + q], ca);
-                    dd_add(ta, ca);
+                    esum_add(ta, ca);
                 }
                 if (cm & 4u) {
                     double cb = 0.0;
 #pragma unroll
                     for (int q = 0; q < 16; ++q) cb = __fma_rn(p[q], col.fb[cc + q], cb);
-                    dd_add(tb, cb);
+                    esum_add(tb, cb);
                 }
             };
             if (have_acc) {
@@ -937,23 +964,23 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             PROF_WORK_END
             // row-side class combination, carried in this lane across the CTA's items of the same window
 #ifdef IMPOP_DBG_NO_REDUCE      // timing experiment only: skip the per-item merges and the per-window warp reduction
-            v[0].hi += ts.hi + ta.hi + tb.hi;
+            v[0].hi += ts.hi + ta.hi + tb.hi;   // (esum or dd: .hi exists in both)
             double *rec = prm.partials + t * PART_STRIDE + e * 8;
             if (last) { if (lane < 8) rec[lane] = v[0].hi; v[0].hi = 0.0; }
             if (true) {
             } else if (last) {
 #else
-            if (fi & IMPOP_LAB_SUBSET) dd_merge(v[0], ts);
-            if (fi & IMPOP_LAB_A) { dd_merge(v[1], ta); dd_merge(v[3], tb); }
-            if (fi & IMPOP_LAB_B) { dd_merge(v[2], tb); dd_merge(v[3], ta); }
+            if (fi & IMPOP_LAB_SUBSET) esum_merge(v[0], ts);
+            if (fi & IMPOP_LAB_A) { esum_merge(v[1], ta); esum_merge(v[3], tb); }
+            if (fi & IMPOP_LAB_B) { esum_merge(v[2], tb); esum_merge(v[3], ta); }
             double *rec = prm.partials + t * PART_STRIDE + e * 8;
             if (last) {
 #endif                                        // reduce over the warp's 32 lanes, once per window visit
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const dd tot = warp_sum_dd(v[q]);
-                    if (lane == 0) { rec[q] = tot.hi; rec[4 + q] = tot.lo; }
-                    v[q].hi = 0.0; v[q].lo = 0.0;
+                    const esum tot = esum_warp(v[q]);
+                    if (lane == 0) { rec[q] = tot.hi; rec[4 + q] = esum_lo(tot); }
+                    v[q] = esum_zero();
                 }
             } else if (lane < 8) {
                 rec[lane] = 0.0;                               // the sums travel on to the next item's record
