@@ -641,9 +641,20 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 if (isA) {
                     uint8_t *dst = smem + s * STAGE_BYTES + rl * 16;
                     const uint32_t bw[4] = {bits[0].x, bits[0].y, bits[0].z, bits[0].w};
+                    // the byte weights of four slabs are loaded before the first store of the group: a load behind a store
+                    // to the same shared-memory array is ordered after it (possible alias), which serialised load -> AND ->
+                    // store eight times per chunk
 #pragma unroll
-                    for (int slab = 0; slab < KCHUNK / 16; ++slab)
-                        *reinterpret_cast<uint4 *>(dst + slab * lbo) = expand_slab<2>(bw[slab >> 1], slab & 1, slot.w[slab]);
+                    for (int half = 0; half < 2; ++half) {
+                        uint4 wv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) wv[q] = slot.w[half * 4 + q];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int slab = half * 4 + q;
+                            *reinterpret_cast<uint4 *>(dst + slab * lbo) = expand_slab<2>(bw[slab >> 1], slab & 1, wv[q]);
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int q = 0; q < WS_B_RPL; ++q) {
