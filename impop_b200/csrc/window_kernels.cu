@@ -398,9 +398,9 @@ __device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const d
 //   warp  13     table warp: per item, the column / row values and geometry the epilogue needs, into one of
 //                three tables in shared memory, up to three items ahead
 //   warps 14-15  loaders: cp.async of each chunk's packed presence bits and byte weights into a ring of raw slots
-//   warps 16-23  epilogue: tcgen05.ld, exact integer union, fp64 pi_ij, compensated sums
-// Registers are moved from the producer / MMA / table warpgroups (48 each) to the epilogue warpgroups (144 each):
-// 16 x 32 x 48 + 8 x 32 x 144 = 61 440 = the 768 x 80 registers the CTA owns (a larger sum makes
+//   warps 16-27  epilogue (three per TMEM lane quarter): tcgen05.ld, exact integer union, fp64 pi_ij, per-lane sums
+// Registers are moved from the producer / MMA / table / loader warpgroups (48 each) to the epilogue warpgroups (104
+// each): 16 x 32 x 48 + 12 x 32 x 104 = 64 512 = the 896 x 72 registers the CTA owns (a larger sum makes
 // setmaxnreg.inc wait forever).
 // The integer pipes (expansion) and the fp64 pipe (epilogue) so run concurrently on different
 // warps, and items flow through without CTA-wide barriers.
@@ -736,7 +736,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             // ============================================================ table warp (13): builds, up to three items ahead of
             // the epilogue, everything it needs of an item -- A_j and class flags of the columns, A_i and labels of the
             // rows, the item's geometry -- so that no epilogue warp ever waits for global memory or for another
-            // epilogue warp between two items.  tbl_full[slot]: 1 arrival (this warp); tbl_empty[slot]: 8 (epilogue).
+            // epilogue warp between two items.  tbl_full[slot]: 1 arrival (this warp); tbl_empty[slot]: one per epilogue warp.
             int4 nxt = raw_item(u_lo), nxt_x = raw_ext(u_lo);
             for (int64_t u = u_lo; u < u_hi; ++u) {
                 const int k = (int)(u - u_lo), slot = k % WS_TABLES;
@@ -841,13 +841,13 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 #endif
         }
     } else {
-        // ================================================================ epilogue.  All eight warps work on the same item
-        // (warp -> 32-row quarter q4 of the TMEM lanes x one half of that quarter's valid 16-column chunks) while the
+        // ================================================================ epilogue.  All twelve warps work on the same item
+        // (warp -> 32-row quarter q4 of the TMEM lanes x one third of that quarter's valid 16-column chunks) while the
         // MMA of the next item fills the other TMEM buffer.  Everything else an item needs comes from its table in
         // shared memory (table warps above): a warp that finishes its chunks early moves on to the next item as soon
-        // as the MMA has filled that accumulator -- no barrier couples the eight warps.
+        // as the MMA has filled that accumulator -- no barrier couples the twelve warps.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 " IMPOP_STR(IMPOP_REGS_EPI) ";");
-        const int e = warp - WS_EPI_WARP0;              // 0..7
+        const int e = warp - WS_EPI_WARP0;              // 0..11
         const int q4 = warp & 3;                          // TMEM lane quarter this warp may read
         constexpr int H = WS_EPI_WARPS / 4;               // warps per TMEM lane quarter
         const int hsel = e >> 2;                          // which share of the quarter's chunks
