@@ -445,7 +445,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     b->items = item_off[W];
     Carver cs;
     const size_t s_A = cs.take(4 * (size_t)(row_off[W] + 1)), s_w8 = cs.take((size_t)w8_off[W] + 64),
-                 s_w8n = cs.take((size_t)w8_off[W] + 64);
+                 s_w8n = cs.take((size_t)w8_off[W] + 64), s_planes = cs.take((size_t)w8_off[W] + 64);
     const size_t s_heavy = cs.take(4 * (size_t)(heavy_off[W] + 64)), s_xh = cs.take(4 * (size_t)(xh_off[W] + 4));
     const size_t s_part = cs.take(8 * (size_t)(b->items * PART_STRIDE + 1));
     const size_t s_sums = cs.take(8 * 4 * W1), s_counts = cs.take(8 * IMPOP_NCOUNTS * W1);
@@ -454,7 +454,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     b->scratch = pool_get(ctx, cs.off);
     if (!b->scratch) return bail(IMPOP_ERR_NOMEM, "impop_batch_create: out of device memory (scratch)");
     char *sb = (char *)b->scratch;
-    t.A = (int32_t *)(sb + s_A); t.w8 = (uint8_t *)(sb + s_w8); t.w8n = (uint8_t *)(sb + s_w8n); t.heavy = (uint32_t *)(sb + s_heavy);
+    t.A = (int32_t *)(sb + s_A); t.w8 = (uint8_t *)(sb + s_w8); t.w8n = (uint8_t *)(sb + s_w8n); t.planes = (uint32_t *)(sb + s_planes); t.heavy = (uint32_t *)(sb + s_heavy);
     t.xh = (uint32_t *)(sb + s_xh); t.seg_any = (uint32_t *)(sb + s_any); t.seg_all = (uint32_t *)(sb + s_all);
     t.heavy_n = (int32_t *)(sb + s_hn);
     b->partials = (double *)(sb + s_part); b->sums_tmp = (double *)(sb + s_sums); b->counts_tmp = (int64_t *)(sb + s_counts);

@@ -20,8 +20,8 @@ namespace impop {
 
 // ==========================================================================================
 // Prep, three small kernels (the second is the only one that touches the presence matrix):
-//   prep_cols   one CTA per window: byte weights of the dense columns, heavy-node table, range check
-//               sum(len) < 2^31, label counts, reset of the any / all words
+//   prep_cols   one CTA per window: byte weights of the dense columns and their eight bit planes (ballot over 32 nodes),
+//               heavy-node table, range check sum(len) < 2^31, label counts, reset of the any / all words
 //   prep_rows   one CTA per (window, row slice) -- a window with many haplotypes is cut into slices so that a
 //               batch of few large windows still fills the GPU: path lengths A_i as the sum over the eight bit
 //               planes of the dense byte weights of 2^p popc(row word & plane word) (lane = presence word, planes
@@ -65,7 +65,16 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
         for (int k = threadIdx.x; k < m64; k += PREP_THREADS) {
             uint32_t l = (k < m) ? __ldg(len + k) : 0u;
             tot += l;
-            w8[kperm(k)] = w8n[k] = (uint8_t)(l % HEAVY_Q);
+            const uint32_t bwt = l % HEAVY_Q;
+            w8[kperm(k)] = w8n[k] = (uint8_t)bwt;
+            {   // bit planes of the byte weights for prep_rows (a warp covers 32 consecutive nodes; m64 is a multiple of 128)
+                uint32_t *pl = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(tab.planes) + tab.w8_off[w]) + (k >> 5) * 8;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const uint32_t msk = __ballot_sync(0xffffffffu, (bwt >> p) & 1u);
+                    if (lane == p) pl[p] = msk;
+                }
+            }
             uint32_t q = l / HEAVY_Q;
             while (q > 0) {
                 uint32_t c = q < 255u ? q : 255u;
@@ -104,16 +113,23 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
 // Rows [row_lo, row_hi) of one window against one group of <= 2048 nodes (PASSES x 32 presence words per row).
 // FIRST: the group starts at node 0 (defines A_i and the heavy words; later groups add to them).
 template <int PASSES, bool FIRST>
-__device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS], uint32_t *s_any, uint32_t *s_all,
+__device__ __forceinline__ void prep_rows_group(uint32_t *s_any, uint32_t *s_all,
                                                 const uint32_t *x, int pitch, int wlim, const uint8_t *lab, int row_lo, int row_hi,
                                                 int w0, const uint32_t *heavy, int hwords, int hw_used, uint32_t *xh,
-                                                int32_t *A) {
+                                                int32_t *A, const uint32_t *planes, int plane_words) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t pm[PASSES][8];
 #pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps)
-#pragma unroll
-        for (int p = 0; p < 8; ++p) pm[ps][p] = s_pm[p][ps * 32 + lane];
+    for (int ps = 0; ps < PASSES; ++ps) {
+        const int gw = w0 + ps * 32 + lane;                          // presence word = group of 32 nodes
+        uint4 lo4 = make_uint4(0u, 0u, 0u, 0u), hi4 = lo4;
+        if (gw < plane_words) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(planes + (size_t)gw * 8);
+            lo4 = __ldg(src); hi4 = __ldg(src + 1);
+        }
+        pm[ps][0] = lo4.x; pm[ps][1] = lo4.y; pm[ps][2] = lo4.z; pm[ps][3] = lo4.w;
+        pm[ps][4] = hi4.x; pm[ps][5] = hi4.y; pm[ps][6] = hi4.z; pm[ps][7] = hi4.w;
+    }
     // the first heavy word (32 entries) is kept in registers: lane = entry
     const uint32_t ent0 = hw_used > 0 ? heavy[lane] : 0u;
     const int rel0 = (int)(ent0 >> 13) - w0;                        // word of the entry's node within this group
@@ -233,16 +249,13 @@ __device__ __forceinline__ void prep_rows_group(const uint32_t (*s_pm)[PM_WORDS]
 #define IMPOP_PREP_OCC 4
 #endif
 __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel(const __grid_constant__ WindowTab tab) {
-    __shared__ uint32_t s_pm[8][PM_WORDS];    // bit planes of the dense byte weights, per presence word of the node group
     __shared__ uint32_t s_any[PM_WORDS], s_all[PM_WORDS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int sidx = blockIdx.x; sidx < tab.n_slices; sidx += gridDim.x) {
         const int4 sl = __ldg(tab.slices + sidx);
         const int w = sl.x, row_lo = sl.y, row_hi = sl.z;
         const int m = tab.m[w], pitch = tab.pitch[w];
         const int wlim = min(pitch, ((m + 127) >> 7) << 2);      // words of a row that can hold nodes < m (16-byte groups):
                                                                  // a window may be a column range of a wider matrix
-        const uint8_t *w8n = tab.w8n + tab.w8_off[w];            // natural order; prep_cols ran before this kernel
         const uint32_t *x = tab.x + tab.x_off[w];
         const uint8_t *lab = tab.labels + tab.lab_off[w];
         const uint32_t *heavy = tab.heavy + tab.heavy_off[w];
@@ -251,27 +264,19 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
         uint32_t *xh = tab.xh + tab.xh_off[w];
         int32_t *A = tab.A + tab.row_off[w];
         const int64_t wo = tab.word_off[w];
+        const uint32_t *planes = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(tab.planes) + tab.w8_off[w]);
+        const int plane_words = (((m + KCHUNK - 1) / KCHUNK) * KCHUNK) >> 5;   // prep_cols wrote planes for the padded node count
         for (int c0 = 0; c0 < m || c0 == 0; c0 += 32 * PM_WORDS) {   // groups of 2048 nodes = 64 presence words
-            // plane p of word wv: bit j = bit p of the byte weight of node c0 + 32 wv + j (ballot over the 32 nodes)
-            for (int wv = warp; wv < PM_WORDS; wv += PREP_THREADS / 32) {
-                const int k = c0 + wv * 32 + lane;
-                const uint32_t b = (k < m) ? (uint32_t)w8n[k] : 0u;
-#pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const uint32_t msk = __ballot_sync(0xffffffffu, (b >> p) & 1u);
-                    if (lane == p) s_pm[p][wv] = msk;
-                }
-            }
             if (threadIdx.x < PM_WORDS) { s_any[threadIdx.x] = 0u; s_all[threadIdx.x] = 0xffffffffu; }
             __syncthreads();
             const int w0 = c0 >> 5;                       // first word of this group of nodes
             const bool two = m - c0 > 1024;               // 32 words (1024 nodes) per warp pass
             if (c0 == 0) {
-                if (two) prep_rows_group<2, true>(s_pm, s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
-                else prep_rows_group<1, true>(s_pm, s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+                if (two) prep_rows_group<2, true>(s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A, planes, plane_words);
+                else prep_rows_group<1, true>(s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A, planes, plane_words);
             } else {
-                if (two) prep_rows_group<2, false>(s_pm, s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
-                else prep_rows_group<1, false>(s_pm, s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A);
+                if (two) prep_rows_group<2, false>(s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A, planes, plane_words);
+                else prep_rows_group<1, false>(s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A, planes, plane_words);
             }
             __syncthreads();
             if (threadIdx.x < PM_WORDS && w0 + threadIdx.x < ((m + 31) >> 5)) {
