@@ -369,6 +369,33 @@ int tsv_walk(const char *text, int64_t bytes, NameMap &nm, int64_t &rows, F row)
     return 0;
 }
 
+struct TsvRow { int32_t a, b; double v; };
+
+// impop_tsv_scan keeps what it parsed for the impop_tsv_fill that follows on the same thread with the same text, so the
+// table is walked (names hashed, numbers converted) once, not twice.  Per thread, no shared state; the fill trusts the
+// memo only if pointer, length and a hash of the whole text agree, and parses again otherwise.
+struct TsvMemo {
+    const char *text = nullptr;
+    int64_t bytes = -1;
+    uint64_t hash = 0;
+    std::vector<TsvRow> rows;
+    std::vector<Line> names;                  // first-seen order, pointing into `text`
+};
+thread_local TsvMemo g_tsv_memo;
+
+inline uint64_t tsv_hash(const char *text, int64_t bytes) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes;
+    int64_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        memcpy(&w, text + i, 8);
+        h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+        h ^= h >> 29;
+    }
+    for (; i < bytes; ++i) h = (h ^ (unsigned char)text[i]) * 0x100000001B3ull;
+    return h;
+}
+
 }  // namespace
 
 extern "C" {
@@ -378,12 +405,18 @@ int impop_tsv_scan(const char *text, int64_t bytes, impop_tsv_info_t *info) {
     impop_tsv_info_t out = {0, 0, 0, 0, 0};
     NameMap nm;
     nm.init(1024);
+    TsvMemo &memo = g_tsv_memo;
+    memo.text = nullptr; memo.bytes = -1; memo.rows.clear(); memo.names.clear();
     int64_t rows = 0;
-    out.status = tsv_walk(text, bytes, nm, rows, [](int32_t, int32_t, double) {});
+    out.status = tsv_walk(text, bytes, nm, rows, [&](int32_t a, int32_t b, double v) { memo.rows.push_back(TsvRow{a, b, v}); });
     if (out.status == 0) {
         out.rows = rows;
         out.names = (int64_t)nm.names.size();
         for (const Line &s : nm.names) out.name_bytes += (int64_t)(s.e - s.p) + 1;
+        memo.names = nm.names;
+        memo.text = text; memo.bytes = bytes; memo.hash = tsv_hash(text, bytes);
+    } else {
+        memo.rows.clear();
     }
     *info = out;
     return IMPOP_OK;
@@ -392,12 +425,18 @@ int impop_tsv_scan(const char *text, int64_t bytes, impop_tsv_info_t *info) {
 int impop_tsv_fill(const char *text, int64_t bytes, double *matrix_host, char *names_host, int64_t *name_off_host) {
     if (!text || bytes < 0 || !name_off_host) return IMPOP_ERR_ARG;
     NameMap nm;
-    nm.init(1024);
-    struct Row { int32_t a, b; double v; };
-    std::vector<Row> rows;
-    int64_t count = 0;
-    if (tsv_walk(text, bytes, nm, count, [&](int32_t a, int32_t b, double v) { rows.push_back(Row{a, b, v}); }) != 0)
-        return IMPOP_ERR_ARG;
+    std::vector<TsvRow> rows;
+    TsvMemo &memo = g_tsv_memo;
+    if (memo.text == text && memo.bytes == bytes && memo.hash == tsv_hash(text, bytes)) {
+        rows.swap(memo.rows);                                     // parsed by the impop_tsv_scan just before
+        nm.names.swap(memo.names);
+        memo.text = nullptr; memo.bytes = -1;
+    } else {
+        nm.init(1024);
+        int64_t count = 0;
+        if (tsv_walk(text, bytes, nm, count, [&](int32_t a, int32_t b, double v) { rows.push_back(TsvRow{a, b, v}); }) != 0)
+            return IMPOP_ERR_ARG;
+    }
     const size_t n = nm.names.size();
     if (n && (!matrix_host || !names_host)) return IMPOP_ERR_ARG;
     // names in byte order (= Python's str order on ASCII), first-seen index -> sorted rank
@@ -421,7 +460,7 @@ int impop_tsv_fill(const char *text, int64_t bytes, double *matrix_host, char *n
     name_off_host[n] = off;
     const double nan = __builtin_nan("");
     for (size_t i = 0; i < n * n; ++i) matrix_host[i] = nan;
-    for (const Row &r : rows) {                                   // file order: the last row of a pair stays
+    for (const TsvRow &r : rows) {                                // file order: the last row of a pair stays
         const size_t i = (size_t)rank[r.a], j = (size_t)rank[r.b];
         matrix_host[i * n + j] = r.v;
         matrix_host[j * n + i] = r.v;

@@ -85,3 +85,30 @@ def test_speed_on_a_466_haplotype_table(tmp_path):
     assert np.array_equal(np.nan_to_num(fast[0].matrix, nan=-1.0), np.nan_to_num(ref.matrix, nan=-1.0))
     print(f"native {1e3 * (t1 - t0):.1f} ms, csv {1e3 * (t2 - t1):.1f} ms")
     assert (t1 - t0) * 3 < (t2 - t1)
+
+
+def test_scan_memo_is_not_reused_for_other_text():
+    """impop_tsv_scan keeps its parse for the impop_tsv_fill that follows; a fill on a buffer whose CONTENT changed at
+    the same address, or with no scan before it, must parse the text it is given."""
+    import ctypes as C
+
+    from impop_b200 import _native
+    lib = _native.lib()
+    text = bytearray(b"group.a\tgroup.b\testimated.identity\nx\ty\t0.25\nx\tz\t0.5\ny\tz\t0.75\n")
+    buf = (C.c_char * len(text)).from_buffer(text)
+
+    def fill():
+        mat = np.empty((3, 3), dtype=np.float64)
+        names = np.zeros(16, dtype=np.uint8)
+        off = np.zeros(4, dtype=np.int64)
+        assert lib.impop_tsv_fill(buf, len(text), mat.ctypes.data, names.ctypes.data, off.ctypes.data) == 0
+        return mat
+
+    info = _native.TsvInfo()
+    assert lib.impop_tsv_scan(buf, len(text), C.byref(info)) == 0 and info.status == 0 and info.names == 3
+    assert fill()[0, 1] == 0.25                                   # from the memo
+    assert fill()[0, 1] == 0.25                                   # memo consumed: parsed again
+    assert lib.impop_tsv_scan(buf, len(text), C.byref(info)) == 0
+    text[text.index(b"0.25"):text.index(b"0.25") + 4] = b"0.35"   # same address, same length, other content
+    m = fill()
+    assert m[0, 1] == 0.35 and m[1, 0] == 0.35 and m[0, 2] == 0.5 and m[1, 2] == 0.75 and np.isnan(m[0, 0])
