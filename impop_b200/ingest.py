@@ -76,6 +76,22 @@ def read_gfa(path, want_counts: bool = False, region: str | None = None, length:
         return parse_gfa(fh.read(), want_counts, region, length)
 
 
+def read_gfa_many(items, threads: int | None = None, want_counts: bool = False) -> list:
+    """[(region, path, length), ...] -> [GraphWindow, ...] in the same order.  The native reader runs outside the GIL
+    (ctypes), so the window graphs of a chromosome are parsed on all host cores; `threads=1` reads one by one."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    items = list(items)
+    if threads is None:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, min(int(threads), len(items) or 1))
+    one = lambda it: read_gfa(it[1], want_counts=want_counts, region=it[0], length=int(it[2] or 0))
+    if threads == 1:
+        return [one(it) for it in items]
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        return list(pool.map(one, items))                 # map keeps the input order; the first exception propagates
+
+
 def write_gfa(handle, names, x: np.ndarray, node_len: np.ndarray, walks: bool = False) -> None:
     """Emit a window as GFA v1 (what the synthetic generator hands to the text path and to tests): one S line per
     node (sequence 'N' * len up to 64 bp, else '*' + LN:i:), one P (or W) line per haplotype listing its nodes."""

@@ -129,14 +129,15 @@ def main(argv=None):
     if args.batch:
         graphs = ingest.load_batch(args.batch)
     else:
-        graphs = []
+        todo = []
         with open(args.gfa_list) as fh:
             for line in fh:
                 if not line.strip() or line.startswith("#"):
                     continue
                 region, path = line.rstrip("\n").split("\t")[:2]
                 mt = re.search(r":(\d+)-(\d+)$", region)
-                graphs.append(ingest.read_gfa(path, region=region, length=int(mt.group(2)) - int(mt.group(1)) if mt else 0))
+                todo.append((region, path, int(mt.group(2)) - int(mt.group(1)) if mt else 0))
+        graphs = ingest.read_gfa_many(todo)               # parsed on all host cores (the reader runs outside the GIL)
     if args.save_batch:
         ingest.save_batch(args.save_batch, graphs)
     if (args.fst_out or args.pooled_fst_out) and (args.pop_a is None or args.pop_b is None):

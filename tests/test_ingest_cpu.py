@@ -103,3 +103,28 @@ def test_multiset_expansion_is_the_min_count_intersection():
     assert np.array_equal(inter, want)
     assert np.array_equal(np.diag(inter), counts @ node_len)
     assert ex.m == int(np.maximum(counts.max(axis=0), 1).sum())
+
+
+def test_read_gfa_many_matches_one_by_one(tmp_path):
+    """The threaded reader of a chromosome's window graphs returns the windows in input order, identical to reading
+    them one by one; a malformed file raises as it does in read_gfa."""
+    from impop_b200._native import NativeError
+    ws = synth.make_windows(40, 3000, 3, seed=21)
+    names = synth.haplotype_names(40, "chr2", 0, 3000)
+    items = []
+    for w in range(3):
+        for rep in range(3):
+            p = tmp_path / f"w{w}_{rep}.gfa"
+            with open(p, "w") as fh:
+                ingest.write_gfa(fh, names, ws.dense(w)[:, :ws.m], ws.node_len[w][:ws.m], walks=bool(rep & 1))
+            items.append((f"chr2:{3000 * w}-{3000 * (w + 1)}", str(p), 3000))
+    many = ingest.read_gfa_many(items, threads=4)
+    for it, g in zip(items, many):
+        one = ingest.read_gfa(it[1], region=it[0], length=it[2])
+        assert g.region == it[0] and g.length == 3000 and g.names == one.names
+        assert np.array_equal(g.x_bits, one.x_bits) and np.array_equal(g.node_len, one.node_len)
+    assert [g.region for g in ingest.read_gfa_many(items, threads=1)] == [it[0] for it in items]
+    bad = tmp_path / "bad.gfa"
+    bad.write_text("S\t1\tACGT\nP\tp1\t1+,2+\t*\n")                 # step names a segment that does not exist
+    with pytest.raises(NativeError):
+        ingest.read_gfa_many(items[:2] + [("chr2:0-1", str(bad), 1)], threads=3)
