@@ -84,6 +84,49 @@ struct SegMap {
     }
 };
 
+// Segment name -> node index.  Graph builders number their segments, so when EVERY name is a canonical decimal
+// integer (no sign, no leading zero, at most 9 digits) and the numbers are dense enough, a step is resolved by
+// parsing its digits and indexing an array; any other file goes through the hash map.  A step token that is not a
+// canonical integer cannot equal any name of such a file, so it is reported as undefined either way.
+struct SegIndex {
+    SegMap map;
+    std::vector<int32_t> direct;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    bool numeric = true, use_direct = false;
+    static inline bool canonical(const char *p, size_t len, uint32_t &v) {
+        if (len == 0 || len > 9 || (len > 1 && p[0] == '0')) return false;
+        uint32_t x = 0;
+        for (size_t i = 0; i < len; ++i) {
+            const unsigned d = (unsigned)(p[i] - '0');
+            if (d > 9u) return false;
+            x = x * 10u + d;
+        }
+        v = x;
+        return true;
+    }
+    void init(size_t n) { map.init(n); }
+    bool insert(const char *p, size_t len, int32_t idx) {
+        uint32_t v;
+        if (numeric && canonical(p, len, v)) { lo = v < lo ? v : lo; hi = v > hi ? v : hi; } else numeric = false;
+        return map.insert(p, len, idx);
+    }
+    void finish(size_t n) {                                      // after the last insert
+        if (!numeric || n == 0 || (uint64_t)(hi - lo) + 1 > 8ull * n + 1024) return;
+        direct.assign((size_t)(hi - lo) + 1, -1);
+        for (const SegMap::Slot &sl : map.slots)
+            if (sl.p) { uint32_t v = 0; canonical(sl.p, sl.len, v); direct[v - lo] = sl.idx; }
+        use_direct = true;
+    }
+    inline int32_t find(const char *p, size_t len) const {
+        if (use_direct) {
+            uint32_t v;
+            if (!canonical(p, len, v) || v < lo || v > hi) return -1;
+            return direct[v - lo];
+        }
+        return map.find(p, len);
+    }
+};
+
 // Length of a segment: its sequence, or the LN:i: tag when the sequence is '*'.
 inline bool segment_length(const Line &ln, uint64_t &len) {
     const char *sp, *se;
@@ -114,11 +157,11 @@ inline bool for_each_step(char kind, const char *p, const char *e, F f) {
     if (kind == 'P') {
         if (e - p == 1 && *p == '*') return true;
         while (p < e) {
-            const char *c = (const char *)memchr(p, ',', (size_t)(e - p));
-            const char *se = c ? c : e;
+            const char *se = p;
+            while (se < e && *se != ',') ++se;                  // steps are a few bytes long: a plain loop beats memchr
             if (se - p < 2 || (se[-1] != '+' && se[-1] != '-')) return false;
             if (!f(p, se - 1)) return false;
-            p = c ? c + 1 : e;
+            p = se < e ? se + 1 : e;
         }
         return true;
     }
@@ -158,6 +201,29 @@ inline bool path_name(char kind, const Line &ln, std::string &out) {
 
 inline int steps_field(char kind) { return kind == 'P' ? 2 : 6; }
 
+inline uint64_t text_hash(const char *text, int64_t bytes) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes;
+    int64_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        memcpy(&w, text + i, 8);
+        h = (h ^ w) * 0xD6E8FEB86659FD93ull;
+        h ^= h >> 29;
+    }
+    for (; i < bytes; ++i) h = (h ^ (unsigned char)text[i]) * 0x100000001B3ull;
+    return h;
+}
+
+// What impop_gfa_scan found, kept for the impop_gfa_fill that follows on the same thread with the same text (pointer,
+// length and hash of the text must agree), so that the fill does not walk every step a third time.
+struct GfaMemo {
+    const char *text = nullptr;
+    int64_t bytes = -1;
+    uint64_t hash = 0;
+    impop_gfa_info_t info;
+};
+thread_local GfaMemo g_gfa_memo;
+
 }  // namespace
 
 extern "C" {
@@ -165,6 +231,7 @@ extern "C" {
 int impop_gfa_scan(const char *text, int64_t bytes, impop_gfa_info_t *info) {
     if (!text || bytes < 0 || !info) return IMPOP_ERR_ARG;
     impop_gfa_info_t out = {0, 0, 0, 0, 0};
+    g_gfa_memo.text = nullptr; g_gfa_memo.bytes = -1;
     const char *cur = text, *end = text + bytes;
     Line ln;
     std::string name;
@@ -189,6 +256,7 @@ int impop_gfa_scan(const char *text, int64_t bytes, impop_gfa_info_t *info) {
         }
     }
     *info = out;
+    g_gfa_memo.text = text; g_gfa_memo.bytes = bytes; g_gfa_memo.hash = text_hash(text, bytes); g_gfa_memo.info = out;
     return IMPOP_OK;
 }
 
@@ -197,14 +265,20 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
     if (error_line) *error_line = 0;
     if (!text || bytes < 0 || pitch_words < 0 || pitch_words % 4 != 0) return IMPOP_ERR_ARG;
     impop_gfa_info_t info;
-    int rc = impop_gfa_scan(text, bytes, &info);
-    if (rc != IMPOP_OK) { if (error_line) *error_line = info.error_line; return rc; }
+    if (g_gfa_memo.text == text && g_gfa_memo.bytes == bytes && g_gfa_memo.hash == text_hash(text, bytes)) {
+        info = g_gfa_memo.info;                                   // scanned (and validated) just before
+        g_gfa_memo.text = nullptr; g_gfa_memo.bytes = -1;
+    } else {
+        int rc = impop_gfa_scan(text, bytes, &info);
+        g_gfa_memo.text = nullptr; g_gfa_memo.bytes = -1;
+        if (rc != IMPOP_OK) { if (error_line) *error_line = info.error_line; return rc; }
+    }
     if ((int64_t)pitch_words * 32 < info.segments) return IMPOP_ERR_ARG;
     if ((info.paths && (!x_bits_host || !names_host || !name_off_host)) || (info.segments && !node_len_host)) return IMPOP_ERR_ARG;
     if (info.segments > 0x7FFFFFFFll || info.paths > 0x7FFFFFFFll) return IMPOP_ERR_RANGE;
 
     // pass 1: segments in file order
-    SegMap map;
+    SegIndex map;
     map.init((size_t)info.segments);
     const char *cur = text, *end = text + bytes;
     Line ln;
@@ -222,6 +296,7 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
         }
         node_len_host[seg++] = (uint32_t)len;
     }
+    map.finish((size_t)info.segments);
     // pass 2: path lines in file order
     if (info.paths) memset(x_bits_host, 0, sizeof(uint32_t) * (size_t)info.paths * (size_t)pitch_words);
     if (counts_host && info.paths) memset(counts_host, 0, sizeof(uint16_t) * (size_t)info.paths * (size_t)info.segments);
@@ -383,19 +458,6 @@ struct TsvMemo {
 };
 thread_local TsvMemo g_tsv_memo;
 
-inline uint64_t tsv_hash(const char *text, int64_t bytes) {
-    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes;
-    int64_t i = 0;
-    for (; i + 8 <= bytes; i += 8) {
-        uint64_t w;
-        memcpy(&w, text + i, 8);
-        h = (h ^ w) * 0xD6E8FEB86659FD93ull;
-        h ^= h >> 29;
-    }
-    for (; i < bytes; ++i) h = (h ^ (unsigned char)text[i]) * 0x100000001B3ull;
-    return h;
-}
-
 }  // namespace
 
 extern "C" {
@@ -414,7 +476,7 @@ int impop_tsv_scan(const char *text, int64_t bytes, impop_tsv_info_t *info) {
         out.names = (int64_t)nm.names.size();
         for (const Line &s : nm.names) out.name_bytes += (int64_t)(s.e - s.p) + 1;
         memo.names = nm.names;
-        memo.text = text; memo.bytes = bytes; memo.hash = tsv_hash(text, bytes);
+        memo.text = text; memo.bytes = bytes; memo.hash = text_hash(text, bytes);
     } else {
         memo.rows.clear();
     }
@@ -427,7 +489,7 @@ int impop_tsv_fill(const char *text, int64_t bytes, double *matrix_host, char *n
     NameMap nm;
     std::vector<TsvRow> rows;
     TsvMemo &memo = g_tsv_memo;
-    if (memo.text == text && memo.bytes == bytes && memo.hash == tsv_hash(text, bytes)) {
+    if (memo.text == text && memo.bytes == bytes && memo.hash == text_hash(text, bytes)) {
         rows.swap(memo.rows);                                     // parsed by the impop_tsv_scan just before
         nm.names.swap(memo.names);
         memo.text = nullptr; memo.bytes = -1;
