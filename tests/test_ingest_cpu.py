@@ -128,3 +128,32 @@ def test_read_gfa_many_matches_one_by_one(tmp_path):
     bad.write_text("S\t1\tACGT\nP\tp1\t1+,2+\t*\n")                 # step names a segment that does not exist
     with pytest.raises(NativeError):
         ingest.read_gfa_many(items[:2] + [("chr2:0-1", str(bad), 1)], threads=3)
+
+
+@pytest.mark.parametrize("text", [
+    # dense numeric names (direct index), P and W lines, a revisit
+    "S\t5\tACG\nS\t6\t*\tLN:i:7\nS\t8\tT\nP\ta#1#c\t5+,8-,5+\t*\nW\ts\t2\tc\t0\t9\t>6<8\n",
+    # '7' and '007' are different segments: not canonical -> hash path
+    "S\t7\tA\nS\t007\tCC\nS\t70\tGGG\nP\tp\t007+,70-\t*\nP\tq\t7+\t*\n",
+    # sparse numbers (range far wider than the segment count) -> hash path
+    "S\t1\tA\nS\t900000000\tCC\nP\tp\t900000000+,1+\t*\n",
+    # ten-digit and non-numeric names
+    "S\t1234567890\tA\nS\tutg1\tCC\nS\t3\tG\nW\ts\t1\tc\t*\t*\t>utg1>1234567890<3\n",
+    # numeric file whose paths visit nothing / everything
+    "S\t0\tA\nS\t1\tC\nS\t2\tG\nP\tempty\t*\t*\nP\tall\t0+,1+,2+\t*\n",
+])
+def test_segment_index_paths_agree_with_oracle(text):
+    check(text)
+
+
+@pytest.mark.parametrize("text", [
+    "S\t1\tA\nS\t2\tC\nP\tp\t1+,02+\t*\n",          # '02' is not the name of any segment of this (numeric) file
+    "S\t1\tA\nS\t2\tC\nP\tp\t1+,3+\t*\n",           # undefined number inside the range's neighbourhood
+    "S\t1\tA\nS\t2\tC\nP\tp\t1+,x+\t*\n",           # non-numeric step in a numeric file
+    "S\t10\tA\nS\t12\tC\nP\tp\t11+\t*\n",           # hole in the numbering
+])
+def test_undefined_steps_are_errors(text):
+    with pytest.raises(NativeError):
+        ingest.parse_gfa(text)
+    with pytest.raises(KeyError):
+        ogfa.parse(text)
