@@ -531,3 +531,116 @@ int impop_tsv_fill(const char *text, int64_t bytes, double *matrix_host, char *n
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// Column compaction of a batch of windows (ingest, once per window; exact).
+//   * nodes visited by EVERY haplotype of the window (the backbone of a pangenome window graph: a third of the nodes
+//     of an HPRC-shaped window) add the same constant to every intersection I_ij and path length A_i: they are
+//     merged into ONE node whose length is the sum of theirs;
+//   * nodes visited by no haplotype, and nodes of length 0, contribute nothing and are dropped;
+//   * the remaining nodes are ordered by length (ties: original order), so that the presence words of unit-length
+//     nodes (SNP alleles) come first: prep_rows then needs one popcount per 32 such nodes and row.
+// I, A, U, the segregating-node count and hence every statistic are unchanged (no node that is dropped or merged
+// is segregating in any subset of the rows).  The similarity tools do the equivalent implicitly: they walk paths,
+// not matrix columns.  Fewer columns = fewer operand bytes to expand and multiply, and fewer bytes to upload.
+// ------------------------------------------------------------------------------------------------------------
+#include <thread>
+
+namespace {
+
+struct CompactPlan {
+    std::vector<int32_t> order;      // surviving variable nodes, output order
+    uint64_t const_len = 0;          // summed length of the nodes every row visits
+    int32_t m_out = 0;
+};
+
+void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const uint32_t *len, CompactPlan &pl) {
+    const int words = (m + 31) / 32;
+    std::vector<uint32_t> any((size_t)words, 0u), all((size_t)words, 0xffffffffu);
+    for (int32_t i = 0; i < n; ++i) {
+        const uint32_t *row = x + (size_t)i * pitch;
+        for (int w = 0; w < words; ++w) { any[w] |= row[w]; all[w] &= row[w]; }
+    }
+    pl.order.clear();
+    pl.const_len = 0;
+    for (int32_t k = 0; k < m; ++k) {
+        if (len[k] == 0u) continue;
+        const uint32_t bit = 1u << (k & 31);
+        if (n > 0 && (all[k >> 5] & bit)) pl.const_len += len[k];
+        else if (any[k >> 5] & bit) pl.order.push_back(k);
+    }
+    std::stable_sort(pl.order.begin(), pl.order.end(), [&](int32_t a, int32_t b) { return len[a] < len[b]; });
+    pl.m_out = (int32_t)pl.order.size() + (pl.const_len > 0 ? 1 : 0);
+}
+
+template <typename F>
+void for_windows(int32_t windows, int32_t threads, F fn) {
+    threads = std::max(1, std::min(threads, windows));
+    if (threads == 1) { for (int32_t w = 0; w < windows; ++w) fn(w); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([=] { for (int32_t w = t; w < windows; w += threads) fn(w); });
+    for (auto &th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+int impop_compact_scan(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
+                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
+                       int32_t *m_out) {
+    if (windows < 0 || (windows > 0 && (!n || !m || !pitch_words || !x_off || !len_off || !m_out))) return IMPOP_ERR_ARG;
+    for (int32_t w = 0; w < windows; ++w)
+        if (n[w] < 0 || m[w] < 0 || (int64_t)pitch_words[w] * 32 < m[w] || (m[w] > 0 && n[w] > 0 && (!x_bits || !node_len)))
+            return IMPOP_ERR_ARG;
+    for_windows(windows, threads, [&](int32_t w) {
+        CompactPlan pl;
+        compact_plan(n[w], m[w], pitch_words[w], x_bits + x_off[w], node_len + len_off[w], pl);
+        m_out[w] = pl.m_out;
+    });
+    return IMPOP_OK;
+}
+
+int impop_compact_fill(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
+                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
+                       const int32_t *out_pitch_words, const int64_t *out_x_off, const int64_t *out_len_off,
+                       uint32_t *x_out, uint32_t *len_out) {
+    if (windows < 0 || (windows > 0 && (!n || !m || !pitch_words || !x_off || !len_off || !out_pitch_words || !out_x_off ||
+                                        !out_len_off || !x_out || !len_out)))
+        return IMPOP_ERR_ARG;
+    std::vector<int> bad((size_t)std::max(windows, 1), 0);
+    for_windows(windows, threads, [&](int32_t w) {
+        CompactPlan pl;
+        const uint32_t *x = x_bits + x_off[w], *len = node_len + len_off[w];
+        compact_plan(n[w], m[w], pitch_words[w], x, len, pl);
+        const int32_t op = out_pitch_words[w];
+        if ((int64_t)op * 32 < pl.m_out || pl.const_len > 0xffffffffull) { bad[w] = 1; return; }
+        uint32_t *lo = len_out + out_len_off[w];
+        const int32_t nv = (int32_t)pl.order.size();
+        for (int32_t j = 0; j < nv; ++j) lo[j] = len[pl.order[j]];
+        if (pl.const_len > 0) lo[nv] = (uint32_t)pl.const_len;
+        const int32_t m_pad = op * 32;                        // lengths of the padding columns: 0 (the caller sizes len_out per pitch)
+        (void)m_pad;
+        // source (word, shift) per output column, then one pass per row
+        std::vector<uint32_t> sw((size_t)nv), ss((size_t)nv);
+        for (int32_t j = 0; j < nv; ++j) { sw[j] = (uint32_t)pl.order[j] >> 5; ss[j] = (uint32_t)pl.order[j] & 31u; }
+        for (int32_t i = 0; i < n[w]; ++i) {
+            const uint32_t *row = x + (size_t)i * pitch_words[w];
+            uint32_t *out = x_out + out_x_off[w] + (size_t)i * op;
+            int32_t j = 0;
+            for (int32_t ow = 0; ow < op; ++ow) {
+                uint32_t v = 0u;
+                const int32_t jend = std::min(nv, (ow + 1) * 32);
+                for (; j < jend; ++j) v |= ((row[sw[j]] >> ss[j]) & 1u) << (j & 31);
+                out[ow] = v;
+            }
+            if (pl.const_len > 0) out[nv >> 5] |= 1u << (nv & 31);
+        }
+    });
+    for (int32_t w = 0; w < windows; ++w)
+        if (bad[w]) return IMPOP_ERR_RANGE;
+    return IMPOP_OK;
+}
+
+}  // extern "C"

@@ -13,6 +13,8 @@
 // the A operand because the A tile has at most half the rows of the B tile (fewer weighted expansions).
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "stats_math.cuh"
 
@@ -23,16 +25,15 @@ namespace impop {
 //   prep_cols   one CTA per window: byte weights of the dense columns and their eight bit planes (ballot over 32 nodes),
 //               heavy-node table, range check sum(len) < 2^31, label counts, reset of the any / all words
 //   prep_rows   one CTA per (window, row slice) -- a window with many haplotypes is cut into slices so that a
-//               batch of few large windows still fills the GPU: path lengths A_i as the sum over the eight bit
-//               planes of the dense byte weights of 2^p popc(row word & plane word) (lane = presence word, planes
-//               in registers, four rows in flight per warp) plus 255 c per present heavy column, presence bits of
-//               the heavy columns (shuffle of the row words already in registers + ballot), any / all masks over
-//               the SEG rows
+//               batch of few large windows still fills the GPU: path lengths A_i as the sum over the non-zero bit
+//               planes of the dense byte weights of 2^p popc(row word & plane word) (rows staged through a shared
+//               tile: coalesced loads with lane = word, arithmetic with lane = row and the planes of the current
+//               word broadcast) plus 255 c per present heavy column, presence bits of the heavy columns, any / all
+//               masks over the SEG rows
 //   seg_count   S = #{k : 0 < sum_{i in SEG} x_ik < |SEG|, len_k > 0} (replaces `povu gfa2vcf | wc -l`,
 //               run_tajd.sh:126-148) -> counts row nS nA nB pS pAA pBB pAB S
 // ==========================================================================================
 constexpr int PREP_THREADS = 256;
-constexpr int PM_WORDS = 64;                 // presence words per node group of prep_rows = 2048 nodes
 
 __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
     __shared__ int s_heavy, s_cnt[4];
@@ -110,146 +111,27 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
     }
 }
 
-// Rows [row_lo, row_hi) of one window against one group of <= 2048 nodes (PASSES x 32 presence words per row).
-// FIRST: the group starts at node 0 (defines A_i and the heavy words; later groups add to them).
-template <int PASSES, bool FIRST>
-__device__ __forceinline__ void prep_rows_group(uint32_t *s_any, uint32_t *s_all,
-                                                const uint32_t *x, int pitch, int wlim, const uint8_t *lab, int row_lo, int row_hi,
-                                                int w0, const uint32_t *heavy, int hwords, int hw_used, uint32_t *xh,
-                                                int32_t *A, const uint32_t *planes, int plane_words) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t pm[PASSES][8];
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-        const int gw = w0 + ps * 32 + lane;                          // presence word = group of 32 nodes
-        uint4 lo4 = make_uint4(0u, 0u, 0u, 0u), hi4 = lo4;
-        if (gw < plane_words) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(planes + (size_t)gw * 8);
-            lo4 = __ldg(src); hi4 = __ldg(src + 1);
-        }
-        pm[ps][0] = lo4.x; pm[ps][1] = lo4.y; pm[ps][2] = lo4.z; pm[ps][3] = lo4.w;
-        pm[ps][4] = hi4.x; pm[ps][5] = hi4.y; pm[ps][6] = hi4.z; pm[ps][7] = hi4.w;
-    }
-    // the first heavy word (32 entries) is kept in registers: lane = entry
-    const uint32_t ent0 = hw_used > 0 ? heavy[lane] : 0u;
-    const int rel0 = (int)(ent0 >> 13) - w0;                        // word of the entry's node within this group
-    const bool in0 = (ent0 & 255u) && rel0 >= 0 && rel0 < 32 * PASSES;
-    const uint32_t add0 = in0 ? HEAVY_Q * (ent0 & 255u) : 0u;
-    const uint32_t sh0 = in0 ? ((ent0 >> 8) & 31u) : 32u;           // funnel shift by 32 yields 0: entry not in this group
-    const int src0 = rel0 & 31;
-    const bool any_in0 = __any_sync(0xffffffffu, in0);
-    constexpr int RU = PASSES == 1 ? 8 : 4;                         // rows in flight per warp (memory-level parallelism)
-    uint32_t any[PASSES], all[PASSES];
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) { any[ps] = 0u; all[ps] = 0xffffffffu; }
-    bool lane_ok[PASSES];                                           // this lane's word of pass ps can hold nodes < m
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) lane_ok[ps] = w0 + ps * 32 + lane < wlim;
-    const uint32_t *rowp = x + (size_t)(row_lo + warp * RU) * pitch + w0 + lane;      // first row of this warp, this lane's word
-    const size_t step = (size_t)(PREP_THREADS / 32) * RU * pitch;
-    for (int i0 = row_lo + warp * RU; i0 < row_hi; i0 += (PREP_THREADS / 32) * RU, rowp += step) {
-        uint32_t word[PASSES][RU], acc[RU];
-        const uint32_t segrows = __ballot_sync(0xffffffffu, lane < RU && i0 + lane < row_hi && (lab[i0 + lane] & IMPOP_LAB_SEG));
-        const int nrows = min(RU, row_hi - i0);
-#pragma unroll
-        for (int r = 0; r < RU; ++r) {
-#pragma unroll
-            for (int ps = 0; ps < PASSES; ++ps)
-                word[ps][r] = (r < nrows && lane_ok[ps]) ? __ldg(rowp + (size_t)r * pitch + ps * 32) : 0u;
-        }
-#pragma unroll
-        for (int r = 0; r < RU; ++r) {
-            uint32_t a = 0u;
-#pragma unroll
-            for (int ps = 0; ps < PASSES; ++ps) {
-#pragma unroll
-                for (int p = 0; p < 8; ++p) a += (uint32_t)__popc(word[ps][r] & pm[ps][p]) << p;
-                if ((segrows >> r) & 1u) { any[ps] |= word[ps][r]; all[ps] &= word[ps][r]; }
-            }
-            acc[r] = a;
-        }
-        // lane 4 g (g = 0..7) ends up owning row i0 + g: it holds the row's total after the transposed reduction below
-        // and stores the row's path length and heavy word -- two store instructions per eight rows
-        const int g = RU == 8 ? lane >> 2 : lane >> 3;
-        const bool owner = (lane & (RU == 8 ? 3 : 7)) == 0 && i0 + g < row_hi;
-        if (FIRST || any_in0) {
-            uint32_t bw[RU];
-#pragma unroll
-            for (int r = 0; r < RU; ++r) {
-                uint32_t wsrc = __shfl_sync(0xffffffffu, word[0][r], src0);
-                if (PASSES > 1) {
-                    const uint32_t w_hi = __shfl_sync(0xffffffffu, word[PASSES - 1][r], src0);
-                    wsrc = (rel0 >= 32) ? w_hi : wsrc;
-                }
-                const uint32_t on = __funnelshift_rc(wsrc, 0u, sh0) & 1u;        // clamped: a shift of 32 gives 0
-                bw[r] = __ballot_sync(0xffffffffu, on != 0u);
-                acc[r] += on * add0;
-            }
-            if (owner && hw_used > 0) {
-                uint32_t mine = bw[0];
-#pragma unroll
-                for (int r = 1; r < RU; ++r) mine = (g == r) ? bw[r] : mine;
-                uint32_t *dst = xh + (size_t)(i0 + g) * hwords;
-                if (FIRST) *dst = mine; else if (mine) *dst |= mine;   // (xh was zeroed by prep_cols)
-            }
-        }
-        for (int hw = 1; hw < hw_used; ++hw) {                      // further heavy words (windows with > 32 nodes of >= 255 bp):
-            const uint32_t ent = heavy[hw * 32 + lane];             // same scheme as the first word, entry values re-read per word
-            const int rel = (int)(ent >> 13) - w0;
-            const bool in = (ent & 255u) && rel >= 0 && rel < 32 * PASSES;
-            if (!FIRST && !__any_sync(0xffffffffu, in)) continue;
-            const uint32_t add = in ? HEAVY_Q * (ent & 255u) : 0u;
-            const uint32_t sh = in ? ((ent >> 8) & 31u) : 32u;
-            uint32_t mine = 0u;
-#pragma unroll
-            for (int r = 0; r < RU; ++r) {
-                uint32_t wsrc = __shfl_sync(0xffffffffu, word[0][r], rel & 31);
-                if (PASSES > 1) {
-                    const uint32_t w_hi = __shfl_sync(0xffffffffu, word[PASSES - 1][r], rel & 31);
-                    wsrc = (rel >= 32) ? w_hi : wsrc;
-                }
-                const uint32_t on = __funnelshift_rc(wsrc, 0u, sh) & 1u;
-                const uint32_t bw = __ballot_sync(0xffffffffu, on != 0u);
-                acc[r] += on * add;
-                mine = (g == r) ? bw : mine;
-            }
-            if (owner) {                                            // one store instruction per group of rows and word
-                uint32_t *dst = xh + (size_t)(i0 + g) * hwords + hw;
-                if (FIRST) *dst = mine; else if (mine) *dst |= mine;
-            }
-        }
-        {   // transposed warp reduction of the RU row totals: 9 shuffles for eight rows instead of 40
-            const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
-            uint32_t t;
-            if constexpr (RU == 8) {
-                uint32_t v[4], u[2];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)      // rows r | r + 4
-                    v[r] = (up16 ? acc[r + 4] : acc[r]) + __shfl_xor_sync(0xffffffffu, up16 ? acc[r] : acc[r + 4], 16);
-#pragma unroll
-                for (int r = 0; r < 2; ++r)      // rows r | r + 2 (+ 4)
-                    u[r] = (up8 ? v[r + 2] : v[r]) + __shfl_xor_sync(0xffffffffu, up8 ? v[r] : v[r + 2], 8);
-                t = (up4 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, up4 ? u[0] : u[1], 4);              // row g = lane >> 2
-            } else {
-                const uint32_t v0 = (up16 ? acc[2] : acc[0]) + __shfl_xor_sync(0xffffffffu, up16 ? acc[0] : acc[2], 16);   // rows 0 | 2
-                const uint32_t v1 = (up16 ? acc[3] : acc[1]) + __shfl_xor_sync(0xffffffffu, up16 ? acc[1] : acc[3], 16);   // rows 1 | 3
-                t = (up8 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, up8 ? v0 : v1, 8);                       // row g = lane >> 3
-                t += __shfl_xor_sync(0xffffffffu, t, 4);
-            }
-            t += __shfl_xor_sync(0xffffffffu, t, 2);
-            t += __shfl_xor_sync(0xffffffffu, t, 1);
-            if (owner) A[i0 + g] = (int32_t)(t + (FIRST ? 0u : (uint32_t)A[i0 + g]));
-        }
-    }
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) { atomicOr(&s_any[ps * 32 + lane], any[ps]); atomicAnd(&s_all[ps * 32 + lane], all[ps]); }
-}
+// prep_rows.  A warp takes 32 rows of a window at a time, 32 presence words (1024 nodes) per pass:
+//   load     lane = word: the 32 rows are read coalesced (128 bytes per row) into a padded tile in shared memory; the any /
+//            all words over the SEG rows are folded in registers on the way
+//   compute  lane = row: the row's words come back from the tile (conflict-free), the bit planes of the byte weights of
+//            the current word are the same for every lane (shared memory, broadcast), so planes that are zero for all 32
+//            nodes of a word are skipped with warp-uniform branches: a word whose nodes all weigh 1 (SNP-dominated windows
+//            once the constant columns are merged and the columns ordered by weight, impop_compact_scan / _fill) costs
+//            ONE popc per 32 rows, a padding word none.  Heavy columns: one tile probe per entry and 32 rows.
+// PR_WORDS presence words (2048 nodes) of planes are staged per group.
+constexpr int PR_WORDS = 64;
+constexpr int PR_TILE = 33;                   // tile row pitch in words (32 + 1: lane = row reads hit 32 banks)
 
 #ifndef IMPOP_PREP_OCC
 #define IMPOP_PREP_OCC 4
 #endif
 __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel(const __grid_constant__ WindowTab tab) {
-    __shared__ uint32_t s_any[PM_WORDS], s_all[PM_WORDS];
+    __shared__ __align__(16) uint32_t s_pl[PR_WORDS][8];
+    __shared__ uint32_t s_mk[PR_WORDS], s_any[PR_WORDS], s_all[PR_WORDS];
+    __shared__ uint32_t s_tile[PREP_THREADS / 32][32 * PR_TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *tile = s_tile[warp];
     for (int sidx = blockIdx.x; sidx < tab.n_slices; sidx += gridDim.x) {
         const int4 sl = __ldg(tab.slices + sidx);
         const int w = sl.x, row_lo = sl.y, row_hi = sl.z;
@@ -260,26 +142,98 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
         const uint8_t *lab = tab.labels + tab.lab_off[w];
         const uint32_t *heavy = tab.heavy + tab.heavy_off[w];
         const int hwords = (int)((tab.heavy_off[w + 1] - tab.heavy_off[w]) >> 5);
-        const int hw_used = (tab.heavy_n[w] + 31) >> 5;      // words of the heavy table that hold real entries
+        const int heavy_n = tab.heavy_n[w];
+        const int hw_used = (heavy_n + 31) >> 5;             // words of the heavy table that hold real entries
         uint32_t *xh = tab.xh + tab.xh_off[w];
         int32_t *A = tab.A + tab.row_off[w];
         const int64_t wo = tab.word_off[w];
         const uint32_t *planes = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(tab.planes) + tab.w8_off[w]);
         const int plane_words = (((m + KCHUNK - 1) / KCHUNK) * KCHUNK) >> 5;   // prep_cols wrote planes for the padded node count
-        for (int c0 = 0; c0 < m || c0 == 0; c0 += 32 * PM_WORDS) {   // groups of 2048 nodes = 64 presence words
-            if (threadIdx.x < PM_WORDS) { s_any[threadIdx.x] = 0u; s_all[threadIdx.x] = 0xffffffffu; }
+        for (int w0 = 0; w0 < wlim || w0 == 0; w0 += PR_WORDS) {
+            const int gw = max(0, min(PR_WORDS, wlim - w0));       // words of this group (a multiple of 4)
+            for (int t = threadIdx.x; t < gw * 8; t += PREP_THREADS)
+                s_pl[t >> 3][t & 7] = (w0 + (t >> 3) < plane_words) ? __ldg(planes + (size_t)(w0 + (t >> 3)) * 8 + (t & 7)) : 0u;
+            if (threadIdx.x < PR_WORDS) { s_any[threadIdx.x] = 0u; s_all[threadIdx.x] = 0xffffffffu; }
             __syncthreads();
-            const int w0 = c0 >> 5;                       // first word of this group of nodes
-            const bool two = m - c0 > 1024;               // 32 words (1024 nodes) per warp pass
-            if (c0 == 0) {
-                if (two) prep_rows_group<2, true>(s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A, planes, plane_words);
-                else prep_rows_group<1, true>(s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A, planes, plane_words);
-            } else {
-                if (two) prep_rows_group<2, false>(s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A, planes, plane_words);
-                else prep_rows_group<1, false>(s_any, s_all, x, pitch, wlim, lab, row_lo, row_hi, w0, heavy, hwords, hw_used, xh, A, planes, plane_words);
+            if (threadIdx.x < gw) {
+                uint32_t mk = 0u;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) mk |= (s_pl[threadIdx.x][p] != 0u ? 1u : 0u) << p;
+                s_mk[threadIdx.x] = mk;
             }
             __syncthreads();
-            if (threadIdx.x < PM_WORDS && w0 + threadIdx.x < ((m + 31) >> 5)) {
+            uint32_t any[PR_WORDS / 32], all[PR_WORDS / 32];        // lane = word of pass ps
+#pragma unroll
+            for (int ps = 0; ps < PR_WORDS / 32; ++ps) { any[ps] = 0u; all[ps] = 0xffffffffu; }
+            for (int i0 = row_lo + warp * 32; i0 < row_hi; i0 += PREP_THREADS) {
+                const int i = i0 + lane;
+                const bool valid = i < row_hi;
+                const uint32_t segrows = __ballot_sync(0xffffffffu, valid && (lab[valid ? i : row_lo] & IMPOP_LAB_SEG));
+                const int nrows = min(32, row_hi - i0);
+                uint32_t acc = 0u;
+#pragma unroll
+                for (int ps = 0; ps < PR_WORDS / 32; ++ps) {
+                    const int pw = min(32, gw - ps * 32);           // words of this pass
+                    if (pw <= 0) break;
+                    {   // load: lane = word
+                        const bool lane_ok = lane < pw;
+                        const uint32_t *src = x + (size_t)i0 * pitch + w0 + ps * 32 + lane;
+                        __syncwarp();
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            const uint32_t v = (lane_ok && r < nrows) ? __ldg(src + (size_t)r * pitch) : 0u;
+                            tile[r * PR_TILE + lane] = v;
+                            if ((segrows >> r) & 1u) { any[ps] |= v; all[ps] &= v; }
+                        }
+                        __syncwarp();
+                    }
+                    const uint32_t *mine = tile + lane * PR_TILE;   // compute: lane = row
+                    for (int wd = 0; wd < pw; ++wd) {
+                        const uint32_t mk = s_mk[ps * 32 + wd];
+                        if (!mk) continue;
+                        const uint32_t v = mine[wd];
+                        if (mk == 1u) {
+                            acc += (uint32_t)__popc(v & s_pl[ps * 32 + wd][0]);
+                        } else {
+                            const uint4 lo4 = *reinterpret_cast<const uint4 *>(&s_pl[ps * 32 + wd][0]);
+                            acc += (uint32_t)__popc(v & lo4.x) + ((uint32_t)__popc(v & lo4.y) << 1) +
+                                   ((uint32_t)__popc(v & lo4.z) << 2) + ((uint32_t)__popc(v & lo4.w) << 3);
+                            if (mk >> 4) {
+                                const uint4 hi4 = *reinterpret_cast<const uint4 *>(&s_pl[ps * 32 + wd][4]);
+                                acc += ((uint32_t)__popc(v & hi4.x) << 4) + ((uint32_t)__popc(v & hi4.y) << 5) +
+                                       ((uint32_t)__popc(v & hi4.z) << 6) + ((uint32_t)__popc(v & hi4.w) << 7);
+                            }
+                        }
+                    }
+                    // heavy columns (nodes of >= 255 bp) whose node lies in this pass: entry e = (node << 8 | c) adds 255 c to
+                    // the rows that carry the node and becomes bit e of the row's heavy presence words (operand of the heavy
+                    // chunks of the pairs kernel)
+                    const int pass_w0 = w0 + ps * 32;
+                    for (int hw = 0; hw < hw_used; ++hw) {
+                        uint32_t hbits = 0u;
+                        bool touched = false;
+                        const int e_end = min(32, heavy_n - hw * 32);                    // entries in use (the rest is padding)
+                        for (int e = 0; e < e_end; ++e) {
+                            const uint32_t ent = __ldg(heavy + hw * 32 + e);
+                            const int rel = (int)(ent >> 13) - pass_w0;                  // word of the entry's node within this pass
+                            if (!(ent & 255u) || rel < 0 || rel >= pw) continue;        // other pass (uniform)
+                            const uint32_t on = (mine[rel] >> ((ent >> 8) & 31u)) & 1u;
+                            acc += on * (HEAVY_Q * (ent & 255u));
+                            hbits |= on << e;
+                            touched = true;
+                        }
+                        if (valid && touched && hbits) xh[(size_t)i * hwords + hw] |= hbits;   // (xh was zeroed by prep_cols)
+                    }
+                }
+                if (valid) A[i] = (int32_t)(acc + (w0 ? (uint32_t)A[i] : 0u));
+            }
+#pragma unroll
+            for (int ps = 0; ps < PR_WORDS / 32; ++ps) {
+                if (any[ps]) atomicOr(&s_any[ps * 32 + lane], any[ps]);
+                if (all[ps] != 0xffffffffu) atomicAnd(&s_all[ps * 32 + lane], all[ps]);
+            }
+            __syncthreads();
+            if (threadIdx.x < gw && w0 + threadIdx.x < ((m + 31) >> 5)) {
                 atomicOr(&tab.seg_any[wo + w0 + threadIdx.x], s_any[threadIdx.x]);
                 atomicAnd(&tab.seg_all[wo + w0 + threadIdx.x], s_all[threadIdx.x]);
             }
@@ -396,17 +350,20 @@ __device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const d
 }
 
 // ==========================================================================================
-// tcgen05 implementation, warp specialised.  One CTA per SM:
-//   warps 0-11   producers: expand the presence bits of a raw slot into the u8 operand tiles of a ring of stages
-//                (warps 0-3: the 128 A rows, warps 4-11: up to 256 B rows; lane = row); shared memory only
-//   warp  12     MMA issuer (one elected lane): tcgen05.mma kind::i8 into one of two TMEM buffers
-//   warp  13     table warp: per item, the column / row values and geometry the epilogue needs, into one of
-//                three tables in shared memory, up to three items ahead
-//   warps 14-15  loaders: cp.async of each chunk's packed presence bits and byte weights into a ring of raw slots
-//   warps 16-27  epilogue (three per TMEM lane quarter): tcgen05.ld, exact integer union, fp64 pi_ij, per-lane sums
-// Registers are moved from the producer / MMA / table / loader warpgroups (48 each) to the epilogue warpgroups (104
-// each): 16 x 32 x 48 + 12 x 32 x 104 = 64 512 = the 896 x 72 registers the CTA owns (a larger sum makes
-// setmaxnreg.inc wait forever).
+// tcgen05 implementation, warp specialised.  One CTA per SM, P producer + 4 service + E epilogue warps
+// (shipped: P = 4, E = 16, 768 threads):
+//   warps 0..P-1      producers: expand the presence bits of a raw slot into the u8 operand tiles of a ring of stages
+//                     (P = 4: lane = one A row and two B rows; P = 8 / 12: four A warps + four / eight B warps); shared memory only
+//   warp  P           MMA issuer (one elected lane): tcgen05.mma kind::i8 into one of two TMEM buffers
+//   warp  P+1         table warp: per item, the column / row values and geometry the epilogue needs, into one of
+//                     three tables in shared memory, up to three items ahead
+//   warps P+2, P+3    loaders: cp.async of each chunk's packed presence bits and byte weights into a ring of raw slots
+//   warps P+4 ..      epilogue (E / 4 per TMEM lane quarter = per SM scheduler): tcgen05.ld, exact integer union, fp64 pi_ij,
+//                     per-lane sums
+// The fp64 epilogue is the critical role (18 fp64 + 4 XU instructions per pair): it gets four warps per scheduler --
+// what the stand-alone micro-benchmark of the same math needs to keep the fp64 pipe 80 % busy -- and the registers the
+// service roles give up with setmaxnreg (P = 4, E = 16: 8 x 32 x 48 + 16 x 32 x 96 = 61 440 = the 768 x 80 registers
+// the CTA owns; a larger sum makes setmaxnreg.inc wait forever).
 // The integer pipes (expansion) and the fp64 pipe (epilogue) so run concurrently on different
 // warps, and items flow through without CTA-wide barriers.
 // ==========================================================================================
@@ -417,35 +374,52 @@ __device__ __forceinline__ void warp_partial(const dd &ts, const dd &ta, const d
 #define IMPOP_EPI_SLEEP 20       // ns between polls of a waiting epilogue warp
 #endif
 #ifndef IMPOP_PROD_WARPS
-#define IMPOP_PROD_WARPS 12      // 4 for the A tile (lane = row) + 8 or 4 for the B tile (1 or 2 rows per lane)
-#endif
+#define IMPOP_PROD_WARPS 4       // 4: every producer warp expands one A row and two B rows per lane; 8: four A warps + four B warps
+#endif                           // (two rows per lane); 12: four A warps + eight B warps (one row per lane)
 #ifndef IMPOP_EPI_WARPS
-#define IMPOP_EPI_WARPS 12       // a multiple of 4: IMPOP_EPI_WARPS / 4 warps share each TMEM lane quarter
+#define IMPOP_EPI_WARPS 16       // a multiple of 4: IMPOP_EPI_WARPS / 4 warps share each TMEM lane quarter
 #endif
 constexpr int WS_PROD_WARPS = IMPOP_PROD_WARPS;
 constexpr int WS_EPI_WARPS = IMPOP_EPI_WARPS;
-constexpr int WS_B_RPL = TILE_N / (32 * (WS_PROD_WARPS - 4));   // B rows per producer lane
-static_assert(WS_PROD_WARPS % 4 == 0 && WS_EPI_WARPS % 4 == 0 && WS_B_RPL * 32 * (WS_PROD_WARPS - 4) == TILE_N, "warp roles");
+constexpr bool WS_PROD_SHARED = WS_PROD_WARPS == 4;                                   // every producer warp serves both operand tiles
+constexpr int WS_B_WARPS = WS_PROD_SHARED ? 4 : WS_PROD_WARPS - 4;
+constexpr int WS_B_RPL = TILE_N / (32 * WS_B_WARPS);                                  // B rows per producer lane
+static_assert(WS_PROD_WARPS % 4 == 0 && WS_EPI_WARPS % 4 == 0 && WS_B_RPL * 32 * WS_B_WARPS == TILE_N, "warp roles");
 static_assert(WS_EPI_WARPS == PART_SLOTS, "one partial record per epilogue warp");
 constexpr int WS_MMA_WARP = WS_PROD_WARPS;
 constexpr int WS_EPI_WARP0 = WS_PROD_WARPS + 4;
-constexpr int WS_THREADS = 32 * (WS_EPI_WARP0 + WS_EPI_WARPS);        // 768
+constexpr int WS_THREADS = 32 * (WS_EPI_WARP0 + WS_EPI_WARPS);        // 768 (P = 4, E = 16)
 constexpr int WS_STAGES = 3;                                    // operand stages (expanded u8 tiles)
 constexpr int WS_RAW = 8;                                       // raw ring: packed presence bits + byte weights of a chunk
-constexpr int WS_LOADER_LANES = 64;                             // warps 14-15
+constexpr int WS_LOADER_LANES = 64;                             // two loader warps
 constexpr int RAW_ROWS = TILE_M + TILE_N;                       // 384 operand rows per chunk
 constexpr int WS_TABLES = 3;                                    // item tables in flight (see the table warps)
-constexpr int WS_TBL_WARPS = 1;                                 // warp 13
-#ifndef IMPOP_REGS_LOW
-#define IMPOP_REGS_LOW 48        // producer / MMA / table / loader warps
-#define IMPOP_REGS_EPI 104       // epilogue warps: 16 x 32 x 48 + 12 x 32 x 104 = 64 512 = the 896 x 72 registers the CTA owns
+constexpr int WS_TBL_WARPS = 1;
+#ifndef IMPOP_REGS_LOW           // registers of the service warps (producer / MMA / table / loader) and of the epilogue warps
+#if IMPOP_PROD_WARPS == 4 && IMPOP_EPI_WARPS == 16
+#define IMPOP_REGS_LOW 48
+#define IMPOP_REGS_EPI 96
+#elif IMPOP_PROD_WARPS == 8 && IMPOP_EPI_WARPS == 16
+#define IMPOP_REGS_LOW 40
+#define IMPOP_REGS_EPI 96
+#elif IMPOP_PROD_WARPS == 8 && IMPOP_EPI_WARPS == 12
+#define IMPOP_REGS_LOW 48
+#define IMPOP_REGS_EPI 112
+#elif IMPOP_PROD_WARPS == 4 && IMPOP_EPI_WARPS == 12
+#define IMPOP_REGS_LOW 48
+#define IMPOP_REGS_EPI 128
+#else
+#define IMPOP_REGS_LOW 48
+#define IMPOP_REGS_EPI 104       // 12 + 12: 16 x 32 x 48 + 12 x 32 x 104 = 64 512 = 896 x 72
 #endif
+#endif
+constexpr int WS_LAUNCH_REGS = (65536 / WS_THREADS) & ~7;       // what __launch_bounds__(WS_THREADS, 1) lets ptxas allocate
+static_assert((WS_PROD_WARPS + 4) * 32 * IMPOP_REGS_LOW + WS_EPI_WARPS * 32 * IMPOP_REGS_EPI <= WS_THREADS * WS_LAUNCH_REGS,
+              "setmaxnreg targets exceed the registers the CTA owns");
 #ifndef IMPOP_EPI_NP
-#define IMPOP_EPI_NP 8           // pairs whose division chains advance together
+#define IMPOP_EPI_NP 4           // pairs whose division chains advance together (x 4 warps per scheduler)
 #endif
-#ifndef IMPOP_EPI_PREFETCH
-#define IMPOP_EPI_PREFETCH (IMPOP_EPI_WARPS <= 8)   // second TMEM register buffer: worth its 16 registers only with few warps
-#endif
+static_assert(IMPOP_EPI_NP == 4, "the epilogue loads and processes its accumulators four columns at a time");
 #define IMPOP_STR2(x) #x
 #define IMPOP_STR(x) IMPOP_STR2(x)
 constexpr int A_STAGE_BYTES = TILE_M * KCHUNK;                  // 16 KB
@@ -462,8 +436,12 @@ struct __align__(16) EpiCols {          // everything the epilogue needs of one 
     int32_t have_acc, last, rev, pad1;  // m > 0 (an accumulator exists); last item of this CTA's visit to the window;
                                         // rev: TMEM lane quarter q holds row quarter 3 - q (see ITEM_REV)
     uint32_t aj[EPI_COLS];              // path length A_j
+#if IMPOP_EPI_UNION_F64
+    double ajd[EPI_COLS];               // the same as doubles (union formed in fp64)
+#endif
     double fs[EPI_COLS], fa[EPI_COLS], fb[EPI_COLS];   // 1.0 / 0.0: column carries SUBSET / A / B
-    uint32_t cmask[EPI_COLS / 16];      // per 16-column chunk: bit 0 all columns valid and in SUBSET, bit 1 any A, bit 2 any B
+    uint32_t cmask[EPI_COLS / 16];      // per 16-column chunk: bit 0 all columns valid and in SUBSET, bit 1 any A, bit 2 any B,
+                                        // bit 3 all in A, bit 4 all in B (a column carrying a label is a valid column)
     uint32_t ai[TILE_M];                // path length A_i of the item's rows
     uint32_t fi[TILE_M];                // cleaned labels of the item's rows
 };
@@ -608,10 +586,12 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
     if (warp < WS_PROD_WARPS) {
         // ================================================================ producers
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " IMPOP_STR(IMPOP_REGS_LOW) ";");
-        const bool isA = warp < 4;
-        const int rl = (isA ? warp : warp - 4) * 32 + lane;          // (first) row of the operand tile
-        const uint32_t lbo = isA ? LBO_A : LBO_B;
-        const int nrows = isA ? 1 : WS_B_RPL;                         // B warps: rows rl, rl + 128 when there are only four
+        // Row tasks of this lane: the A row of its warp quarter (doA) and WS_B_RPL B rows (doB).  With four producer
+        // warps every warp does both; otherwise warps 0-3 own the A tile and the rest the B tile.
+        const bool doA = WS_PROD_SHARED || warp < 4;
+        const bool doB = WS_PROD_SHARED || warp >= 4;
+        const int rlA = (warp & 3) * 32 + lane;                                       // row of the A tile
+        const int rlB = (WS_PROD_SHARED ? warp : warp - 4) * 32 + lane;               // first row of the B tile
         uint32_t g = 0;                                               // chunks produced so far
         Win wi;
         int4 nxt = raw_item(u_lo);
@@ -623,7 +603,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             PROF_AUX_END
             const int ncols = cur.w;
             const int nch = wi.nch, dense_chunks = wi.dense_chunks;
-            const int a_src = (((cur.y & ITEM_REV) ? 3 - warp : warp) & 3) * 32 + lane;   // A warps: block row behind tile row rl
+            const int a_src = (((cur.y & ITEM_REV) ? 3 - warp : warp) & 3) * 32 + lane;   // A rows: block row behind tile row rlA
             // Presence bits and byte weights arrive through the raw ring (loader warps, cp.async): the producers touch
             // shared memory only, so the proxy fence after the expansion has no global load to wait for.
             for (int c = 0; c < nch; ++c, ++g) {
@@ -633,19 +613,20 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 PROF_AUX_END          // aux = wait for the raw slot (+ item setup)
 #endif
                 const RawSlot &slot = raw[rs];
-                uint4 bits[WS_B_RPL];
+                uint4 bitsA = make_uint4(0u, 0u, 0u, 0u), bits[WS_B_RPL];
+                if (doA) bitsA = slot.bits[a_src];
 #pragma unroll
                 for (int q = 0; q < WS_B_RPL; ++q) {
-                    const int r = rl + q * (TILE_N / WS_B_RPL);
-                    bits[q] = (q < nrows && (isA || r < ncols)) ? slot.bits[isA ? a_src : TILE_M + r] : make_uint4(0u, 0u, 0u, 0u);
+                    const int r = rlB + q * (TILE_N / WS_B_RPL);
+                    bits[q] = (doB && r < ncols) ? slot.bits[TILE_M + r] : make_uint4(0u, 0u, 0u, 0u);
                 }
                 if (alive) alive = mbar_wait<IMPOP_PROD_SLEEP>(&sh.empty[s], ((g / WS_STAGES) & 1u) ^ 1u, tab.err);
                 PROF_WAIT_END
 #ifndef IMPOP_DBG_NO_EXPAND   // (timing experiment: skip the operand expansion)
                 const uint4 none = make_uint4(0u, 0u, 0u, 0u);
-                if (isA) {
-                    uint8_t *dst = smem + s * STAGE_BYTES + rl * 16;
-                    const uint32_t bw[4] = {bits[0].x, bits[0].y, bits[0].z, bits[0].w};
+                if (doA) {
+                    uint8_t *dst = smem + s * STAGE_BYTES + rlA * 16;
+                    const uint32_t bw[4] = {bitsA.x, bitsA.y, bitsA.z, bitsA.w};
                     // the byte weights of four slabs are loaded before the first store of the group: a load behind a store
                     // to the same shared-memory array is ordered after it (possible alias), which serialised load -> AND ->
                     // store eight times per chunk
@@ -657,24 +638,25 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int slab = half * 4 + q;
-                            *reinterpret_cast<uint4 *>(dst + slab * lbo) = expand_slab<2>(bw[slab >> 1], slab & 1, wv[q]);
+                            *reinterpret_cast<uint4 *>(dst + slab * LBO_A) = expand_slab<2>(bw[slab >> 1], slab & 1, wv[q]);
                         }
                     }
-                } else {
+                }
+                if (doB) {
 #pragma unroll
                     for (int q = 0; q < WS_B_RPL; ++q) {
-                        const int r = rl + q * (TILE_N / WS_B_RPL);
+                        const int r = rlB + q * (TILE_N / WS_B_RPL);
                         if (r >= ncols) continue;
                         uint8_t *dst = smem + s * STAGE_BYTES + A_STAGE_BYTES + r * 16;
                         const uint32_t bw[4] = {bits[q].x, bits[q].y, bits[q].z, bits[q].w};
                         if (c < dense_chunks) {
 #pragma unroll
                             for (int slab = 0; slab < KCHUNK / 16; ++slab)
-                                *reinterpret_cast<uint4 *>(dst + slab * lbo) = expand_slab<0>(bw[slab >> 1], slab & 1, none);
+                                *reinterpret_cast<uint4 *>(dst + slab * LBO_B) = expand_slab<0>(bw[slab >> 1], slab & 1, none);
                         } else {
 #pragma unroll
                             for (int slab = 0; slab < KCHUNK / 16; ++slab)
-                                *reinterpret_cast<uint4 *>(dst + slab * lbo) = expand_slab<1>(bw[slab >> 1], slab & 1, none);
+                                *reinterpret_cast<uint4 *>(dst + slab * LBO_B) = expand_slab<1>(bw[slab >> 1], slab & 1, none);
                         }
                     }
                 }
@@ -686,7 +668,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             }
         }
         if (warp == 0) PROF_STORE(0)
-        if (warp == 4) PROF_STORE(1)
+        if (warp == (WS_PROD_SHARED ? 1 : 4)) PROF_STORE(1)
     } else if (warp < WS_EPI_WARP0) {
         // ================================================================ MMA issuer (warp 12, one lane issues; 13-15 idle)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " IMPOP_STR(IMPOP_REGS_LOW) ";");
@@ -757,13 +739,13 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     const int cc = ps * 32 + lane, j = col0 + cc;
                     const bool ok = cc < ncols && j < n;
                     cf[ps] = ok ? clean_label(__ldg(lab + j)) : 0u;
-                    ca[ps] = ok ? (uint32_t)__ldg(Aw + j) : 0u;
+                    ca[ps] = ok ? max((uint32_t)__ldg(Aw + j), 1u) : 1u;     // empty path: 1 instead of 0 (see pi_batch)
                 }
 #pragma unroll
                 for (int ps = 0; ps < TILE_M / 32; ++ps) {
                     const int i = (cur.y & ITEM_BI_MASK) * TILE_M + ps * 32 + lane;
                     rf[ps] = i < n ? clean_label(__ldg(lab + i)) : 0u;
-                    ra_[ps] = i < n ? (uint32_t)__ldg(Aw + i) : 0u;
+                    ra_[ps] = i < n ? max((uint32_t)__ldg(Aw + i), 1u) : 1u;
                 }
                 if (alive) alive = mbar_wait<100>(&sh.tbl_empty[slot], ((uint32_t)(k / WS_TABLES) & 1u) ^ 1u, tab.err);
                 EpiCols &col = sh.col[slot];
@@ -772,6 +754,9 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     const int cc = ps * 32 + lane;
                     const uint32_t f = cf[ps];
                     col.aj[cc] = ca[ps];
+#if IMPOP_EPI_UNION_F64
+                    col.ajd[cc] = (double)ca[ps];
+#endif
                     col.fs[cc] = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
                     col.fa[cc] = (f & IMPOP_LAB_A) ? 1.0 : 0.0;
                     col.fb[cc] = (f & IMPOP_LAB_B) ? 1.0 : 0.0;
@@ -781,7 +766,8 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     if (lane < 2) {
                         const uint32_t hs = lane ? (bs >> 16) : (bs & 0xFFFFu), ha = lane ? (ba >> 16) : (ba & 0xFFFFu),
                                        hb = lane ? (bb >> 16) : (bb & 0xFFFFu);
-                        col.cmask[ps * 2 + lane] = (hs == 0xFFFFu ? 1u : 0u) | (ha ? 2u : 0u) | (hb ? 4u : 0u);
+                        col.cmask[ps * 2 + lane] = (hs == 0xFFFFu ? 1u : 0u) | (ha ? 2u : 0u) | (hb ? 4u : 0u) |
+                                                   (ha == 0xFFFFu ? 8u : 0u) | (hb == 0xFFFFu ? 16u : 0u);
                     }
                 }
 #pragma unroll
@@ -794,7 +780,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 if (lane == 0) mbar_arrive(&sh.tbl_full[slot]);
             }
         } else {
-            // ============================================================ loader warps (14-15): copy every chunk as it lies in
+            // ============================================================ loader warps: copy every chunk as it lies in
             // global memory -- 16 bytes of presence bits per operand row, the 128 byte weights -- into the raw ring with
             // cp.async (no registers, no waiting: up to WS_RAW chunks in flight), completion counted by the slot's mbarrier.
             const int ll = (warp - WS_MMA_WARP - 2) * 32 + lane;     // 0..63
@@ -810,17 +796,21 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 load_win(wi, cur.x);
                 PROF_AUX_END
                 const int nch = wi.nch, dense_chunks = wi.dense_chunks, hwords = wi.hwords;
-                int growv[ROWS_PER_LANE];                               // global row per slot row of this lane, -1: none
+                // Once per item: the global row behind each of this lane's slot rows and its copy size (a slot row without a
+                // haplotype behind it copies 0 bytes -- zero fill -- from row 0).  Per chunk and row: one wide multiply-add
+                // for the address and the copy.
+                const uint32_t *xw = tab.x + wi.x_off, *xhw = tab.xh + wi.xh_off;
+                const uint8_t *w8 = tab.w8 + wi.w8_off;
+                uint32_t grow[ROWS_PER_LANE], sz[ROWS_PER_LANE];
 #pragma unroll
                 for (int r = 0; r < ROWS_PER_LANE; ++r) {
                     const int tr = ll + r * WS_LOADER_LANES;            // 0..383: row of the raw slot
                     const bool isArow = tr < TILE_M;
-                    const int grow = isArow ? (cur.y & ITEM_BI_MASK) * TILE_M + tr : cur.z + (tr - TILE_M);
-                    growv[r] = ((isArow || tr - TILE_M < cur.w) && grow < wi.n) ? grow : -1;
+                    const int gr = isArow ? (cur.y & ITEM_BI_MASK) * TILE_M + tr : cur.z + (tr - TILE_M);
+                    const bool ok = (isArow || tr - TILE_M < cur.w) && gr < wi.n;
+                    grow[r] = ok ? (uint32_t)gr : 0u;
+                    sz[r] = ok ? 16u : 0u;
                 }
-                const uint32_t *xw = tab.x + wi.x_off, *xhw = tab.xh + wi.xh_off;
-                const uint8_t *w8 = tab.w8 + wi.w8_off;
-                const int pitch = wi.pitch;
                 for (int c = 0; c < nch; ++c, ++g) {
                     const uint32_t rs = g % WS_RAW;
                     if (alive) alive = mbar_wait<100>(&sh.raw_empty[rs], ((g / WS_RAW) & 1u) ^ 1u, tab.err);
@@ -828,15 +818,14 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     const uint32_t slot_u32 = raw_u32 + rs * (uint32_t)sizeof(RawSlot) + (uint32_t)ll * 16u;
                     const bool heavy_chunk = c >= dense_chunks;
                     const uint32_t *base = heavy_chunk ? xhw + 4 * (c - dense_chunks) : xw + 4 * c;
-                    const int stride = heavy_chunk ? hwords : pitch;
+                    const uint32_t stride = (uint32_t)(heavy_chunk ? hwords : wi.pitch);
+#ifndef IMPOP_DBG_NO_LOAD     // timing experiment only: no copies into the raw ring
 #pragma unroll
-                    for (int r = 0; r < ROWS_PER_LANE; ++r) {
-                        const bool ok = growv[r] >= 0;
-                        cp_async16(slot_u32 + (uint32_t)(r * WS_LOADER_LANES) * 16u,
-                                   ok ? (const void *)(base + (size_t)growv[r] * stride) : (const void *)w8, ok ? 16u : 0u);
-                    }
+                    for (int r = 0; r < ROWS_PER_LANE; ++r)
+                        cp_async16(slot_u32 + (uint32_t)(r * WS_LOADER_LANES) * 16u, base + (size_t)grow[r] * stride, sz[r]);
                     if (ll < KCHUNK / 16)
                         cp_async16(slot_u32 + (uint32_t)RAW_ROWS * 16u, w8 + (size_t)c * KCHUNK + ll * 16, 16u);
+#endif
                     cp_async_arrive_noinc(&sh.raw_full[rs]);
                     PROF_WORK_END
                 }
@@ -846,13 +835,13 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
 #endif
         }
     } else {
-        // ================================================================ epilogue.  All twelve warps work on the same item
-        // (warp -> 32-row quarter q4 of the TMEM lanes x one third of that quarter's valid 16-column chunks) while the
+        // ================================================================ epilogue.  All epilogue warps work on the same item
+        // (warp -> 32-row quarter q4 of the TMEM lanes x one share of that quarter's valid 16-column chunks) while the
         // MMA of the next item fills the other TMEM buffer.  Everything else an item needs comes from its table in
         // shared memory (table warps above): a warp that finishes its chunks early moves on to the next item as soon
-        // as the MMA has filled that accumulator -- no barrier couples the twelve warps.
+        // as the MMA has filled that accumulator -- no barrier couples the epilogue warps.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 " IMPOP_STR(IMPOP_REGS_EPI) ";");
-        const int e = warp - WS_EPI_WARP0;              // 0..11
+        const int e = warp - WS_EPI_WARP0;              // 0 .. WS_EPI_WARPS - 1
         const int q4 = warp & 3;                          // TMEM lane quarter this warp may read
         constexpr int H = WS_EPI_WARPS / 4;               // warps per TMEM lane quarter
         const int hsel = e >> 2;                          // which share of the quarter's chunks
@@ -873,6 +862,9 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             const int r0 = geo.y + rq * 32;
             const int i = r0 + lane;
             const uint32_t ai = col.ai[rq * 32 + lane];
+#if IMPOP_EPI_UNION_F64
+            const double dai = (double)ai;
+#endif
             const uint32_t fi = col.fi[rq * 32 + lane];
             // this quarter's valid chunks [c_lo, c_hi): columns below n, not entirely left of the diagonal; split in two
             int c_lo = 0, c_hi = 0;
@@ -892,88 +884,121 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             PROF_WAIT_END
             esum ts = esum_zero(), ta = esum_zero(), tb = esum_zero();
             const uint32_t tm0 = tmem_base + buf * TILE_N + ((uint32_t)(q4 * 32) << 16);
-            uint32_t ra[16];
-            auto chunk = [&](const uint32_t (&r)[16], int c) {
-                const int cc = c << 4;
+            // One 16-column chunk of this warp's 32 rows, IMPOP_EPI_NP = 4 pairs at a time: the contract's fp64 sequence, the
+            // group's pi_ij straight into the chunk's class sums (only the accumulator registers and one group's division
+            // chains are live: 16 epilogue warps at 96 registers).  Two bodies behind one warp-uniform branch per chunk:
+            //   FAST     every class holds all 16 columns or none: one tcgen05.ld of 16 columns, the four groups unrolled, one
+            //            shared pairwise tree -- 17 fp64 + 9 other instructions per pair;
+            //   general  per-column class flags (chunks that straddle a population boundary or the matrix edge): the group
+            //            loop is NOT unrolled and loads four columns at a time, so that this rarely used body stays small.
+            // Why two bodies: the kernel is bound by issue slots (an fp64 instruction holds the port for two cycles,
+            // tools/micro/issue_mix.cu), and with the class tests inside one body ptxas predicates the flag paths -- 3 fp64 +
+            // 1.5 load instructions per pair issued and discarded on every chunk.  Why the general one is small: the hot code
+            // of a scheduler's four epilogue warps has to stay in the instruction cache; two unrolled bodies (2 x 8 KB) ran
+            // 30 % slower than either alone.
+            auto group = [&](const uint32_t *r, int cc, int g0, bool on_diag, auto fast_tag, double &cs, double &ca, double &cb,
+                             double &call) {
+                constexpr bool FAST = decltype(fast_tag)::value;
                 const int jbase = col0 + cc;
-                const uint32_t cm = col.cmask[c];
-                uint32_t aj[16];
+                uint32_t aj[IMPOP_EPI_NP];
+                double p[IMPOP_EPI_NP];
+#if IMPOP_EPI_UNION_F64 && !defined(IMPOP_DBG_NO_EPI)
+                double daj[IMPOP_EPI_NP];
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(&col.aj[cc + 4 * k4]);
-                    aj[4 * k4] = q.x; aj[4 * k4 + 1] = q.y; aj[4 * k4 + 2] = q.z; aj[4 * k4 + 3] = q.w;
-                }
-                double p[16];
-#ifdef IMPOP_DBG_NO_EPI      // timing experiment only: skip the fp64 math
-#pragma unroll
-                for (int q = 0; q < 16; ++q) p[q] = __hiloint2double(r[q] + aj[q], ai);
-#else
-#pragma unroll
-                for (int q = 0; q < 16; q += IMPOP_EPI_NP) pi_batch<IMPOP_EPI_NP>(r + q, ai, aj + q, p + q);
-#endif
-                if (jbase <= r0 + 31) {                            // the chunk touches the diagonal of this warp's rows
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) p[q] = (jbase + q > i) ? p[q] : 0.0;
+                for (int k2 = 0; k2 < IMPOP_EPI_NP / 2; ++k2) {
+                    const double2 q = *reinterpret_cast<const double2 *>(&col.ajd[cc + g0 + 2 * k2]);
+                    daj[2 * k2] = q.x; daj[2 * k2 + 1] = q.y;
                 }
                 if (DUMP) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) pair_dump(prm, n, i, jbase + q, r[q], ai, aj[q]);
+                    for (int q = 0; q < IMPOP_EPI_NP; ++q) aj[q] = col.aj[cc + g0 + q];
                 }
-                double cs;
-                if (cm & 1u) {
-                    cs = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])),
-                                             __dadd_rn(__dadd_rn(p[4], p[5]), __dadd_rn(p[6], p[7]))),
-                                   __dadd_rn(__dadd_rn(__dadd_rn(p[8], p[9]), __dadd_rn(p[10], p[11])),
-                                             __dadd_rn(__dadd_rn(p[12], p[13]), __dadd_rn(p[14], p[15]))));
-                } else {
-                    cs = 0.0;
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) cs = __fma_rn(p[q], col.fs[cc + q], cs);   // p * 1.0 or p * 0.0: exact
+                pi_batch_f64<IMPOP_EPI_NP>(r, dai, daj, p);
+#else
+                {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(&col.aj[cc + g0]);
+                    aj[0] = q.x; aj[1] = q.y; aj[2] = q.z; aj[3] = q.w;
                 }
-                esum_add(ts, cs);
-                if (cm & 2u) {
-                    double ca = 0.0;
+#ifdef IMPOP_DBG_NO_EPI      // timing experiment only: skip the fp64 math
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) ca = __fma_rn(p[q], col.fa[cc + q], ca);
-                    esum_add(ta, ca);
+                for (int q = 0; q < IMPOP_EPI_NP; ++q) p[q] = __hiloint2double(r[q] + aj[q], ai);
+#else
+                pi_batch<IMPOP_EPI_NP>(r, ai, aj, p);
+#endif
+#endif
+                if (on_diag) {
+#pragma unroll
+                    for (int q = 0; q < IMPOP_EPI_NP; ++q) p[q] = (jbase + g0 + q > i) ? p[q] : 0.0;
                 }
-                if (cm & 4u) {
-                    double cb = 0.0;
+                if (DUMP) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) cb = __fma_rn(p[q], col.fb[cc + q], cb);
-                    esum_add(tb, cb);
+                    for (int q = 0; q < IMPOP_EPI_NP; ++q) pair_dump(prm, n, i, jbase + g0 + q, r[q], ai, aj[q]);
+                }
+                if (FAST) {                                     // plain pairwise tree over the group, shared by the classes
+                    call = __dadd_rn(call, __dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])));
+                } else {                                        // p * 1.0 or p * 0.0: exact
+#pragma unroll
+                    for (int q = 0; q < IMPOP_EPI_NP; ++q) cs = __fma_rn(p[q], col.fs[cc + g0 + q], cs);
+#pragma unroll
+                    for (int q = 0; q < IMPOP_EPI_NP; ++q) ca = __fma_rn(p[q], col.fa[cc + g0 + q], ca);
+#pragma unroll
+                    for (int q = 0; q < IMPOP_EPI_NP; ++q) cb = __fma_rn(p[q], col.fb[cc + g0 + q], cb);
                 }
             };
-            if (have_acc) {
-#if IMPOP_EPI_PREFETCH
-                // two chunks per trip: the TMEM load of the next chunk is in flight while this one is computed
-                uint32_t rb[16];
-                if (cbeg < cend) tmem_ld16(tm0 + (uint32_t)(cbeg << 4), ra);
-                for (int c = cbeg; c < cend; c += 2) {
-                    tmem_ld_wait();
-                    if (c + 1 < cend) tmem_ld16(tm0 + (uint32_t)((c + 1) << 4), rb);
-                    chunk(ra, c);
-                    if (c + 1 < cend) {
-                        tmem_ld_wait();
-                        if (c + 2 < cend) tmem_ld16(tm0 + (uint32_t)((c + 2) << 4), ra);
-                        chunk(rb, c + 1);
-                    }
-                }
+#pragma unroll 1
+            for (int c = cbeg; c < cend; ++c) {
+#ifdef IMPOP_DBG_NO_CLASS      // timing experiment only: every chunk treated as all-SUBSET, no A / B columns
+                const uint32_t cm = 1u;
 #else
-                for (int c = cbeg; c < cend; ++c) {
-                    tmem_ld16(tm0 + (uint32_t)(c << 4), ra);
-                    tmem_ld_wait();
-                    chunk(ra, c);
-                }
+                const uint32_t cm = col.cmask[c];
 #endif
+#ifdef IMPOP_DBG_FORCE_GENERAL  // timing experiment only
+                const bool fast = false;
+#else
+                // every column in SUBSET, and A (B) holds all of them or none
+                const bool fast = (cm & 1u) && ((cm & (2u | 8u)) != 2u) && ((cm & (4u | 16u)) != 4u);
+#endif
+                const int cc = c << 4;
+                const bool on_diag = col0 + cc <= r0 + 31;         // the chunk touches the diagonal of this warp's rows
+                double cs = 0.0, ca = 0.0, cb = 0.0, call = 0.0;   // sums over the chunk's SUBSET / A / B / all columns
+                if (fast) {
+                    uint32_t r[16];
+                    if (have_acc) {
+                        tmem_ld16(tm0 + (uint32_t)cc, r);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) r[q] = 0u;
+                    }
+#pragma unroll
+                    for (int g0 = 0; g0 < 16; g0 += IMPOP_EPI_NP) group(r + g0, cc, g0, on_diag, std::true_type{}, cs, ca, cb, call);
+                    esum_add(ts, call);                             // fast implies all 16 columns in SUBSET
+                    if (cm & 8u) esum_add(ta, call);
+                    if (cm & 16u) esum_add(tb, call);
+                } else {
+#pragma unroll 1
+                    for (int g0 = 0; g0 < 16; g0 += IMPOP_EPI_NP) {
+                        uint32_t r[IMPOP_EPI_NP];
+                        if (have_acc) {
+                            tmem_ld4(tm0 + (uint32_t)(cc + g0), r);
+                            tmem_ld_wait();
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < IMPOP_EPI_NP; ++q) r[q] = 0u;
+                        }
+                        group(r, cc, g0, on_diag, std::false_type{}, cs, ca, cb, call);
+                    }
+                    esum_add(ts, cs);
+                    if (cm & 2u) esum_add(ta, ca);
+                    if (cm & 4u) esum_add(tb, cb);
+                }
+            }
+            if (have_acc) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&sh.acc_empty[buf]); mbar_arrive(&sh.tbl_empty[slot]); }
                 if (buf) ++uses1; else ++uses0;
             } else {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) ra[q] = 0u;
-                for (int c = cbeg; c < cend; ++c) chunk(ra, c);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.tbl_empty[slot]);
             }

@@ -189,3 +189,74 @@ def multiset_expand(win: GraphWindow, max_copies: int = 255) -> GraphWindow:
     padded[:, :m2] = dense
     bits = np.packbits(padded, axis=1, bitorder="little").view("<u4").reshape(win.n, pitch).copy()
     return GraphWindow(list(win.names), bits, win.node_len[node].astype(np.uint32), None, win.region, win.length)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Column compaction (impop_compact_scan / impop_compact_fill): once per window, before the upload
+# ------------------------------------------------------------------------------------------------------------
+def _host_threads(threads):
+    import os
+    if threads is None:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, int(threads))
+
+
+def compact_batch(n, m, pitch_words, x_off, len_off, x_bits, node_len, threads=None, uniform_pitch: bool = False):
+    """Compact every window of a host batch (descriptor arrays as WindowBatch takes them; x_bits / node_len flat uint32).
+
+    Nodes carried by every haplotype of a window are merged into one node of their summed length, nodes carried by
+    none (or of length 0) are dropped, the rest is ordered by length: every I_ij, A_i, U_ij, S and statistic is
+    unchanged, while an HPRC-shaped window loses the third of its columns that is backbone.
+    Returns (m_out, pitch_out, x_off_out, len_off_out, x_out, len_out); len_out rows are padded with zeros to
+    32 * pitch_out nodes so that a window's lengths can be sliced like its presence words."""
+    L = lib()
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    m = np.ascontiguousarray(m, dtype=np.int32)
+    pitch_words = np.ascontiguousarray(pitch_words, dtype=np.int32)
+    x_off = np.ascontiguousarray(x_off, dtype=np.int64)
+    len_off = np.ascontiguousarray(len_off, dtype=np.int64)
+    x_bits = np.ascontiguousarray(x_bits).view(np.uint32).reshape(-1)
+    node_len = np.ascontiguousarray(node_len).view(np.uint32).reshape(-1)
+    W = int(n.shape[0])
+    th = _host_threads(threads)
+    m_out = np.zeros(W, dtype=np.int32)
+    rc = L.impop_compact_scan(W, n.ctypes.data, m.ctypes.data, pitch_words.ctypes.data, x_off.ctypes.data,
+                              len_off.ctypes.data, x_bits.ctypes.data, node_len.ctypes.data, th, m_out.ctypes.data)
+    if rc:
+        raise NativeError(rc, "impop_compact_scan")
+    pitch_out = np.maximum(4, ((m_out + 127) // 128) * 4).astype(np.int32)
+    if uniform_pitch and W:
+        pitch_out[:] = pitch_out.max()
+    rows = n.astype(np.int64) * pitch_out
+    x_off_out = np.concatenate([[0], np.cumsum(rows)[:-1]]).astype(np.int64) if W else np.zeros(0, np.int64)
+    cols = pitch_out.astype(np.int64) * 32
+    len_off_out = np.concatenate([[0], np.cumsum(cols)[:-1]]).astype(np.int64) if W else np.zeros(0, np.int64)
+    x_out = np.zeros(int(rows.sum()) if W else 0, dtype=np.uint32)
+    len_out = np.zeros(int(cols.sum()) if W else 0, dtype=np.uint32)
+    rc = L.impop_compact_fill(W, n.ctypes.data, m.ctypes.data, pitch_words.ctypes.data, x_off.ctypes.data,
+                              len_off.ctypes.data, x_bits.ctypes.data, node_len.ctypes.data, th, pitch_out.ctypes.data,
+                              x_off_out.ctypes.data, len_off_out.ctypes.data, x_out.ctypes.data, len_out.ctypes.data)
+    if rc:
+        raise NativeError(rc, "impop_compact_fill")
+    return m_out, pitch_out, x_off_out, len_off_out, x_out, len_out
+
+
+def compact_uniform(x_bits: np.ndarray, node_len: np.ndarray, threads=None):
+    """Same-shape windows x_bits [W, n, pitch] / node_len [W, m_pad] (host uint32) -> compacted same-shape windows
+    (x_out [W, n, pitch_out], len_out [W, 32 * pitch_out], m_out [W]); pitch_out fits the widest compacted window."""
+    W, n, pitch = x_bits.shape
+    m_pad = node_len.shape[1]
+    ar = np.arange(W, dtype=np.int64)
+    m_out, pitch_out, _, _, x_out, len_out = compact_batch(np.full(W, n), np.full(W, m_pad), np.full(W, pitch),
+                                                           ar * (n * pitch), ar * m_pad, x_bits, node_len, threads,
+                                                           uniform_pitch=True)
+    po = int(pitch_out[0]) if W else 4
+    return x_out.reshape(W, n, po), len_out.reshape(W, po * 32), m_out
+
+
+def compact_window(win: GraphWindow) -> GraphWindow:
+    """One GraphWindow -> its compacted form (visit counts are not carried over: expand multisets first)."""
+    m_out, pitch_out, _, _, x_out, len_out = compact_batch([win.n], [win.m], [win.x_bits.shape[1]], [0], [0], win.x_bits,
+                                                           win.node_len, threads=1)
+    mo, po = int(m_out[0]), int(pitch_out[0])
+    return GraphWindow(list(win.names), x_out.reshape(win.n, po), len_out[:mo].copy(), None, win.region, win.length)

@@ -218,6 +218,24 @@ int impop_gfa_scan(const char *text, int64_t bytes, impop_gfa_info_t *info);
 int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_t *x_bits_host, uint32_t *node_len_host,
                    uint16_t *counts_host, char *names_host, int64_t *name_off_host, int64_t *error_line);
 
+/* ---- Ingest (host side, no device work): column compaction of a batch of windows ---------------------------------
+ * The similarity tools walk paths (run_pica2_odgi.sh:96 `odgi similarity -i tmp.gfa`, run_h-fst.sh:65-67); a presence
+ * MATRIX of the same window carries columns that cannot change any result, and this step removes them once, before the
+ * matrices are uploaded: nodes visited by every haplotype are merged into one node of their summed length (they add
+ * the same constant to every intersection and path length), nodes visited by none and nodes of length 0 are dropped,
+ * the rest is ordered by length (original order within equal lengths).  Exact: I, A, U, segregating-node counts and all
+ * statistics of the compacted window equal those of the original.
+ * Descriptor arrays as in impop_batch_desc_t, but every pointer is a HOST pointer.  impop_compact_scan reports the node
+ * count of every compacted window; the caller sizes the outputs (out_pitch_words[w] * 32 >= m_out[w], a multiple of 4
+ * words; len_out zero-filled beyond m_out) and impop_compact_fill writes them.  `threads` host threads share the windows. */
+int impop_compact_scan(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
+                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
+                       int32_t *m_out);
+int impop_compact_fill(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
+                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
+                       const int32_t *out_pitch_words, const int64_t *out_x_off, const int64_t *out_len_off,
+                       uint32_t *x_out, uint32_t *len_out);
+
 /* All-pairs similarity table (the TSV the similarity tools print; pica2.py:6-58 and h-fst.py:84-119 parse it with
  * csv.DictReader, 47-92 % of those scripts' run time at 466 haplotypes) -> names in sorted order + dense n x n identity
  * matrix (NaN = pair absent; a repeated pair keeps its last row, pica2.py:44), the form impop_reduce_identity takes.

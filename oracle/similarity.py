@@ -118,3 +118,25 @@ def write_similarity_tsv(path, names, res, extra_columns: bool = True) -> None:
                              f"{float(jac[i, j])!r}\t{float(ident[i, j])!r}\n")
                 else:
                     fh.write(f"{names[i]}\t{names[j]}\t{float(ident[i, j])!r}\n")
+
+
+def compact_columns(x: np.ndarray, node_len: np.ndarray):
+    """Restatement of the ingest-time column compaction (impop_compact_scan / _fill, include/impop_b200.h): nodes every
+    row visits merge into one node of their summed length, nodes no row visits and nodes of length 0 vanish, the rest is
+    ordered by length (stable).  Returns (x', node_len') with the merged node last.  I, A, U and S are unchanged."""
+    x = np.asarray(x).astype(np.uint8)
+    node_len = np.asarray(node_len).astype(np.int64)
+    n = x.shape[0]
+    cnt = x.astype(np.int64).sum(axis=0)
+    live = node_len > 0
+    const = live & (cnt == n) & (n > 0)
+    var = live & (cnt > 0) & ~const
+    idx = np.flatnonzero(var)
+    idx = idx[np.argsort(node_len[idx], kind="stable")]
+    c = int(node_len[const].sum())
+    cols = [x[:, idx]]
+    lens = [node_len[idx]]
+    if c > 0:
+        cols.append(np.ones((n, 1), dtype=np.uint8))
+        lens.append(np.array([c], dtype=np.int64))
+    return np.concatenate(cols, axis=1), np.concatenate(lens)

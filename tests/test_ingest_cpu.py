@@ -157,3 +157,52 @@ def test_undefined_steps_are_errors(text):
         ingest.parse_gfa(text)
     with pytest.raises(KeyError):
         ogfa.parse(text)
+
+
+# ---------------------------------------------------------------------------------- column compaction (ingest)
+def _rand_window(rng, n, m, p_const=0.3, p_empty=0.1, p_zero=0.1, heavy=False):
+    x = (rng.random((n, m)) < rng.random(m)[None, :]).astype(np.uint8)
+    kind = rng.random(m)
+    x[:, kind < p_const] = 1
+    x[:, (kind >= p_const) & (kind < p_const + p_empty)] = 0
+    hi = 100000 if heavy else 60
+    nl = rng.integers(1, hi, size=m).astype(np.uint32)
+    nl[rng.random(m) < 0.5] = 1
+    nl[rng.random(m) < p_zero] = 0
+    return x, nl
+
+
+@pytest.mark.parametrize("n,m,heavy", [(1, 5, False), (2, 1, False), (7, 33, False), (40, 300, True), (130, 1009, False),
+                                       (466, 1009, True), (5, 0, False), (0, 9, False)])
+def test_compact_columns_matches_oracle_and_keeps_every_count(n, m, heavy):
+    rng = np.random.default_rng(n * 1000 + m)
+    x, nl = _rand_window(rng, n, m, heavy=heavy)
+    win = ingest.GraphWindow([f"h{i}" for i in range(n)], similarity.pack_bits(x) if (m and n) else np.zeros((n, 4), np.uint32), nl)
+    got = ingest.compact_window(win)
+    x2, nl2 = similarity.compact_columns(x, nl)
+    assert got.m == x2.shape[1] and got.x_bits.shape[1] % 4 == 0
+    assert np.array_equal(got.node_len.astype(np.int64), nl2)
+    if n:
+        assert np.array_equal(similarity.unpack_bits(got.x_bits, got.m), x2)
+        assert not similarity.unpack_bits(got.x_bits, got.x_bits.shape[1] * 32)[:, got.m:].any()  # padding bits are clear
+    # the contract: intersections, path lengths, pi_ij and segregating nodes are those of the original window
+    a, b = similarity.pairwise(x, nl), similarity.pairwise(x2, nl2)
+    assert np.array_equal(a["I"], b["I"]) and np.array_equal(a["A"], b["A"]) and np.array_equal(a["pi"], b["pi"])
+    assert similarity.segregating_nodes(x, nl) == similarity.segregating_nodes(x2, nl2)
+    if n >= 4:
+        rows = np.arange(0, n, 2)
+        assert similarity.segregating_nodes(x, nl, rows) == similarity.segregating_nodes(x2, nl2, rows)
+    if got.m:
+        assert (np.diff(got.node_len[:got.m - 1].astype(np.int64)) >= 0).all()                      # ordered by length
+
+
+def test_compact_uniform_batch_threads():
+    ws = synth.make_windows(60, 20000, 5, seed=91)
+    xo, lo, mo = ingest.compact_uniform(ws.x_bits, ws.node_len, threads=3)
+    assert xo.shape[0] == 5 and xo.shape[1] == 60 and lo.shape[1] == xo.shape[2] * 32
+    K = (ws.m - 1) // 3
+    for w in range(5):
+        x2, nl2 = similarity.compact_columns(ws.dense(w), ws.node_len[w])
+        assert mo[w] == x2.shape[1] <= 2 * K + 1
+        assert np.array_equal(similarity.unpack_bits(xo[w], int(mo[w])), x2)
+        assert np.array_equal(lo[w, :mo[w]].astype(np.int64), nl2) and not lo[w, mo[w]:].any()

@@ -16,9 +16,15 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--algo", type=int, default=0)
 ap.add_argument("--n", type=int, default=466)
 ap.add_argument("--length", type=int, default=50000)
+ap.add_argument("--compact", action="store_true", help="compact the columns at ingest (impop_compact_scan / _fill)")
 args = ap.parse_args()
 ctx = Context(0)
 x, nl, pops, m, m_pad = synth.make_windows_device(ctx, args.n, args.length, args.windows, seed=0xB201)
+if args.compact:
+    from impop_b200 import ingest  # noqa: E402
+    xc, lc, mo = ingest.compact_uniform(x.cpu().numpy().view(np.uint32), nl.cpu().numpy().view(np.uint32))
+    x = torch.from_numpy(xc.view(np.int32)).to(ctx.torch_device)
+    nl = torch.from_numpy(lc.view(np.int32)).to(ctx.torch_device)
 lab = np.full(args.n, 9, dtype=np.uint8)
 lab[pops == 0] |= 2
 lab[pops == 2] |= 4

@@ -6,9 +6,14 @@ import ctypes as C
 import numpy as np, torch
 from impop_b200 import synth
 from impop_b200.engine import Context, WindowBatch
-W = int(sys.argv[1]) if len(sys.argv) > 1 else 4854
+W = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 4854
 ctx = Context(0)
 x, nl, pops, m, m_pad = synth.make_windows_device(ctx, 466, 50000, W, seed=0xB201)
+if "--compact" in sys.argv:            # columns compacted at ingest (impop_compact_scan / _fill)
+    from impop_b200 import ingest
+    xc, lc, mo = ingest.compact_uniform(x.cpu().numpy().view(np.uint32), nl.cpu().numpy().view(np.uint32))
+    x = torch.from_numpy(xc.view(np.int32)).to(ctx.torch_device); nl = torch.from_numpy(lc.view(np.int32)).to(ctx.torch_device)
+    print("compacted: nodes", m, "->", int(mo.max()))
 lab = np.full(466, 9, dtype=np.uint8); lab[pops == 0] |= 2; lab[pops == 2] |= 4
 b = WindowBatch.from_uniform(ctx, x, nl, torch.from_numpy(lab).to(ctx.torch_device), 50000)
 for _ in range(3):

@@ -7,7 +7,7 @@ cp impop_b200/libimpop_b200.so /tmp/default.so
 for v in $(ls variants/roles*.so | xargs -n1 basename | sed 's/\.so$//'); do
   cp "variants/$v.so" impop_b200/libimpop_b200.so
   echo "=== $v" >> gpurun_out/roles.log
-  timeout 120 python tools/role_times.py >> gpurun_out/roles.log 2>&1
+  timeout 120 python tools/role_times.py $ROLE_ARGS >> gpurun_out/roles.log 2>&1
 done
 cp /tmp/default.so impop_b200/libimpop_b200.so
 cat gpurun_out/roles.log
