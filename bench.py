@@ -1,17 +1,28 @@
 #!/usr/bin/env python3
 """bench.py -- haplotype-pair*bp/s of the windowed pi / Hudson Fst / Tajima's D hot path.
 
-Workload (BASELINE.json configs[1]): h-fst.py-style Hudson Fst, AFR (140) vs EAS (100) panels inside a
-466-haplotype synthetic HPRC-shaped panel, 50 kb windows over a chr2-length graph (4 854 windows; every
-window also yields pi, S and Tajima's D in the same pass).  One "step" = one pass of the fused path over
-the whole batch; at N > 1 every rank owns its own chromosome-length batch (weak scaling) and the result
-rows are all-gathered once per step.
+Default workload (BASELINE.json configs[1]): h-fst.py-style Hudson Fst, AFR (140) vs EAS (100) panels inside a
+466-haplotype synthetic HPRC-shaped panel, 50 kb windows over a chr2-length graph (4 854 windows; every window also
+yields pi, S and Tajima's D in the same pass).  One "step" = one pass of the fused path over the whole batch; at N > 1
+every rank owns its own chromosome-length batch (weak scaling) and the result rows are all-gathered once per step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config {1,2,3,4,5}] [--strong]
 
-Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = through the
-public API with host buffers, roofline = dominant kernel vs its bound, cpu_baseline = the CPU oracle port
-timed on this box's host cores.
+  --config 3   tj_d.py genome-wide: 20 kb windows, 466 haplotypes, S from segregating nodes; one GPU's share of the
+               155 864 windows of a CHM13-length genome per rank (weak), or the whole genome split over the ranks (--strong)
+  --config 5   scale-up: 16 windows of 10 000 haplotypes x 200 kb, the tile grid of every window split over the ranks
+               (X broadcast once with NCCL, partial sums all-gathered and added in rank order): strong scaling
+  --config 4   af.py per-site allele counts, 10^7 sites x 466 haplotypes x 5 panels (sites sharded over the ranks)
+  --config 1   pica2.py on one 90-haplotype similarity table: latency of the drop-in CLI (N = 1 only)
+
+Ingest: the windows are generated as full presence matrices (every node a column); `impop_compact_scan / _fill`
+(host, once per window, timed and reported as `ingest`) merges the columns every haplotype carries, drops empty ones
+and orders the rest by length.  Every result is unchanged (the line carries the comparison with the oracle run on the
+ORIGINAL columns); the roofline counts algorithmic operations from the ORIGINAL node count.
+
+Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = through the public API with
+host buffers, roofline = dominant kernel vs its bound, cpu_baseline = the CPU oracle port timed on this box's host
+cores, other_configs (N = 1, default config only) = short measurements of the other BASELINE configs.
 """
 from __future__ import annotations
 
@@ -29,33 +40,51 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_HAP = 466
-WINDOW_BP = 50_000
 CHR2_BP = 242_696_752                     # CHM13 v2.0 chr2
-WINDOWS = -(-CHR2_BP // WINDOW_BP)        # 4 854
+GENOME_BP = 3_117_275_501                 # CHM13 v2.0 total
 METRIC = "haplotype-pair*bp/s (windowed pi / Hudson Fst / Tajima's D)"
 UNIT = "hap-pair*bp/s"
 LAB_SUBSET, LAB_A, LAB_B, LAB_SEG = 1, 2, 4, 8
+TILE_M, TILE_N, KCHUNK = 128, 256, 128    # tile geometry of the pairs kernel (impop_b200/csrc/common.cuh)
 
-
-def labels_for(pops: np.ndarray) -> np.ndarray:
-    lab = np.full(pops.shape[0], LAB_SUBSET | LAB_SEG, dtype=np.uint8)
-    lab[pops == 0] |= LAB_A               # AFR
-    lab[pops == 2] |= LAB_B               # EAS
-    return lab
+CONFIGS = {
+    2: {"n": N_HAP, "L": 50_000, "W": -(-CHR2_BP // 50_000), "labels": "afr_eas", "seed": 0xB200 + 1,
+        "workload": f"h-fst AFR(140) vs EAS(100) Hudson Fst + pi + Tajima's D, {N_HAP} haplotypes, 50000 bp windows, chr2-length graph"},
+    3: {"n": N_HAP, "L": 20_000, "W": -(-GENOME_BP // 20_000) // 8 + 1, "W_total": -(-GENOME_BP // 20_000), "labels": "all", "seed": 0xB200 + 2,
+        "workload": f"tj_d Tajima's D genome-wide (S = segregating nodes) + pi, {N_HAP} haplotypes, 20000 bp windows, CHM13-length genome"},
+    5: {"n": 10_000, "L": 200_000, "W": 16, "labels": "halves", "seed": 0xB200 + 4,
+        "workload": "scale-up pi + Hudson Fst, 10000 haplotypes (two panels of 5000), 200000 bp windows, tile grid split over the GPUs"},
+}
 
 
 def units_per_window(n: int, length: int) -> float:
     return n * (n - 1) / 2.0 * length
 
 
+def labels_for(kind: str, pops: np.ndarray) -> np.ndarray:
+    lab = np.full(pops.shape[0], LAB_SUBSET | LAB_SEG, dtype=np.uint8)
+    if kind == "afr_eas":
+        lab[pops == 0] |= LAB_A               # AFR
+        lab[pops == 2] |= LAB_B               # EAS
+    elif kind == "halves":
+        lab[: pops.shape[0] // 2] |= LAB_A
+        lab[pops.shape[0] // 2:] |= LAB_B
+    return lab
+
+
+def host_threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def load_peaks():
     """Roofline denominators: MEASURED_PEAKS.json (driver-written) and profiles/int8_peak.json (measured by
     tools/measure_int8_peak.py on this pool); else the stated fallbacks."""
-    out = {"hbm_gbs": 6650.0, "hbm_src": "fallback", "int8_tops": None, "int8_src": None, "bf16_tflops": 1590.0}
+    out = {"hbm_gbs": 6650.0, "hbm_src": "fallback", "int8_tops": None, "int8_src": None, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             mp = json.load(fh)
-        out.update(hbm_gbs=float(mp["hbm_gbs"]), hbm_src="measured", bf16_tflops=float(mp["bf16_tflops"]))
+        out.update(hbm_gbs=float(mp["hbm_gbs"]), hbm_src="measured", bf16_tflops=float(mp["bf16_tflops"]),
+                   sm_max_mhz=float(mp.get("sm_max_mhz", 1965.0)))
     except Exception:
         pass
     try:
@@ -118,52 +147,95 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_oracle_rate(x_bits, node_len, labels, n, m_pad, pitch, length, threads, target_s=12.0, max_windows=None):
-    """Time the plain-C oracle port (oracle/csrc/oracle_impop.c, pthreads) on a bounded sample sized to
-    ~target_s seconds.  Returns (pair*bp/s, windows in the sample, seconds, stats, counts)."""
-    from oracle import clib
-    total = x_bits.shape[0] if max_windows is None else min(max_windows, x_bits.shape[0])
-
-    def run(S):
-        ar = np.arange(S, dtype=np.int64)
-        t0 = time.perf_counter()
-        st, ct = clib.batch_stats(np.full(S, n), np.full(S, m_pad), np.full(S, pitch), ar * (n * pitch), ar * m_pad,
-                                  np.zeros(S, dtype=np.int64), np.full(S, length), x_bits[:S], node_len[:S], labels, threads)
-        return time.perf_counter() - t0, st, ct
-
-    s0 = min(total, max(threads * 2, 8))
-    t0, st, ct = run(s0)
-    S = int(min(total, max(s0, s0 * target_s / max(t0, 1e-3))))
-    if S > s0:
-        t0, st, ct = run(S)
+# ------------------------------------------------------------------------------------------------------------------
+# Workload: generated windows -> ingest (column compaction) -> arrays the batch is built from
+# ------------------------------------------------------------------------------------------------------------------
+def make_workload(gen, cfg: dict, windows: int, seed: int, threads: int, keep_original: int = 0):
+    """Generate `windows` windows of config `cfg` with `gen` (a device Context or synth.HostGenerator), then run the
+    ingest-time column compaction on the host.  Returns a dict of HOST arrays (uint32 views) + meta; `keep_original`
+    windows of the uncompacted input are kept for the oracle cross-check."""
+    from impop_b200 import ingest, synth
+    n, L = cfg["n"], cfg["L"]
+    if cfg["labels"] == "halves":
+        pops = np.repeat([0, 1], n // 2)
+        x, nl, pops, m, m_pad = synth.make_windows_device(gen, n, L, windows, seed=seed, pops=pops, chunk=4)
     else:
-        S = s0
-    return S * units_per_window(n, length) / t0, S, t0, st, ct
+        x, nl, pops, m, m_pad = synth.make_windows_device(gen, n, L, windows, seed=seed)
+    xh = x.cpu().numpy().view(np.uint32)
+    lh = nl.cpu().numpy().view(np.uint32)
+    del x, nl
+    t0 = time.perf_counter()
+    xc, lc, m_out = ingest.compact_uniform(xh, lh, threads=threads)
+    t1 = time.perf_counter()
+    heavy = ((lc.astype(np.int64) // 255 + 254) // 255).sum(axis=1)               # heavy-table entries per window
+    k_exec = ((m_out.astype(np.int64) + KCHUNK - 1) // KCHUNK + (heavy + KCHUNK - 1) // KCHUNK) * KCHUNK
+    nl_max = int(lh.max()) if lh.size else 0
+    planes = 1 if nl_max < 256 else (2 if nl_max < 65536 else (3 if nl_max < (1 << 24) else 4))
+    return {"x": xc, "len": lc, "m_out": m_out, "pops": pops, "labels": labels_for(cfg["labels"], pops), "n": n, "L": L,
+            "m_in": int(m), "m_pad_in": int(m_pad), "pitch": int(xc.shape[2]), "m_pad": int(lc.shape[1]), "planes": planes,
+            "k_exec": k_exec, "ingest_s": t1 - t0, "ingest_threads": threads,
+            "orig_x": xh[:keep_original].copy() if keep_original else None,
+            "orig_len": lh[:keep_original].copy() if keep_original else None,
+            "bytes_in": int(xh.nbytes + lh.nbytes), "bytes_out": int(xc.nbytes + lc.nbytes)}
 
 
+def item_geometry(n: int):
+    """Work items of one n-haplotype window: [(rows of the block, columns of the item), ...] (common.cuh)."""
+    out = []
+    for bi in range((n + TILE_M - 1) // TILE_M):
+        rng = n - bi * TILE_M
+        cnt = (rng + TILE_N - 1) // TILE_N
+        width = ((rng + cnt - 1) // cnt + 15) & ~15
+        out += [(TILE_M, width)] * cnt
+    return out
+
+
+def cpu_oracle(x_bits, node_len, labels, n, m_pad, pitch, length, threads, windows):
+    """One pass of the plain-C oracle port (oracle/csrc/oracle_impop.c, pthreads) over `windows` same-shape windows."""
+    from oracle import clib
+    ar = np.arange(windows, dtype=np.int64)
+    t0 = time.perf_counter()
+    st, ct = clib.batch_stats(np.full(windows, n), np.full(windows, m_pad), np.full(windows, pitch), ar * (n * pitch),
+                              ar * m_pad, np.zeros(windows, dtype=np.int64), np.full(windows, length),
+                              x_bits[:windows], node_len[:windows], labels, threads)
+    return time.perf_counter() - t0, st, ct
+
+
+def max_rel_errors(got, want):
+    """Largest plain relative error |got - want| / |want| per statistic over the rows (NaN rows must agree)."""
+    from impop_b200._native import ST
+    out = {}
+    for name in ("pi", "pi_per_site", "pi_a", "pi_b", "dxy", "da", "fst", "tajima_d"):
+        g, w = got[:, ST[name]], want[:, ST[name]]
+        ok = np.isfinite(w) & (w != 0)
+        err = np.abs(g[ok] - w[ok]) / np.abs(w[ok]) if ok.any() else np.zeros(1)
+        out[name] = float(err.max()) if err.size else 0.0
+    out["nan_pattern_equal"] = bool(np.array_equal(np.isnan(got), np.isnan(want)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Reference arm: the CPU restatement of the reference path on the same workload
+# ------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """--impl reference: the CPU restatement of the reference path (oracle port; the reference itself is
-    Python scripts + external odgi/impg binaries, neither of which travels to the GPU box) with all host
-    threads, each step a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU path for this workload = `odgi/impg similarity` per window + the
+    scripts' reductions.  Neither the external binaries nor /root/reference travel to the GPU box, so the arm times the
+    plain-C oracle port of that path (oracle/csrc/oracle_impop.c) with every host thread, over ALL windows of the
+    workload per step (same inputs as the GPU arm: compacted columns)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import torch  # noqa: F401  (host tensor plumbing for the generator only)
     from impop_b200 import synth
-    threads = len(os.sched_getaffinity(0))
-    gen = synth.HostGenerator()
-    sample = min(WINDOWS, max(threads * 24, 96))
-    x_bits, node_len, pops, m, m_pad = synth.make_windows_device(gen, N_HAP, WINDOW_BP, sample, seed=0xB200 + 1, chunk=128)
-    xb = x_bits.numpy().view(np.uint32)
-    nl = node_len.numpy().view(np.uint32)
-    lab = labels_for(pops)
-    pitch = m_pad // 32
-    from oracle import clib
-    ar = np.arange(sample, dtype=np.int64)
+    cfg = CONFIGS[args.config if args.config in CONFIGS else 2]
+    threads = host_threads()
+    W = args.windows or cfg["W"]
+    if args.config == 5:
+        W = min(W, 1)                         # 5e7 pairs x 5 888 nodes per window: one window per step is ~minutes of CPU
+    wl = make_workload(synth.HostGenerator(), cfg, W, cfg["seed"], threads)
 
     def step():
-        clib.batch_stats(np.full(sample, N_HAP), np.full(sample, m_pad), np.full(sample, pitch), ar * (N_HAP * pitch),
-                         ar * m_pad, np.zeros(sample, dtype=np.int64), np.full(sample, WINDOW_BP), xb, nl, lab, threads)
+        return cpu_oracle(wl["x"], wl["len"], wl["labels"], wl["n"], wl["m_pad"], wl["pitch"], wl["L"], threads, W)[0]
 
     for _ in range(args.warmup):
         step()
@@ -171,15 +243,16 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    value = sample * units_per_window(N_HAP, WINDOW_BP) / dt
+    value = W * units_per_window(wl["n"], wl["L"]) / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.config == 5 or args.strong else "weak", "vs_baseline": None,
         "dtype": "int64 intersections + f64 statistics", "data": "synthetic",
-        "config": {"workload": f"h-fst AFR(140) vs EAS(100), {N_HAP} haplotypes, {WINDOW_BP} bp windows, chr2-length graph",
-                   "windows_per_step": sample, "nodes_per_window": int(m_pad)},
+        "config": {"workload": cfg["workload"], "windows_per_step": W, "nodes_per_window": wl["m_in"],
+                   "nodes_after_ingest": int(wl["m_out"].max()), "haplotypes": wl["n"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} of {WINDOWS} windows per step, plain-C oracle (byte-LUT intersections) on {threads} pthreads"},
+                         "sample": f"all {W} windows of the workload per step, plain-C oracle port (byte-LUT intersections) on {threads} pthreads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -187,11 +260,124 @@ def run_reference(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Secondary configs (short; embedded in the default line so that the driver's record carries them)
+# ------------------------------------------------------------------------------------------------------------------
+def _timed(torch, fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench_sites(ctx, torch, peaks, sites=10_000_000, reps=10, rank=0, world=1):
+    """Config 4: per-site allele counts and frequencies, `sites` sites x 466 haplotypes x 5 panels (this rank's share)."""
+    from impop_b200 import synth
+    dev = ctx.torch_device
+    mine = sites // world + (1 if rank < sites % world else 0)
+    small, masks = synth.make_site_matrix(1 << 20, N_HAP, seed=0xB200 + 3 + rank)
+    ds = torch.from_numpy(small.view(np.int64)).to(dev).repeat((mine + (1 << 20) - 1) // (1 << 20), 1)[:mine].contiguous()
+    dm = torch.from_numpy(masks[:5].view(np.int64)).to(dev)
+    counts = torch.empty((mine, 5), dtype=torch.int32, device=dev)
+    freq = torch.empty((mine, 5), dtype=torch.float64, device=dev)
+    ms = _timed(torch, lambda: ctx.site_counts(ds, dm, out_counts=counts, out_freq=freq), reps)
+    bytes_alg = mine * (64 + 5 * 4 + 5 * 8)
+    return {"sites": sites, "sites_this_gpu": mine, "ms": ms, "sites_per_s_per_gpu": mine / (ms * 1e-3),
+            "algorithmic_bytes": bytes_alg, "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9,
+            "hbm_frac": bytes_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "bound": "hbm", "kernel": "site_counts_w8_kernel"}
+
+
+def bench_windows_short(ctx, torch, peaks, cfg, windows, reps, threads):
+    """Resident timing of the fused path on `windows` windows of a config (this GPU only), with the int8 / fp64 fractions."""
+    from impop_b200.engine import ALGO_TCGEN05, WindowBatch
+    dev = ctx.torch_device
+    wl = make_workload(ctx, cfg, windows, cfg["seed"], threads)
+    xd = torch.from_numpy(wl["x"].view(np.int32)).to(dev)
+    ld = torch.from_numpy(wl["len"].view(np.int32)).to(dev)
+    lab = torch.from_numpy(wl["labels"]).to(dev)
+    b = WindowBatch.from_uniform(ctx, xd, ld, lab, wl["L"])
+    ms = _timed(torch, lambda: b.stats(ALGO_TCGEN05), reps)
+    ctx.timing(True)
+    b.stats(ALGO_TCGEN05)
+    torch.cuda.synchronize()
+    pairs_ms, prep_ms = ctx.timing_read("pairs")[0], ctx.timing_read("prep")[0]
+    ctx.timing(False)
+    ctx.check()
+    b.close()
+    n, L = wl["n"], wl["L"]
+    ops = 2.0 * windows * (n * (n + 1) / 2.0) * wl["m_pad_in"] * wl["planes"]
+    sms = torch.cuda.get_device_properties(ctx.device).multi_processor_count
+    eps = windows * n * (n - 1) / 2.0 / (pairs_ms * 1e-3)
+    return {"windows": windows, "haplotypes": n, "window_bp": L, "nodes_per_window": wl["m_in"], "nodes_after_ingest": int(wl["m_out"].max()),
+            "ms_per_pass": ms, "pairs_kernel_ms": pairs_ms, "prep_ms": prep_ms,
+            "hap_pair_bp_per_s": windows * units_per_window(n, L) / (ms * 1e-3),
+            "int8_tops_algorithmic": ops / (pairs_ms * 1e-3) / 1e12, "int8_frac": ops / (pairs_ms * 1e-3) / 1e12 / peaks["int8_tops"],
+            "fp64_frac": eps * 18 / (64.0 * sms * peaks["sm_max_mhz"] * 1e6), "ingest_s": wl["ingest_s"]}
+
+
+def bench_cli_latency(reps=3):
+    """Config 1: wall time of the drop-in `scripts/pica2.py` on one 90-haplotype, 100 kb window (TSV mode: the all-pairs
+    table the similarity tool prints; written here by the matrix-mode driver's own dump).  Process start to exit, i.e.
+    what a wrapper's per-window loop pays (run_pica2_impg.sh:175).  The reference's own figure for this table, measured
+    in the build container, is in profiles/r2_reference_scripts.json."""
+    import tempfile
+    from impop_b200 import synth
+    from impop_b200.engine import Context, WindowBatch
+    ws = synth.make_windows(90, 100_000, 1, seed=0xB200)
+    names = synth.haplotype_names(90, "chr2", 109_000_000, 109_100_000)
+    ctx = Context(0)
+    b = WindowBatch.from_uniform(ctx, ws.x_bits, ws.node_len, np.full(90, 9, dtype=np.uint8), 100_000)
+    _, _, pi = b.pairwise(0)
+    ident = (1.0 - pi).cpu().numpy()
+    b.close()
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        tsv = os.path.join(tmp, "edar.sim.tsv")
+        with open(tsv, "w") as fh:
+            fh.write("group.a\tgroup.b\testimated.identity\n")
+            for i in range(90):
+                for j in range(i + 1, 90):
+                    fh.write(f"{names[i]}\t{names[j]}\t{float(ident[i, j])!r}\n")
+        for script, extra in (("pica2.py", ["-t", "1.0", "-l", "100000", "-d", tmp]),):
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", script), tsv, *extra], capture_output=True, text=True)
+                ts.append(time.perf_counter() - t0)
+            out[script] = {"wall_s_median": float(np.median(ts)), "wall_s_min": float(min(ts)), "rc": r.returncode,
+                           "stdout": r.stdout.strip()[:80]}
+    return out
+
+
+def other_configs(ctx, torch, peaks, threads):
+    out = {}
+    for key, fn in (("config3", lambda: bench_windows_short(ctx, torch, peaks, CONFIGS[3], CONFIGS[3]["W"], 5, threads)),
+                    ("config4", lambda: bench_sites(ctx, torch, peaks)),
+                    ("config5", lambda: bench_windows_short(ctx, torch, peaks, CONFIGS[5], 4, 3, threads)),
+                    ("config1", bench_cli_latency)):
+        try:
+            t0 = time.perf_counter()
+            out[key] = fn()
+            out[key]["measured_in_s"] = time.perf_counter() - t0
+        except Exception as exc:  # a secondary measurement must never take the headline down
+            out[key] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Our arm
+# ------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from impop_b200 import synth
-    from impop_b200.distributed import gather_rows
+    from impop_b200.distributed import gather_parts, gather_rows
     from impop_b200.engine import ALGO_SIMT, ALGO_TCGEN05, Context, WindowBatch, NCOUNTS, NSTATS
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,28 +389,97 @@ def run_ours(args):
     ctx = Context(local)
     dev = ctx.torch_device
     algo = ALGO_SIMT if args.algo == "simt" else ALGO_TCGEN05
-    W = args.windows
-
-    # ---------------------------------------------------------------- synthetic batch, resident in HBM
-    x_bits, node_len, pops, m, m_pad = synth.make_windows_device(ctx, N_HAP, WINDOW_BP, W, seed=0xB200 + 1 + 1000 * rank)
-    pitch = m_pad // 32
-    lab_host = labels_for(pops)
-    labels = torch.from_numpy(lab_host).to(dev)
-    batch = WindowBatch.from_uniform(ctx, x_bits, node_len, labels, WINDOW_BP)
-    stats = torch.empty((W, NSTATS), dtype=torch.float64, device=dev)
-    counts = torch.empty((W, NCOUNTS), dtype=torch.int64, device=dev)
-    bounds = np.arange(world + 1, dtype=np.int64) * W
-
-    def step():
-        batch.stats(algo, out_stats=stats, out_counts=counts)
-        if world > 1:                     # the single result gather of the north star (W x 20 fp64 per rank)
-            return gather_rows(stats, bounds)
-        return stats
+    peaks = load_peaks()
+    threads = max(1, host_threads() // max(1, world))          # the ranks of one box share its host cores
+    sms = int(torch.cuda.get_device_properties(local).multi_processor_count)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.config == 4:
+        return run_sites(args, ctx, torch, dist, peaks, rank, world, local)
+    if args.config == 1:
+        if rank == 0:
+            print(json.dumps({"metric": "wall seconds of scripts/pica2.py on a 90-haplotype similarity table", "unit": "s",
+                              "higher_is_better": False, "n_gpus": 1, "config": {"workload": "BASELINE config 1"}, **bench_cli_latency(5)}))
+        return 0
+
+    cfg = CONFIGS[args.config]
+    split = args.config == 5                                   # one batch, tile grid split over the ranks
+    strong = split or args.strong
+    W_total = args.windows or (cfg.get("W_total", cfg["W"]) if (strong and not split) else cfg["W"])
+    n, L = cfg["n"], cfg["L"]
+
+    # ---------------------------------------------------------------- synthetic batch -> ingest -> resident in HBM
+    if split:
+        # rank 0 holds the windows; X, node lengths and labels are broadcast once (NCCL), every rank builds the
+        # same batch and works the items t with t % world == rank
+        W = W_total
+        keep = min(W, 1)
+        if rank == 0:
+            wl = make_workload(ctx, cfg, W, cfg["seed"], host_threads(), keep_original=0)
+            meta = [wl["pitch"], wl["m_pad"], wl["m_in"], wl["m_pad_in"], wl["planes"], int(wl["m_out"].max()), int(wl["k_exec"].max())]
+        else:
+            wl, meta = None, [0] * 7
+        if world > 1:
+            mt = torch.tensor(meta, dtype=torch.int64, device=dev)
+            dist.broadcast(mt, 0)
+            meta = [int(v) for v in mt.tolist()]
+        pitch, m_pad, m_in, m_pad_in, planes, m_out_max, k_exec_max = meta
+        if rank == 0:
+            hx = torch.from_numpy(wl["x"].view(np.int32)).pin_memory()
+            hl = torch.from_numpy(wl["len"].view(np.int32)).pin_memory()
+            lab_host = wl["labels"]
+        else:
+            hx = hl = None
+            lab_host = labels_for(cfg["labels"], np.zeros(n, dtype=np.int64))
+        x_c = torch.empty((W, n, pitch), dtype=torch.int32, device=dev)
+        len_c = torch.empty((W, m_pad), dtype=torch.int32, device=dev)
+        if rank == 0:
+            x_c.copy_(hx); len_c.copy_(hl)
+        if world > 1:
+            dist.broadcast(x_c, 0); dist.broadcast(len_c, 0)
+        k_exec = np.full(W, k_exec_max)
+        ingest = {"seconds": wl["ingest_s"], "threads": wl["ingest_threads"], "bytes_in": wl["bytes_in"], "bytes_out": wl["bytes_out"]} if rank == 0 else None
+        bounds = None
+    else:
+        W = W_total // world + (1 if rank < W_total % world else 0) if strong else W_total
+        keep = min(W, 96) if (rank == 0 and world == 1) else 0
+        wl = make_workload(ctx, cfg, W, cfg["seed"] + 1000 * rank, threads, keep_original=keep)
+        pitch, m_pad, m_in, m_pad_in, planes = wl["pitch"], wl["m_pad"], wl["m_in"], wl["m_pad_in"], wl["planes"]
+        m_out_max, k_exec = int(wl["m_out"].max()), wl["k_exec"]
+        lab_host = wl["labels"]
+        hx = torch.from_numpy(wl["x"].view(np.int32)).pin_memory()
+        hl = torch.from_numpy(wl["len"].view(np.int32)).pin_memory()
+        x_c, len_c = hx.to(dev), hl.to(dev)
+        ingest = {"seconds": wl["ingest_s"], "threads": wl["ingest_threads"], "bytes_in": wl["bytes_in"], "bytes_out": wl["bytes_out"]}
+        sizes = torch.tensor([W], dtype=torch.int64, device=dev)
+        if world > 1:
+            allw = [torch.zeros_like(sizes) for _ in range(world)]
+            dist.all_gather(allw, sizes)
+            bounds = np.concatenate([[0], np.cumsum([int(t.item()) for t in allw])]).astype(np.int64)
+        else:
+            bounds = np.array([0, W], dtype=np.int64)
+    labels = torch.from_numpy(lab_host).to(dev)
+    resident_mb = (x_c.numel() * 4 + len_c.numel() * 4) / 1e6
+    l2_note = (f"{W} windows of {n * pitch * 4 / 1e6:.1f} MB each ({resident_mb:.0f} MB per GPU), read every step" if split
+               else f"inputs larger than L2 ({resident_mb:.0f} MB per GPU read every step)")
+    batch = WindowBatch.from_uniform(ctx, x_c, len_c, labels, L)
+    stats = torch.empty((W, NSTATS), dtype=torch.float64, device=dev)
+    counts = torch.empty((W, NCOUNTS), dtype=torch.int64, device=dev)
+
+    def step():
+        if split:                              # partial sums of this rank's items, one all-gather, rank-ordered finalize
+            sums = batch.window_sums(rank, world, algo)
+            st, ct = batch.finalize(gather_parts(sums))
+            stats.copy_(st); counts.copy_(ct)
+            return stats
+        batch.stats(algo, out_stats=stats, out_counts=counts)
+        if world > 1:                          # the single result gather of the north star (W x 20 fp64 per rank)
+            return gather_rows(stats, bounds)
+        return stats
 
     for _ in range(args.warmup):
         step()
@@ -249,86 +504,79 @@ def run_ours(args):
     ctx.timing(False)
     ctx.check()
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_step, pairs_ms / max(pairs_n, 1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item())
-    units_step = world * W * units_per_window(N_HAP, WINDOW_BP)
+    ms_step, pairs_avg_ms = float(t[0].item()), float(t[1].item())
+    tot = torch.tensor([float(W)], dtype=torch.float64, device=dev)
+    if world > 1 and not split:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    windows_job = int(tot.item())
+    units_step = windows_job * units_per_window(n, L)
     value = units_step / (ms_step * 1e-3)
 
     # ---------------------------------------------------------------- e2e: host buffers through the public API
-    # Every step: pinned host -> device copies of that step's inputs, batch set-up, the fused kernels and the
-    # device -> host read of the result rows, all inside the timed region.  The batch is cut into sub-batches
-    # that alternate between two streams so copies overlap kernels (public API: WindowBatch + stream arguments).
-    hx = torch.empty(x_bits.shape, dtype=torch.int32, pin_memory=True); hx.copy_(x_bits)
-    hl = torch.empty(node_len.shape, dtype=torch.int32, pin_memory=True); hl.copy_(node_len)
-    hlab = torch.from_numpy(lab_host).pin_memory()
+    # Every step: pinned host -> device copies of that step's inputs (the ingested matrices), batch set-up, the fused kernels
+    # and the device -> host read of the result rows, all inside the timed region.  Window-sharded configs cut the batch
+    # into sub-batches that alternate between two streams so copies overlap kernels; the split config uploads on rank 0,
+    # broadcasts over NVLink and reads the finalized rows back.
     hs = torch.empty((W, NSTATS), dtype=torch.float64, pin_memory=True)
     hc = torch.empty((W, NCOUNTS), dtype=torch.int64, pin_memory=True)
-    dx, dl = torch.empty_like(x_bits), torch.empty_like(node_len)
+    hlab = torch.from_numpy(lab_host).pin_memory()
+    dx, dl = torch.empty_like(x_c), torch.empty_like(len_c)
     ds, dc = torch.empty_like(stats), torch.empty_like(counts)
-    nsub = max(1, min(args.sub_batches, W))
-    if args.e2e_plain or nsub < 4:
-        cuts = [int(v) for v in np.linspace(0, W, nsub + 1)]
-    else:
-        # the last two sub-batches are smaller: what is left to compute after the final copy lands is the step's tail
-        wts = np.ones(nsub); wts[-2], wts[-1] = 0.6, 0.3
-        cuts = [0] + [int(v) for v in np.round(np.cumsum(wts) / wts.sum() * W)]
-        cuts[-1] = W
-    streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.e2e_streams))]
-    dlabs = [torch.empty_like(labels) for _ in range(nsub)]
-
     pending = []          # batches of the previous step: closed while this step's copies and kernels run
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event() for _ in range(nsub)]
+    if split:
+        dlab = torch.empty_like(labels)
+        nsub = 1
 
-    def e2e_step():
-        live = []
-        for k in range(nsub):
-            lo, hi = cuts[k], cuts[k + 1]
-            if hi <= lo:
-                continue
-            st = streams[k % len(streams)]
-            if args.e2e_copy_stream:
-                # every host -> device copy goes through ONE stream, in sub-batch order, so the copy engine (the bottleneck
-                # of the step) never waits for a kernel; the set-up's small table upload follows its sub-batch's big copy in
-                # the same stream; the kernels run on the two compute streams behind an event
-                with torch.cuda.stream(copy_stream):
+        def e2e_step():
+            if rank == 0:
+                dx.copy_(hx, non_blocking=True); dl.copy_(hl, non_blocking=True)
+            dlab.copy_(hlab, non_blocking=True)
+            if world > 1:
+                dist.broadcast(dx, 0); dist.broadcast(dl, 0)
+            b = WindowBatch.from_uniform(ctx, dx, dl, dlab, L)
+            sums = b.window_sums(rank, world, algo)
+            st, ct = b.finalize(gather_parts(sums))
+            hs.copy_(st, non_blocking=True); hc.copy_(ct, non_blocking=True)
+            torch.cuda.synchronize()
+            b.close()
+    else:
+        nsub = max(1, min(args.sub_batches, W))
+        if nsub < 4:
+            cuts = [int(v) for v in np.linspace(0, W, nsub + 1)]
+        else:
+            # the last two sub-batches are smaller: what is left to compute after the final copy lands is the step's tail
+            wts = np.ones(nsub); wts[-2], wts[-1] = 0.6, 0.3
+            cuts = [0] + [int(v) for v in np.round(np.cumsum(wts) / wts.sum() * W)]
+            cuts[-1] = W
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        dlabs = [torch.empty_like(labels) for _ in range(nsub)]
+
+        def e2e_step():
+            live = []
+            for k in range(nsub):
+                lo, hi = cuts[k], cuts[k + 1]
+                if hi <= lo:
+                    continue
+                st = streams[k % len(streams)]
+                with torch.cuda.stream(st):
+                    # this sub-batch's copies first, its set-up (host-side tables + their small upload) while they run: the copy
+                    # engine is the bottleneck of the step and must never wait for the host
                     dlabs[k].copy_(hlab, non_blocking=True)
                     dl[lo:hi].copy_(hl[lo:hi], non_blocking=True)
                     dx[lo:hi].copy_(hx[lo:hi], non_blocking=True)
-                    b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], WINDOW_BP, node_len_host=hl[lo:hi], stream=copy_stream)
-                    copied[k].record(copy_stream)
-                with torch.cuda.stream(st):
-                    st.wait_event(copied[k])
+                    b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], L, node_len_host=hl[lo:hi], stream=st)
                     b.stats(algo, stream=st, out_stats=ds[lo:hi], out_counts=dc[lo:hi])
                     hs[lo:hi].copy_(ds[lo:hi], non_blocking=True)
                     hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)
                 live.append(b)
-                continue
-            with torch.cuda.stream(st):
-                # this sub-batch's copies first, its set-up (host-side tables + their small upload) while they run: the copy
-                # engine is the bottleneck of the step and must never wait for the host; the table upload lands in the
-                # engine's FIFO right behind this sub-batch's own big copy, ahead of the OTHER stream's next one
-                dlabs[k].copy_(hlab, non_blocking=True)
-                dl[lo:hi].copy_(hl[lo:hi], non_blocking=True)
-                dx[lo:hi].copy_(hx[lo:hi], non_blocking=True)
-                b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], WINDOW_BP, node_len_host=hl[lo:hi], stream=st)
-                b.stats(algo, stream=st, out_stats=ds[lo:hi], out_counts=dc[lo:hi])
-                hs[lo:hi].copy_(ds[lo:hi], non_blocking=True)
-                hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)
-            live.append(b)
-        if args.e2e_plain:
+            while pending:                      # host work hidden behind the copies just enqueued
+                pending.pop().close()
             for st in streams:
                 st.synchronize()
-            for b in live:
-                b.close()
-            return
-        while pending:                      # host work hidden behind the copies just enqueued
-            pending.pop().close()
-        for st in streams:
-            st.synchronize()
-        pending.extend(live)
+            pending.extend(live)
 
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(3):
@@ -346,7 +594,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     ctx.check()
-    # the sub-batched run must reproduce the resident run: same NaN pattern, every statistic within 1e-12 of the column's scale
+    # the e2e run must reproduce the resident run: same NaN pattern, every statistic within 1e-12 of the column's scale
     # (the per-lane sums of the pairs kernel are plain fp64, so the last bits depend on how a batch is dealt to the CTAs)
     ha, hb = hs.numpy(), stats.cpu().numpy()
     scale = np.nanmax(np.abs(hb), axis=0, keepdims=True)
@@ -356,75 +604,142 @@ def run_ours(args):
     same = bool(np.array_equal(np.isnan(ha), np.isnan(hb)) and bool(np.all(close | np.isnan(hb)))
                 and torch.equal(hc, counts.cpu()))
     bitwise = bool(torch.equal(hs.nan_to_num(7.0), stats.cpu().nan_to_num(7.0)))
-    h2d = world * (hx.numel() * 4 + hl.numel() * 4 + hlab.numel() * nsub)      # whole job: every rank copies its own batch
-    d2h = world * (hs.numel() * 8 + hc.numel() * 8)
+    if split:
+        h2d = x_c.numel() * 4 + len_c.numel() * 4 + world * hlab.numel()            # uploaded once (rank 0), broadcast over NVLink
+        d2h = world * (hs.numel() * 8 + hc.numel() * 8)
+    else:
+        h2d = windows_job * (n * pitch * 4 + m_pad * 4) + world * hlab.numel() * nsub   # whole job: every rank copies its own batch
+        d2h = windows_job * (NSTATS * 8 + NCOUNTS * 8)
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
-    peaks = load_peaks()
-    nl_max = int(node_len.max().item())
-    planes = 1 if nl_max < 256 else (2 if nl_max < 65536 else (3 if nl_max < (1 << 24) else 4))
-    ops_launch = 2.0 * W * (N_HAP * (N_HAP + 1) / 2.0) * m_pad * planes          # int8 ops, input m, P planes
-    bytes_launch = W * (N_HAP * (m_pad // 8) + 4 * m_pad + N_HAP + 8 * 14)       # algorithmic HBM bytes
-    pairs_avg_s = (pairs_ms / max(pairs_n, 1)) * 1e-3
-    tops = ops_launch / pairs_avg_s / 1e12
-    roofline = {"bound": "tensor", "algorithmic_ops_per_launch": ops_launch, "algorithmic_bytes_per_launch": bytes_launch,
-                "achieved": tops, "peak": peaks["int8_tops"], "unit": "TOP/s (int8)",
-                "frac": tops / peaks["int8_tops"], "traffic": None, "kernel": "window_pairs_tc_kernel" if algo == ALGO_TCGEN05 else "window_pairs_simt_kernel",
-                "kernel_ms": pairs_avg_s * 1e3, "peak_source": peaks["int8_src"], "byte_planes": planes,
-                "hbm": {"achieved_gbs": bytes_launch / pairs_avg_s / 1e9, "peak_gbs": peaks["hbm_gbs"],
-                        "frac": bytes_launch / pairs_avg_s / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_src"]},
-                "fp64_pair_epilogues_per_s": W * N_HAP * (N_HAP - 1) / 2.0 / pairs_avg_s,
-                # the co-limit DESIGN.md 4.2 derives: 18 fp64 instructions per haplotype pair (2 correctly rounded divisions:
-                # 16, + sums) on a pipe of 64 lanes / clk / SM; clock = the SM clock sampled during the timed region
-                "fp64": {"instr_per_pair": 18, "lanes_per_clk_per_sm": 64, "sms": int(torch.cuda.get_device_properties(local).multi_processor_count),
-                         "frac": None},
+    # algorithmic int8 ops from the INPUT node count and byte planes; executed ops = what the tensor pipe really
+    # multiplies (128 x item width x virtual columns after ingest, every item); fp64 = 18 instructions per pair on a pipe of
+    # 64 lanes / clk / SM, the binding pipe of configs 2 and 3 (an fp64 instruction also holds the sub-partition's issue port
+    # for two cycles: DESIGN.md 4.2).
+    w_launch = W                                                                     # windows one launch of this rank touches
+    share = (1.0 / world) if split else 1.0                                          # ... and the share of their items it works
+    pairs_s = pairs_avg_ms * 1e-3
+    ops_launch = 2.0 * w_launch * (n * (n + 1) / 2.0) * m_pad_in * planes * share
+    geom = item_geometry(n)
+    exec_ops = 2.0 * float(sum(r * c for r, c in geom)) * float(np.sum(k_exec)) * share
+    bytes_launch = w_launch * (n * (m_pad_in // 8) + 4 * m_pad_in + n + 8 * 14) * (1.0 if not split else 1.0)
+    eps = w_launch * n * (n - 1) / 2.0 * share / pairs_s
+    mhz_max = peaks["sm_max_mhz"]
+    fp64_peak_eps = 64.0 * sms * mhz_max * 1e6 / 18.0
+    tensor = {"algorithmic_ops_per_launch": ops_launch, "executed_ops_per_launch": exec_ops, "achieved": ops_launch / pairs_s / 1e12,
+              "achieved_executed": exec_ops / pairs_s / 1e12, "peak": peaks["int8_tops"], "unit": "TOP/s (int8)",
+              "frac": ops_launch / pairs_s / 1e12 / peaks["int8_tops"], "frac_executed": exec_ops / pairs_s / 1e12 / peaks["int8_tops"],
+              "peak_source": peaks["int8_src"], "byte_planes": planes}
+    fp64 = {"achieved": eps, "peak": fp64_peak_eps, "unit": "pair epilogues/s", "frac": eps / fp64_peak_eps, "instr_per_pair": 18,
+            "lanes_per_clk_per_sm": 64, "sms": sms, "clock_mhz": mhz_max,
+            "peak_source": "64 fp64 lanes / clk / SM (tools/micro/pi_bench.cu: 2.0 cycles per warp DFMA and sub-partition) x SMs x max SM clock / 18 instructions per pair"}
+    hbm = {"algorithmic_bytes_per_launch": bytes_launch, "achieved_gbs": bytes_launch / pairs_s / 1e9, "peak_gbs": peaks["hbm_gbs"],
+           "frac": bytes_launch / pairs_s / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_src"]}
+    bound = "tensor" if args.config == 5 else "fp64"
+    head = tensor if bound == "tensor" else fp64
+    roofline = {"bound": bound, "achieved": head["achieved"], "peak": head["peak"], "unit": head["unit"], "frac": head["frac"],
+                "traffic": None, "kernel": "window_pairs_tc_kernel" if algo == ALGO_TCGEN05 else "window_pairs_simt_kernel",
+                "kernel_ms": pairs_avg_ms, "tensor": tensor, "fp64": fp64, "hbm": hbm,
+                "frac_round1_formula": tensor["frac"],          # round 1 reported the algorithmic int8 fraction as `frac`
                 "step_share": {k: v / ms_step for k, v in per_kernel.items()}}
     traffic_file = os.path.join(ROOT, "profiles", "pairs_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_window"] * W   # ncu dram read+write, scaled to this launch
+            tj = json.load(open(traffic_file))
+            roofline["traffic"] = tj["dram_bytes_per_window"] * w_launch * share
+            roofline["traffic_source"] = "static: " + tj.get("source", "ncu dram__bytes_read.sum + dram__bytes_write.sum of the pairs kernel, scaled to this launch")
+            if "step_dram_bytes_per_window" in tj:
+                roofline["traffic_whole_step"] = tj["step_dram_bytes_per_window"] * w_launch
         except Exception:
             pass
 
-    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
+    # ---------------------------------------------------------------- CPU baseline + parity on a sample (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        threads = len(os.sched_getaffinity(0))
-        cap = W
-        xb = x_bits[:cap].cpu().numpy().view(np.uint32)
-        nl = node_len[:cap].cpu().numpy().view(np.uint32)
-        rate, S, secs, st_cpu, ct_cpu = cpu_oracle_rate(xb, nl, lab_host, N_HAP, m_pad, pitch, WINDOW_BP, threads)
-        got_s, got_c = stats[:S].cpu().numpy(), counts[:S].cpu().numpy()
+    if rank == 0 and world == 1 and not args.no_cpu and not split:
         from oracle.compare import rows_close
+        ht = host_threads()
+        S0 = min(W, max(ht * 2, 8))
+        dt, _, _ = cpu_oracle(wl["x"], wl["len"], lab_host, n, m_pad, pitch, L, ht, S0)
+        S = int(min(W, max(S0, S0 * 12.0 / max(dt, 1e-3))))
+        dt, st_cpu, ct_cpu = cpu_oracle(wl["x"], wl["len"], lab_host, n, m_pad, pitch, L, ht, S)
+        rate = S * units_per_window(n, L) / dt
+        got_s, got_c = stats[:S].cpu().numpy(), counts[:S].cpu().numpy()
         ok_counts = bool((got_c == ct_cpu).all())
         ok_stats, why = rows_close(got_s, st_cpu)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{S} of {W} windows of this workload in {secs:.2f} s, plain-C oracle (byte-LUT intersections) on {threads} pthreads",
-               "gpu_matches_oracle_on_sample": {"counts_exact": ok_counts, "stats_within_1e-12": ok_stats, "detail": why}}
+        # the same windows with their ORIGINAL columns (no ingest-time compaction) through the oracle
+        K = min(keep, S)
+        _, st_orig, ct_orig = cpu_oracle(wl["orig_x"], wl["orig_len"], lab_host, n, m_pad_in, m_pad_in // 32, L, ht, K)
+        errs = max_rel_errors(got_s[:K], st_orig)
+        strict = bool(errs["nan_pattern_equal"] and max(errs[k] for k in ("pi", "pi_per_site", "pi_a", "pi_b", "dxy", "da", "fst", "tajima_d")) <= 1e-12)
+        cpu = {"value": rate, "unit": UNIT, "cores": ht, "kind": "port",
+               "sample": f"{S} of {W} windows of this workload (ingested columns) in {dt:.2f} s, plain-C oracle port (byte-LUT intersections) on {ht} pthreads",
+               "gpu_matches_oracle_on_sample": {"counts_exact": ok_counts, "stats_within_1e-12": ok_stats, "detail": why},
+               "gpu_vs_oracle_on_original_columns": {"windows": K, "counts_exact": bool((got_c[:K] == ct_orig).all()),
+                                                     "max_plain_relative_error": errs, "strict_1e-12_without_scale_policy": strict}}
+
+    others = None
+    if rank == 0 and world == 1 and args.config == 2 and not args.no_others:
+        batch.close()
+        del x_c, len_c, dx, dl, hx, hl
+        torch.cuda.empty_cache()
+        others = other_configs(ctx, torch, peaks, host_threads())
 
     if rank == 0:
-        mhz = (clocks or {}).get("sm_mhz") or 1965.0
         f64 = roofline["fp64"]
-        f64["frac"] = roofline["fp64_pair_epilogues_per_s"] * f64["instr_per_pair"] / (f64["lanes_per_clk_per_sm"] * f64["sms"] * mhz * 1e6)
+        mhz = (clocks or {}).get("sm_mhz")
+        if mhz:
+            f64["frac_at_sampled_clock"] = f64["achieved"] * 18 / (64.0 * sms * mhz * 1e6)
+        scaling = "strong" if strong else "weak"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "u8 x u8 -> s32 intersections (tcgen05 kind::i8) + f64 statistics" if algo == ALGO_TCGEN05 else "u8 dp4a -> u32 + f64 statistics",
             "data": "synthetic",
-            "config": {"workload": f"h-fst AFR(140) vs EAS(100) Hudson Fst + pi + Tajima's D, {N_HAP} haplotypes, {WINDOW_BP} bp windows, chr2-length graph",
-                       "windows_per_gpu": W, "nodes_per_window": int(m_pad), "haplotypes": N_HAP,
-                       "parallelism": f"windows sharded over {world} GPU(s), one all-gather of result rows per step",
-                       "l2": f"inputs larger than L2 ({(x_bits.numel() * 4 + node_len.numel() * 4) / 1e6:.0f} MB per GPU read every step)",
-                       "algo": args.algo},
+            "config": {"workload": cfg["workload"], "baseline_config": args.config,
+                       "windows_per_gpu": W, "windows_job": windows_job, "nodes_per_window": m_in, "nodes_after_ingest": m_out_max,
+                       "haplotypes": n,
+                       "parallelism": (f"tile grid of every window split over {world} GPU(s): X broadcast once (NCCL), partial sums all-gathered, rank-ordered finalize"
+                                       if split else f"windows sharded over {world} GPU(s), one all-gather of result rows per step"),
+                       "l2": l2_note,
+                       "algo": args.algo, "ingest": ingest},
             "e2e": {"value": units_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": nsub, "matches_resident_run": same, "bitwise_equal_to_resident_run": bitwise},
+                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": nsub, "matches_resident_run": same,
+                    "bitwise_equal_to_resident_run": bitwise,
+                    "h2d_bytes_per_step_without_ingest": int(windows_job * (n * (m_pad_in // 8) + m_pad_in * 4)) if not split else None},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        if others is not None:
+            line["other_configs"] = others
         print(json.dumps(line))
-    batch.close()
+    if others is None:
+        batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_sites(args, ctx, torch, dist, peaks, rank, world, local):
+    """--config 4 as the headline: sites sharded over the ranks, no exchange (each rank keeps its own counts)."""
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    r = bench_sites(ctx, torch, peaks, reps=max(args.steps, 3), rank=rank, world=world)
+    t = torch.tensor([r["ms"]], dtype=torch.float64, device=ctx.torch_device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        print(json.dumps({"metric": "variant sites/s (per-site allele counts and frequencies, 5 panels)", "value": r["sites"] / (ms * 1e-3),
+                          "unit": "sites/s", "n_gpus": world, "steps": max(args.steps, 3), "warmup": 3, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 popcounts -> i32 counts + f64 frequencies",
+                          "data": "synthetic", "config": {"workload": "af per-site allele frequencies, 10^7 sites x 466 haplotypes x 5 panels", "baseline_config": 4},
+                          "roofline": {"bound": "hbm", "achieved": r["achieved_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["hbm_frac"],
+                                       "traffic": None, "kernel": r["kernel"], "algorithmic_bytes_per_launch": r["algorithmic_bytes"]},
+                          "gpu_launches": max(args.steps, 3) + 3, "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -436,13 +751,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json config (1-based); default 2 = the metric's config")
+    ap.add_argument("--strong", action="store_true", help="config 3: the whole genome's windows split over the ranks (fixed total work)")
     ap.add_argument("--algo", default="tc", choices=["tc", "simt"])
-    ap.add_argument("--windows", type=int, default=WINDOWS, help="windows per GPU (default: chr2 / 50 kb = 4854)")
+    ap.add_argument("--windows", type=int, default=0, help="windows per GPU (weak) / in total (strong); default: the config's own")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the short measurements of the other BASELINE configs")
     ap.add_argument("--sub-batches", type=int, default=8, help="e2e leg: sub-batches alternating between two streams")
-    ap.add_argument("--e2e-streams", type=int, default=2, help="e2e leg: streams the sub-batches rotate over")
-    ap.add_argument("--e2e-copy-stream", type=int, default=0, help="e2e leg: 1 = all host->device copies on one stream, kernels behind events")
-    ap.add_argument("--e2e-plain", action="store_true", help="e2e leg: equal sub-batches, batches closed at the end of their own step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

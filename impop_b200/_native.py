@@ -67,6 +67,10 @@ SIGNATURES = {
     "impop_selftest_division": (C.c_int, [_p, C.c_uint64, _i64, C.POINTER(_i64), _p]),
     "impop_debug_role_times": (C.c_int, [_p, _p, _i32]),
     "impop_greedy_groups": (C.c_int, [_p, _p, _i32, _i64, _f64, _p, _p, _p]),
+    "impop_round_decimal": (C.c_int, [_p, _p, _i64, _i32, _p]),
+    "impop_dev_alloc": (C.c_int, [_p, _i64, C.POINTER(_p)]),
+    "impop_dev_free": (C.c_int, [_p, _p]),
+    "impop_dev_copy": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "impop_tsv_scan": (C.c_int, [C.c_char_p, _i64, C.POINTER(TsvInfo)]),
     "impop_tsv_fill": (C.c_int, [C.c_char_p, _i64, _p, _p, _p]),
     "impop_gfa_scan": (C.c_int, [C.c_char_p, _i64, C.POINTER(GfaInfo)]),

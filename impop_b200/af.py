@@ -93,10 +93,9 @@ def site_allele_counts(site_bits: np.ndarray, pop_masks: np.ndarray, ctx=None, w
 
     site_bits: (sites, words) uint64, bit h of a row = haplotype h carries the allele;
     pop_masks: (pops, words) uint64."""
-    import torch
     ctx = ctx or default_context()
-    sites = torch.from_numpy(np.ascontiguousarray(site_bits, dtype=np.uint64).view(np.int64)).to(ctx.torch_device)
-    masks = torch.from_numpy(np.ascontiguousarray(pop_masks, dtype=np.uint64).view(np.int64)).to(ctx.torch_device)
+    sites = ctx.upload(np.ascontiguousarray(site_bits, dtype=np.uint64).view(np.int64))
+    masks = ctx.upload(np.ascontiguousarray(pop_masks, dtype=np.uint64).view(np.int64))
     counts, freq = ctx.site_counts(sites, masks, want_freq=want_freq)
     ctx.check()
     return counts.cpu().numpy(), (freq.cpu().numpy() if freq is not None else None)

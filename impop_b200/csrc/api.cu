@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <math.h>
+
 #include <algorithm>
 #include <thread>
 #include <new>
@@ -14,23 +16,24 @@
 
 namespace impop {
 cudaError_t launch_heavy_count(const uint32_t *, const int64_t *, const int32_t *, int32_t, int32_t *, cudaStream_t);
-cudaError_t launch_harmonic_table(double2 *, int32_t, cudaStream_t);
-cudaError_t launch_prep(const WindowTab &, int64_t *, int, cudaStream_t);
-cudaError_t launch_division_selftest(uint64_t, int64_t, unsigned long long *, cudaStream_t);
+int prep_rows_ctas_per_sm();
+cudaError_t launch_prep(const WindowTab &, int64_t *, int, int, cudaStream_t);
+cudaError_t launch_division_selftest(uint64_t, int64_t, unsigned long long *, int, cudaStream_t);
 cudaError_t configure_kernels();
 cudaError_t launch_pairs(const WindowTab &, const ItemParams &, int, int, cudaStream_t);
-cudaError_t launch_window_sums(const WindowTab &, const double *, int, int, double *, cudaStream_t);
-cudaError_t launch_finalize(const WindowTab &, const double *, int, const int64_t *, double *, cudaStream_t);
+cudaError_t launch_window_sums(const WindowTab &, const double *, int, int, double *, int, cudaStream_t);
+cudaError_t launch_finalize(const WindowTab &, const double *, int, const int64_t *, double *, int, cudaStream_t);
 cudaError_t launch_export_a(const int32_t *, int32_t, int64_t *, cudaStream_t);
-cudaError_t launch_pack_bits(const uint8_t *, int32_t, int32_t, int64_t, uint32_t *, int32_t, cudaStream_t);
-int reduce_identity_blocks(int32_t n);
+cudaError_t launch_pack_bits(const uint8_t *, int32_t, int32_t, int64_t, uint32_t *, int32_t, int, cudaStream_t);
+int reduce_identity_blocks(int32_t n, int sm_count);
 cudaError_t launch_reduce_identity(const double *, int32_t, int64_t, const uint8_t *, const double *, int64_t, double,
-                                   const double2 *, int32_t, double *, double *, int64_t *, double *, cudaStream_t);
+                                   const double2 *, int32_t, double *, int, double *, int64_t *, double *, cudaStream_t);
 cudaError_t launch_tajima(const int64_t *, const double *, const double *, int32_t, double *, double *, cudaStream_t);
 cudaError_t launch_site_counts(const uint64_t *, int64_t, int32_t, const uint64_t *, int32_t, int32_t *, double *, int,
                                cudaStream_t);
-cudaError_t launch_cluster(const double *, int32_t, int64_t, double, int32_t *, int32_t *, cudaStream_t);
+cudaError_t launch_cluster(const double *, int32_t, int64_t, double, int32_t *, int32_t *, int, cudaStream_t);
 cudaError_t launch_greedy_groups(const double *, int32_t, int64_t, double, int32_t *, double *, cudaStream_t);
+cudaError_t launch_round_decimal(double *, int64_t, int32_t, int, cudaStream_t);
 }  // namespace impop
 
 using namespace impop;
@@ -40,9 +43,9 @@ constexpr int32_t HARM_N = 1 << 16;
 struct impop_ctx {
     int device = 0;
     int sm_count = 0;
+    int prep_per_sm = 2;              // resident prep_rows CTAs per SM on this device
     int32_t *err_dev = nullptr;
     double2 *harm_dev = nullptr;
-    double *ri_scratch = nullptr;     // reduce_identity partials
     long long *prof_dev = nullptr;    // role-time counters of the last pairs launch (IMPOP_PROFILE_ROLES builds)
     int32_t *cluster_parent = nullptr;
     int32_t cluster_cap = 0;
@@ -55,36 +58,50 @@ struct impop_ctx {
     std::vector<Slot> spare;       // recycled event pairs
     // device scratch pool and pinned staging buffers, recycled across batches (no cudaMalloc / cudaFree,
     // which synchronise the device, on the per-batch path)
-    struct Block { void *p; size_t cap; bool used; };
+    // A block handed back while work on `st` may still use it carries an event: it is reused at once by work on the same
+    // stream (ordered behind it), by another stream only after the event has completed.
+    struct Block { void *p; size_t cap; bool used; cudaEvent_t ev; cudaStream_t st; bool pending; };
     std::vector<Block> pool;
     struct Staging { void *host; size_t cap; cudaEvent_t done; bool busy; };
     std::vector<Staging> staging;
 };
 
-static void *pool_get(impop_ctx *ctx, size_t bytes) {
+static void *pool_get(impop_ctx *ctx, size_t bytes, cudaStream_t st) {
     bytes = (bytes + 255) & ~(size_t)255;
     if (bytes == 0) bytes = 256;
     int best = -1;
     for (int k = 0; k < (int)ctx->pool.size(); ++k) {
         auto &b = ctx->pool[k];
-        if (!b.used && b.cap >= bytes && b.cap <= 2 * bytes + (1u << 20) && (best < 0 || b.cap < ctx->pool[best].cap)) best = k;
+        if (b.used || b.cap < bytes || b.cap > 2 * bytes + (1u << 20)) continue;
+        if (b.pending && b.st != st) {                       // still (possibly) in use by another stream
+            if (cudaEventQuery(b.ev) != cudaSuccess) { cudaGetLastError(); continue; }
+            b.pending = false;
+        }
+        if (best < 0 || b.cap < ctx->pool[best].cap) best = k;
     }
     if (best >= 0) { ctx->pool[best].used = true; return ctx->pool[best].p; }
     void *p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {
         cudaGetLastError();
+        cudaDeviceSynchronize();                             // every pending block is free after this
         for (auto it = ctx->pool.begin(); it != ctx->pool.end();) {     // give unused blocks back and retry
-            if (!it->used) { cudaFree(it->p); it = ctx->pool.erase(it); } else ++it;
+            if (!it->used) { cudaFree(it->p); if (it->ev) cudaEventDestroy(it->ev); it = ctx->pool.erase(it); } else ++it;
         }
         if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     }
-    ctx->pool.push_back({p, bytes, true});
+    ctx->pool.push_back({p, bytes, true, nullptr, nullptr, false});
     return p;
 }
 
-static void pool_put(impop_ctx *ctx, void *p) {
+static void pool_put(impop_ctx *ctx, void *p, cudaStream_t st) {
     for (auto &b : ctx->pool)
-        if (b.p == p) { b.used = false; return; }
+        if (b.p == p) {
+            b.used = false;
+            if (!b.ev && cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); b.ev = nullptr; }
+            if (b.ev && cudaEventRecord(b.ev, st) == cudaSuccess) { b.pending = true; b.st = st; }
+            else { cudaGetLastError(); cudaStreamSynchronize(st); b.pending = false; }
+            return;
+        }
 }
 
 // A pinned buffer whose previous asynchronous copy has completed.
@@ -131,6 +148,7 @@ struct impop_batch {
     std::vector<int64_t> item_off;    // host copy
     std::vector<int32_t> n;
     int64_t items = 0;
+    cudaStream_t last_stream = nullptr;   // stream of the most recent work on this batch (its blocks go back to the pool behind it)
     double *partials = nullptr;
     double *sums_tmp = nullptr;
     int64_t *counts_tmp = nullptr;
@@ -185,25 +203,48 @@ int impop_create(int device, impop_ctx_t **ctx_out) {
         return IMPOP_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    // Harmonic tables a1(n), a2(n) exactly as Python >= 3.12 builtin sum() (Neumaier) forms them in tj_d.py:41-45: computed
+    // on the host (IEEE double, no contraction: the same bits as the device's _rn intrinsics) and uploaded -- a serial
+    // 65 536-step loop is 6.6 ms as a one-thread kernel and 0.3 ms here, on every context creation of every CLI call.
+    std::vector<double2> harm((size_t)HARM_N + 1);
+    {
+        volatile double t1 = 0.0, c1 = 0.0, t2 = 0.0, c2 = 0.0;
+        auto nadd = [](volatile double &total, volatile double &comp, double x) {
+            const double tot = total;
+            const volatile double t = tot + x;
+            if (fabs(tot) >= fabs(x)) { const volatile double u = tot - t; const volatile double w = u + x; comp = comp + w; }
+            else { const volatile double u = x - t; const volatile double w = u + tot; comp = comp + w; }
+            total = t;
+        };
+        auto nval = [](double total, double comp) { return (comp != 0.0 && std::isfinite(comp)) ? total + comp : total; };
+        harm[0] = make_double2(0.0, 0.0);
+        harm[1] = make_double2(0.0, 0.0);
+        for (int n = 2; n <= HARM_N; ++n) {      // a(n) sums i = 1 .. n-1
+            const double di = (double)(n - 1);
+            const volatile double sq = di * di;
+            nadd(t1, c1, 1.0 / di);
+            nadd(t2, c2, 1.0 / sq);
+            harm[n] = make_double2(nval(t1, c1), nval(t2, c2));
+        }
+    }
     const char *step = "";
     cudaError_t es = cudaSuccess;
     auto run = [&](const char *what, cudaError_t r) { if (es == cudaSuccess && r != cudaSuccess) { es = r; step = what; } return es == cudaSuccess; };
     bool ok = run("alloc err flag", cudaMalloc(&ctx->err_dev, sizeof(int32_t))) &&
               run("memset", cudaMemset(ctx->err_dev, 0, sizeof(int32_t))) &&
               run("alloc harmonic table", cudaMalloc(&ctx->harm_dev, sizeof(double2) * (HARM_N + 1))) &&
-              run("alloc scratch", cudaMalloc(&ctx->ri_scratch, sizeof(double) * 16 * 148 * 4)) &&
+              run("upload harmonic table", cudaMemcpy(ctx->harm_dev, harm.data(), sizeof(double2) * (HARM_N + 1), cudaMemcpyHostToDevice)) &&
               run("alloc counters", cudaMalloc(&ctx->prof_dev, sizeof(long long) * 16 * 1024)) &&
               run("memset", cudaMemset(ctx->prof_dev, 0, sizeof(long long) * 16 * 1024)) &&
-              run("shared-memory attribute of the pairs kernel", configure_kernels()) &&
-              run("harmonic table launch", launch_harmonic_table(ctx->harm_dev, HARM_N, 0)) &&
-              run("synchronize", cudaDeviceSynchronize());
+              run("shared-memory attribute of the pairs kernel", configure_kernels());
+    if (ok) ctx->prep_per_sm = prep_rows_ctas_per_sm();
     if (!ok) {
         fprintf(stderr, "impop_create: CUDA set-up failed at '%s': %s\n", step, cudaGetErrorString(es));
-        cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->ri_scratch); cudaFree(ctx->prof_dev);
+        cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->prof_dev);
         delete ctx;
         return IMPOP_ERR_CUDA;
     }
-    ctx->launches = 1;
+    ctx->launches = 0;
     *ctx_out = ctx;
     return IMPOP_OK;
 }
@@ -211,10 +252,11 @@ int impop_create(int device, impop_ctx_t **ctx_out) {
 int impop_destroy(impop_ctx_t *ctx) {
     if (!ctx) return IMPOP_ERR_ARG;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->ri_scratch); cudaFree(ctx->cluster_parent);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->prof_dev); cudaFree(ctx->cluster_parent);
     for (auto *v : {&ctx->slots, &ctx->spare})
         for (auto &s : *v) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
-    for (auto &b : ctx->pool) cudaFree(b.p);
+    for (auto &b : ctx->pool) { cudaFree(b.p); if (b.ev) cudaEventDestroy(b.ev); }
     for (auto &s : ctx->staging) { cudaFreeHost(s.host); cudaEventDestroy(s.done); }
     delete ctx;
     return IMPOP_OK;
@@ -271,15 +313,18 @@ int impop_pack_bits(impop_ctx_t *ctx, const uint8_t *dense_dev, int32_t n, int32
         (int64_t)pitch_words * 32 < m)
         return fail(ctx, IMPOP_ERR_ARG, "impop_pack_bits: bad argument");
     CU(cudaSetDevice(ctx->device));
-    CU(launch_pack_bits(dense_dev, n, m, dense_pitch, x_dev, pitch_words, (cudaStream_t)stream));
-    ctx->launches += 1;
+    CU(launch_pack_bits(dense_dev, n, m, dense_pitch, x_dev, pitch_words, ctx->sm_count, (cudaStream_t)stream));
+    ctx->launches += ((int64_t)n * pitch_words > 0);
     return IMPOP_OK;
 }
 
 int impop_batch_destroy(impop_ctx_t *ctx, impop_batch_t *batch) {
     if (!ctx || !batch) return IMPOP_ERR_ARG;
-    if (batch->tables) pool_put(ctx, batch->tables);     // kernels still in flight on the stream stay valid:
-    if (batch->scratch) pool_put(ctx, batch->scratch);   // a later batch on the same stream is ordered after them
+    // kernels still in flight on the batch's stream stay valid: the blocks are reused at once only by work on that same
+    // stream (ordered behind them), by other streams after the event recorded here has completed
+    cudaSetDevice(ctx->device);
+    if (batch->tables) pool_put(ctx, batch->tables, batch->last_stream);
+    if (batch->scratch) pool_put(ctx, batch->scratch, batch->last_stream);
     delete batch;
     return IMPOP_OK;
 }
@@ -355,7 +400,8 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t o_heavy = ca.take(8 * W1), o_w8 = ca.take(8 * W1), o_xh = ca.take(8 * W1);
     const size_t o_cnt = ca.take(4 * W1);
     const size_t tables_bytes = ca.off;
-    b->tables = pool_get(ctx, tables_bytes);
+    b->last_stream = st;
+    b->tables = pool_get(ctx, tables_bytes, st);
     impop_ctx::Staging *sg = staging_get(ctx, tables_bytes);
     if (!b->tables || !sg) return bail(IMPOP_ERR_NOMEM, "impop_batch_create: out of memory (tables)");
     char *hb = (char *)sg->host, *db = (char *)b->tables;
@@ -451,7 +497,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t s_sums = cs.take(8 * 4 * W1), s_counts = cs.take(8 * IMPOP_NCOUNTS * W1);
     const size_t s_any = cs.take(4 * (size_t)(word_off[W] + 1)), s_all = cs.take(4 * (size_t)(word_off[W] + 1));
     const size_t s_hn = cs.take(4 * W1);
-    b->scratch = pool_get(ctx, cs.off);
+    b->scratch = pool_get(ctx, cs.off, st);
     if (!b->scratch) return bail(IMPOP_ERR_NOMEM, "impop_batch_create: out of device memory (scratch)");
     char *sb = (char *)b->scratch;
     t.A = (int32_t *)(sb + s_A); t.w8 = (uint8_t *)(sb + s_w8); t.w8n = (uint8_t *)(sb + s_w8n); t.planes = (uint32_t *)(sb + s_planes); t.heavy = (uint32_t *)(sb + s_heavy);
@@ -471,14 +517,18 @@ static int run_sums(impop_ctx_t *ctx, impop_batch_t *b, int32_t algo, int32_t ra
     if (algo != IMPOP_ALGO_TCGEN05 && algo != IMPOP_ALGO_SIMT) return fail(ctx, IMPOP_ERR_ARG, "unknown algo");
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, IMPOP_ERR_ARG, "bad rank/world");
     if (b->tab.W == 0) return IMPOP_OK;
-    CU(timed(ctx, IMPOP_KERNEL_PREP, st, [&] { return launch_prep(b->tab, b->counts_tmp, ctx->sm_count, st); }));
+    b->last_stream = st;
+    CU(timed(ctx, IMPOP_KERNEL_PREP, st, [&] { return launch_prep(b->tab, b->counts_tmp, ctx->sm_count, ctx->prep_per_sm, st); }));
+    ctx->launches += 3;                                        // prep_cols, prep_rows, seg_count
     ItemParams prm{};
     prm.partials = b->partials;
     prm.item_begin = 0; prm.item_end = b->items; prm.rank = rank; prm.world = world;
     prm.dumpI = nullptr; prm.dumpPi = nullptr; prm.prof = ctx->prof_dev;
+    const int64_t mine = (b->items - rank + world - 1) / world;
     CU(timed(ctx, IMPOP_KERNEL_PAIRS, st, [&] { return launch_pairs(b->tab, prm, algo, ctx->sm_count, st); }));
-    CU(timed(ctx, IMPOP_KERNEL_SUMS, st, [&] { return launch_window_sums(b->tab, b->partials, rank, world, sums_dev, st); }));
-    ctx->launches += 5;
+    ctx->launches += (mine > 0);
+    CU(timed(ctx, IMPOP_KERNEL_SUMS, st, [&] { return launch_window_sums(b->tab, b->partials, rank, world, sums_dev, ctx->sm_count, st); }));
+    ctx->launches += 1;
     return IMPOP_OK;
 }
 
@@ -497,7 +547,8 @@ int impop_window_finalize(impop_ctx_t *ctx, impop_batch_t *batch, const double *
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     // label counts and segregating nodes were formed by the prep pass of the preceding impop_window_sums / _stats
-    CU(timed(ctx, IMPOP_KERNEL_FINALIZE, st, [&] { return launch_finalize(batch->tab, sums_dev, parts, batch->counts_tmp, stats_dev, st); }));
+    batch->last_stream = st;
+    CU(timed(ctx, IMPOP_KERNEL_FINALIZE, st, [&] { return launch_finalize(batch->tab, sums_dev, parts, batch->counts_tmp, stats_dev, ctx->sm_count, st); }));
     if (counts_dev)
         CU(cudaMemcpyAsync(counts_dev, batch->counts_tmp, sizeof(int64_t) * IMPOP_NCOUNTS * (size_t)batch->tab.W,
                            cudaMemcpyDeviceToDevice, st));
@@ -523,7 +574,8 @@ int impop_pairwise(impop_ctx_t *ctx, impop_batch_t *batch, int32_t window, int32
     if (algo != IMPOP_ALGO_TCGEN05 && algo != IMPOP_ALGO_SIMT) return fail(ctx, IMPOP_ERR_ARG, "unknown algo");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CU(launch_prep(batch->tab, batch->counts_tmp, ctx->sm_count, st));
+    batch->last_stream = st;
+    CU(launch_prep(batch->tab, batch->counts_tmp, ctx->sm_count, ctx->prep_per_sm, st));
     ctx->launches += 3;
     if (I_dev || pi_dev) {
         ItemParams prm{};
@@ -548,8 +600,14 @@ int impop_reduce_identity(impop_ctx_t *ctx, const double *ident_dev, int32_t n, 
     if (!ctx) return IMPOP_ERR_ARG;
     if (n < 0 || ld < n || (n > 0 && !ident_dev)) return fail(ctx, IMPOP_ERR_ARG, "impop_reduce_identity: bad argument");
     CU(cudaSetDevice(ctx->device));
-    CU(launch_reduce_identity(ident_dev, n, ld, labels_dev, weight_dev, length, seg_sites, ctx->harm_dev, HARM_N,
-                              ctx->ri_scratch, stats_dev, counts_dev, wsum_dev, (cudaStream_t)stream));
+    // per-call scratch from the pool (calls on different streams never share it)
+    cudaStream_t st = (cudaStream_t)stream;
+    double *scratch = (double *)pool_get(ctx, sizeof(double) * 16 * (size_t)reduce_identity_blocks(n, ctx->sm_count), st);
+    if (!scratch) return fail(ctx, IMPOP_ERR_NOMEM, "impop_reduce_identity: out of device memory");
+    cudaError_t e = launch_reduce_identity(ident_dev, n, ld, labels_dev, weight_dev, length, seg_sites, ctx->harm_dev, HARM_N,
+                                           scratch, ctx->sm_count, stats_dev, counts_dev, wsum_dev, st);
+    pool_put(ctx, scratch, st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "impop_reduce_identity");
     ctx->launches += 2;
     return IMPOP_OK;
 }
@@ -593,7 +651,7 @@ int impop_cluster(impop_ctx_t *ctx, const double *ident_dev, int32_t n, int64_t 
         CU(cudaMalloc(&ctx->cluster_parent, sizeof(int32_t) * (size_t)n));
         ctx->cluster_cap = n;
     }
-    CU(launch_cluster(ident_dev, n, ld, threshold, ctx->cluster_parent, comp_dev, (cudaStream_t)stream));
+    CU(launch_cluster(ident_dev, n, ld, threshold, ctx->cluster_parent, comp_dev, ctx->sm_count, (cudaStream_t)stream));
     ctx->launches += (n > 0) ? 3 : 0;
     return IMPOP_OK;
 }
@@ -615,7 +673,7 @@ int impop_selftest_division(impop_ctx_t *ctx, uint64_t seed, int64_t count, int6
     unsigned long long *dev = nullptr;
     CU(cudaMalloc(&dev, sizeof(unsigned long long)));
     cudaError_t e = cudaMemsetAsync(dev, 0, sizeof(unsigned long long), (cudaStream_t)stream);
-    if (e == cudaSuccess) e = launch_division_selftest(seed, count, dev, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = launch_division_selftest(seed, count, dev, ctx->sm_count, (cudaStream_t)stream);
     unsigned long long host = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&host, dev, sizeof(host), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
@@ -623,6 +681,44 @@ int impop_selftest_division(impop_ctx_t *ctx, uint64_t seed, int64_t count, int6
     if (e != cudaSuccess) return cuda_fail(ctx, e, "impop_selftest_division");
     ctx->launches += 1;
     *mismatches_host = (int64_t)host;
+    return IMPOP_OK;
+}
+
+int impop_round_decimal(impop_ctx_t *ctx, double *values_dev, int64_t count, int32_t digits, void *stream) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    if (count < 0 || digits < 0 || digits > 22 || (count > 0 && !values_dev))
+        return fail(ctx, IMPOP_ERR_ARG, "impop_round_decimal: bad argument (0 <= digits <= 22)");
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_round_decimal(values_dev, count, digits, ctx->sm_count, (cudaStream_t)stream));
+    ctx->launches += (count > 0);
+    return IMPOP_OK;
+}
+
+int impop_dev_alloc(impop_ctx_t *ctx, int64_t bytes, void **ptr_out) {
+    if (!ctx || !ptr_out || bytes < 0) return IMPOP_ERR_ARG;
+    *ptr_out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    if (cudaMalloc(ptr_out, (size_t)(bytes > 0 ? bytes : 1)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, IMPOP_ERR_NOMEM, "impop_dev_alloc: out of device memory");
+    }
+    return IMPOP_OK;
+}
+
+int impop_dev_free(impop_ctx_t *ctx, void *ptr) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFree(ptr));
+    return IMPOP_OK;
+}
+
+int impop_dev_copy(impop_ctx_t *ctx, void *dst, const void *src, int64_t bytes, int32_t kind, void *stream) {
+    if (!ctx || bytes < 0 || kind < 0 || kind > 2 || (bytes > 0 && (!dst || !src))) return IMPOP_ERR_ARG;
+    if (bytes == 0) return IMPOP_OK;
+    CU(cudaSetDevice(ctx->device));
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    CU(cudaMemcpyAsync(dst, src, (size_t)bytes, k, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
     return IMPOP_OK;
 }
 

@@ -326,24 +326,68 @@ __global__ void __launch_bounds__(GROUP_THREADS) greedy_groups_kernel(const doub
 }
 
 // ------------------------------------------------------------------------------------------
+// round(x, r) as CPython rounds a float (pica2.py:81-83, h-fst.py:149-150): the decimal value of the double, rounded
+// half-even at the r-th decimal, converted back to the nearest double.  rint(x * 10^r) / 10^r is NOT that: x * 10^r is
+// rounded once before the tie test (one value in ~5 10^5 lands on the wrong side).  Here the product is
+// exact as a double-double (p, e) = two_prod(|x|, 10^r) with 10^r exact for r <= 22; t = floor(p); the fraction's
+// distance from one half, d = (p - t) - 0.5, is exact, and the sign of d + e is the sign of the exact sum (a
+// floating-point sum of two doubles is zero only when the exact sum is).  k = t or t + 1 (ties to even), and the result is
+// the correctly rounded quotient k / 10^r -- the nearest double to the decimal string CPython's dtoa round trip forms.
+// From 2^52 on p is an integer and |e| <= 1/2: the one extra case is e = -1/2 exactly (tie between p - 1 and p).  Values
+// with |x| 10^r >= 2^53 cannot move (the rounded decimal is within ulp(x) / 4 of x) and come back unchanged, like NaN and
+// infinities.
+// ------------------------------------------------------------------------------------------
+__global__ void round_decimal_kernel(double *v, int64_t count, double pow10) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const double x = v[t];
+        const double ax = fabs(x);
+        const double p = __dmul_rn(ax, pow10);
+        if (!(p < 9007199254740992.0)) continue;             // NaN, infinities, nothing to round
+        const double e = __fma_rn(ax, pow10, -p);            // exact error of the product
+        const double fl = floor(p);
+        const bool odd = fmod(fl, 2.0) != 0.0;
+        double k = fl;
+        if (p == fl && e == -0.5) {                          // exact value p - 1/2: tie between p - 1 and p
+            if (odd) k = __dadd_rn(fl, -1.0);
+        } else {
+            const double d = __dadd_rn(__dadd_rn(p, -fl), -0.5);
+            const double s = __dadd_rn(d, e);
+            if (s > 0.0 || (s == 0.0 && odd)) k = __dadd_rn(fl, 1.0);
+        }
+        const double r = __ddiv_rn(k, pow10);
+        v[t] = copysign(r, x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Launchers
 // ------------------------------------------------------------------------------------------
+cudaError_t launch_round_decimal(double *v, int64_t count, int32_t digits, int sm_count, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    double p = 1.0;
+    for (int k = 0; k < digits; ++k) p *= 10.0;               // exact up to 10^22
+    int64_t blocks = (count + 255) / 256;
+    if (blocks > (int64_t)sm_count * 16) blocks = (int64_t)sm_count * 16;
+    round_decimal_kernel<<<(int)blocks, 256, 0, st>>>(v, count, p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack_bits(const uint8_t *dense, int32_t n, int32_t m, int64_t dpitch, uint32_t *x,
-                             int32_t pitch_words, cudaStream_t st) {
+                             int32_t pitch_words, int sm_count, cudaStream_t st) {
     int64_t total = (int64_t)n * pitch_words;
     if (total == 0) return cudaSuccess;
     int64_t blocks = (total + 7) / 8;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > (int64_t)sm_count * 32) blocks = (int64_t)sm_count * 32;
     pack_bits_kernel<<<(int)blocks, 256, 0, st>>>(dense, n, m, dpitch, x, pitch_words);
     return cudaGetLastError();
 }
 
-int reduce_identity_blocks(int32_t n) { return n < 1 ? 1 : (n < 148 * 4 ? n : 148 * 4); }
+int reduce_identity_blocks(int32_t n, int sm_count) { return n < 1 ? 1 : (n < sm_count * 4 ? n : sm_count * 4); }
 
 cudaError_t launch_reduce_identity(const double *ident, int32_t n, int64_t ld, const uint8_t *labels,
                                    const double *weight, int64_t L, double seg, const double2 *harm, int32_t harm_n,
-                                   double *scratch, double *stats, int64_t *counts, double *wsum, cudaStream_t st) {
-    int blocks = reduce_identity_blocks(n);
+                                   double *scratch, int sm_count, double *stats, int64_t *counts, double *wsum, cudaStream_t st) {
+    int blocks = reduce_identity_blocks(n, sm_count);
     reduce_identity_stage1<<<blocks, RI_THREADS, 0, st>>>(ident, n, ld, labels, weight, scratch);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -372,10 +416,10 @@ cudaError_t launch_site_counts(const uint64_t *sites, int64_t M, int32_t words, 
 }
 
 cudaError_t launch_cluster(const double *ident, int32_t n, int64_t ld, double threshold, int32_t *parent, int32_t *comp,
-                           cudaStream_t st) {
+                           int sm_count, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     cluster_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(parent, n);
-    cluster_link_kernel<<<n < 148 * 8 ? n : 148 * 8, 128, 0, st>>>(ident, n, ld, threshold, parent);
+    cluster_link_kernel<<<n < sm_count * 8 ? n : sm_count * 8, 128, 0, st>>>(ident, n, ld, threshold, parent);
     cluster_flatten_kernel<<<(n + 255) / 256, 256, 0, st>>>(parent, n, comp);
     return cudaGetLastError();
 }

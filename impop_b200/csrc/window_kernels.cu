@@ -287,20 +287,6 @@ __global__ void heavy_count_kernel(const uint32_t *len, const int64_t *len_off, 
     }
 }
 
-// Harmonic tables a1(n), a2(n) (see stats_math.cuh).  Sequential by nature; run once per context.
-__global__ void harmonic_table_kernel(double2 *harm, int32_t nmax) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    double t1 = 0.0, c1 = 0.0, t2 = 0.0, c2 = 0.0;
-    harm[0] = make_double2(0.0, 0.0);
-    if (nmax >= 1) harm[1] = make_double2(0.0, 0.0);
-    for (int n = 2; n <= nmax; ++n) {  // a(n) sums i = 1 .. n-1
-        double di = (double)(n - 1);
-        neumaier_add(t1, c1, __ddiv_rn(1.0, di));
-        neumaier_add(t2, c2, __ddiv_rn(1.0, __dmul_rn(di, di)));
-        harm[n] = make_double2(neumaier_value(t1, c1), neumaier_value(t2, c2));
-    }
-}
-
 // ==========================================================================================
 // Work-item bookkeeping
 // ==========================================================================================
@@ -1246,19 +1232,14 @@ cudaError_t launch_heavy_count(const uint32_t *len, const int64_t *len_off, cons
     return cudaGetLastError();
 }
 
-cudaError_t launch_harmonic_table(double2 *harm, int32_t nmax, cudaStream_t st) {
-    harmonic_table_kernel<<<1, 32, 0, st>>>(harm, nmax);
-    return cudaGetLastError();
+int prep_rows_ctas_per_sm() {                      // resident prep_rows CTAs per SM (registers / shared memory) on the current device
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, prep_rows_kernel, PREP_THREADS, 0) != cudaSuccess || v < 1) v = 2;
+    return v;
 }
 
-cudaError_t launch_prep(const WindowTab &tab, int64_t *counts, int sm_count, cudaStream_t st) {
+cudaError_t launch_prep(const WindowTab &tab, int64_t *counts, int sm_count, int per_sm, cudaStream_t st) {
     if (tab.W == 0) return cudaSuccess;
-    static int per_sm = 0;                         // resident prep_rows CTAs per SM (registers / shared memory), queried once
-    if (per_sm == 0) {
-        int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, prep_rows_kernel, PREP_THREADS, 0) != cudaSuccess || v < 1) v = 2;
-        per_sm = v;
-    }
     prep_cols_kernel<<<min(tab.W, sm_count * 8), PREP_THREADS, 0, st>>>(tab, counts);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -1298,17 +1279,17 @@ cudaError_t launch_pairs(const WindowTab &tab, const ItemParams &prm, int algo, 
 }
 
 cudaError_t launch_window_sums(const WindowTab &tab, const double *partials, int rank, int world, double *sums,
-                               cudaStream_t st) {
+                               int sm_count, cudaStream_t st) {
     if (tab.W == 0) return cudaSuccess;
-    int blocks = min((tab.W + 3) / 4, 148 * 8);
+    int blocks = min((tab.W + 3) / 4, sm_count * 8);
     window_sums_kernel<<<blocks, 128, 0, st>>>(tab, partials, rank, world, sums);
     return cudaGetLastError();
 }
 
 cudaError_t launch_finalize(const WindowTab &tab, const double *sums, int parts, const int64_t *counts, double *stats,
-                            cudaStream_t st) {
+                            int sm_count, cudaStream_t st) {
     if (tab.W == 0) return cudaSuccess;
-    finalize_kernel<<<min((tab.W + 127) / 128, 148 * 4), 128, 0, st>>>(tab, sums, parts, counts, stats);
+    finalize_kernel<<<min((tab.W + 127) / 128, sm_count * 4), 128, 0, st>>>(tab, sums, parts, counts, stats);
     return cudaGetLastError();
 }
 
@@ -1318,9 +1299,9 @@ cudaError_t launch_export_a(const int32_t *A, int32_t n, int64_t *out, cudaStrea
     return cudaGetLastError();
 }
 
-cudaError_t launch_division_selftest(uint64_t seed, int64_t count, unsigned long long *out, cudaStream_t st) {
+cudaError_t launch_division_selftest(uint64_t seed, int64_t count, unsigned long long *out, int sm_count, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    division_selftest_kernel<<<148 * 4, 256, 0, st>>>(seed, count, out);
+    division_selftest_kernel<<<sm_count * 4, 256, 0, st>>>(seed, count, out);
     return cudaGetLastError();
 }
 

@@ -3,15 +3,32 @@
 PyTorch is used only for device memory, streams and (in distributed.py) the process group;
 every computation below is a call into the hand-written sm_100a library.  There is no CPU
 fallback: constructing a Context without a CUDA device raises.
+
+torch is imported lazily: window batches (matrix mode, bench, multi-GPU) use torch tensors; the TSV-mode
+reductions also take plain `devmem.DevArray` buffers, so that the per-window command lines never pay
+the import (`Context(lite=True)`).
 """
 from __future__ import annotations
 
 import ctypes as C
+import sys
 
 import numpy as np
-import torch
 
 from . import _native as N
+from .devmem import DevArray
+
+
+class _LazyTorch:
+    def __getattr__(self, name):
+        import torch as _t
+        globals()["torch"] = _t
+        return getattr(_t, name)
+
+
+torch = _LazyTorch()
+
+_NP = {"f64": np.float64, "i64": np.int64, "i32": np.int32, "u8": np.uint8}
 
 LAB_SUBSET, LAB_A, LAB_B, LAB_SEG = N.LAB_SUBSET, N.LAB_A, N.LAB_B, N.LAB_SEG
 ALGO_TCGEN05, ALGO_SIMT = N.ALGO_TCGEN05, N.ALGO_SIMT
@@ -19,17 +36,24 @@ NSTATS, NCOUNTS, ST = N.NSTATS, N.NCOUNTS, N.ST
 
 
 def _ptr(t):
-    """Raw pointer of a torch tensor / numpy array (None -> NULL)."""
+    """Raw pointer of a torch tensor / DevArray / numpy array (None -> NULL)."""
     if t is None:
         return None
-    if isinstance(t, torch.Tensor):
+    if hasattr(t, "data_ptr"):
         return C.c_void_p(t.data_ptr())
     return C.c_void_p(t.ctypes.data)
 
 
 def _stream_ptr(stream=None):
-    s = stream if stream is not None else torch.cuda.current_stream()
-    return C.c_void_p(s.cuda_stream)
+    if stream is None:
+        if "torch" not in sys.modules:                      # lite contexts: the default stream
+            return None
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+def _is_f64(t) -> bool:
+    return t.dtype == np.float64 if isinstance(t, DevArray) else t.dtype == torch.float64
 
 
 def _u32_tensor(a: np.ndarray) -> torch.Tensor:
@@ -44,24 +68,45 @@ def _u64_tensor(a: np.ndarray) -> torch.Tensor:
 class Context:
     """One impop_ctx_t per device (impop_create / impop_destroy)."""
 
-    def __init__(self, device: int = 0):
-        if not torch.cuda.is_available():
-            raise RuntimeError("impop_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    def __init__(self, device: int = 0, lite: bool = False):
+        """lite=True: no torch import (TSV-mode command lines); arrays are devmem.DevArray buffers."""
         self.lib = N.lib()
         self.device = int(device)
-        self.torch_device = torch.device("cuda", self.device)
-        torch.cuda.set_device(self.device)
-        torch.zeros(1, device=self.torch_device)          # make sure the primary context exists
+        self.lite = bool(lite)
+        if not lite:
+            if not torch.cuda.is_available():
+                raise RuntimeError("impop_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            torch.cuda.set_device(self.device)
+            torch.zeros(1, device=self.torch_device)      # make sure the primary context exists
         h = C.c_void_p()
         rc = self.lib.impop_create(self.device, C.byref(h))
         if rc != 0:
             raise N.NativeError(rc, "impop_create", "no sm_100a device or CUDA failure")
         self.handle = h
 
+    @property
+    def torch_device(self):
+        return torch.device("cuda", self.device)
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.impop_destroy(self.handle)
             self.handle = None
+
+    def _empty(self, shape, kind: str, like=None, zero: bool = False):
+        """Uninitialised (or zeroed) device array of the caller's flavour: DevArray next to DevArrays / on lite contexts."""
+        if self.lite or isinstance(like, DevArray):
+            out = DevArray(self, shape, _NP[kind])
+            return out.zero_() if zero else out
+        dt = {"f64": torch.float64, "i64": torch.int64, "i32": torch.int32, "u8": torch.uint8}[kind]
+        dev = like.device if like is not None and hasattr(like, "device") else self.torch_device
+        return (torch.zeros if zero else torch.empty)(shape, dtype=dt, device=dev)
+
+    def upload(self, a: np.ndarray):
+        """Host array -> device array of this context's flavour."""
+        if self.lite:
+            return DevArray.from_numpy(self, a)
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.torch_device)
 
     def __del__(self):  # pragma: no cover - interpreter shutdown order
         try:
@@ -108,19 +153,19 @@ class Context:
                         length: int = 0, seg_sites: float = 0.0, stream=None):
         """K3 alone (TSV mode): (stats[NSTATS] f64, counts[NCOUNTS] i64, wsum[4] f64) device tensors.
         wsum = weighted sum, weighted pair count, grouped pi, grouped pi / length (see include/impop_b200.h)."""
-        assert ident.dtype == torch.float64 and ident.dim() == 2 and ident.is_cuda
+        assert _is_f64(ident) and ident.dim() == 2 and ident.is_cuda
         n = ident.shape[0]
-        stats = torch.empty(NSTATS, dtype=torch.float64, device=ident.device)
-        counts = torch.empty(NCOUNTS, dtype=torch.int64, device=ident.device)
-        wsum = torch.zeros(4, dtype=torch.float64, device=ident.device)
+        stats = self._empty(NSTATS, "f64", ident)
+        counts = self._empty(NCOUNTS, "i64", ident)
+        wsum = self._empty(4, "f64", ident, zero=True)
         self._call("impop_reduce_identity", _ptr(ident), n, ident.stride(0) if n else 0, _ptr(labels), _ptr(weight),
                    int(length or 0), float(seg_sites), _ptr(stats), _ptr(counts), _ptr(wsum), _stream_ptr(stream))
         return stats, counts, wsum
 
     def tajima_d(self, n: torch.Tensor, S: torch.Tensor, pi: torch.Tensor, with_parts: bool = False, stream=None):
         count = n.numel()
-        D = torch.empty(count, dtype=torch.float64, device=n.device)
-        parts = torch.empty((count, 10), dtype=torch.float64, device=n.device) if with_parts else None
+        D = self._empty(count, "f64", n)
+        parts = self._empty((count, 10), "f64", n) if with_parts else None
         self._call("impop_tajima_d", _ptr(n), _ptr(S), _ptr(pi), count, _ptr(D), _ptr(parts), _stream_ptr(stream))
         return (D, parts) if with_parts else D
 
@@ -129,12 +174,16 @@ class Context:
         """K4: sites [M, words] int64 (u64 bits), masks [P, words] -> counts [M, P] i32, freq [M, P] f64."""
         M, words = sites.shape
         P = masks.shape[0]
-        counts = out_counts if out_counts is not None else torch.empty((M, P), dtype=torch.int32, device=sites.device)
-        freq = out_freq if out_freq is not None else (
-            torch.empty((M, P), dtype=torch.float64, device=sites.device) if want_freq else None)
+        counts = out_counts if out_counts is not None else self._empty((M, P), "i32", sites)
+        freq = out_freq if out_freq is not None else (self._empty((M, P), "f64", sites) if want_freq else None)
         self._call("impop_site_counts", _ptr(sites), M, words, _ptr(masks), P, _ptr(counts), _ptr(freq),
                    _stream_ptr(stream))
         return counts, freq
+
+    def round_decimal(self, values, digits: int, stream=None):
+        """CPython's round(x, digits) on every element of a device fp64 array, in place (impop_round_decimal)."""
+        self._call("impop_round_decimal", _ptr(values), values.numel(), int(digits), _stream_ptr(stream))
+        return values
 
     def selftest_division(self, count: int = 1 << 24, seed: int = 1, stream=None) -> int:
         """Mismatches between the epilogue's in-range division and __ddiv_rn over `count` random triples."""
@@ -145,8 +194,8 @@ class Context:
     def greedy_groups(self, ident: torch.Tensor, threshold: float, stream=None):
         """pica2 step 1 on the device: (group [n] i32 = seed index, weight [n] f64 = |G|/n on seeds)."""
         n = ident.shape[0]
-        group = torch.empty(n, dtype=torch.int32, device=ident.device)
-        weight = torch.empty(n, dtype=torch.float64, device=ident.device)
+        group = self._empty(n, "i32", ident)
+        weight = self._empty(n, "f64", ident)
         self._call("impop_greedy_groups", _ptr(ident), n, ident.stride(0) if n else 0, float(threshold), _ptr(group),
                    _ptr(weight), _stream_ptr(stream))
         return group, weight
@@ -154,7 +203,7 @@ class Context:
     def cluster(self, ident: torch.Tensor, threshold: float, stream=None) -> torch.Tensor:
         """K5: component label (= smallest member index) per row of a dense identity matrix."""
         n = ident.shape[0]
-        comp = torch.empty(n, dtype=torch.int32, device=ident.device)
+        comp = self._empty(n, "i32", ident)
         self._call("impop_cluster", _ptr(ident), n, ident.stride(0) if n else 0, float(threshold), _ptr(comp),
                    _stream_ptr(stream))
         return comp

@@ -8,7 +8,7 @@ population; here the seed is always the smallest remaining name (as in the pica2
 reference wherever the reference agrees with itself.  On a table with absent pairs the reference takes the first
 member pair it finds between two groups (hud.py:86-97); here it is the representatives' pair or nothing
 (odgi / impg tables are complete).  Grouping, the weighted sums and the pair counts run on the GPU
-(`impop_greedy_groups`, `impop_reduce_identity`); torch only selects sub-matrices.
+(`impop_greedy_groups`, `impop_reduce_identity`); sub-matrices of the (device-rounded) table are selected on the host.
 """
 from __future__ import annotations
 
@@ -16,7 +16,7 @@ import argparse
 import os
 import sys
 
-import torch
+import numpy as np
 
 from . import hfst
 from .hfst import read_similarity_file, read_subset_file  # noqa: F401  (same readers: hud.py:15-62)
@@ -30,8 +30,8 @@ def _population(table: SimilarityTable, ctx, ident, members):
     """(row indices sorted by name, group id per row, weight per row, grouped diversity, groups, group pairs with data)."""
     idx = sorted(table.index[s] for s in members if s in table.index)
     n = len(idx)
-    sel = torch.tensor(idx, dtype=torch.long, device=ident.device)
-    sub = ident.index_select(0, sel).index_select(1, sel).contiguous()
+    sel = np.asarray(idx, dtype=np.int64)
+    sub = ctx.upload(np.ascontiguousarray(ident[np.ix_(sel, sel)])) if n else None
     return idx, sel, sub, n
 
 
@@ -39,7 +39,7 @@ def group_sequences(similarities, sequences, threshold=0.999, round_digits=None,
     """Sorted list of sorted groups (hud.py:64-84), seed = smallest remaining name."""
     ctx = ctx or default_context()
     table = SimilarityTable.from_mapping(similarities, sequences)
-    ident = table.device(ctx, round_digits)
+    ident = table.host(ctx, round_digits)
     idx, sel, sub, n = _population(table, ctx, ident, sequences)
     if n == 0:
         return []
@@ -55,7 +55,7 @@ def calculate_diversity_grouped(similarities, sequences, threshold=0.999, round_
     """(diversity, number of groups, group pairs without data) -- hud.py:99-128."""
     ctx = ctx or default_context()
     table = SimilarityTable.from_mapping(similarities, sequences)
-    ident = table.device(ctx, round_digits)
+    ident = table.host(ctx, round_digits)
     div, groups, missing, _ = _grouped(table, ctx, ident, sequences, threshold)
     return div, groups, missing
 
@@ -67,7 +67,8 @@ def _grouped(table, ctx, ident, members, threshold):
     group, weight = ctx.greedy_groups(sub, threshold)
     _, _, wsum = ctx.reduce_identity(sub, None, weight)
     ctx.check()
-    g = int((weight > 0).sum().item())
+    weight = weight.cpu().numpy()
+    g = int((weight > 0).sum())
     if n <= 1:
         return 0.0, g, 0, (idx, weight)                                       # hud.py:104-105
     ws = wsum.cpu().tolist()
@@ -101,7 +102,7 @@ def calculate_fst(similarities, pop_a, pop_b, sequence_length=None, round_digits
     if round_digits is not None:
         log_print(f"Rounding similarities to {round_digits} decimal places")
     log_print("")
-    ident = table.device(ctx, round_digits)
+    ident = table.host(ctx, round_digits)
     pi_a, groups_a, miss_a, (ia, wa) = _grouped(table, ctx, ident, pop_a, threshold)
     pi_b, groups_b, miss_b, (ib, wb) = _grouped(table, ctx, ident, pop_b, threshold)
     log_print("Within-population diversity (π) using grouped method:")
@@ -114,11 +115,10 @@ def calculate_fst(similarities, pop_a, pop_b, sequence_length=None, round_digits
     dxy, missing = 0.0, groups_a * groups_b
     if wa is not None and wb is not None:
         # representatives of both populations, weights |G_a| / n_A and |G_b| / n_B, one cross-population reduction
-        rows = torch.tensor(ia + ib, dtype=torch.long, device=ident.device)
-        sub = ident.index_select(0, rows).index_select(1, rows).contiguous()
-        lab = torch.cat([torch.full((len(ia),), 2, dtype=torch.uint8, device=ident.device),
-                         torch.full((len(ib),), 4, dtype=torch.uint8, device=ident.device)])
-        _, _, wsum = ctx.reduce_identity(sub, lab, torch.cat([wa, wb]).contiguous())
+        rows = np.asarray(ia + ib, dtype=np.int64)
+        sub = ctx.upload(np.ascontiguousarray(ident[np.ix_(rows, rows)]))
+        lab = ctx.upload(np.concatenate([np.full(len(ia), 2, dtype=np.uint8), np.full(len(ib), 4, dtype=np.uint8)]))
+        _, _, wsum = ctx.reduce_identity(sub, lab, ctx.upload(np.concatenate([wa, wb])))
         ctx.check()
         ws = wsum.cpu().tolist()
         dxy, missing = ws[0], groups_a * groups_b - int(ws[1])                 # hud.py:246-258

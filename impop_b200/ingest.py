@@ -134,17 +134,152 @@ def save_batch(path, windows) -> None:
 def load_batch(path) -> list:
     z = np.load(path)
     n, m, pitch = z["n"], z["m"], z["pitch"]
+    x_all, len_all, L_all = z["x"], z["node_len"], z["length"]        # NpzFile re-reads a member on every access: once each
     names = z["names"].tobytes().decode().split("\n") if len(n) else []
     regions = z["regions"].tobytes().decode().split("\n") if len(n) else []
     out, xo, lo = [], 0, 0
     for w in range(len(n)):
         xs = int(n[w]) * int(pitch[w])
         out.append(GraphWindow(names[w].split("\t") if names[w] else [],
-                               z["x"][xo:xo + xs].reshape(int(n[w]), int(pitch[w])).copy(),
-                               z["node_len"][lo:lo + int(m[w])].copy(), None, regions[w] or None, int(z["length"][w])))
+                               x_all[xo:xo + xs].reshape(int(n[w]), int(pitch[w])).copy(),
+                               len_all[lo:lo + int(m[w])].copy(), None, regions[w] or None, int(L_all[w])))
         xo += xs
         lo += int(m[w])
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Flat container: one file, fixed little-endian layout, every array usable in place (np.memmap) -- a chromosome's
+# windows go from disk to one WindowBatch without a per-window Python loop and without copies.
+#   header  8 x int64: magic, version, W, rows (sum n), x words, nodes (sum m), unique names U, text bytes
+#   int64   n[W] m[W] pitch[W] x_off[W] len_off[W] row_off[W] length[W]
+#   int32   name_id[rows]            index of the row's haplotype in the unique-name table
+#   uint32  node_len[nodes]  then  x[x words]   (x starts on a 64-byte boundary)
+#   text    unique names ('\n' joined; a row name = unique name + ':' + the window's coordinates when the source had them)
+#           + '\x00' + regions ('\n' joined) + '\x00' + per-window coordinate suffixes ('\n' joined)
+# ------------------------------------------------------------------------------------------------------------
+FLAT_MAGIC = 0x31574F504D49          # "IMPOW1"
+
+
+@dataclass
+class FlatBatch:
+    n: np.ndarray
+    m: np.ndarray
+    pitch: np.ndarray
+    x_off: np.ndarray
+    len_off: np.ndarray
+    row_off: np.ndarray
+    length: np.ndarray
+    name_id: np.ndarray
+    node_len: np.ndarray
+    x: np.ndarray
+    uniq: list
+    regions: list
+    suffix: list
+
+    @property
+    def windows(self) -> int:
+        return int(self.n.shape[0])
+
+    def names(self, w: int) -> list:
+        ids = self.name_id[int(self.row_off[w]):int(self.row_off[w]) + int(self.n[w])]
+        sfx = self.suffix[w]
+        return [self.uniq[i] + ((":" + sfx) if sfx else "") for i in ids]
+
+    def labels(self, pop_a=None, pop_b=None, subset=None, seg=None) -> np.ndarray:
+        """Label byte per row of the whole batch from PREFIX lists (after h-fst.py:18-61 canonicalisation): the classes
+        are decided once per unique haplotype name and gathered per row."""
+        def flags(prefixes, bit, default):
+            if prefixes is None:
+                return np.full(len(self.uniq), bit if default else 0, dtype=np.uint8)
+            pre = tuple(prefixes)
+            return np.array([bit if u.startswith(pre) else 0 for u in self.uniq], dtype=np.uint8) if pre else np.zeros(len(self.uniq), np.uint8)
+        per = (flags(subset, _native.LAB_SUBSET, True) | flags(seg if seg is not None else subset, _native.LAB_SEG, True)
+               | flags(pop_a, _native.LAB_A, False) | flags(pop_b, _native.LAB_B, False))
+        return per[self.name_id]
+
+    def window(self, w: int) -> GraphWindow:
+        xs, pw, nn = int(self.x_off[w]), int(self.pitch[w]), int(self.n[w])
+        lo = int(self.len_off[w])
+        return GraphWindow(self.names(w), np.asarray(self.x[xs:xs + nn * pw]).reshape(nn, pw), np.asarray(self.node_len[lo:lo + int(self.m[w])]),
+                           None, self.regions[w] or None, int(self.length[w]))
+
+
+def _split_name(name: str):
+    head, sep, tail = name.rpartition(":")
+    if sep and "-" in tail and tail.replace("-", "").isdigit():
+        return head, tail
+    return name, ""
+
+
+def save_flat(path, windows) -> None:
+    """GraphWindow list -> flat container.  Row names are stored once per haplotype (the part before ':start-end')."""
+    W = len(windows)
+    n = np.array([w.n for w in windows], dtype=np.int64)
+    m = np.array([w.m for w in windows], dtype=np.int64)
+    pitch = np.array([w.x_bits.shape[1] for w in windows], dtype=np.int64)
+    rows = n * pitch
+    x_off = np.concatenate([[0], np.cumsum(rows)[:-1]]).astype(np.int64) if W else np.zeros(0, np.int64)
+    len_off = np.concatenate([[0], np.cumsum(m)[:-1]]).astype(np.int64) if W else np.zeros(0, np.int64)
+    row_off = np.concatenate([[0], np.cumsum(n)[:-1]]).astype(np.int64) if W else np.zeros(0, np.int64)
+    length = np.array([w.length for w in windows], dtype=np.int64)
+    uniq, index, ids, suffix = [], {}, [], []
+    for w in windows:
+        sfx = None
+        for name in w.names:
+            head, tail = _split_name(name)
+            if sfx is None:
+                sfx = tail
+            elif tail != sfx:                      # mixed coordinates inside one window: keep full names
+                head, tail = name, ""
+            k = index.get(head)
+            if k is None:
+                k = index[head] = len(uniq)
+                uniq.append(head)
+            ids.append(k)
+        suffix.append(sfx or "")
+    name_id = np.array(ids, dtype=np.int32)
+    text = ("\n".join(uniq) + "\x00" + "\n".join(w.region or "" for w in windows) + "\x00" + "\n".join(suffix)).encode()
+    node_len = np.concatenate([w.node_len for w in windows]).astype(np.uint32) if W else np.zeros(0, np.uint32)
+    x = np.concatenate([w.x_bits.reshape(-1) for w in windows]).astype(np.uint32) if W else np.zeros(0, np.uint32)
+    hdr = np.array([FLAT_MAGIC, 1, W, int(n.sum()), int(x.size), int(m.sum()), len(uniq), len(text)], dtype=np.int64)
+    with open(path, "wb") as fh:
+        fh.write(hdr.tobytes())
+        for a in (n, m, pitch, x_off, len_off, row_off, length):
+            fh.write(a.tobytes())
+        fh.write(name_id.tobytes())
+        fh.write(node_len.tobytes())
+        fh.write(b"\x00" * ((-fh.tell()) % 64))
+        fh.write(x.tobytes())
+        fh.write(text)
+
+
+def load_flat(path, mmap: bool = True) -> FlatBatch:
+    """Flat container -> FlatBatch whose arrays are views of the file (np.memmap) -- no per-window work."""
+    buf = np.memmap(path, dtype=np.uint8, mode="r") if mmap else np.fromfile(path, dtype=np.uint8)
+    hdr = np.frombuffer(buf, dtype=np.int64, count=8)
+    if int(hdr[0]) != FLAT_MAGIC or int(hdr[1]) != 1:
+        raise ValueError(f"{path}: not an impop window container")
+    W, rows, xw, nodes, U, tb = (int(v) for v in hdr[2:8])
+    off = 64
+    out = []
+    for _ in range(7):
+        out.append(np.frombuffer(buf, dtype=np.int64, count=W, offset=off))
+        off += 8 * W
+    name_id = np.frombuffer(buf, dtype=np.int32, count=rows, offset=off)
+    off += 4 * rows
+    node_len = np.frombuffer(buf, dtype=np.uint32, count=nodes, offset=off)
+    off += 4 * nodes
+    off += (-off) % 64
+    x = np.frombuffer(buf, dtype=np.uint32, count=xw, offset=off)
+    off += 4 * xw
+    text = bytes(buf[off:off + tb]).decode()
+    uniq, regions, suffix = (part.split("\n") if part else [] for part in (text.split("\x00") + ["", ""])[:3])
+    if W and not regions:
+        regions = [""] * W
+    if W and not suffix:
+        suffix = [""] * W
+    return FlatBatch(*out, name_id, node_len, x, uniq, regions, suffix)
 
 
 def labels_from_names(names, pop_a=None, pop_b=None, subset=None, seg=None) -> np.ndarray:

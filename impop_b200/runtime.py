@@ -7,11 +7,13 @@ _ctx = None
 
 
 def default_context():
-    """One Context on cuda:LOCAL_RANK (cuda:0 outside torchrun).  Raises without a GPU: no CPU fallback."""
+    """One Context on cuda:LOCAL_RANK (cuda:0 outside torchrun) for the script drop-ins (TSV mode).  It is a `lite`
+    context: plain device buffers over the C ABI, no torch import -- the wrappers start these command lines once per
+    window.  Raises without a GPU: no CPU fallback."""
     global _ctx
     if _ctx is None:
         from .engine import Context
-        _ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+        _ctx = Context(int(os.environ.get("LOCAL_RANK", "0")), lite=True)
     return _ctx
 
 

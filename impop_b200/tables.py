@@ -24,7 +24,7 @@ class SimilarityTable(Mapping):
         self.names = list(names)
         self.index = {s: i for i, s in enumerate(self.names)}
         self.matrix = matrix
-        self._device = {}          # (device index, round_digits) -> torch tensor
+        self._device = {}          # (context, round_digits) -> device array
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -41,7 +41,9 @@ class SimilarityTable(Mapping):
             ib = np.fromiter((index[r[1]] for r in rows), dtype=np.int64, count=len(rows))
             v = np.fromiter((r[2] for r in rows), dtype=np.float64, count=len(rows))
             if combine == "max":
-                order = np.argsort(v, kind="stable")       # later (larger) assignments win
+                # later (larger) assignments win; a literal `nan` row never hides a real one (af.py:38 links on ANY row that
+                # reaches the threshold, and nan >= t is False): NaNs first, then the finite values in ascending order
+                order = np.argsort(np.where(np.isnan(v), -np.inf, v), kind="stable")
                 ia, ib, v = ia[order], ib[order], v[order]
             lo, hi = np.minimum(ia, ib), np.maximum(ia, ib)
             mat[lo, hi] = v                                # repeated index: the last assignment stays
@@ -95,27 +97,41 @@ class SimilarityTable(Mapping):
 
     # ------------------------------------------------------------------ device side
     def rounded(self, digits) -> np.ndarray:
-        """round(sim, r) exactly as CPython rounds (pica2.py:81-83, h-fst.py:149-150): correctly
-        rounded decimal, which rint(x * 10^r) / 10^r is not (SURVEY.md 7.2 #3).  Text-level ingest."""
+        """Host restatement of round(sim, r) (one CPython round() per element): only for `digits` the device kernel does
+        not take (negative, or beyond 22 where 10^r is no longer exact)."""
         if digits is None:
             return self.matrix
         flat = [v if v != v else round(v, digits) for v in self.matrix.ravel().tolist()]
         return np.array(flat, dtype=np.float64).reshape(self.matrix.shape)
 
     def device(self, ctx, round_digits=None):
-        """The (optionally rounded) matrix as a device tensor, uploaded once per context."""
-        import torch
-        key = (ctx.device, round_digits)
+        """The (optionally rounded) matrix as a device array, uploaded once per context.  round(sim, r) as the reference
+        applies it to every value (pica2.py:81-83, h-fst.py:149-150) runs on the device (impop_round_decimal: exact CPython
+        semantics -- correctly rounded decimal, which rint(x * 10^r) / 10^r is not, SURVEY.md 7.2 #3)."""
+        key = (id(ctx), round_digits)
         if key not in self._device:
-            host = np.ascontiguousarray(self.rounded(round_digits))
+            on_device = round_digits is not None and 0 <= round_digits <= 22
+            host = self.matrix if (round_digits is None or on_device) else self.rounded(round_digits)
+            host = np.ascontiguousarray(host)
             if host.size == 0:
                 host = np.zeros((0, 0), dtype=np.float64)
-            self._device[key] = torch.from_numpy(host).to(ctx.torch_device)
+            dev = ctx.upload(host)
+            if on_device and host.size:
+                ctx.round_decimal(dev, round_digits)
+            self._device[key] = dev
+        return self._device[key]
+
+    def host(self, ctx, round_digits=None) -> np.ndarray:
+        """The (optionally rounded) matrix back on the host (sub-matrix selection of hud.py's grouped method)."""
+        if round_digits is None:
+            return self.matrix
+        key = (id(ctx), round_digits, "host")
+        if key not in self._device:
+            self._device[key] = self.device(ctx, round_digits).cpu().numpy()
         return self._device[key]
 
     def labels(self, ctx, **classes):
         """uint8 label vector on the device from name collections: subset=..., a=..., b=..., seg=..."""
-        import torch
         bits = {"subset": 1, "a": 2, "b": 4, "seg": 8}
         lab = np.zeros(len(self.names), dtype=np.uint8)
         for cls_name, members in classes.items():
@@ -123,7 +139,7 @@ class SimilarityTable(Mapping):
                 continue
             idx = [self.index[s] for s in members if s in self.index]
             lab[idx] |= bits[cls_name]
-        return torch.from_numpy(lab).to(ctx.torch_device)
+        return ctx.upload(lab)
 
 
 def read_table_fast(path):

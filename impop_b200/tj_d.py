@@ -11,6 +11,8 @@ import argparse
 import sys
 from dataclasses import dataclass
 
+import numpy as np
+
 from .runtime import default_context
 
 
@@ -30,7 +32,6 @@ class TajimaComponents:
 
 def tajimas_d_batch(n, S, pi, ctx=None, with_parts=False):
     """Vectorised tj_d.tajimas_d: sequences of n (int), S, pi (float) -> list of D (and component rows)."""
-    import torch
     ctx = ctx or default_context()
     n, S, pi = list(n), list(S), list(pi)
     for nn, ss, pp in zip(n, S, pi):
@@ -38,10 +39,9 @@ def tajimas_d_batch(n, S, pi, ctx=None, with_parts=False):
             raise ValueError("n must be >= 2")
         if ss < 0 or pp < 0:
             raise ValueError("S and pi must be non-negative")
-    dev = ctx.torch_device
-    nt = torch.tensor(n, dtype=torch.int64, device=dev)
-    st = torch.tensor(S, dtype=torch.float64, device=dev)
-    pt = torch.tensor(pi, dtype=torch.float64, device=dev)
+    nt = ctx.upload(np.asarray(n, dtype=np.int64))
+    st = ctx.upload(np.asarray(S, dtype=np.float64))
+    pt = ctx.upload(np.asarray(pi, dtype=np.float64))
     out = ctx.tajima_d(nt, st, pt, with_parts=with_parts)
     ctx.check()
     if with_parts:

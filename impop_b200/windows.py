@@ -43,12 +43,16 @@ def fst_rows(regions, lengths, stats):
         yield [reg, str(int(L))] + [f"{row[ST[k]]:.8f}" for k in keys]
 
 
-def tajd_rows(regions, lengths, stats, counts):
-    """PI = per-site pi at 8 decimals (run_tajd.sh:166-174), D as tj_d.py prints a float, NaN -> NA (run_tajd.sh:192-194)."""
-    for reg, L, row, cnt in zip(regions, lengths, stats, counts):
-        d = float(row[ST["tajima_d"]])
+def tajd_rows(regions, lengths, stats, counts, d_from_text=None, samples=None):
+    """PI = per-site pi at 8 decimals (run_tajd.sh:166-174), D as tj_d.py prints a float, NaN -> NA (run_tajd.sh:192-194).
+    `d_from_text`: D recomputed from the PRINTED pi (what run_tajd.sh:180 hands tj_d.py is pica2's 8-decimal text), so that
+    the D of a row follows from the PI of the same row; default: the device's D from the unrounded pi.  `samples`: SAMPLES
+    column / n of tj_d.py when it is the size of the sample list (run_tajd.sh:83) rather than the rows found in the window."""
+    for k, (reg, L, row, cnt) in enumerate(zip(regions, lengths, stats, counts)):
+        d = float(row[ST["tajima_d"]]) if d_from_text is None else float(d_from_text[k])
         pi = row[ST["pi_per_site"]] if L else row[ST["pi"]]
-        yield [reg, str(int(L)), str(int(cnt[0])), str(int(cnt[7])), f"{pi:.8f}", "NA" if math.isnan(d) else repr(d)]
+        yield [reg, str(int(L)), str(int(cnt[0]) if samples is None else int(samples)), str(int(cnt[7])), f"{pi:.8f}",
+               "NA" if math.isnan(d) else repr(d)]
 
 
 def pooled_fst_text(pi_a: str, pi_b: str, pi_c: str):
@@ -96,18 +100,71 @@ def batch_from_graphs(ctx, graphs, pop_a_ids=None, pop_b_ids=None, subset_ids=No
     return WindowBatch.from_windows(ctx, wins)
 
 
+def batch_from_flat(ctx, flat, pop_a_ids=None, pop_b_ids=None, subset_ids=None):
+    """ingest.FlatBatch (memory-mapped container) -> WindowBatch: one upload of the presence words, node lengths and labels;
+    the classes are decided once per unique haplotype (h-fst.py:18-61 prefixes) and gathered per row -- no per-window loop."""
+    import numpy as np
+    import torch
+
+    from .engine import WindowBatch
+    from .hfst import canonicalize_identifier
+
+    def prefixes(ids):
+        return None if ids is None else [p for p in (canonicalize_identifier(i) for i in ids) if p]
+    lab = flat.labels(prefixes(pop_a_ids), prefixes(pop_b_ids), prefixes(subset_ids))
+    both = (lab & 6) == 6                                  # h-fst.py:181-185: listed in both populations -> in neither
+    lab = np.where(both, lab & ~np.uint8(6), lab).astype(np.uint8)
+    import warnings
+    dev = ctx.torch_device
+    with warnings.catch_warnings():                        # the memory-mapped file is read-only; the tensors are only copied from
+        warnings.simplefilter("ignore", UserWarning)
+        x = torch.from_numpy(np.ascontiguousarray(flat.x).view(np.int32)).to(dev)
+        nl = torch.from_numpy(np.ascontiguousarray(flat.node_len).view(np.int32)).to(dev)
+    return WindowBatch(ctx, flat.n, flat.m, flat.pitch, flat.x_off, flat.len_off, flat.row_off, flat.length, x, nl,
+                       torch.from_numpy(lab).to(dev), node_len_host=np.ascontiguousarray(flat.node_len))
+
+
+def stats_disjoint_absent(ctx, batch, labels_host, lab_off):
+    """Per-window statistics with the convention of a similarity tool that prints NO row for a pair of paths that share no
+    node [UPSTREAM-UNVERIFIED: odgi similarity]: such a pair is absent -- not counted in any denominator -- which is how
+    pica2.py:132-134 and h-fst.py:147-153 treat a missing row.  (The fused path counts it with pi_ij = 1.)  Materialises
+    every window's table on the device and reduces it with NaN in place of those pairs."""
+    import numpy as np
+    import torch
+    stats = np.zeros((batch.windows, 20), dtype=np.float64)
+    counts = np.zeros((batch.windows, 8), dtype=np.int64)
+    fused_s, fused_c = batch.stats()
+    ctx.check()
+    fused_s, fused_c = fused_s.cpu().numpy(), fused_c.cpu().numpy()
+    for w in range(batch.windows):
+        n = int(batch.n[w])
+        I, _, pi = batch.pairwise(w)
+        ident = 1.0 - pi
+        off = ~torch.eye(n, dtype=torch.bool, device=ident.device)
+        ident[(I == 0) & off] = float("nan")
+        lab = torch.from_numpy(np.ascontiguousarray(labels_host[int(lab_off[w]):int(lab_off[w]) + n])).to(ident.device)
+        st, ct, _ = ctx.reduce_identity(ident.contiguous(), lab, None, length=int(batch.length[w]), seg_sites=float(fused_c[w][7]))
+        ctx.check()
+        stats[w], counts[w] = st.cpu().numpy(), ct.cpu().numpy()
+        counts[w][7] = fused_c[w][7]
+    return stats, counts
+
+
 def main(argv=None):
     """impop-windows: windowed pi / Hudson Fst / Tajima's D straight from window graphs.
 
         impop-windows.py --gfa-list windows.tsv [-a popA.txt -b popB.txt] [-s subset.txt]
-                         [--pi-out pi.tsv] [--fst-out fst.tsv] [--tajd-out tajd.tsv] [--save-batch windows.npz]
-        impop-windows.py --batch windows.npz ...
+                         [--pi-out pi.tsv] [--fst-out fst.tsv] [--tajd-out tajd.tsv] [--save-batch windows.impw]
+        impop-windows.py --batch windows.impw ...
 
     windows.tsv: one line per window, `REGION<TAB>path/to/window.gfa` with REGION like CHM13#0#chr2:100000-150000
     (its end - start is the window length L the wrappers pass as -l)."""
     import argparse
     import re
     import sys
+    import time
+
+    import numpy as np
 
     from . import ingest
     from .engine import Context
@@ -116,18 +173,39 @@ def main(argv=None):
     ap = argparse.ArgumentParser(prog="impop-windows", description=main.__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     src = ap.add_mutually_exclusive_group(required=True)
     src.add_argument("--gfa-list", help="TSV: REGION <tab> GFA file of that window")
-    src.add_argument("--batch", help="binary container written by --save-batch")
+    src.add_argument("--batch", help="binary container written by --save-batch (flat .impw, or .npz)")
     ap.add_argument("-a", "--pop-a", help="file listing population A (h-fst.py -a)")
     ap.add_argument("-b", "--pop-b", help="file listing population B (h-fst.py -b)")
     ap.add_argument("-s", "--subset", help="file listing the samples pi / S / Tajima's D are computed over (run_tajd.sh -l)")
     ap.add_argument("--pi-out"), ap.add_argument("--fst-out"), ap.add_argument("--tajd-out")
     ap.add_argument("--pooled-fst-out", help="run_fst_impg.sh's table: pica2 pi of subset A, B and their union, pooled Fst (needs -a, -b)")
-    ap.add_argument("--save-batch", help="also write the parsed windows as one binary container")
+    ap.add_argument("--save-batch", help="also write the parsed (ingested) windows as one binary container (.npz: numpy archive, else flat)")
+    ap.add_argument("--presence-only", action="store_true",
+                    help="a path that visits a node several times counts it once (default: multiset coverage, min(count_a, count_b) per node, as the similarity tools accumulate steps)")
+    ap.add_argument("--no-compact", action="store_true", help="keep every node as a matrix column (default: constant columns merged, empty ones dropped at ingest)")
+    ap.add_argument("--disjoint-absent", action="store_true",
+                    help="a pair of paths sharing no node is treated as absent from the table (not counted), as the scripts treat a row the similarity tool did not print")
+    ap.add_argument("--tajd-samples-from-list", action="store_true", help="SAMPLES / n of Tajima's D = size of the -s list (run_tajd.sh:83) instead of the rows found per window")
+    ap.add_argument("--timings", action="store_true", help="print stage times (parse / ingest / upload / kernels / format) on stderr")
     ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args(argv)
+    if (args.fst_out or args.pooled_fst_out) and (args.pop_a is None or args.pop_b is None):
+        ap.error("--fst-out / --pooled-fst-out need both -a and -b")
+    t = {"start": time.perf_counter()}
 
+    def mark(name):
+        t[name] = time.perf_counter()
+
+    flat = None
     if args.batch:
-        graphs = ingest.load_batch(args.batch)
+        with open(args.batch, "rb") as fh:
+            magic = fh.read(8)
+        if len(magic) == 8 and int.from_bytes(magic, "little") == ingest.FLAT_MAGIC:
+            flat = ingest.load_flat(args.batch)
+            graphs = None
+        else:
+            graphs = ingest.load_batch(args.batch)
+        mark("load")
     else:
         todo = []
         with open(args.gfa_list) as fh:
@@ -137,35 +215,76 @@ def main(argv=None):
                 region, path = line.rstrip("\n").split("\t")[:2]
                 mt = re.search(r":(\d+)-(\d+)$", region)
                 todo.append((region, path, int(mt.group(2)) - int(mt.group(1)) if mt else 0))
-        graphs = ingest.read_gfa_many(todo)               # parsed on all host cores (the reader runs outside the GIL)
+        # parsed on all host cores (the reader runs outside the GIL), visit counts kept: a path that revisits a node
+        # (duplication, inversion, loop) contributes min(count_a, count_b) * len to an intersection
+        graphs = ingest.read_gfa_many(todo, want_counts=not args.presence_only)
+        mark("parse")
+        if not args.presence_only:
+            revisits = sum(1 for g in graphs if g.counts is not None and g.counts.size and int(g.counts.max()) > 1)
+            if revisits:
+                print(f"impop-windows: {revisits} window(s) have paths that visit a node more than once: multiset coverage "
+                      f"(copy-node expansion); --presence-only counts a node once", file=sys.stderr)
+                graphs = [ingest.multiset_expand(g) if (g.counts is not None and g.counts.size and int(g.counts.max()) > 1) else g
+                          for g in graphs]
+        if not args.no_compact:
+            graphs = [ingest.compact_window(g) for g in graphs]
+        mark("ingest")
     if args.save_batch:
-        ingest.save_batch(args.save_batch, graphs)
-    if (args.fst_out or args.pooled_fst_out) and (args.pop_a is None or args.pop_b is None):
-        ap.error("--fst-out / --pooled-fst-out need both -a and -b")
+        src_graphs = graphs if graphs is not None else [flat.window(w) for w in range(flat.windows)]
+        (ingest.save_batch if args.save_batch.endswith(".npz") else ingest.save_flat)(args.save_batch, src_graphs)
     pop_a = read_subset_file(args.pop_a) if args.pop_a else None
     pop_b = read_subset_file(args.pop_b) if args.pop_b else None
     subset = read_subset_file(args.subset) if args.subset else None
     ctx = Context(args.device)
-    batch = batch_from_graphs(ctx, graphs, pop_a, pop_b, subset)
-    stats, counts = batch.stats()
-    ctx.check()
-    stats, counts = stats.cpu().numpy(), counts.cpu().numpy()
+    mark("context")
+    make = (lambda **kw: batch_from_flat(ctx, flat, **kw)) if flat is not None else (lambda **kw: batch_from_graphs(ctx, graphs, **kw))
+    batch = make(pop_a_ids=pop_a, pop_b_ids=pop_b, subset_ids=subset)
+    mark("upload")
+    if args.disjoint_absent:
+        stats, counts = stats_disjoint_absent(ctx, batch, batch.labels.cpu().numpy(), batch.lab_off)
+    else:
+        stats, counts = batch.stats()
+        ctx.check()
+        stats, counts = stats.cpu().numpy(), counts.cpu().numpy()
     batch.close()
-    regions = [g.region or f"window{i}" for i, g in enumerate(graphs)]
-    lengths = [g.length for g in graphs]
+    mark("kernels")
+    if flat is not None:
+        regions = [r or f"window{i}" for i, r in enumerate(flat.regions)]
+        lengths = [int(v) for v in flat.length]
+    else:
+        regions = [g.region or f"window{i}" for i, g in enumerate(graphs)]
+        lengths = [g.length for g in graphs]
     if args.pooled_fst_out:
         per_subset = []
         for ids in (pop_a, pop_b, set(pop_a) | set(pop_b)):           # run_fst_impg.sh:143-147: C = union list
-            b = batch_from_graphs(ctx, graphs, subset_ids=ids)
+            b = make(subset_ids=ids)
             per_subset.append(b.stats()[0].cpu().numpy())
             ctx.check()
             b.close()
         with (sys.stdout if args.pooled_fst_out == "-" else open(args.pooled_fst_out, "w")) as out:
             write_tsv(out, "pooled_fst", pooled_fst_rows(regions, lengths, *per_subset))
+    d_text = None
+    if args.tajd_out:
+        # run_tajd.sh:166-180: tj_d.py receives the pi pica2 PRINTED (8 decimals) and the sample count
+        from .tj_d import tajimas_d_batch
+        nS = [int(len(subset)) if (args.tajd_samples_from_list and subset is not None) else int(c[0]) for c in counts]
+        pis = [float(f"{(row[ST['pi_per_site']] if L else row[ST['pi']]):.8f}") for row, L in zip(stats, lengths)]
+        ok = [k for k in range(len(nS)) if nS[k] >= 2]
+        d_text = [float("nan")] * len(nS)
+        if ok:
+            vals = tajimas_d_batch([nS[k] for k in ok], [float(counts[k][7]) for k in ok], [pis[k] for k in ok], ctx=ctx)
+            for k, v in zip(ok, vals):
+                d_text[k] = v
+    samples = len(subset) if (args.tajd_samples_from_list and subset is not None) else None
     for path, kind, rows in ((args.pi_out, "pi", pi_rows(regions, lengths, stats)),
                              (args.fst_out, "fst", fst_rows(regions, lengths, stats)),
-                             (args.tajd_out, "tajd", tajd_rows(regions, lengths, stats, counts))):
+                             (args.tajd_out, "tajd", tajd_rows(regions, lengths, stats, counts, d_text, samples))):
         if path:
             with (sys.stdout if path == "-" else open(path, "w")) as out:
                 write_tsv(out, kind, rows)
+    mark("format")
+    if args.timings:
+        keys = list(t)
+        print("impop-windows timings (s): " + ", ".join(f"{b} {t[b] - t[a]:.3f}" for a, b in zip(keys, keys[1:]))
+              + f", total {t[keys[-1]] - t['start']:.3f}; windows {len(regions)}", file=sys.stderr)
     return 0

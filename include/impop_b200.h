@@ -129,7 +129,10 @@ int impop_pack_bits(impop_ctx_t *ctx, const uint8_t *dense_dev, int32_t n, int32
 /* Batch set-up: uploads the descriptor tables (asynchronously, from pinned staging), sizes the scratch (path
  * lengths, byte weights, heavy-node table and bits, per-item partial sums).  Device blocks come from a pool kept
  * by the context, so repeated create / destroy does not call cudaMalloc / cudaFree.  With node_len_host given the
- * call does not synchronise; without it there is one small device->host read. */
+ * call does not synchronise; without it there is one small device->host read.
+ * impop_batch_destroy may be called while the batch's kernels are still in flight: its blocks go back to the pool
+ * behind an event on the stream of the batch's last call, and are handed to work on ANOTHER stream only once that event
+ * has completed (work on the same stream is ordered behind the kernels anyway). */
 int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *desc, impop_batch_t **batch_out);
 int impop_batch_destroy(impop_ctx_t *ctx, impop_batch_t *batch);
 int64_t impop_batch_items(const impop_batch_t *batch); /* number of 128 x (<= 256) tile work items */
@@ -174,6 +177,18 @@ int impop_reduce_identity(impop_ctx_t *ctx, const double *ident_dev, int32_t n, 
  * parts_dev (nullable): count x 10 = a1 a2 b1 b2 c1 c2 e1 e2 numerator denominator. */
 int impop_tajima_d(impop_ctx_t *ctx, const int64_t *n_dev, const double *S_dev, const double *pi_dev,
                    int32_t count, double *D_dev, double *parts_dev, void *stream);
+
+/* round(x, digits) of every element, in place, exactly as CPython rounds a float (pica2.py:81-83 and h-fst.py:149-150
+ * call round(sim, r) on every table value): the double's decimal value rounded half-even at that decimal, then the
+ * nearest double.  0 <= digits <= 22.  NaN (pair absent) and infinities stay. */
+int impop_round_decimal(impop_ctx_t *ctx, double *values_dev, int64_t count, int32_t digits, void *stream);
+
+/* Plain device memory for callers without a tensor library (the TSV-mode command lines: scripts/pica2.py, h-fst.py,
+ * af.py, tj_d.py, hud.py run without importing torch).  impop_dev_copy: kind 0 host -> device, 1 device -> host,
+ * 2 device -> device; synchronous with respect to `stream`. */
+int impop_dev_alloc(impop_ctx_t *ctx, int64_t bytes, void **ptr_out);
+int impop_dev_free(impop_ctx_t *ctx, void *ptr);
+int impop_dev_copy(impop_ctx_t *ctx, void *dst, const void *src, int64_t bytes, int32_t kind, void *stream);
 
 /* K4, BASELINE config 4: per-site allele counts of a site-major bit matrix (sites x words u64,
  * bit h of a row = haplotype h carries the allele) under `pops` population masks (pops x words u64).

@@ -1,0 +1,171 @@
+"""Round-2 additions on the device: exact decimal rounding, ingest-time column compaction through the
+fused kernels, the torch-free command lines (lite context), stream-aware scratch pool."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from impop_b200.engine import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+HARD = [0.5, 1.5, 2.5, 0.125, 0.375, 0.625, 0.0625, 0.15, 0.25, 0.35, 0.45, 2.675, 1.005, 0.285, 1.115, 8.345, 0.00005, 0.000015,
+        0.99999, 0.999995, 0.9999949999999999, 0.9999950000000001, 1e-9, 5e-6, 4.9999999999999996e-06, 123456.789, 1e15, 4503599627370497.0,
+        1e22, 1e300, 0.0, -0.0, -0.5, -1.5, -2.675, -0.125, float("nan"), float("inf"), -float("inf"),
+        0.49999999999999994, 0.5000000000000001, 5e-324, 2.2250738585072014e-308]
+
+
+@pytest.mark.parametrize("digits", [0, 1, 2, 3, 5, 8, 12, 17, 22])
+def test_round_decimal_matches_cpython(ctx, digits):
+    import torch
+    rng = np.random.default_rng(100 + digits)
+    vals = np.concatenate([
+        np.array(HARD, dtype=np.float64),
+        rng.random(400_000),                                             # identities
+        1.0 - rng.random(200_000) * 1e-3,                                # near 1, as real identities are
+        np.round(rng.random(100_000), min(digits + 1, 15)) ,             # decimal ties and near-ties at the next digit
+        (rng.integers(0, 10 ** min(digits + 1, 15), 100_000) * 2 + 1) / (2.0 * 10.0 ** min(digits, 15)),   # k + 1/2 patterns
+        rng.standard_normal(50_000) * 10.0 ** rng.integers(-8, 12, 50_000),
+    ])
+    dev = torch.from_numpy(vals.copy()).to(ctx.torch_device)
+    ctx.round_decimal(dev, digits)
+    ctx.check()
+    got = dev.cpu().numpy()
+    want = np.array([v if (v != v or math.isinf(v)) else round(v, digits) for v in vals.tolist()], dtype=np.float64)
+    same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want)) | ((got == 0) & (want == 0))
+    bad = np.flatnonzero(~same)
+    assert bad.size == 0, [(float(vals[k]), float(got[k]), float(want[k])) for k in bad[:5]]
+
+
+def test_round_digits_through_the_table_path(ctx):
+    """pica2 -r / h-fst -r: the table's device copy is rounded by the kernel; same values as a host round() per element."""
+    from impop_b200.tables import SimilarityTable
+    rng = np.random.default_rng(5)
+    n = 60
+    m = 1.0 - rng.random((n, n)) * 1e-2
+    m = np.triu(m, 1) + np.triu(m, 1).T
+    m[3, 7] = m[7, 3] = np.nan
+    tab = SimilarityTable([f"s{i:03d}" for i in range(n)], m)
+    for digits in (3, 5):
+        dev = tab.device(ctx, digits).cpu().numpy()
+        want = tab.rounded(digits)
+        assert np.array_equal(np.isnan(dev), np.isnan(want))
+        assert np.array_equal(dev[~np.isnan(dev)], want[~np.isnan(want)])
+
+
+def test_compacted_batch_gives_the_same_rows(ctx):
+    """Ingest-time column compaction (impop_compact_scan / _fill) leaves every count and statistic of the fused path as it
+    was: ragged windows with constant, empty, zero-length and heavy columns, both algorithms."""
+    from impop_b200 import ingest
+    from impop_b200.engine import ALGO_SIMT, ALGO_TCGEN05, WindowBatch
+    from oracle import similarity
+    rng = np.random.default_rng(77)
+    wins, cwins = [], []
+    for n, m, heavy in ((37, 70, False), (130, 300, True), (466, 1009, False), (200, 1500, True), (5, 3, False)):
+        x = (rng.random((n, m)) < rng.random(m)[None, :]).astype(np.uint8)
+        kind = rng.random(m)
+        x[:, kind < 0.3] = 1
+        x[:, (kind >= 0.3) & (kind < 0.4)] = 0
+        nl = rng.integers(1, 100000 if heavy else 60, size=m).astype(np.uint32)
+        nl[rng.random(m) < 0.5] = 1
+        nl[rng.random(m) < 0.1] = 0
+        lab = np.full(n, 9, dtype=np.uint8)
+        lab[: n // 3] |= 2
+        lab[n // 3: n // 2] |= 4
+        lab[rng.random(n) < 0.1] &= 0xF6                     # a few rows outside SUBSET / SEG
+        bits = similarity.pack_bits(x)
+        wins.append((bits, nl, lab, 1234))
+        g = ingest.compact_window(ingest.GraphWindow([f"h{i}" for i in range(n)], bits, nl))
+        assert g.m < m
+        cwins.append((g.x_bits, g.node_len, lab, 1234))
+    a, b = WindowBatch.from_windows(ctx, wins), WindowBatch.from_windows(ctx, cwins)
+    for algo in (ALGO_TCGEN05, ALGO_SIMT):
+        sa, ca = a.stats(algo)
+        sb, cb = b.stats(algo)
+        ctx.check()
+        assert np.array_equal(ca.cpu().numpy(), cb.cpu().numpy())
+        sa, sb = sa.cpu().numpy(), sb.cpu().numpy()
+        assert np.array_equal(np.isnan(sa), np.isnan(sb))
+        ok = np.isnan(sa) | (np.abs(sa - sb) <= 1e-13 * np.maximum(np.abs(sa), np.abs(sb)))
+        assert ok.all(), np.argwhere(~ok)[:5]
+    I0, A0, p0 = a.pairwise(1)
+    I1, A1, p1 = b.pairwise(1)
+    ctx.check()
+    assert np.array_equal(I0.cpu().numpy(), I1.cpu().numpy()) and np.array_equal(A0.cpu().numpy(), A1.cpu().numpy())
+    assert np.array_equal(p0.cpu().numpy(), p1.cpu().numpy())            # pi_ij bit for bit
+    a.close(); b.close()
+
+
+def test_command_lines_run_without_torch(tmp_path):
+    """TSV mode: scripts/pica2.py, h-fst.py, af.py and tj_d.py use the lite context (plain device buffers over the C ABI);
+    the wrappers start them once per window, so the torch import must never happen there."""
+    from impop_b200 import synth
+    from oracle import similarity
+    ws = synth.make_windows(24, 20000, 1, seed=3)
+    res = similarity.pairwise(ws.dense(0), ws.node_len[0])
+    names = synth.haplotype_names(24, "chr2", 1000, 21000)
+    tsv = tmp_path / "w.sim.tsv"
+    similarity.write_similarity_tsv(str(tsv), names, res)
+    (tmp_path / "a.txt").write_text("\n".join(synth.assembly_names(range(0, 8))) + "\n")
+    (tmp_path / "b.txt").write_text("\n".join(synth.assembly_names(range(8, 16))) + "\n")
+    for mod, argv in (("pica2", [str(tsv), "-t", "1.0", "-l", "20000", "-r", "5", "-d", str(tmp_path)]),
+                      ("hfst", [str(tsv), "-a", str(tmp_path / "a.txt"), "-b", str(tmp_path / "b.txt"), "-l", "20000", "-r", "4", "-d", str(tmp_path)]),
+                      ("af", ["--input", str(tsv), "--threshold", "0.999", "--output", str(tmp_path / "af.tsv")]),
+                      ("tj_d", ["-n", "446", "-p", "0.59146123", "-S", "20"])):
+        code = (f"import sys; sys.path.insert(0, {ROOT!r}); sys.argv = ['x'] + {argv!r}\n"
+                f"from impop_b200.{mod} import main\n"
+                "rc = main()\n"
+                "assert 'torch' not in sys.modules, 'torch was imported'\n"
+                "sys.exit(rc or 0)\n")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+        assert r.returncode == 0, (mod, r.stdout[-500:], r.stderr[-1500:])
+        if mod == "tj_d":
+            assert r.stdout.strip() == "Tajima's D: -1.992648227415639"
+
+
+def test_scratch_pool_across_streams(ctx):
+    """A batch destroyed while its kernels are in flight: its blocks are not handed to another stream's batch before the
+    first stream's work has finished (event-guarded pool) -- results of interleaved create / stats / destroy on two streams
+    equal the serial ones."""
+    import torch
+    from impop_b200 import synth
+    from impop_b200.engine import WindowBatch
+    ws = synth.make_windows(200, 20000, 24, seed=11)
+    lab = np.full(200, 9, dtype=np.uint8)
+    ref = WindowBatch.from_uniform(ctx, ws.x_bits, ws.node_len, lab, 20000)
+    want_s, want_c = ref.stats()
+    ctx.check()
+    want_s, want_c = want_s.cpu().numpy(), want_c.cpu().numpy()
+    ref.close()
+    xd = torch.from_numpy(ws.x_bits.view(np.int32)).to(ctx.torch_device)
+    ld = torch.from_numpy(ws.node_len.view(np.int32)).to(ctx.torch_device)
+    labd = torch.from_numpy(lab).to(ctx.torch_device)
+    streams = [torch.cuda.Stream(device=ctx.torch_device) for _ in range(2)]
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(6):
+        st = streams[rep % 2]
+        with torch.cuda.stream(st):
+            b = WindowBatch.from_uniform(ctx, xd, ld, labd, 20000, stream=st)
+            s, c = b.stats(stream=st)
+            b.close()                                     # kernels still in flight
+            outs.append((s, c))
+    torch.cuda.synchronize()
+    ctx.check()
+    for s, c in outs:
+        assert np.array_equal(c.cpu().numpy(), want_c)
+        got = s.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want_s))
+        assert (np.isnan(got) | (np.abs(got - want_s) <= 1e-12 * np.abs(want_s))).all()

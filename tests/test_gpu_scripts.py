@@ -261,7 +261,7 @@ def test_reduce_identity_with_missing_pairs(ctx):
     # with absent pairs pica2's n/(n-1) * sum uses the present pairs only -- same on the device
     assert rel_close(stats[0], pi, TOL) and rel_close(stats[1], pps, TOL)
     d, _ = popstats.tajimas_d(n, 37.0, pps)
-    assert stats[9] == d or rel_close(stats[9], d, 1e-9)
+    assert stats[9] == d or rel_close(stats[9], d, TOL)         # plain 1e-12 relative (north star)
 
 
 def test_greedy_groups_transitive_and_threshold_edges(ctx):
@@ -288,7 +288,7 @@ def test_greedy_groups_transitive_and_threshold_edges(ctx):
     for a in range(n):
         for b in range(n):
             assert (g[a] == g[b]) == (member[a] == member[b])
-    assert abs(float(weight.sum().cpu()) - 1.0) < 1e-12
+    assert abs(float(weight.cpu().numpy().sum()) - 1.0) < 1e-12
 
 
 def test_cluster_random_graph(ctx):

@@ -206,3 +206,35 @@ def test_compact_uniform_batch_threads():
         assert mo[w] == x2.shape[1] <= 2 * K + 1
         assert np.array_equal(similarity.unpack_bits(xo[w], int(mo[w])), x2)
         assert np.array_equal(lo[w, :mo[w]].astype(np.int64), nl2) and not lo[w, mo[w]:].any()
+
+
+# ---------------------------------------------------------------------------------- flat window container
+def test_flat_container_round_trip_and_labels(tmp_path):
+    ws = synth.make_windows(30, 20000, 5, seed=5)
+    wins = []
+    for w in range(5):
+        names = synth.haplotype_names(30, "chr2", 1000 * w, 1000 * w + 20000)
+        if w == 3:
+            names = names[::-1]                           # another row order in one window
+        wins.append(ingest.GraphWindow(names, ws.x_bits[w], ws.node_len[w, :ws.m].copy(), None,
+                                       f"CHM13#0#chr2:{1000 * w}-{1000 * w + 20000}", 20000))
+    wins.append(ingest.GraphWindow(["plain_name", "other"], np.zeros((2, 4), np.uint32), np.array([3, 0, 7], np.uint32), None, None, 0))
+    path = tmp_path / "w.impw"
+    ingest.save_flat(path, wins)
+    for mmap in (True, False):
+        fb = ingest.load_flat(path, mmap=mmap)
+        assert fb.windows == 6 and len(fb.uniq) == 32
+        for w, g in enumerate(wins):
+            h = fb.window(w)
+            assert h.names == g.names and h.region == g.region and h.length == g.length
+            assert np.array_equal(h.x_bits, g.x_bits) and np.array_equal(h.node_len, g.node_len)
+        lab = fb.labels(pop_a=["S00000#1#", "S00001#"], pop_b=["S00002#2#"], subset=["S0000"])
+        for w, g in enumerate(wins):
+            pa = {s for s in g.names if s.startswith(("S00000#1#", "S00001#"))}
+            pb = {s for s in g.names if s.startswith("S00002#2#")}
+            sub = {s for s in g.names if s.startswith("S0000")}
+            want = ingest.labels_from_names(g.names, pa, pb, sub, sub)
+            assert np.array_equal(lab[int(fb.row_off[w]):int(fb.row_off[w]) + g.n], want), w
+    with pytest.raises(ValueError):
+        (tmp_path / "bad").write_bytes(b"\0" * 128)
+        ingest.load_flat(tmp_path / "bad")
