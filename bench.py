@@ -167,11 +167,12 @@ def make_workload(gen, cfg: dict, windows: int, seed: int, threads: int, keep_or
     t0 = time.perf_counter()
     xc, lc, m_out = ingest.compact_uniform(xh, lh, threads=threads)
     t1 = time.perf_counter()
+    site_runs = ingest.compact_uniform.last_site_runs
     heavy = ((lc.astype(np.int64) // 255 + 254) // 255).sum(axis=1)               # heavy-table entries per window
     k_exec = ((m_out.astype(np.int64) + KCHUNK - 1) // KCHUNK + (heavy + KCHUNK - 1) // KCHUNK) * KCHUNK
     nl_max = int(lh.max()) if lh.size else 0
     planes = 1 if nl_max < 256 else (2 if nl_max < 65536 else (3 if nl_max < (1 << 24) else 4))
-    return {"x": xc, "len": lc, "m_out": m_out, "pops": pops, "labels": labels_for(cfg["labels"], pops), "n": n, "L": L,
+    return {"x": xc, "len": lc, "m_out": m_out, "site_runs": site_runs, "pops": pops, "labels": labels_for(cfg["labels"], pops), "n": n, "L": L,
             "m_in": int(m), "m_pad_in": int(m_pad), "pitch": int(xc.shape[2]), "m_pad": int(lc.shape[1]), "planes": planes,
             "k_exec": k_exec, "ingest_s": t1 - t0, "ingest_threads": threads,
             "orig_x": xh[:keep_original].copy() if keep_original else None,
@@ -466,7 +467,8 @@ def run_ours(args):
     resident_mb = (x_c.numel() * 4 + len_c.numel() * 4) / 1e6
     l2_note = (f"{W} windows of {n * pitch * 4 / 1e6:.1f} MB each ({resident_mb:.0f} MB per GPU), read every step" if split
                else f"inputs larger than L2 ({resident_mb:.0f} MB per GPU read every step)")
-    batch = WindowBatch.from_uniform(ctx, x_c, len_c, labels, L)
+    runs = None if (split or wl is None) else wl["site_runs"]       # variant sites counted at ingest on the original node order
+    batch = WindowBatch.from_uniform(ctx, x_c, len_c, labels, L, site_runs=runs)
     stats = torch.empty((W, NSTATS), dtype=torch.float64, device=dev)
     counts = torch.empty((W, NCOUNTS), dtype=torch.int64, device=dev)
 
@@ -567,7 +569,8 @@ def run_ours(args):
                     dlabs[k].copy_(hlab, non_blocking=True)
                     dl[lo:hi].copy_(hl[lo:hi], non_blocking=True)
                     dx[lo:hi].copy_(hx[lo:hi], non_blocking=True)
-                    b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], L, node_len_host=hl[lo:hi], stream=st)
+                    b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], L, node_len_host=hl[lo:hi], stream=st,
+                                                 site_runs=None if runs is None else runs[lo:hi])
                     b.stats(algo, stream=st, out_stats=ds[lo:hi], out_counts=dc[lo:hi])
                     hs[lo:hi].copy_(ds[lo:hi], non_blocking=True)
                     hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)
@@ -675,6 +678,7 @@ def run_ours(args):
                "sample": f"{S} of {W} windows of this workload (ingested columns) in {dt:.2f} s, plain-C oracle port (byte-LUT intersections) on {ht} pthreads",
                "gpu_matches_oracle_on_sample": {"counts_exact": ok_counts, "stats_within_1e-12": ok_stats, "detail": why},
                "gpu_vs_oracle_on_original_columns": {"windows": K, "counts_exact": bool((got_c[:K] == ct_orig).all()),
+                                                     "variant_sites_exact": bool((got_s[:K, 19] == st_orig[:, 19]).all()),
                                                      "max_plain_relative_error": errs, "strict_1e-12_without_scale_policy": strict}}
 
     others = None

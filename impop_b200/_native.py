@@ -17,7 +17,7 @@ ALGO_TCGEN05, ALGO_SIMT = 0, 1
 KERNELS = {"prep": 0, "pairs": 1, "sums": 2, "colstat": 3, "finalize": 4, "sites": 5}
 ST = {"pi": 0, "pi_per_site": 1, "pi_a": 2, "pi_b": 3, "pi_xy": 4, "dxy": 5, "da": 6, "fst": 7, "S": 8,
       "tajima_d": 9, "a1": 10, "e1": 11, "e2": 12, "n": 13, "sum_S": 14, "sum_AA": 15, "sum_BB": 16,
-      "sum_AB": 17, "tajima_d_raw": 18}
+      "sum_AB": 17, "tajima_d_raw": 18, "S_bubbles": 19}
 
 ERRORS = {-1: "IMPOP_ERR_ARG", -2: "IMPOP_ERR_CUDA", -3: "IMPOP_ERR_NOMEM", -4: "IMPOP_ERR_RANGE", -5: "IMPOP_ERR_DEVICE"}
 
@@ -29,7 +29,7 @@ class BatchDesc(C.Structure):
     """impop_batch_desc_t"""
     _fields_ = [("windows", _i32), ("n_host", _p), ("m_host", _p), ("pitch_words_host", _p), ("x_off_host", _p),
                 ("len_off_host", _p), ("lab_off_host", _p), ("length_host", _p), ("x_dev", _p), ("node_len_dev", _p),
-                ("labels_dev", _p), ("node_len_host", _p), ("stream", _p)]
+                ("labels_dev", _p), ("node_len_host", _p), ("stream", _p), ("site_runs_host", _p)]
 
 
 class GfaInfo(C.Structure):
@@ -75,7 +75,7 @@ SIGNATURES = {
     "impop_tsv_fill": (C.c_int, [C.c_char_p, _i64, _p, _p, _p]),
     "impop_gfa_scan": (C.c_int, [C.c_char_p, _i64, C.POINTER(GfaInfo)]),
     "impop_gfa_fill": (C.c_int, [C.c_char_p, _i64, _i32, _p, _p, _p, _p, _p, C.POINTER(_i64)]),
-    "impop_compact_scan": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p]),
+    "impop_compact_scan": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "impop_compact_fill": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
 }
 

@@ -399,6 +399,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t phase1 = ca.off;
     const size_t o_heavy = ca.take(8 * W1), o_w8 = ca.take(8 * W1), o_xh = ca.take(8 * W1);
     const size_t o_cnt = ca.take(4 * W1);
+    const size_t o_runs = ca.take(8 * W1);
     const size_t tables_bytes = ca.off;
     b->last_stream = st;
     b->tables = pool_get(ctx, tables_bytes, st);
@@ -483,7 +484,10 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
         w8_off[w + 1] = w8_off[w] + m64 + hpad;                 // virtual columns: dense | heavy
         xh_off[w + 1] = xh_off[w] + (int64_t)n[w] * (hpad / 32);
     }
-    e = cudaMemcpyAsync(db + o_heavy, hb + o_heavy, o_cnt - o_heavy, cudaMemcpyHostToDevice, st);
+    if (d->site_runs_host && W > 0) memcpy(hb + o_runs, d->site_runs_host, 8 * (size_t)W);
+    t.site_runs_given = (d->site_runs_host && W > 0) ? (const int64_t *)(db + o_runs) : nullptr;
+    if (e == cudaSuccess && t.site_runs_given) e = cudaMemcpyAsync(db + o_runs, hb + o_runs, 8 * (size_t)W, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(db + o_heavy, hb + o_heavy, o_cnt - o_heavy, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) { e = cudaEventRecord(sg->done, st); sg->busy = true; }
     if (e != cudaSuccess) return bail(IMPOP_ERR_CUDA, std::string("upload tables: ") + cudaGetErrorString(e));
 
@@ -496,13 +500,13 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t s_part = cs.take(8 * (size_t)(b->items * PART_STRIDE + 1));
     const size_t s_sums = cs.take(8 * 4 * W1), s_counts = cs.take(8 * IMPOP_NCOUNTS * W1);
     const size_t s_any = cs.take(4 * (size_t)(word_off[W] + 1)), s_all = cs.take(4 * (size_t)(word_off[W] + 1));
-    const size_t s_hn = cs.take(4 * W1);
+    const size_t s_hn = cs.take(4 * W1), s_runs = cs.take(4 * W1);
     b->scratch = pool_get(ctx, cs.off, st);
     if (!b->scratch) return bail(IMPOP_ERR_NOMEM, "impop_batch_create: out of device memory (scratch)");
     char *sb = (char *)b->scratch;
     t.A = (int32_t *)(sb + s_A); t.w8 = (uint8_t *)(sb + s_w8); t.w8n = (uint8_t *)(sb + s_w8n); t.planes = (uint32_t *)(sb + s_planes); t.heavy = (uint32_t *)(sb + s_heavy);
     t.xh = (uint32_t *)(sb + s_xh); t.seg_any = (uint32_t *)(sb + s_any); t.seg_all = (uint32_t *)(sb + s_all);
-    t.heavy_n = (int32_t *)(sb + s_hn);
+    t.heavy_n = (int32_t *)(sb + s_hn); t.site_runs = (int32_t *)(sb + s_runs);
     b->partials = (double *)(sb + s_part); b->sums_tmp = (double *)(sb + s_sums); b->counts_tmp = (int64_t *)(sb + s_counts);
     b->item_off = item_off;
     b->n.assign(n, n + W);

@@ -552,6 +552,7 @@ struct CompactPlan {
     std::vector<int32_t> order;      // surviving variable nodes, output order
     uint64_t const_len = 0;          // summed length of the nodes every row visits
     int32_t m_out = 0;
+    int64_t site_runs = 0;           // runs of segregating nodes between nodes every row visits (original node order)
 };
 
 void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const uint32_t *len, CompactPlan &pl) {
@@ -563,11 +564,16 @@ void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const 
     }
     pl.order.clear();
     pl.const_len = 0;
+    pl.site_runs = 0;
+    bool in_run = false;
     for (int32_t k = 0; k < m; ++k) {
         if (len[k] == 0u) continue;
         const uint32_t bit = 1u << (k & 31);
-        if (n > 0 && (all[k >> 5] & bit)) pl.const_len += len[k];
-        else if (any[k >> 5] & bit) pl.order.push_back(k);
+        if (n > 0 && (all[k >> 5] & bit)) { pl.const_len += len[k]; in_run = false; }
+        else if (any[k >> 5] & bit) {
+            pl.order.push_back(k);
+            if (!in_run) { ++pl.site_runs; in_run = true; }
+        }
     }
     std::stable_sort(pl.order.begin(), pl.order.end(), [&](int32_t a, int32_t b) { return len[a] < len[b]; });
     pl.m_out = (int32_t)pl.order.size() + (pl.const_len > 0 ? 1 : 0);
@@ -589,7 +595,7 @@ extern "C" {
 
 int impop_compact_scan(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
                        const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
-                       int32_t *m_out) {
+                       int32_t *m_out, int64_t *site_runs_out) {
     if (windows < 0 || (windows > 0 && (!n || !m || !pitch_words || !x_off || !len_off || !m_out))) return IMPOP_ERR_ARG;
     for (int32_t w = 0; w < windows; ++w)
         if (n[w] < 0 || m[w] < 0 || (int64_t)pitch_words[w] * 32 < m[w] || (m[w] > 0 && n[w] > 0 && (!x_bits || !node_len)))
@@ -598,6 +604,7 @@ int impop_compact_scan(int32_t windows, const int32_t *n, const int32_t *m, cons
         CompactPlan pl;
         compact_plan(n[w], m[w], pitch_words[w], x_bits + x_off[w], node_len + len_off[w], pl);
         m_out[w] = pl.m_out;
+        if (site_runs_out) site_runs_out[w] = pl.site_runs;
     });
     return IMPOP_OK;
 }

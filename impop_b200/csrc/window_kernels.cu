@@ -242,6 +242,11 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
     }
 }
 
+// S (segregating nodes) and the number of variant SITES in the sense of a bubble caller (run_tajd.sh:126-148 counts the
+// records `povu gfa2vcf` prints: one per bubble of the window graph, not one per node): with the nodes in graph order, a
+// site is a maximal run of segregating nodes that no node carried by EVERY SEG row interrupts; nodes no SEG row carries and
+// zero-length nodes neither extend nor interrupt a run.  (A bi-allelic SNP bubble = two segregating nodes = one site.)
+// Parity unpinned (povu is not in the reference tree); restated in oracle/similarity.py:site_runs.
 __global__ void seg_count_kernel(const __grid_constant__ WindowTab tab, int64_t *counts) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
@@ -252,19 +257,54 @@ __global__ void seg_count_kernel(const __grid_constant__ WindowTab tab, int64_t 
         const int words = (m + 31) >> 5;
         int64_t *row = counts + (size_t)w * IMPOP_NCOUNTS;
         const bool have_rows = row[7] > 0;                       // prep_cols left the number of SEG rows here
-        int seg = 0;
-        for (int wd = lane; wd < words && have_rows; wd += 32) {
-            uint32_t sg = tab.seg_any[wo + wd] & ~tab.seg_all[wo + wd];
-            while (sg) {
-                const int k = wd * 32 + (__ffs(sg) - 1);
-                if (k < m && __ldg(len + k) > 0u) ++seg;
-                sg &= sg - 1;
+        int seg = 0, runs = 0;
+        bool carry = false;                                       // the last relevant node so far is segregating (lane-uniform)
+        for (int w0 = 0; w0 < words && have_rows; w0 += 32) {
+            const int wd = w0 + lane;
+            uint32_t sg = 0u, sep = 0u;
+            if (wd < words) {
+                const uint32_t any = tab.seg_any[wo + wd], all = tab.seg_all[wo + wd];
+                uint32_t live = 0u;                               // nodes < m of positive length
+                for (int b = 0; b < 32; ++b) {
+                    const int k = wd * 32 + b;
+                    if (k < m && __ldg(len + k) > 0u) live |= 1u << b;
+                }
+                sg = any & ~all & live;
+                sep = all & live;
+            }
+            seg += __popc(sg);
+            // word summary: runs that start inside the word, and the kind of its first / last relevant node
+            uint32_t rel = sg | sep;
+            int internal = 0;
+            bool have_prev = false, prev_seg = false, first_seg = false;
+            while (rel) {
+                const uint32_t b = rel & (0u - rel);
+                const bool is_seg = (sg & b) != 0u;
+                if (!have_prev) { first_seg = is_seg; have_prev = true; }
+                else if (is_seg && !prev_seg) ++internal;
+                prev_seg = is_seg;
+                rel ^= b;
+            }
+            // chain the 32 word summaries in order (lane 0 .. 31)
+            for (int l = 0; l < 32; ++l) {
+                const int hv = __shfl_sync(0xffffffffu, (int)have_prev, l);
+                const int fs = __shfl_sync(0xffffffffu, (int)first_seg, l);
+                const int ls = __shfl_sync(0xffffffffu, (int)prev_seg, l);
+                const int in = __shfl_sync(0xffffffffu, internal, l);
+                if (hv) {
+                    runs += in + ((fs && !carry) ? 1 : 0);
+                    carry = ls != 0;
+                }
             }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) seg += __shfl_xor_sync(0xffffffffu, seg, off);
         __syncwarp();
-        if (lane == 0) row[7] = seg;
+        if (lane == 0) {
+            row[7] = seg;
+            const int64_t given = tab.site_runs_given ? tab.site_runs_given[w] : -1;
+            tab.site_runs[w] = given >= 0 ? (int32_t)given : runs;
+        }
     }
 }
 
@@ -1177,6 +1217,7 @@ __global__ void finalize_kernel(const __grid_constant__ WindowTab tab, const dou
 #pragma unroll
         for (int k = 0; k < IMPOP_NCOUNTS; ++k) cnt[k] = counts[(size_t)w * IMPOP_NCOUNTS + k];
         finalize_row(s, cnt, tab.L[w], (double)cnt[7], tab.harm, tab.harm_n, stats + (size_t)w * IMPOP_NSTATS);
+        stats[(size_t)w * IMPOP_NSTATS + IMPOP_ST_S_BUBBLES] = (double)tab.site_runs[w];
     }
 }
 

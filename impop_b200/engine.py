@@ -217,7 +217,7 @@ class WindowBatch:
     """
 
     def __init__(self, ctx: Context, n, m, pitch_words, x_off, len_off, lab_off, length,
-                 x: torch.Tensor, node_len: torch.Tensor, labels: torch.Tensor, node_len_host=None, stream=None):
+                 x: torch.Tensor, node_len: torch.Tensor, labels: torch.Tensor, node_len_host=None, stream=None, site_runs=None):
         self.ctx = ctx
         self.n = np.ascontiguousarray(n, dtype=np.int32)
         self.m = np.ascontiguousarray(m, dtype=np.int32)
@@ -228,9 +228,11 @@ class WindowBatch:
         self.length = np.ascontiguousarray(length, dtype=np.int64)
         self.windows = int(self.n.shape[0])
         self.x, self.node_len, self.labels = x, node_len, labels      # keep the device buffers alive
+        # site_runs: IMPOP_ST_S_BUBBLES per window as counted at ingest on the original node order (None: counted on the device)
+        self.site_runs = None if site_runs is None else np.ascontiguousarray(site_runs, dtype=np.int64)
         d = N.BatchDesc(self.windows, _ptr(self.n), _ptr(self.m), _ptr(self.pitch_words), _ptr(self.x_off),
                         _ptr(self.len_off), _ptr(self.lab_off), _ptr(self.length), _ptr(x), _ptr(node_len),
-                        _ptr(labels), _ptr(node_len_host), _stream_ptr(stream))
+                        _ptr(labels), _ptr(node_len_host), _stream_ptr(stream), _ptr(self.site_runs))
         h = C.c_void_p()
         rc = ctx.lib.impop_batch_create(ctx.handle, C.byref(d), C.byref(h))
         if rc != 0:
@@ -240,7 +242,7 @@ class WindowBatch:
     # ------------------------------------------------------------------ constructors
     @classmethod
     def from_uniform(cls, ctx: Context, x_bits, node_len, labels, length, m: int | None = None, node_len_host=None,
-                     stream=None):
+                     stream=None, site_runs=None):
         """W same-shape windows: x_bits [W, n, pitch] u32, node_len [W, m_pad] u32, labels [n] or [W, n] u8.
 
         Arguments may be numpy arrays (copied to the device) or device tensors (used in place).
@@ -256,10 +258,10 @@ class WindowBatch:
         L = np.full(W, int(length or 0), dtype=np.int64) if np.isscalar(length) or length is None else np.asarray(length)
         return cls(ctx, np.full(W, n), np.full(W, m_pad if m is None else m), np.full(W, pitch), ar * (n * pitch),
                    ar * m_pad, ar * n if per_window_labels else np.zeros(W, dtype=np.int64), L, xd, ld, lab,
-                   node_len_host=node_len_host, stream=stream)
+                   node_len_host=node_len_host, stream=stream, site_runs=site_runs)
 
     @classmethod
-    def from_windows(cls, ctx: Context, windows):
+    def from_windows(cls, ctx: Context, windows, site_runs=None):
         """Ragged batch from a list of (x_bits [n, pitch] u32, node_len [m] u32, labels [n] u8, L) host arrays."""
         n, m, pitch, x_off, len_off, lab_off, L = [], [], [], [], [], [], []
         xs, ls, labs = [], [], []
@@ -284,7 +286,7 @@ class WindowBatch:
         x = _u32_tensor(cat(xs, np.uint32)).to(dev)
         nl = _u32_tensor(cat(ls, np.uint32)).to(dev)
         lab = torch.from_numpy(cat(labs, np.uint8)).to(dev)
-        return cls(ctx, n, m, pitch, x_off, len_off, lab_off, L, x, nl, lab)
+        return cls(ctx, n, m, pitch, x_off, len_off, lab_off, L, x, nl, lab, site_runs=site_runs)
 
     # ------------------------------------------------------------------ life cycle
     def close(self):

@@ -27,6 +27,7 @@ class GraphWindow:
     counts: np.ndarray | None = None   # [n, m] uint16 visit counts (multiset coverage), when requested
     region: str | None = None
     length: int = 0        # window length L in bp (BED end - start); 0 = unknown
+    site_runs: int = -1    # variant sites (bubble-like runs of segregating nodes) counted before compaction; -1: not counted
 
     @property
     def n(self) -> int:
@@ -355,8 +356,11 @@ def compact_batch(n, m, pitch_words, x_off, len_off, x_bits, node_len, threads=N
     W = int(n.shape[0])
     th = _host_threads(threads)
     m_out = np.zeros(W, dtype=np.int32)
+    runs = np.zeros(W, dtype=np.int64)
     rc = L.impop_compact_scan(W, n.ctypes.data, m.ctypes.data, pitch_words.ctypes.data, x_off.ctypes.data,
-                              len_off.ctypes.data, x_bits.ctypes.data, node_len.ctypes.data, th, m_out.ctypes.data)
+                              len_off.ctypes.data, x_bits.ctypes.data, node_len.ctypes.data, th, m_out.ctypes.data,
+                              runs.ctypes.data)
+    compact_batch.last_site_runs = runs              # variant sites (bubble-like runs) of each window in its original node order
     if rc:
         raise NativeError(rc, "impop_compact_scan")
     pitch_out = np.maximum(4, ((m_out + 127) // 128) * 4).astype(np.int32)
@@ -386,6 +390,7 @@ def compact_uniform(x_bits: np.ndarray, node_len: np.ndarray, threads=None):
                                                            ar * (n * pitch), ar * m_pad, x_bits, node_len, threads,
                                                            uniform_pitch=True)
     po = int(pitch_out[0]) if W else 4
+    compact_uniform.last_site_runs = compact_batch.last_site_runs
     return x_out.reshape(W, n, po), len_out.reshape(W, po * 32), m_out
 
 
@@ -394,4 +399,6 @@ def compact_window(win: GraphWindow) -> GraphWindow:
     m_out, pitch_out, _, _, x_out, len_out = compact_batch([win.n], [win.m], [win.x_bits.shape[1]], [0], [0], win.x_bits,
                                                            win.node_len, threads=1)
     mo, po = int(m_out[0]), int(pitch_out[0])
-    return GraphWindow(list(win.names), x_out.reshape(win.n, po), len_out[:mo].copy(), None, win.region, win.length)
+    out = GraphWindow(list(win.names), x_out.reshape(win.n, po), len_out[:mo].copy(), None, win.region, win.length)
+    out.site_runs = int(compact_batch.last_site_runs[0])     # counted on the original node order (IMPOP_ST_S_BUBBLES)
+    return out

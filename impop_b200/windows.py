@@ -97,7 +97,8 @@ def batch_from_graphs(ctx, graphs, pop_a_ids=None, pop_b_ids=None, subset_ids=No
         sub = expand_population(subset_ids, g.names)[0] if subset_ids else None
         lab = ingest.labels_from_names(g.names, pa, pb, sub, sub)
         wins.append((g.x_bits, g.node_len, lab, g.length))
-    return WindowBatch.from_windows(ctx, wins)
+    runs = [getattr(g, "site_runs", -1) for g in graphs]      # counted before compaction (the node order is gone afterwards)
+    return WindowBatch.from_windows(ctx, wins, site_runs=runs if any(r >= 0 for r in runs) else None)
 
 
 def batch_from_flat(ctx, flat, pop_a_ids=None, pop_b_ids=None, subset_ids=None):
@@ -185,6 +186,9 @@ def main(argv=None):
     ap.add_argument("--no-compact", action="store_true", help="keep every node as a matrix column (default: constant columns merged, empty ones dropped at ingest)")
     ap.add_argument("--disjoint-absent", action="store_true",
                     help="a pair of paths sharing no node is treated as absent from the table (not counted), as the scripts treat a row the similarity tool did not print")
+    ap.add_argument("--tajd-sites", choices=["nodes", "bubbles"], default="nodes",
+                    help="S of Tajima's D: segregating nodes (default) or variant sites counted like a bubble caller's VCF records "
+                         "(runs of segregating nodes between nodes every haplotype carries; run_tajd.sh:126-148 counts povu's records)")
     ap.add_argument("--tajd-samples-from-list", action="store_true", help="SAMPLES / n of Tajima's D = size of the -s list (run_tajd.sh:83) instead of the rows found per window")
     ap.add_argument("--timings", action="store_true", help="print stage times (parse / ingest / upload / kernels / format) on stderr")
     ap.add_argument("--device", type=int, default=0)
@@ -267,6 +271,9 @@ def main(argv=None):
     if args.tajd_out:
         # run_tajd.sh:166-180: tj_d.py receives the pi pica2 PRINTED (8 decimals) and the sample count
         from .tj_d import tajimas_d_batch
+        if args.tajd_sites == "bubbles":
+            counts = counts.copy()
+            counts[:, 7] = np.asarray(stats)[:, ST["S_bubbles"]].astype(np.int64)
         nS = [int(len(subset)) if (args.tajd_samples_from_list and subset is not None) else int(c[0]) for c in counts]
         pis = [float(f"{(row[ST['pi_per_site']] if L else row[ST['pi']]):.8f}") for row, L in zip(stats, lengths)]
         ok = [k for k in range(len(nS)) if nS[k] >= 2]

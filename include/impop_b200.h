@@ -66,7 +66,9 @@ extern "C" {
 #define IMPOP_ST_SUM_BB 16
 #define IMPOP_ST_SUM_AB 17
 #define IMPOP_ST_TAJIMA_D_RAW 18 /* tj_d.py on (n, S, pi) with pi not divided by L */
-#define IMPOP_ST_RESERVED 19
+#define IMPOP_ST_S_BUBBLES 19    /* variant sites as a bubble caller counts them (run_tajd.sh:126-148: records of `povu gfa2vcf`): maximal runs,
+                                   in node order, of segregating nodes not interrupted by a node every SEG row carries; parity unpinned.
+                                   After ingest-time compaction the node order is gone: pass the count taken before (site_runs_host). */
 
 /* Columns of one counts row (int64). */
 #define IMPOP_NCOUNTS 8 /* nS nA nB pairsS pairsAA pairsBB pairsAB S */
@@ -97,6 +99,8 @@ typedef struct {
                                         any device->host read, i.e. fully asynchronously on `stream` */
     void *stream;                    /* cudaStream_t the set-up copies are enqueued on (NULL = default stream); use the
                                         stream the kernels will run on */
+    const int64_t *site_runs_host;   /* optional [windows]: IMPOP_ST_S_BUBBLES of each window as counted at ingest on the
+                                        original node order (impop_compact_scan); < 0 or NULL: counted on the device */
 } impop_batch_desc_t;
 
 int impop_version(void);
@@ -245,7 +249,7 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
  * words; len_out zero-filled beyond m_out) and impop_compact_fill writes them.  `threads` host threads share the windows. */
 int impop_compact_scan(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
                        const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
-                       int32_t *m_out);
+                       int32_t *m_out, int64_t *site_runs_out /* nullable: IMPOP_ST_S_BUBBLES over all rows, original order */);
 int impop_compact_fill(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
                        const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
                        const int32_t *out_pitch_words, const int64_t *out_x_off, const int64_t *out_len_off,

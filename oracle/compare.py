@@ -18,7 +18,7 @@ import math
 
 TOL = 1e-12
 COLS = ("pi", "pi_per_site", "pi_a", "pi_b", "pi_xy", "dxy", "da", "fst", "S", "tajima_d", "a1", "e1", "e2", "n",
-        "sum_S", "sum_AA", "sum_BB", "sum_AB", "tajima_d_raw", "reserved")
+        "sum_S", "sum_AA", "sum_BB", "sum_AB", "tajima_d_raw", "S_bubbles")
 
 
 def _close(a, b, scale, tol):
@@ -31,8 +31,10 @@ def _close(a, b, scale, tol):
     return abs(a - b) <= tol * scale
 
 
-def row_mismatches(got, want, tol: float = TOL):
-    """List of (column name, got, want, allowed) for the columns of one 20-wide statistics row that disagree."""
+def row_mismatches(got, want, tol: float = TOL, sites: bool = False):
+    """List of (column name, got, want, allowed) for the columns of one 20-wide statistics row that disagree.
+    `sites`: also compare S_bubbles (site runs depend on the node ORDER: only comparable when both sides saw the same
+    column order, i.e. not between an ingest-compacted batch and its original)."""
     got = [float(v) for v in got]
     want = [float(v) for v in want]
     bad = []
@@ -41,6 +43,8 @@ def row_mismatches(got, want, tol: float = TOL):
     den = math.sqrt(e1 * S + e2 * S * (S - 1.0)) if (S > 0 and a1 == a1 and e1 * S + e2 * S * (S - 1.0) > 0) else float("nan")
     for k, name in enumerate(COLS):
         g, w = got[k], want[k]
+        if name == "S_bubbles" and not sites:
+            continue
         if name == "da":
             scale = max(dxy, pi_xy, abs(w))
         elif name == "fst":
@@ -55,10 +59,10 @@ def row_mismatches(got, want, tol: float = TOL):
     return bad
 
 
-def rows_close(got, want, tol: float = TOL):
+def rows_close(got, want, tol: float = TOL, sites: bool = False):
     """(ok, first mismatch description) over 2-D arrays of rows."""
     for r in range(len(want)):
-        bad = row_mismatches(got[r], want[r], tol)
+        bad = row_mismatches(got[r], want[r], tol, sites)
         if bad:
             return False, f"row {r}: {bad[:3]}"
     return True, ""

@@ -185,9 +185,28 @@ int64_t oracle_segregating_nodes(const uint32_t *x, int n, int m, int pitch_word
     return S;
 }
 
+/* Variant sites as a bubble caller would count them (run_tajd.sh:126-148 counts `povu gfa2vcf` records; povu is not in the
+ * reference tree: parity unpinned): maximal runs, in node order, of segregating nodes (among the LAB_SEG rows, length > 0) not
+ * interrupted by a node every LAB_SEG row carries; nodes none of them carries and zero-length nodes are transparent. */
+int64_t oracle_site_runs(const uint32_t *x, int n, int m, int pitch_words, const uint32_t *len, const uint8_t *labels) {
+    int64_t runs = 0;
+    int in_run = 0, rows = 0;
+    for (int i = 0; i < n; ++i) rows += (labels[i] & LAB_SEG) != 0;
+    if (!rows) return 0;
+    for (int k = 0; k < m; ++k) {
+        if (len[k] == 0) continue;
+        int c = 0;
+        for (int i = 0; i < n; ++i)
+            if ((labels[i] & LAB_SEG) && ((x[(size_t)i * pitch_words + (k >> 5)] >> (k & 31)) & 1u)) ++c;
+        if (c == rows) in_run = 0;
+        else if (c > 0) { if (!in_run) { ++runs; in_run = 1; } }
+    }
+    return runs;
+}
+
 /* Derived statistics from raw sums -- the definition the device finalize kernel mirrors.
  * stats[20]: 0 pi 1 pi_per_site 2 pi_a 3 pi_b 4 pi_xy 5 dxy 6 da 7 fst 8 S 9 tajima_d 10 a1 11 e1 12 e2 13 n
- *            14 sum_S 15 sum_AA 16 sum_BB 17 sum_AB 18 tajima_d_raw 19 reserved(0)
+ *            14 sum_S 15 sum_AA 16 sum_BB 17 sum_AB 18 tajima_d_raw 19 S_bubbles (set by oracle_window_stats)
  * counts[8]: nS nA nB pairsS pairsAA pairsBB pairsAB S */
 void oracle_finalize(const double sums[4], const int64_t cnt[8], int64_t L, double *stats) {
     int64_t nS = cnt[0];
@@ -266,6 +285,7 @@ int oracle_window_stats(const uint32_t *x, int n, int m, int pitch_words, const 
     double sums[4];
     for (int k = 0; k < 4; ++k) sums[k] = nsum_value(&acc[k]);
     oracle_finalize(sums, cnt, L, stats);
+    stats[19] = (double)oracle_site_runs(x, n, m, pitch_words, len, labels);
     if (counts) memcpy(counts, cnt, sizeof(cnt));
     free(A);
     free(lut.tab);

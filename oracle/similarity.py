@@ -73,6 +73,26 @@ def segregating_nodes(x: np.ndarray, node_len: np.ndarray, rows=None) -> int:
     return int(np.count_nonzero((cnt > 0) & (cnt < xs.shape[0]) & (node_len > 0)))
 
 
+def site_runs(x: np.ndarray, node_len: np.ndarray, rows=None) -> int:
+    """Variant sites as a bubble caller would count them -- the reference's S is the number of `povu gfa2vcf` records of
+    the window graph (run_tajd.sh:126-148), one per bubble rather than one per node.  povu is absent and unpinned, so this
+    is a stated approximation (parity unpinned): with the nodes in graph order, a site is a maximal run of segregating
+    nodes not interrupted by a node EVERY row carries; nodes no row carries and zero-length nodes are transparent."""
+    xs = x if rows is None else x[np.asarray(rows)]
+    if xs.shape[0] == 0:
+        return 0
+    cnt = xs.astype(np.int64).sum(axis=0)
+    runs, in_run = 0, False
+    for k in range(xs.shape[1]):
+        if node_len[k] == 0:
+            continue
+        if cnt[k] == xs.shape[0]:
+            in_run = False
+        elif cnt[k] > 0 and not in_run:
+            runs, in_run = runs + 1, True
+    return runs
+
+
 def pack_bits(x: np.ndarray, pitch_words: int | None = None) -> np.ndarray:
     """Bit-pack rows of a 0/1 matrix into little-endian u32 words.
 

@@ -238,3 +238,28 @@ def test_flat_container_round_trip_and_labels(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "bad").write_bytes(b"\0" * 128)
         ingest.load_flat(tmp_path / "bad")
+
+
+# ---------------------------------------------------------------------------------- variant sites (bubble-like runs)
+def test_site_runs_on_hand_built_graphs():
+    """S as a bubble caller would count it (run_tajd.sh:126-148 counts `povu gfa2vcf` records): the
+    ingest step's count against the restatement, on graphs whose sites are known by construction."""
+    #            backbone | SNP bubble (ref, alt) | backbone | nested / adjacent alleles without backbone between | bb | absent node | bb
+    x = np.array([[1, 1, 0, 1, 1, 0, 0, 1, 0, 1],
+                  [1, 0, 1, 1, 0, 1, 0, 1, 0, 1],
+                  [1, 1, 0, 1, 0, 0, 1, 1, 0, 1],
+                  [1, 1, 0, 1, 1, 0, 0, 1, 0, 1]], dtype=np.uint8)
+    nl = np.array([10, 1, 1, 20, 3, 4, 5, 30, 9, 2], dtype=np.uint32)
+    assert similarity.site_runs(x, nl) == 2 and similarity.segregating_nodes(x, nl) == 5
+    nl0 = nl.copy(); nl0[3] = 0                               # a zero-length backbone node does not separate: one site
+    assert similarity.site_runs(x, nl0) == 1
+    for xx, ll in ((x, nl), (x, nl0), (x[:1], nl), (np.ones((3, 4), np.uint8), np.ones(4, np.uint32)), (np.zeros((3, 4), np.uint8), np.ones(4, np.uint32))):
+        win = ingest.GraphWindow([f"h{i}" for i in range(xx.shape[0])], similarity.pack_bits(xx), ll)
+        assert ingest.compact_window(win).site_runs == similarity.site_runs(xx, ll)
+    ws = synth.make_windows(40, 20000, 3, seed=12)
+    K = (ws.m - 1) // 3
+    for w in range(3):
+        d = ws.dense(w)[:, :ws.m]
+        poly = sum(1 for s in range(K) if 0 < d[:, 2 + 3 * s].sum() < 40)          # sites whose alt allele segregates
+        assert similarity.site_runs(d, ws.node_len[w, :ws.m]) == poly
+        assert 2 * poly == similarity.segregating_nodes(d, ws.node_len[w, :ws.m])
