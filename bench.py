@@ -322,37 +322,56 @@ def bench_windows_short(ctx, torch, peaks, cfg, windows, reps, threads):
             "fp64_frac": eps * 18 / (64.0 * sms * peaks["sm_max_mhz"] * 1e6), "ingest_s": wl["ingest_s"]}
 
 
-def bench_cli_latency(reps=3):
-    """Config 1: wall time of the drop-in `scripts/pica2.py` on one 90-haplotype, 100 kb window (TSV mode: the all-pairs
-    table the similarity tool prints; written here by the matrix-mode driver's own dump).  Process start to exit, i.e.
-    what a wrapper's per-window loop pays (run_pica2_impg.sh:175).  The reference's own figure for this table, measured
-    in the build container, is in profiles/r2_reference_scripts.json."""
+def bench_cli_latency(reps=3, sizes=((90, 100_000), (466, 50_000))):
+    """Config 1 (and its 466-haplotype sibling): wall time of the drop-in command lines `scripts/pica2.py`, `h-fst.py`, `af.py`
+    on one window's all-pairs table (TSV mode: the table the similarity tool prints, written here from the matrix-mode
+    dump).  Process start to exit, i.e. what a wrapper's per-window loop pays (run_pica2_impg.sh:175, run_h-fst.sh:74-85).
+    The unmodified reference scripts on the same tables, timed in the build container: profiles/r2_reference_scripts.json
+    (the reference tree does not travel to the GPU box)."""
     import tempfile
     from impop_b200 import synth
     from impop_b200.engine import Context, WindowBatch
-    ws = synth.make_windows(90, 100_000, 1, seed=0xB200)
-    names = synth.haplotype_names(90, "chr2", 109_000_000, 109_100_000)
+    ref = {}
+    try:
+        rj = json.load(open(os.path.join(ROOT, "profiles", "r2_reference_scripts.json")))
+        for case in rj["cases"].values():
+            ref[case["haplotypes"]] = {k.split()[0]: v["single_process_wall_s"] for k, v in case["scripts"].items() if "-r 5" not in k}
+    except Exception:
+        pass
     ctx = Context(0)
-    b = WindowBatch.from_uniform(ctx, ws.x_bits, ws.node_len, np.full(90, 9, dtype=np.uint8), 100_000)
-    _, _, pi = b.pairwise(0)
-    ident = (1.0 - pi).cpu().numpy()
-    b.close()
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
-        tsv = os.path.join(tmp, "edar.sim.tsv")
-        with open(tsv, "w") as fh:
-            fh.write("group.a\tgroup.b\testimated.identity\n")
-            for i in range(90):
-                for j in range(i + 1, 90):
-                    fh.write(f"{names[i]}\t{names[j]}\t{float(ident[i, j])!r}\n")
-        for script, extra in (("pica2.py", ["-t", "1.0", "-l", "100000", "-d", tmp]),):
-            ts = []
-            for _ in range(reps):
-                t0 = time.perf_counter()
-                r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", script), tsv, *extra], capture_output=True, text=True)
-                ts.append(time.perf_counter() - t0)
-            out[script] = {"wall_s_median": float(np.median(ts)), "wall_s_min": float(min(ts)), "rc": r.returncode,
-                           "stdout": r.stdout.strip()[:80]}
+        for n, L in sizes:
+            ws = synth.make_windows(n, L, 1, seed=0xB200 + (0 if n == 90 else 1))
+            names = synth.haplotype_names(n, "chr2", 109_000_000, 109_000_000 + L)
+            b = WindowBatch.from_uniform(ctx, ws.x_bits, ws.node_len, np.full(n, 9, dtype=np.uint8), L)
+            _, _, pi = b.pairwise(0)
+            ident = (1.0 - pi).cpu().numpy()
+            b.close()
+            tsv = os.path.join(tmp, f"n{n}.sim.tsv")
+            with open(tsv, "w") as fh:
+                fh.write("group.a\tgroup.b\testimated.identity\n")
+                for i in range(n):
+                    fh.write("".join(f"{names[i]}\t{names[j]}\t{float(ident[i, j])!r}\n" for j in range(i + 1, n)))
+            pops, _ = synth.panel(n)
+            asm = synth.assembly_names(range(n))
+            fa, fb = os.path.join(tmp, f"n{n}.a.txt"), os.path.join(tmp, f"n{n}.b.txt")
+            open(fa, "w").write("\n".join(a for a, p in zip(asm, pops) if p == 0) + "\n")
+            open(fb, "w").write("\n".join(a for a, p in zip(asm, pops) if p == 2) + "\n")
+            case = {}
+            for script, extra in (("pica2.py", [tsv, "-t", "1.0", "-l", str(L), "-d", tmp]),
+                                  ("h-fst.py", [tsv, "-a", fa, "-b", fb, "-l", str(L), "-d", tmp]),
+                                  ("af.py", ["--input", tsv, "--threshold", "0.9995", "--output", os.path.join(tmp, "af.out")])):
+                ts = []
+                for _ in range(reps):
+                    t0 = time.perf_counter()
+                    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", script), *extra], capture_output=True, text=True)
+                    ts.append(time.perf_counter() - t0)
+                case[script] = {"wall_s_median": float(np.median(ts)), "wall_s_min": float(min(ts)), "rc": r.returncode,
+                                "stdout": r.stdout.strip().splitlines()[-1][:80] if r.stdout.strip() else "",
+                                "reference_wall_s_build_container": ref.get(n, {}).get(script)}
+            out[f"n{n}"] = case
+    ctx.close()
     return out
 
 
@@ -403,8 +422,11 @@ def run_ours(args):
         return run_sites(args, ctx, torch, dist, peaks, rank, world, local)
     if args.config == 1:
         if rank == 0:
-            print(json.dumps({"metric": "wall seconds of scripts/pica2.py on a 90-haplotype similarity table", "unit": "s",
-                              "higher_is_better": False, "n_gpus": 1, "config": {"workload": "BASELINE config 1"}, **bench_cli_latency(5)}))
+            r = bench_cli_latency(5)
+            print(json.dumps({"metric": "wall seconds of scripts/pica2.py on a 90-haplotype similarity table", "value": r["n90"]["pica2.py"]["wall_s_median"],
+                              "unit": "s", "higher_is_better": False, "n_gpus": 1, "steps": 5, "warmup": 0, "data": "synthetic",
+                              "config": {"workload": "pica2.py nucleotide diversity, one EDAR-shaped 100 kb window, 90 haplotypes, similarity TSV input", "baseline_config": 1},
+                              "command_lines": r}))
         return 0
 
     cfg = CONFIGS[args.config]

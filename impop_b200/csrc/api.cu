@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <math.h>
+#include <time.h>
 
 #include <algorithm>
 #include <thread>
@@ -43,7 +44,8 @@ constexpr int32_t HARM_N = 1 << 16;
 struct impop_ctx {
     int device = 0;
     int sm_count = 0;
-    int prep_per_sm = 2;              // resident prep_rows CTAs per SM on this device
+    int prep_per_sm = 0;              // resident prep_rows CTAs per SM on this device (queried at the first window batch)
+    bool kernels_configured = false;  // shared-memory attribute of the pairs kernel set (first window batch)
     int32_t *err_dev = nullptr;
     double2 *harm_dev = nullptr;
     long long *prof_dev = nullptr;    // role-time counters of the last pairs launch (IMPOP_PROFILE_ROLES builds)
@@ -183,6 +185,8 @@ int impop_create(int device, impop_ctx_t **ctx_out) {
     if (!ctx_out) return IMPOP_ERR_ARG;
     *ctx_out = nullptr;
     int count = 0;
+    struct timespec ts_enter; clock_gettime(CLOCK_MONOTONIC, &ts_enter);
+    const double t_enter = ts_enter.tv_sec + 1e-9 * ts_enter.tv_nsec;
     cudaError_t e0 = cudaGetDeviceCount(&count);
     if (e0 != cudaSuccess || count <= 0 || device < 0 || device >= count) {
         fprintf(stderr, "impop_create: no usable CUDA device (%s, %d devices)\n", cudaGetErrorString(e0), count);
@@ -191,6 +195,10 @@ int impop_create(int device, impop_ctx_t **ctx_out) {
     impop_ctx *ctx = new (std::nothrow) impop_ctx();
     if (!ctx) return IMPOP_ERR_NOMEM;
     ctx->device = device;
+    const bool trace = getenv("IMPOP_TRACE_CREATE") != nullptr;       // where context creation spends its time (stderr)
+    auto now = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    const double t_start = now();
+    if (trace) fprintf(stderr, "impop_create: cudaGetDeviceCount (driver initialisation) took %.3f s\n", t_start - t_enter);
     cudaDeviceProp prop;
     if ((e0 = cudaSetDevice(device)) != cudaSuccess || (e0 = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
         fprintf(stderr, "impop_create: %s\n", cudaGetErrorString(e0));
@@ -235,15 +243,16 @@ int impop_create(int device, impop_ctx_t **ctx_out) {
               run("alloc harmonic table", cudaMalloc(&ctx->harm_dev, sizeof(double2) * (HARM_N + 1))) &&
               run("upload harmonic table", cudaMemcpy(ctx->harm_dev, harm.data(), sizeof(double2) * (HARM_N + 1), cudaMemcpyHostToDevice)) &&
               run("alloc counters", cudaMalloc(&ctx->prof_dev, sizeof(long long) * 16 * 1024)) &&
-              run("memset", cudaMemset(ctx->prof_dev, 0, sizeof(long long) * 16 * 1024)) &&
-              run("shared-memory attribute of the pairs kernel", configure_kernels());
-    if (ok) ctx->prep_per_sm = prep_rows_ctas_per_sm();
+              run("memset", cudaMemset(ctx->prof_dev, 0, sizeof(long long) * 16 * 1024));
+    // (the pairs kernel's shared-memory attribute and the prep occupancy query load those kernels' module: done at the first
+    // window batch, so that the TSV-mode command lines -- one process per window in the reference's wrappers -- do not pay it)
     if (!ok) {
         fprintf(stderr, "impop_create: CUDA set-up failed at '%s': %s\n", step, cudaGetErrorString(es));
         cudaFree(ctx->err_dev); cudaFree(ctx->harm_dev); cudaFree(ctx->prof_dev);
         delete ctx;
         return IMPOP_ERR_CUDA;
     }
+    if (trace) fprintf(stderr, "impop_create: device context, allocations and table upload took %.3f s\n", now() - t_start);
     ctx->launches = 0;
     *ctx_out = ctx;
     return IMPOP_OK;
@@ -345,6 +354,12 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     if (W > 0 && (!d->n_host || !d->m_host || !d->pitch_words_host || !d->x_off_host || !d->len_off_host ||
                   !d->lab_off_host || !d->length_host))
         return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: null descriptor array");
+    if (!ctx->kernels_configured) {
+        CU(cudaSetDevice(ctx->device));
+        CU(configure_kernels());
+        ctx->prep_per_sm = prep_rows_ctas_per_sm();
+        ctx->kernels_configured = true;
+    }
     const int32_t *n = d->n_host, *m = d->m_host, *pitch = d->pitch_words_host;
     std::vector<int64_t> row_off(W + 1, 0), item_off(W + 1, 0), word_off(W + 1, 0);
     bool any_rows = false, any_nodes = false;
@@ -500,12 +515,14 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t s_part = cs.take(8 * (size_t)(b->items * PART_STRIDE + 1));
     const size_t s_sums = cs.take(8 * 4 * W1), s_counts = cs.take(8 * IMPOP_NCOUNTS * W1);
     const size_t s_any = cs.take(4 * (size_t)(word_off[W] + 1)), s_all = cs.take(4 * (size_t)(word_off[W] + 1));
+    const size_t s_live = cs.take(4 * (size_t)(word_off[W] + 1));
     const size_t s_hn = cs.take(4 * W1), s_runs = cs.take(4 * W1);
     b->scratch = pool_get(ctx, cs.off, st);
     if (!b->scratch) return bail(IMPOP_ERR_NOMEM, "impop_batch_create: out of device memory (scratch)");
     char *sb = (char *)b->scratch;
     t.A = (int32_t *)(sb + s_A); t.w8 = (uint8_t *)(sb + s_w8); t.w8n = (uint8_t *)(sb + s_w8n); t.planes = (uint32_t *)(sb + s_planes); t.heavy = (uint32_t *)(sb + s_heavy);
     t.xh = (uint32_t *)(sb + s_xh); t.seg_any = (uint32_t *)(sb + s_any); t.seg_all = (uint32_t *)(sb + s_all);
+    t.live = (uint32_t *)(sb + s_live);
     t.heavy_n = (int32_t *)(sb + s_hn); t.site_runs = (int32_t *)(sb + s_runs);
     b->partials = (double *)(sb + s_part); b->sums_tmp = (double *)(sb + s_sums); b->counts_tmp = (int64_t *)(sb + s_counts);
     b->item_off = item_off;

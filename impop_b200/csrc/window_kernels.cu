@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
                     const uint32_t msk = __ballot_sync(0xffffffffu, (bwt >> p) & 1u);
                     if (lane == p) pl[p] = msk;
                 }
+                const uint32_t lv = __ballot_sync(0xffffffffu, l > 0u);        // nodes of positive length (l = 0 beyond m)
+                if (lane == 0 && (k >> 5) < ((m + 31) >> 5)) tab.live[tab.word_off[w] + (k >> 5)] = lv;
             }
             uint32_t q = l / HEAVY_Q;
             while (q > 0) {
@@ -252,7 +254,6 @@ __global__ void seg_count_kernel(const __grid_constant__ WindowTab tab, int64_t 
     const int warps_per_block = blockDim.x >> 5;
     for (int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < tab.W; w += gridDim.x * warps_per_block) {
         const int m = tab.m[w];
-        const uint32_t *len = tab.len + tab.len_off[w];
         const int64_t wo = tab.word_off[w];
         const int words = (m + 31) >> 5;
         int64_t *row = counts + (size_t)w * IMPOP_NCOUNTS;
@@ -264,11 +265,7 @@ __global__ void seg_count_kernel(const __grid_constant__ WindowTab tab, int64_t 
             uint32_t sg = 0u, sep = 0u;
             if (wd < words) {
                 const uint32_t any = tab.seg_any[wo + wd], all = tab.seg_all[wo + wd];
-                uint32_t live = 0u;                               // nodes < m of positive length
-                for (int b = 0; b < 32; ++b) {
-                    const int k = wd * 32 + b;
-                    if (k < m && __ldg(len + k) > 0u) live |= 1u << b;
-                }
+                const uint32_t live = tab.live[wo + wd];          // nodes < m of positive length (prep_cols)
                 sg = any & ~all & live;
                 sep = all & live;
             }

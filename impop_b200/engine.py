@@ -249,10 +249,8 @@ class WindowBatch:
         """
         W, n, pitch = x_bits.shape
         m_pad = node_len.shape[1]
-        dev = ctx.torch_device
-        xd = x_bits if isinstance(x_bits, torch.Tensor) else _u32_tensor(x_bits).to(dev)
-        ld = node_len if isinstance(node_len, torch.Tensor) else _u32_tensor(node_len).to(dev)
-        lab = labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(labels, dtype=np.uint8)).to(dev)
+        as_dev = lambda a, dt: ctx.upload(np.ascontiguousarray(a, dtype=dt).view(np.int32 if dt == np.uint32 else dt)) if isinstance(a, np.ndarray) else a
+        xd, ld, lab = as_dev(x_bits, np.uint32), as_dev(node_len, np.uint32), as_dev(labels, np.uint8)
         per_window_labels = lab.dim() == 2
         ar = np.arange(W, dtype=np.int64)
         L = np.full(W, int(length or 0), dtype=np.int64) if np.isscalar(length) or length is None else np.asarray(length)
@@ -282,10 +280,9 @@ class WindowBatch:
             lo += len(nl)
             bo += nn
         cat = lambda parts, dt: np.concatenate(parts).astype(dt, copy=False) if parts and sum(p.size for p in parts) else np.zeros(4, dtype=dt)
-        dev = ctx.torch_device
-        x = _u32_tensor(cat(xs, np.uint32)).to(dev)
-        nl = _u32_tensor(cat(ls, np.uint32)).to(dev)
-        lab = torch.from_numpy(cat(labs, np.uint8)).to(dev)
+        x = ctx.upload(cat(xs, np.uint32).view(np.int32))
+        nl = ctx.upload(cat(ls, np.uint32).view(np.int32))
+        lab = ctx.upload(cat(labs, np.uint8))
         return cls(ctx, n, m, pitch, x_off, len_off, lab_off, L, x, nl, lab, site_runs=site_runs)
 
     # ------------------------------------------------------------------ life cycle
@@ -307,24 +304,22 @@ class WindowBatch:
     # ------------------------------------------------------------------ kernels
     def stats(self, algo: int = ALGO_TCGEN05, stream=None, out_stats=None, out_counts=None):
         """Fused K2+K3 over every window: (stats [W, NSTATS] f64, counts [W, NCOUNTS] i64) on the device."""
-        dev = self.ctx.torch_device
-        stats = out_stats if out_stats is not None else torch.empty((self.windows, NSTATS), dtype=torch.float64, device=dev)
-        counts = out_counts if out_counts is not None else torch.empty((self.windows, NCOUNTS), dtype=torch.int64, device=dev)
+        stats = out_stats if out_stats is not None else self.ctx._empty((self.windows, NSTATS), "f64")
+        counts = out_counts if out_counts is not None else self.ctx._empty((self.windows, NCOUNTS), "i64")
         self.ctx._call("impop_window_stats", self.handle, algo, _ptr(stats), _ptr(counts), _stream_ptr(stream))
         return stats, counts
 
     def window_sums(self, rank: int, world: int, algo: int = ALGO_TCGEN05, stream=None) -> torch.Tensor:
         """Raw pair sums [W, 4] over the work items t with t % world == rank (tile-grid split)."""
-        sums = torch.empty((self.windows, 4), dtype=torch.float64, device=self.ctx.torch_device)
+        sums = self.ctx._empty((self.windows, 4), "f64")
         self.ctx._call("impop_window_sums", self.handle, algo, rank, world, _ptr(sums), _stream_ptr(stream))
         return sums
 
     def finalize(self, sums_parts: torch.Tensor, stream=None):
         """sums_parts [parts, W, 4] -> (stats, counts); parts are added in index order (reproducible)."""
-        assert sums_parts.dim() == 3 and sums_parts.shape[1:] == (self.windows, 4) and sums_parts.is_contiguous()
-        dev = self.ctx.torch_device
-        stats = torch.empty((self.windows, NSTATS), dtype=torch.float64, device=dev)
-        counts = torch.empty((self.windows, NCOUNTS), dtype=torch.int64, device=dev)
+        assert sums_parts.dim() == 3 and tuple(sums_parts.shape[1:]) == (self.windows, 4)
+        stats = self.ctx._empty((self.windows, NSTATS), "f64")
+        counts = self.ctx._empty((self.windows, NCOUNTS), "i64")
         self.ctx._call("impop_window_finalize", self.handle, _ptr(sums_parts), sums_parts.shape[0], _ptr(stats),
                        _ptr(counts), _stream_ptr(stream))
         return stats, counts
@@ -332,9 +327,8 @@ class WindowBatch:
     def pairwise(self, window: int, algo: int = ALGO_TCGEN05, want_i=True, want_pi=True, stream=None):
         """Materialise one window: (I [n, n] i64, A [n] i64, pi [n, n] f64); the table `impg similarity` prints."""
         n = int(self.n[window])
-        dev = self.ctx.torch_device
-        I = torch.zeros((n, n), dtype=torch.int64, device=dev) if want_i else None
-        A = torch.zeros(n, dtype=torch.int64, device=dev)
-        pi = torch.zeros((n, n), dtype=torch.float64, device=dev) if want_pi else None
+        I = self.ctx._empty((n, n), "i64", zero=True) if want_i else None
+        A = self.ctx._empty(n, "i64", zero=True)
+        pi = self.ctx._empty((n, n), "f64", zero=True) if want_pi else None
         self.ctx._call("impop_pairwise", self.handle, window, algo, _ptr(I), _ptr(A), _ptr(pi), _stream_ptr(stream))
         return I, A, pi

@@ -105,7 +105,6 @@ def batch_from_flat(ctx, flat, pop_a_ids=None, pop_b_ids=None, subset_ids=None):
     """ingest.FlatBatch (memory-mapped container) -> WindowBatch: one upload of the presence words, node lengths and labels;
     the classes are decided once per unique haplotype (h-fst.py:18-61 prefixes) and gathered per row -- no per-window loop."""
     import numpy as np
-    import torch
 
     from .engine import WindowBatch
     from .hfst import canonicalize_identifier
@@ -115,14 +114,10 @@ def batch_from_flat(ctx, flat, pop_a_ids=None, pop_b_ids=None, subset_ids=None):
     lab = flat.labels(prefixes(pop_a_ids), prefixes(pop_b_ids), prefixes(subset_ids))
     both = (lab & 6) == 6                                  # h-fst.py:181-185: listed in both populations -> in neither
     lab = np.where(both, lab & ~np.uint8(6), lab).astype(np.uint8)
-    import warnings
-    dev = ctx.torch_device
-    with warnings.catch_warnings():                        # the memory-mapped file is read-only; the tensors are only copied from
-        warnings.simplefilter("ignore", UserWarning)
-        x = torch.from_numpy(np.ascontiguousarray(flat.x).view(np.int32)).to(dev)
-        nl = torch.from_numpy(np.ascontiguousarray(flat.node_len).view(np.int32)).to(dev)
+    x = ctx.upload(np.ascontiguousarray(flat.x).view(np.int32))
+    nl = ctx.upload(np.ascontiguousarray(flat.node_len).view(np.int32))
     return WindowBatch(ctx, flat.n, flat.m, flat.pitch, flat.x_off, flat.len_off, flat.row_off, flat.length, x, nl,
-                       torch.from_numpy(lab).to(dev), node_len_host=np.ascontiguousarray(flat.node_len))
+                       ctx.upload(lab), node_len_host=np.ascontiguousarray(flat.node_len))
 
 
 def stats_disjoint_absent(ctx, batch, labels_host, lab_off):
@@ -131,7 +126,6 @@ def stats_disjoint_absent(ctx, batch, labels_host, lab_off):
     pica2.py:132-134 and h-fst.py:147-153 treat a missing row.  (The fused path counts it with pi_ij = 1.)  Materialises
     every window's table on the device and reduces it with NaN in place of those pairs."""
     import numpy as np
-    import torch
     stats = np.zeros((batch.windows, 20), dtype=np.float64)
     counts = np.zeros((batch.windows, 8), dtype=np.int64)
     fused_s, fused_c = batch.stats()
@@ -140,14 +134,16 @@ def stats_disjoint_absent(ctx, batch, labels_host, lab_off):
     for w in range(batch.windows):
         n = int(batch.n[w])
         I, _, pi = batch.pairwise(w)
-        ident = 1.0 - pi
-        off = ~torch.eye(n, dtype=torch.bool, device=ident.device)
-        ident[(I == 0) & off] = float("nan")
-        lab = torch.from_numpy(np.ascontiguousarray(labels_host[int(lab_off[w]):int(lab_off[w]) + n])).to(ident.device)
-        st, ct, _ = ctx.reduce_identity(ident.contiguous(), lab, None, length=int(batch.length[w]), seg_sites=float(fused_c[w][7]))
+        ctx.check()
+        ident = 1.0 - pi.cpu().numpy()
+        disjoint = (I.cpu().numpy() == 0) & ~np.eye(n, dtype=bool)
+        ident[disjoint] = np.nan
+        lab = ctx.upload(np.ascontiguousarray(labels_host[int(lab_off[w]):int(lab_off[w]) + n]))
+        st, ct, _ = ctx.reduce_identity(ctx.upload(ident), lab, None, length=int(batch.length[w]), seg_sites=float(fused_c[w][7]))
         ctx.check()
         stats[w], counts[w] = st.cpu().numpy(), ct.cpu().numpy()
         counts[w][7] = fused_c[w][7]
+        stats[w][19] = fused_s[w][19]
     return stats, counts
 
 
@@ -239,7 +235,7 @@ def main(argv=None):
     pop_a = read_subset_file(args.pop_a) if args.pop_a else None
     pop_b = read_subset_file(args.pop_b) if args.pop_b else None
     subset = read_subset_file(args.subset) if args.subset else None
-    ctx = Context(args.device)
+    ctx = Context(args.device, lite=True)           # plain device buffers over the C ABI: no torch import on this command line
     mark("context")
     make = (lambda **kw: batch_from_flat(ctx, flat, **kw)) if flat is not None else (lambda **kw: batch_from_graphs(ctx, graphs, **kw))
     batch = make(pop_a_ids=pop_a, pop_b_ids=pop_b, subset_ids=subset)

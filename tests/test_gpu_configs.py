@@ -19,8 +19,10 @@ TOL = 1e-12
 
 @pytest.fixture(scope="module")
 def ctx():
-    from impop_b200.runtime import default_context
-    return default_context()
+    from impop_b200.engine import Context
+    c = Context(0)
+    yield c
+    c.close()
 
 
 def _labels(n, ia, ib, subset=None, seg=None):
