@@ -403,8 +403,19 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = None
     if world > 1:
         torch.cuda.set_device(local)
+        # host threads (and with them the first-touch placement of this rank's pinned buffers) on the CPUs next to this
+        # rank's GPU: all ranks' host-to-device copies otherwise leave from whichever NUMA node the launcher started on
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa = sorted(os.sched_getaffinity(0))
+            numa = f"{len(numa)} CPUs {numa[0]}-{numa[-1]}"
+        except Exception as exc:
+            numa = f"not set ({type(exc).__name__})"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = Context(local)
     dev = ctx.torch_device
@@ -727,7 +738,7 @@ def run_ours(args):
                        "parallelism": (f"tile grid of every window split over {world} GPU(s): X broadcast once (NCCL), partial sums all-gathered, rank-ordered finalize"
                                        if split else f"windows sharded over {world} GPU(s), one all-gather of result rows per step"),
                        "l2": l2_note,
-                       "algo": args.algo, "ingest": ingest},
+                       "algo": args.algo, "ingest": ingest, "rank0_cpu_affinity": numa},
             "e2e": {"value": units_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": nsub, "matches_resident_run": same,
                     "bitwise_equal_to_resident_run": bitwise,

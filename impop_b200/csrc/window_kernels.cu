@@ -1198,6 +1198,45 @@ __global__ void window_sums_kernel(const __grid_constant__ WindowTab tab, const 
     }
 }
 
+// The same for batches of few, large windows (10 000 haplotypes: ~3 200 items x 16 records each): one CTA per window, its
+// eight warps take the records warp-strided, the eight warp sums are added in warp order -- fixed order, reproducible.
+__global__ void __launch_bounds__(256) window_sums_block_kernel(const __grid_constant__ WindowTab tab, const double *partials, int32_t rank,
+                                                                int32_t world, double *sums) {
+    __shared__ double s_hi[8][4], s_lo[8][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int w = blockIdx.x; w < tab.W; w += gridDim.x) {
+        const int64_t t0 = tab.item_off[w], t1 = tab.item_off[w + 1];
+        dd v[4] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+        const int64_t first = t0 + ((rank - (t0 % world)) % world + world) % world;
+        const int64_t mine = (t1 > first) ? (t1 - first + world - 1) / world : 0;
+        for (int64_t r = threadIdx.x; r < mine * PART_SLOTS; r += 256) {
+            const int64_t t = first + (r / PART_SLOTS) * world;
+            const double *rec = partials + t * PART_STRIDE + (r % PART_SLOTS) * 8;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                dd p = {rec[k], rec[4 + k]};
+                dd_merge(v[k], p);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = warp_sum_dd(v[k]);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { s_hi[warp][k] = v[k].hi; s_lo[warp][k] = v[k].lo; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            dd acc = {0.0, 0.0};
+            for (int q = 0; q < 8; ++q) {
+                dd p = {s_hi[q][threadIdx.x], s_lo[q][threadIdx.x]};
+                dd_merge(acc, p);
+            }
+            sums[(size_t)w * 4 + threadIdx.x] = dd_value(acc);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void finalize_kernel(const __grid_constant__ WindowTab tab, const double *sums, int32_t parts,
                                 const int64_t *counts, double *stats) {
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < tab.W; w += gridDim.x * blockDim.x) {
@@ -1319,6 +1358,10 @@ cudaError_t launch_pairs(const WindowTab &tab, const ItemParams &prm, int algo, 
 cudaError_t launch_window_sums(const WindowTab &tab, const double *partials, int rank, int world, double *sums,
                                int sm_count, cudaStream_t st) {
     if (tab.W == 0) return cudaSuccess;
+    if (tab.W < sm_count * 4) {                       // few windows: a CTA each (their item lists are long when n is large)
+        window_sums_block_kernel<<<tab.W, 256, 0, st>>>(tab, partials, rank, world, sums);
+        return cudaGetLastError();
+    }
     int blocks = min((tab.W + 3) / 4, sm_count * 8);
     window_sums_kernel<<<blocks, 128, 0, st>>>(tab, partials, rank, world, sums);
     return cudaGetLastError();

@@ -29,5 +29,6 @@ t0 = time.perf_counter(); xc, lc, mo = ingest.compact_uniform(xh, lh); t1 = time
 print("compaction %.3f s on %d threads; nodes %d -> max %d (pitch %d words)" % (t1 - t0, len(os.sched_getaffinity(0)), m, mo.max(), xc.shape[2]), flush=True)
 xd = torch.from_numpy(xc.view(np.int32)).to(dev); ld = torch.from_numpy(lc.view(np.int32)).to(dev)
 s1, c1 = run(xd, ld, "compacted")
+s0, s1 = s0[:, :19], s1[:, :19]            # column 19 (variant sites) depends on the node order
 print("counts equal:", bool((c0 == c1).all()), " stats max rel diff:", float(np.nanmax(np.abs(s0 - s1) / np.maximum(np.abs(s0), 1e-300))),
       " nan pattern equal:", bool((np.isnan(s0) == np.isnan(s1)).all()))
