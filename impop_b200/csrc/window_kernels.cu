@@ -918,7 +918,9 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             // tools/micro/issue_mix.cu), and with the class tests inside one body ptxas predicates the flag paths -- 3 fp64 +
             // 1.5 load instructions per pair issued and discarded on every chunk.  Why the general one is small: the hot code
             // of a scheduler's four epilogue warps has to stay in the instruction cache; two unrolled bodies (2 x 8 KB) ran
-            // 30 % slower than either alone.
+            // 30 % slower than either alone.  (Also measured: ONE not-unrolled group loop for both variants with the next
+            // group's tcgen05.ld issued under the current group's divisions -- 5 KB of hot code, but ~4 more instructions
+            // per pair for the loop: 1.59 against 1.51 ms.)
             auto group = [&](const uint32_t *r, int cc, int g0, bool on_diag, auto fast_tag, double &cs, double &ca, double &cb,
                              double &call) {
                 constexpr bool FAST = decltype(fast_tag)::value;
