@@ -150,10 +150,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # Workload: generated windows -> ingest (column compaction) -> arrays the batch is built from
 # ------------------------------------------------------------------------------------------------------------------
-def make_workload(gen, cfg: dict, windows: int, seed: int, threads: int, keep_original: int = 0):
+def make_workload(gen, cfg: dict, windows: int, seed: int, threads: int, keep_original: int = 0, plain: int = 0, affine: bool = True,
+                  ragged: bool = True):
     """Generate `windows` windows of config `cfg` with `gen` (a device Context or synth.HostGenerator), then run the
-    ingest-time column compaction on the host.  Returns a dict of HOST arrays (uint32 views) + meta; `keep_original`
-    windows of the uncompacted input are kept for the oracle cross-check."""
+    ingest-time column compaction on the host: the affine form (bubbles merged, constants in C: impop_compact_fill with
+    IMPOP_COMPACT_PAIRS | _REPLICATE) is what the GPU arm takes.  Returns a dict of HOST arrays + meta; `keep_original`
+    windows of the uncompacted input are kept for the oracle cross-check, and the first `plain` windows are also
+    compacted in the plain form (constant columns merged, nothing else) -- the input of the CPU oracle port, which
+    walks node columns like the similarity tools walk path steps."""
     from impop_b200 import ingest, synth
     n, L = cfg["n"], cfg["L"]
     if cfg["labels"] == "halves":
@@ -164,20 +168,81 @@ def make_workload(gen, cfg: dict, windows: int, seed: int, threads: int, keep_or
     xh = x.cpu().numpy().view(np.uint32)
     lh = nl.cpu().numpy().view(np.uint32)
     del x, nl
+    W = int(xh.shape[0])
+    ar = np.arange(W, dtype=np.int64)
     t0 = time.perf_counter()
-    xc, lc, m_out = ingest.compact_uniform(xh, lh, threads=threads)
+    if affine:
+        # every window keeps its own row pitch (a multiple of 128 columns): fewer bytes to upload than one pitch for all
+        c = ingest.compact_batch(np.full(W, n), np.full(W, m_pad), np.full(W, m_pad // 32), ar * (n * (m_pad // 32)), ar * m_pad, xh, lh,
+                                 threads, uniform_pitch=not ragged)
+        xc, lc, m_out, site_runs, pitch_w = c.x_out, c.len_out, c.m_out, c.site_runs, c.pitch_out
+        row_adj, win_const, col_mult = c.row_adj, c.win_const, c.col_mult
+    else:
+        cu = ingest.compact_uniform(xh, lh, threads=threads, pairs=False)
+        xc, lc, m_out, site_runs = cu.x, cu.node_len, cu.m, cu.site_runs
+        pitch_w = np.full(W, xc.shape[2] if W else 4, dtype=np.int32)
+        row_adj = win_const = col_mult = None
     t1 = time.perf_counter()
-    site_runs = ingest.compact_uniform.last_site_runs
-    heavy = ((lc.astype(np.int64) // 255 + 254) // 255).sum(axis=1)               # heavy-table entries per window
+    x_off = np.concatenate([[0], np.cumsum(n * pitch_w.astype(np.int64))]).astype(np.int64)
+    len_off = np.concatenate([[0], np.cumsum(32 * pitch_w.astype(np.int64))]).astype(np.int64)
+    pl = ingest.compact_uniform(xh[:plain], lh[:plain], threads=threads, pairs=False) if (plain and affine) else None
+    lflat = lc.reshape(-1).astype(np.int64)
+    hv = (lflat // 255 + 254) // 255                                               # heavy-table entries per column
+    heavy = np.add.reduceat(hv, len_off[:-1]) if W else np.zeros(0, np.int64)
     k_exec = ((m_out.astype(np.int64) + KCHUNK - 1) // KCHUNK + (heavy + KCHUNK - 1) // KCHUNK) * KCHUNK
     nl_max = int(lh.max()) if lh.size else 0
     planes = 1 if nl_max < 256 else (2 if nl_max < 65536 else (3 if nl_max < (1 << 24) else 4))
+    aff_bytes = int(row_adj.nbytes + col_mult.nbytes + win_const.nbytes) if affine else 0
     return {"x": xc, "len": lc, "m_out": m_out, "site_runs": site_runs, "pops": pops, "labels": labels_for(cfg["labels"], pops), "n": n, "L": L,
-            "m_in": int(m), "m_pad_in": int(m_pad), "pitch": int(xc.shape[2]), "m_pad": int(lc.shape[1]), "planes": planes,
-            "k_exec": k_exec, "ingest_s": t1 - t0, "ingest_threads": threads,
+            "row_adj": row_adj, "win_const": win_const, "col_mult": col_mult, "pitch_w": pitch_w, "x_off": x_off, "len_off": len_off,
+            "m_in": int(m), "m_pad_in": int(m_pad), "pitch": int(pitch_w.max()) if W else 4, "m_pad": int(pitch_w.max()) * 32 if W else 128,
+            "planes": planes, "k_exec": k_exec, "ingest_s": t1 - t0, "ingest_threads": threads,
+            "plain_x": pl.x if pl is not None else None, "plain_len": pl.node_len if pl is not None else None,
+            "plain_m_out": int(pl.m.max()) if (pl is not None and len(pl.m)) else 0,
             "orig_x": xh[:keep_original].copy() if keep_original else None,
             "orig_len": lh[:keep_original].copy() if keep_original else None,
-            "bytes_in": int(xh.nbytes + lh.nbytes), "bytes_out": int(xc.nbytes + lc.nbytes)}
+            "bytes_in": int(xh.nbytes + lh.nbytes), "bytes_out": int(xc.nbytes + lc.nbytes) + aff_bytes}
+
+
+class DeviceWindows:
+    """The ingested windows of a workload as flat device (or pinned host) arrays + what a WindowBatch over windows [lo, hi) needs."""
+
+    def __init__(self, torch, wl, where):
+        mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if where == "pinned" else \
+             (lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(where))
+        self.x = mk(wl["x"].reshape(-1).view(np.int32))
+        self.len = mk(wl["len"].reshape(-1).view(np.int32))
+        self.row_adj = mk(wl["row_adj"].reshape(-1))
+        self.col_mult = mk(wl["col_mult"].reshape(-1))
+
+    @property
+    def nbytes(self):
+        return sum(int(t.numel()) * t.element_size() for t in (self.x, self.len, self.row_adj, self.col_mult))
+
+    def empty_like(self, torch, dev):
+        out = object.__new__(DeviceWindows)
+        for k in ("x", "len", "row_adj", "col_mult"):
+            setattr(out, k, torch.empty(getattr(self, k).shape, dtype=getattr(self, k).dtype, device=dev))
+        return out
+
+    def copy_from(self, src, wl, lo, hi):
+        """Enqueue the copies of windows [lo, hi) from `src` (pinned host) on the current stream: small arrays first."""
+        n = wl["n"]
+        x0, x1, l0, l1 = int(wl["x_off"][lo]), int(wl["x_off"][hi]), int(wl["len_off"][lo]), int(wl["len_off"][hi])
+        self.len[l0:l1].copy_(src.len[l0:l1], non_blocking=True)
+        self.row_adj[lo * n:hi * n].copy_(src.row_adj[lo * n:hi * n], non_blocking=True)
+        self.col_mult[l0:l1].copy_(src.col_mult[l0:l1], non_blocking=True)
+        self.x[x0:x1].copy_(src.x[x0:x1], non_blocking=True)
+
+    def batch(self, ctx, WindowBatch, wl, labels, lo, hi, stream=None, host=None, with_runs=True):
+        n, L = wl["n"], wl["L"]
+        Wn = hi - lo
+        x0, x1, l0, l1 = int(wl["x_off"][lo]), int(wl["x_off"][hi]), int(wl["len_off"][lo]), int(wl["len_off"][hi])
+        return WindowBatch(ctx, np.full(Wn, n), wl["m_out"][lo:hi], wl["pitch_w"][lo:hi], wl["x_off"][lo:hi] - x0, wl["len_off"][lo:hi] - l0,
+                           np.zeros(Wn, dtype=np.int64), np.full(Wn, L), self.x[x0:x1], self.len[l0:l1], labels,
+                           node_len_host=None if host is None else host.len[l0:l1], stream=stream,
+                           site_runs=wl["site_runs"][lo:hi] if with_runs else None, row_adj=self.row_adj[lo * n:hi * n],
+                           win_const=wl["win_const"][lo:hi], col_mult=self.col_mult[l0:l1])
 
 
 def item_geometry(n: int):
@@ -233,7 +298,7 @@ def run_reference(args):
     W = args.windows or cfg["W"]
     if args.config == 5:
         W = min(W, 1)                         # 5e7 pairs x 5 888 nodes per window: one window per step is ~minutes of CPU
-    wl = make_workload(synth.HostGenerator(), cfg, W, cfg["seed"], threads)
+    wl = make_workload(synth.HostGenerator(), cfg, W, cfg["seed"], threads, affine=False)       # plain compaction: constant columns merged
 
     def step():
         return cpu_oracle(wl["x"], wl["len"], wl["labels"], wl["n"], wl["m_pad"], wl["pitch"], wl["L"], threads, W)[0]
@@ -299,10 +364,9 @@ def bench_windows_short(ctx, torch, peaks, cfg, windows, reps, threads):
     from impop_b200.engine import ALGO_TCGEN05, WindowBatch
     dev = ctx.torch_device
     wl = make_workload(ctx, cfg, windows, cfg["seed"], threads)
-    xd = torch.from_numpy(wl["x"].view(np.int32)).to(dev)
-    ld = torch.from_numpy(wl["len"].view(np.int32)).to(dev)
+    dw = DeviceWindows(torch, wl, dev)
     lab = torch.from_numpy(wl["labels"]).to(dev)
-    b = WindowBatch.from_uniform(ctx, xd, ld, lab, wl["L"])
+    b = dw.batch(ctx, WindowBatch, wl, lab, 0, windows)
     ms = _timed(torch, lambda: b.stats(ALGO_TCGEN05), reps)
     ctx.timing(True)
     b.stats(ALGO_TCGEN05)
@@ -454,40 +518,46 @@ def run_ours(args):
         keep = min(W, 1)
         if rank == 0:
             wl = make_workload(ctx, cfg, W, cfg["seed"], host_threads(), keep_original=0)
-            meta = [wl["pitch"], wl["m_pad"], wl["m_in"], wl["m_pad_in"], wl["planes"], int(wl["m_out"].max()), int(wl["k_exec"].max())]
+            host = DeviceWindows(torch, wl, "pinned")
+            meta = [wl["m_in"], wl["m_pad_in"], wl["planes"], int(wl["m_out"].max()), int(wl["k_exec"].max()), wl["pitch"],
+                    host.x.numel(), host.len.numel()]
+            tabs = np.stack([wl["m_out"].astype(np.int64), wl["pitch_w"].astype(np.int64), wl["x_off"][:-1], wl["len_off"][:-1],
+                             wl["win_const"], wl["site_runs"]])
         else:
-            wl, meta = None, [0] * 7
+            wl, host, meta, tabs = None, None, [0] * 8, np.zeros((6, W), dtype=np.int64)
+        mt, tb = torch.tensor(meta, dtype=torch.int64, device=dev), torch.from_numpy(tabs).to(dev)
         if world > 1:
-            mt = torch.tensor(meta, dtype=torch.int64, device=dev)
-            dist.broadcast(mt, 0)
-            meta = [int(v) for v in mt.tolist()]
-        pitch, m_pad, m_in, m_pad_in, planes, m_out_max, k_exec_max = meta
+            dist.broadcast(mt, 0); dist.broadcast(tb, 0)
+        m_in, m_pad_in, planes, m_out_max, k_exec_max, pitch, xw, lw = (int(v) for v in mt.tolist())
+        tabs = tb.cpu().numpy()
+        if rank != 0:                          # the same descriptor tables on every rank; the bulk arrays arrive by broadcast
+            wl = {"n": n, "L": L, "m_out": tabs[0].astype(np.int32), "pitch_w": tabs[1].astype(np.int32),
+                  "x_off": np.concatenate([tabs[2], [xw]]), "len_off": np.concatenate([tabs[3], [lw]]),
+                  "win_const": tabs[4].copy(), "site_runs": tabs[5].copy(), "labels": labels_for(cfg["labels"], np.zeros(n, dtype=np.int64))}
+        lab_host = wl["labels"]
+        res = object.__new__(DeviceWindows)
+        res.x = torch.empty(xw, dtype=torch.int32, device=dev); res.len = torch.empty(lw, dtype=torch.int32, device=dev)
+        res.row_adj = torch.empty(W * n, dtype=torch.int32, device=dev); res.col_mult = torch.empty(lw, dtype=torch.uint8, device=dev)
         if rank == 0:
-            hx = torch.from_numpy(wl["x"].view(np.int32)).pin_memory()
-            hl = torch.from_numpy(wl["len"].view(np.int32)).pin_memory()
-            lab_host = wl["labels"]
-        else:
-            hx = hl = None
-            lab_host = labels_for(cfg["labels"], np.zeros(n, dtype=np.int64))
-        x_c = torch.empty((W, n, pitch), dtype=torch.int32, device=dev)
-        len_c = torch.empty((W, m_pad), dtype=torch.int32, device=dev)
-        if rank == 0:
-            x_c.copy_(hx); len_c.copy_(hl)
+            for k_ in ("x", "len", "row_adj", "col_mult"):
+                getattr(res, k_).copy_(getattr(host, k_))
         if world > 1:
-            dist.broadcast(x_c, 0); dist.broadcast(len_c, 0)
+            for k_ in ("x", "len", "row_adj", "col_mult"):
+                dist.broadcast(getattr(res, k_), 0)
         k_exec = np.full(W, k_exec_max)
         ingest = {"seconds": wl["ingest_s"], "threads": wl["ingest_threads"], "bytes_in": wl["bytes_in"], "bytes_out": wl["bytes_out"]} if rank == 0 else None
         bounds = None
+        m_pad = pitch * 32
     else:
         W = W_total // world + (1 if rank < W_total % world else 0) if strong else W_total
         keep = min(W, 96) if (rank == 0 and world == 1) else 0
-        wl = make_workload(ctx, cfg, W, cfg["seed"] + 1000 * rank, threads, keep_original=keep)
+        wl = make_workload(ctx, cfg, W, cfg["seed"] + 1000 * rank, threads, keep_original=keep,
+                           plain=W if (rank == 0 and world == 1 and not args.no_cpu) else 0)
         pitch, m_pad, m_in, m_pad_in, planes = wl["pitch"], wl["m_pad"], wl["m_in"], wl["m_pad_in"], wl["planes"]
         m_out_max, k_exec = int(wl["m_out"].max()), wl["k_exec"]
         lab_host = wl["labels"]
-        hx = torch.from_numpy(wl["x"].view(np.int32)).pin_memory()
-        hl = torch.from_numpy(wl["len"].view(np.int32)).pin_memory()
-        x_c, len_c = hx.to(dev), hl.to(dev)
+        host = DeviceWindows(torch, wl, "pinned")          # the ingested windows in pinned host memory (what the e2e leg uploads)
+        res = DeviceWindows(torch, wl, dev)                # ... and resident in HBM (the device-timed leg)
         ingest = {"seconds": wl["ingest_s"], "threads": wl["ingest_threads"], "bytes_in": wl["bytes_in"], "bytes_out": wl["bytes_out"]}
         sizes = torch.tensor([W], dtype=torch.int64, device=dev)
         if world > 1:
@@ -497,11 +567,10 @@ def run_ours(args):
         else:
             bounds = np.array([0, W], dtype=np.int64)
     labels = torch.from_numpy(lab_host).to(dev)
-    resident_mb = (x_c.numel() * 4 + len_c.numel() * 4) / 1e6
+    resident_mb = res.nbytes / 1e6
     l2_note = (f"{W} windows of {n * pitch * 4 / 1e6:.1f} MB each ({resident_mb:.0f} MB per GPU), read every step" if split
                else f"inputs larger than L2 ({resident_mb:.0f} MB per GPU read every step)")
-    runs = None if (split or wl is None) else wl["site_runs"]       # variant sites counted at ingest on the original node order
-    batch = WindowBatch.from_uniform(ctx, x_c, len_c, labels, L, site_runs=runs)
+    batch = res.batch(ctx, WindowBatch, wl, labels, 0, W, with_runs=not split)
     stats = torch.empty((W, NSTATS), dtype=torch.float64, device=dev)
     counts = torch.empty((W, NCOUNTS), dtype=torch.int64, device=dev)
 
@@ -558,7 +627,7 @@ def run_ours(args):
     hs = torch.empty((W, NSTATS), dtype=torch.float64, pin_memory=True)
     hc = torch.empty((W, NCOUNTS), dtype=torch.int64, pin_memory=True)
     hlab = torch.from_numpy(lab_host).pin_memory()
-    dx, dl = torch.empty_like(x_c), torch.empty_like(len_c)
+    dwin = res.empty_like(torch, dev)                      # the e2e leg's own device buffers
     ds, dc = torch.empty_like(stats), torch.empty_like(counts)
     pending = []          # batches of the previous step: closed while this step's copies and kernels run
     if split:
@@ -567,11 +636,12 @@ def run_ours(args):
 
         def e2e_step():
             if rank == 0:
-                dx.copy_(hx, non_blocking=True); dl.copy_(hl, non_blocking=True)
+                dwin.copy_from(host, wl, 0, W)
             dlab.copy_(hlab, non_blocking=True)
             if world > 1:
-                dist.broadcast(dx, 0); dist.broadcast(dl, 0)
-            b = WindowBatch.from_uniform(ctx, dx, dl, dlab, L)
+                for k_ in ("x", "len", "row_adj", "col_mult"):
+                    dist.broadcast(getattr(dwin, k_), 0)
+            b = dwin.batch(ctx, WindowBatch, wl, dlab, 0, W, with_runs=False)
             sums = b.window_sums(rank, world, algo)
             st, ct = b.finalize(gather_parts(sums))
             hs.copy_(st, non_blocking=True); hc.copy_(ct, non_blocking=True)
@@ -600,10 +670,8 @@ def run_ours(args):
                     # this sub-batch's copies first, its set-up (host-side tables + their small upload) while they run: the copy
                     # engine is the bottleneck of the step and must never wait for the host
                     dlabs[k].copy_(hlab, non_blocking=True)
-                    dl[lo:hi].copy_(hl[lo:hi], non_blocking=True)
-                    dx[lo:hi].copy_(hx[lo:hi], non_blocking=True)
-                    b = WindowBatch.from_uniform(ctx, dx[lo:hi], dl[lo:hi], dlabs[k], L, node_len_host=hl[lo:hi], stream=st,
-                                                 site_runs=None if runs is None else runs[lo:hi])
+                    dwin.copy_from(host, wl, lo, hi)
+                    b = dwin.batch(ctx, WindowBatch, wl, dlabs[k], lo, hi, stream=st, host=host)
                     b.stats(algo, stream=st, out_stats=ds[lo:hi], out_counts=dc[lo:hi])
                     hs[lo:hi].copy_(ds[lo:hi], non_blocking=True)
                     hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)
@@ -641,10 +709,14 @@ def run_ours(args):
                 and torch.equal(hc, counts.cpu()))
     bitwise = bool(torch.equal(hs.nan_to_num(7.0), stats.cpu().nan_to_num(7.0)))
     if split:
-        h2d = x_c.numel() * 4 + len_c.numel() * 4 + world * hlab.numel()            # uploaded once (rank 0), broadcast over NVLink
+        h2d = res.nbytes + 8 * W + world * hlab.numel()          # uploaded once (rank 0), broadcast over NVLink
         d2h = world * (hs.numel() * 8 + hc.numel() * 8)
     else:
-        h2d = windows_job * (n * pitch * 4 + m_pad * 4) + world * hlab.numel() * nsub   # whole job: every rank copies its own batch
+        # whole job: every rank copies its own windows (presence bits, weights, row terms, multiplicities, constants, labels)
+        hb = torch.tensor([float(host.nbytes + 8 * W + hlab.numel() * nsub)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+        h2d = int(hb.item())
         d2h = windows_job * (NSTATS * 8 + NCOUNTS * 8)
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
@@ -695,9 +767,13 @@ def run_ours(args):
         from oracle.compare import rows_close
         ht = host_threads()
         S0 = min(W, max(ht * 2, 8))
-        dt, _, _ = cpu_oracle(wl["x"], wl["len"], lab_host, n, m_pad, pitch, L, ht, S0)
+        # the oracle port takes the same windows in the PLAIN compacted form (constant columns merged): it walks node
+        # columns, as the similarity tools walk path steps, and knows nothing of the affine form the GPU arm is given
+        px, plen = wl["plain_x"], wl["plain_len"]
+        p_pitch, p_mpad = int(px.shape[2]), int(plen.shape[1])
+        dt, _, _ = cpu_oracle(px, plen, lab_host, n, p_mpad, p_pitch, L, ht, S0)
         S = int(min(W, max(S0, S0 * 12.0 / max(dt, 1e-3))))
-        dt, st_cpu, ct_cpu = cpu_oracle(wl["x"], wl["len"], lab_host, n, m_pad, pitch, L, ht, S)
+        dt, st_cpu, ct_cpu = cpu_oracle(px, plen, lab_host, n, p_mpad, p_pitch, L, ht, S)
         rate = S * units_per_window(n, L) / dt
         got_s, got_c = stats[:S].cpu().numpy(), counts[:S].cpu().numpy()
         ok_counts = bool((got_c == ct_cpu).all())
@@ -708,7 +784,7 @@ def run_ours(args):
         errs = max_rel_errors(got_s[:K], st_orig)
         strict = bool(errs["nan_pattern_equal"] and max(errs[k] for k in ("pi", "pi_per_site", "pi_a", "pi_b", "dxy", "da", "fst", "tajima_d")) <= 1e-12)
         cpu = {"value": rate, "unit": UNIT, "cores": ht, "kind": "port",
-               "sample": f"{S} of {W} windows of this workload (ingested columns) in {dt:.2f} s, plain-C oracle port (byte-LUT intersections) on {ht} pthreads",
+               "sample": f"{S} of {W} windows of this workload (constant columns merged: {wl['plain_m_out']} of {m_in} nodes) in {dt:.2f} s, plain-C oracle port (byte-LUT intersections) on {ht} pthreads",
                "gpu_matches_oracle_on_sample": {"counts_exact": ok_counts, "stats_within_1e-12": ok_stats, "detail": why},
                "gpu_vs_oracle_on_original_columns": {"windows": K, "counts_exact": bool((got_c[:K] == ct_orig).all()),
                                                      "variant_sites_exact": bool((got_s[:K, 19] == st_orig[:, 19]).all()),
@@ -717,7 +793,7 @@ def run_ours(args):
     others = None
     if rank == 0 and world == 1 and args.config == 2 and not args.no_others:
         batch.close()
-        del x_c, len_c, dx, dl, hx, hl
+        del res, dwin, host
         torch.cuda.empty_cache()
         others = other_configs(ctx, torch, peaks, host_threads())
 

@@ -14,6 +14,7 @@ NSTATS = 20
 NCOUNTS = 8
 LAB_SUBSET, LAB_A, LAB_B, LAB_SEG = 1, 2, 4, 8
 ALGO_TCGEN05, ALGO_SIMT = 0, 1
+COMPACT_PAIRS, COMPACT_REPLICATE = 1, 2
 KERNELS = {"prep": 0, "pairs": 1, "sums": 2, "colstat": 3, "finalize": 4, "sites": 5}
 ST = {"pi": 0, "pi_per_site": 1, "pi_a": 2, "pi_b": 3, "pi_xy": 4, "dxy": 5, "da": 6, "fst": 7, "S": 8,
       "tajima_d": 9, "a1": 10, "e1": 11, "e2": 12, "n": 13, "sum_S": 14, "sum_AA": 15, "sum_BB": 16,
@@ -29,7 +30,8 @@ class BatchDesc(C.Structure):
     """impop_batch_desc_t"""
     _fields_ = [("windows", _i32), ("n_host", _p), ("m_host", _p), ("pitch_words_host", _p), ("x_off_host", _p),
                 ("len_off_host", _p), ("lab_off_host", _p), ("length_host", _p), ("x_dev", _p), ("node_len_dev", _p),
-                ("labels_dev", _p), ("node_len_host", _p), ("stream", _p), ("site_runs_host", _p)]
+                ("labels_dev", _p), ("node_len_host", _p), ("stream", _p), ("site_runs_host", _p),
+                ("row_adj_dev", _p), ("win_const_host", _p), ("col_mult_dev", _p)]
 
 
 class GfaInfo(C.Structure):
@@ -75,8 +77,8 @@ SIGNATURES = {
     "impop_tsv_fill": (C.c_int, [C.c_char_p, _i64, _p, _p, _p]),
     "impop_gfa_scan": (C.c_int, [C.c_char_p, _i64, C.POINTER(GfaInfo)]),
     "impop_gfa_fill": (C.c_int, [C.c_char_p, _i64, _i32, _p, _p, _p, _p, _p, C.POINTER(_i64)]),
-    "impop_compact_scan": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
-    "impop_compact_fill": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "impop_compact_scan": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32, C.c_uint32, _p, _p]),
+    "impop_compact_fill": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32, C.c_uint32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

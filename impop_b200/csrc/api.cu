@@ -414,7 +414,7 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     const size_t phase1 = ca.off;
     const size_t o_heavy = ca.take(8 * W1), o_w8 = ca.take(8 * W1), o_xh = ca.take(8 * W1);
     const size_t o_cnt = ca.take(4 * W1);
-    const size_t o_runs = ca.take(8 * W1);
+    const size_t o_runs = ca.take(8 * W1), o_wconst = ca.take(8 * W1);
     const size_t tables_bytes = ca.off;
     b->last_stream = st;
     b->tables = pool_get(ctx, tables_bytes, st);
@@ -502,6 +502,12 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     if (d->site_runs_host && W > 0) memcpy(hb + o_runs, d->site_runs_host, 8 * (size_t)W);
     t.site_runs_given = (d->site_runs_host && W > 0) ? (const int64_t *)(db + o_runs) : nullptr;
     if (e == cudaSuccess && t.site_runs_given) e = cudaMemcpyAsync(db + o_runs, hb + o_runs, 8 * (size_t)W, cudaMemcpyHostToDevice, st);
+    // affine form (optional): window constants travel with the tables, row terms and column multiplicities are the caller's device arrays
+    if (d->win_const_host && W > 0) memcpy(hb + o_wconst, d->win_const_host, 8 * (size_t)W);
+    t.win_const = (d->win_const_host && W > 0) ? (const int64_t *)(db + o_wconst) : nullptr;
+    if (e == cudaSuccess && t.win_const) e = cudaMemcpyAsync(db + o_wconst, hb + o_wconst, 8 * (size_t)W, cudaMemcpyHostToDevice, st);
+    t.row_adj = d->row_adj_dev;
+    t.col_mult = d->col_mult_dev;
     if (e == cudaSuccess) e = cudaMemcpyAsync(db + o_heavy, hb + o_heavy, o_cnt - o_heavy, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) { e = cudaEventRecord(sg->done, st); sg->busy = true; }
     if (e != cudaSuccess) return bail(IMPOP_ERR_CUDA, std::string("upload tables: ") + cudaGetErrorString(e));

@@ -536,47 +536,181 @@ int impop_tsv_fill(const char *text, int64_t bytes, double *matrix_host, char *n
 // Column compaction of a batch of windows (ingest, once per window; exact).
 //   * nodes visited by EVERY haplotype of the window (the backbone of a pangenome window graph: a third of the nodes
 //     of an HPRC-shaped window) add the same constant to every intersection I_ij and path length A_i: they are
-//     merged into ONE node whose length is the sum of theirs;
+//     merged into ONE node whose length is the sum of theirs (flags == 0) or into the window constant C (affine form);
 //   * nodes visited by no haplotype, and nodes of length 0, contribute nothing and are dropped;
 //   * the remaining nodes are ordered by length (ties: original order), so that the presence words of unit-length
 //     nodes (SNP alleles) come first: prep_rows then needs one popcount per 32 such nodes and row.
-// I, A, U, the segregating-node count and hence every statistic are unchanged (no node that is dropped or merged
-// is segregating in any subset of the rows).  The similarity tools do the equivalent implicitly: they walk paths,
-// not matrix columns.  Fewer columns = fewer operand bytes to expand and multiply, and fewer bytes to upload.
+// IMPOP_COMPACT_PAIRS (affine form, include/impop_b200.h):
+//   * nodes with IDENTICAL presence columns (variants in perfect linkage) are merged into one column of their summed
+//     length that counts for all of them in S;
+//   * two columns r, a that are COMPLEMENTARY over the window's rows (x_r + x_a = 1 for every haplotype: the two
+//     branches of a bi-allelic bubble, the commonest shape in a variation graph) become ONE column: with x_r = 1 - x_a,
+//         len_r x_ri x_rj + len_a x_ai x_aj = len_r - len_r x_ai - len_r x_aj + (len_r + len_a) x_ai x_aj ,
+//     i.e. the kept column a gets the weight len_r + len_a, len_r goes into the window constant C and len_r x_ai into the
+//     row term R_i:  I_ij = sum_k len'_k x'_ik x'_jk + C - R_i - R_j  (exact integers), A_i = I_ii.
+// IMPOP_COMPACT_REPLICATE: a weight >= 255 is spread over ceil(w / 254) copies of its column (byte weights, no separate
+//     heavy chunk on the device) when the copies fit into the padding of the window's 128-column chunks.
+// I, A, U, the segregating-node count and hence every statistic are unchanged.  The similarity tools do the equivalent
+// implicitly: they walk paths, not matrix columns.  Fewer columns = fewer operand bytes to expand and multiply, and
+// fewer bytes to upload.
 // ------------------------------------------------------------------------------------------------------------
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 
 namespace {
 
-struct CompactPlan {
-    std::vector<int32_t> order;      // surviving variable nodes, output order
-    uint64_t const_len = 0;          // summed length of the nodes every row visits
-    int32_t m_out = 0;
-    int64_t site_runs = 0;           // runs of segregating nodes between nodes every row visits (original node order)
+struct CompactCol {
+    int32_t src;        // original column whose presence bits the output column carries
+    uint32_t w;         // weight (node length; merged: sum)
+    uint8_t mult;       // nodes of positive length the column stands for in S (0: replica)
 };
 
-void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const uint32_t *len, CompactPlan &pl) {
+struct CompactPlan {
+    std::vector<CompactCol> cols;                          // output columns, output order
+    std::vector<std::pair<int32_t, uint32_t>> radj;        // (kept column, removed length): R_i += length when the row carries the column
+    uint64_t c = 0;                  // window constant C
+    uint64_t total = 0;              // sum of the lengths of all visited nodes (must stay below 2^31)
+    int32_t m_out = 0;
+    int64_t site_runs = 0;           // runs of segregating nodes between nodes every row visits (original node order)
+    bool bad = false;                // a multiplicity or weight does not fit
+};
+
+inline uint64_t mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const uint32_t *len, uint32_t flags, CompactPlan &pl) {
     const int words = (m + 31) / 32;
     std::vector<uint32_t> any((size_t)words, 0u), all((size_t)words, 0xffffffffu);
     for (int32_t i = 0; i < n; ++i) {
         const uint32_t *row = x + (size_t)i * pitch;
         for (int w = 0; w < words; ++w) { any[w] |= row[w]; all[w] &= row[w]; }
     }
-    pl.order.clear();
-    pl.const_len = 0;
-    pl.site_runs = 0;
+    pl.cols.clear(); pl.radj.clear();
+    pl.c = 0; pl.total = 0; pl.site_runs = 0; pl.bad = false;
+    uint64_t const_len = 0;
+    std::vector<int32_t> var;                              // variable columns of positive length, original order
     bool in_run = false;
     for (int32_t k = 0; k < m; ++k) {
         if (len[k] == 0u) continue;
         const uint32_t bit = 1u << (k & 31);
-        if (n > 0 && (all[k >> 5] & bit)) { pl.const_len += len[k]; in_run = false; }
+        if (n > 0 && (all[k >> 5] & bit)) { const_len += len[k]; pl.total += len[k]; in_run = false; }
         else if (any[k >> 5] & bit) {
-            pl.order.push_back(k);
+            var.push_back(k);
+            pl.total += len[k];
             if (!in_run) { ++pl.site_runs; in_run = true; }
         }
     }
-    std::stable_sort(pl.order.begin(), pl.order.end(), [&](int32_t a, int32_t b) { return len[a] < len[b]; });
-    pl.m_out = (int32_t)pl.order.size() + (pl.const_len > 0 ? 1 : 0);
+    const bool affine = (flags & IMPOP_COMPACT_PAIRS) != 0u;
+    if (!affine) {
+        for (int32_t k : var) pl.cols.push_back(CompactCol{k, len[k], 1});
+    } else {
+        // column signatures: h_k = sum of a random 64-bit value per row over the rows that carry k; a column and its
+        // complement add up to the sum over all rows.  Candidates are verified bit by bit.
+        std::vector<uint64_t> h((size_t)m, 0ull);
+        std::vector<uint32_t> vmask((size_t)words, 0u);
+        for (int32_t k : var) vmask[k >> 5] |= 1u << (k & 31);
+        uint64_t tsum = 0;
+        for (int32_t i = 0; i < n; ++i) {
+            const uint64_t r = mix64((uint64_t)i);
+            tsum += r;
+            const uint32_t *row = x + (size_t)i * pitch;
+            for (int w = 0; w < words; ++w) {
+                uint32_t b = row[w] & vmask[w];
+                while (b) { h[(size_t)w * 32 + __builtin_ctz(b)] += r; b &= b - 1; }
+            }
+        }
+        auto related = [&](int32_t a, int32_t b, uint32_t want) {          // want 0: identical columns, 1: complementary
+            const int wa = a >> 5, sa = a & 31, wb = b >> 5, sb = b & 31;
+            for (int32_t i = 0; i < n; ++i) {
+                const uint32_t *row = x + (size_t)i * pitch;
+                if ((((row[wa] >> sa) ^ (row[wb] >> sb)) & 1u) != want) return false;
+            }
+            return true;
+        };
+        struct Group { int32_t rep; uint64_t len; uint32_t cnt; uint64_t h; bool used; };
+        std::vector<Group> groups;
+        std::unordered_map<uint64_t, int32_t> by_hash;
+        by_hash.reserve(var.size() * 2);
+        for (int32_t k : var) {
+            auto it = by_hash.find(h[k]);
+            if (it != by_hash.end()) {
+                Group &g = groups[it->second];
+                if (g.cnt < 127u && related(g.rep, k, 0u)) { g.len += len[k]; ++g.cnt; continue; }
+                groups.push_back(Group{k, len[k], 1u, h[k], false});        // same signature, different column: stays alone
+                continue;
+            }
+            by_hash.emplace(h[k], (int32_t)groups.size());
+            groups.push_back(Group{k, len[k], 1u, h[k], false});
+        }
+        pl.c = const_len;
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            Group &g = groups[gi];
+            if (g.used) continue;
+            g.used = true;
+            auto it = by_hash.find(tsum - g.h);
+            if (it != by_hash.end() && (size_t)it->second != gi) {
+                Group &o = groups[it->second];
+                if (!o.used && related(g.rep, o.rep, 1u)) {
+                    o.used = true;
+                    pl.cols.push_back(CompactCol{g.rep, 0u, (uint8_t)(g.cnt + o.cnt)});
+                    const uint64_t wsum = g.len + o.len;
+                    if (wsum > 0xffffffffull || o.len > 0xffffffffull) { pl.bad = true; return; }
+                    pl.cols.back().w = (uint32_t)wsum;
+                    pl.c += o.len;
+                    pl.radj.emplace_back(g.rep, (uint32_t)o.len);
+                    continue;
+                }
+            }
+            if (g.len > 0xffffffffull) { pl.bad = true; return; }
+            pl.cols.push_back(CompactCol{g.rep, (uint32_t)g.len, (uint8_t)g.cnt});
+        }
+    }
+    std::stable_sort(pl.cols.begin(), pl.cols.end(), [](const CompactCol &a, const CompactCol &b) { return a.w < b.w; });
+    if (!affine) {
+        if (const_len > 0) {
+            if (const_len > 0xffffffffull) { pl.bad = true; return; }
+            pl.cols.push_back(CompactCol{-1, (uint32_t)const_len, 1});          // src -1: the all-ones column
+        }
+    } else if (flags & IMPOP_COMPACT_REPLICATE) {
+        // weights >= 255 as copies of the column with byte weights <= 254, where that does not cost more 128-column
+        // chunks than the device's heavy columns would (one entry per 255 * 255 of weight, padded to a chunk of their own)
+        const int64_t base = (int64_t)pl.cols.size();
+        int64_t extra_all = 0, entries = 0;
+        size_t first_heavy = pl.cols.size();
+        for (size_t j = 0; j < pl.cols.size(); ++j)
+            if (pl.cols[j].w >= 255u) {
+                if (first_heavy == pl.cols.size()) first_heavy = j;
+                extra_all += (int64_t)((pl.cols[j].w + 253u) / 254u) - 1;
+                entries += (int64_t)((pl.cols[j].w / 255u + 254u) / 255u);
+            }
+        if (extra_all > 0) {
+            auto chunks = [](int64_t cols) { return (cols + 127) / 128; };
+            const int64_t dev_chunks = chunks(base) + chunks(entries);
+            int64_t budget = chunks(base + extra_all) <= dev_chunks ? extra_all : chunks(std::max<int64_t>(base, 1)) * 128 - base;
+            std::vector<CompactCol> out(pl.cols.begin(), pl.cols.begin() + (ptrdiff_t)first_heavy), kept_heavy;
+            for (size_t j = first_heavy; j < pl.cols.size(); ++j) {        // ascending weight: the cheapest splits first
+                const CompactCol cc = pl.cols[j];
+                const int64_t copies = (int64_t)((cc.w + 253u) / 254u);
+                if (copies - 1 > budget) { kept_heavy.push_back(cc); continue; }
+                budget -= copies - 1;
+                uint32_t rest = cc.w;
+                for (int64_t t = 0; t < copies; ++t) {
+                    const uint32_t part = (uint32_t)((rest + (uint32_t)(copies - t) - 1u) / (uint32_t)(copies - t));   // even split, each <= 254
+                    out.push_back(CompactCol{cc.src, part, (uint8_t)(t == 0 ? cc.mult : 0)});
+                    rest -= part;
+                }
+            }
+            std::stable_sort(out.begin(), out.end(), [](const CompactCol &a, const CompactCol &b) { return a.w < b.w; });
+            out.insert(out.end(), kept_heavy.begin(), kept_heavy.end());
+            pl.cols.swap(out);
+        }
+    }
+    pl.m_out = (int32_t)pl.cols.size();
 }
 
 template <typename F>
@@ -589,49 +723,90 @@ void for_windows(int32_t windows, int32_t threads, F fn) {
     for (auto &th : pool) th.join();
 }
 
+// The plans of the last impop_compact_scan, kept for the impop_compact_fill that follows on the same arrays
+// (the pair search is the expensive half of the compaction: it runs once).
+struct PlanCache {
+    std::mutex mu;
+    const void *x = nullptr, *len = nullptr;
+    int32_t windows = -1;
+    uint32_t flags = 0;
+    std::vector<CompactPlan> plans;
+} g_plan_cache;
+
 }  // namespace
 
 extern "C" {
 
 int impop_compact_scan(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
-                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
+                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads, uint32_t flags,
                        int32_t *m_out, int64_t *site_runs_out) {
     if (windows < 0 || (windows > 0 && (!n || !m || !pitch_words || !x_off || !len_off || !m_out))) return IMPOP_ERR_ARG;
+    if ((flags & IMPOP_COMPACT_REPLICATE) && !(flags & IMPOP_COMPACT_PAIRS)) return IMPOP_ERR_ARG;
     for (int32_t w = 0; w < windows; ++w)
         if (n[w] < 0 || m[w] < 0 || (int64_t)pitch_words[w] * 32 < m[w] || (m[w] > 0 && n[w] > 0 && (!x_bits || !node_len)))
             return IMPOP_ERR_ARG;
+    std::vector<CompactPlan> plans((size_t)windows);
     for_windows(windows, threads, [&](int32_t w) {
-        CompactPlan pl;
-        compact_plan(n[w], m[w], pitch_words[w], x_bits + x_off[w], node_len + len_off[w], pl);
+        CompactPlan &pl = plans[w];
+        compact_plan(n[w], m[w], pitch_words[w], x_bits + x_off[w], node_len + len_off[w], flags, pl);
         m_out[w] = pl.m_out;
         if (site_runs_out) site_runs_out[w] = pl.site_runs;
     });
-    return IMPOP_OK;
+    bool bad = false;
+    for (const CompactPlan &pl : plans) bad |= pl.bad;
+    {
+        std::lock_guard<std::mutex> lk(g_plan_cache.mu);
+        g_plan_cache.x = x_bits; g_plan_cache.len = node_len; g_plan_cache.windows = windows; g_plan_cache.flags = flags;
+        g_plan_cache.plans.swap(plans);
+    }
+    return bad ? IMPOP_ERR_RANGE : IMPOP_OK;
 }
 
 int impop_compact_fill(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
-                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
+                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads, uint32_t flags,
                        const int32_t *out_pitch_words, const int64_t *out_x_off, const int64_t *out_len_off,
-                       uint32_t *x_out, uint32_t *len_out) {
+                       uint32_t *x_out, uint32_t *len_out, const int64_t *out_row_off, int32_t *row_adj_out,
+                       int64_t *win_const_out, uint8_t *col_mult_out) {
     if (windows < 0 || (windows > 0 && (!n || !m || !pitch_words || !x_off || !len_off || !out_pitch_words || !out_x_off ||
                                         !out_len_off || !x_out || !len_out)))
         return IMPOP_ERR_ARG;
+    const bool affine = (flags & IMPOP_COMPACT_PAIRS) != 0u;
+    if ((flags & IMPOP_COMPACT_REPLICATE) && !affine) return IMPOP_ERR_ARG;
+    if (affine && windows > 0 && (!out_row_off || !row_adj_out || !win_const_out || !col_mult_out)) return IMPOP_ERR_ARG;
+    std::vector<CompactPlan> cached;
+    {
+        std::lock_guard<std::mutex> lk(g_plan_cache.mu);
+        if (g_plan_cache.x == x_bits && g_plan_cache.len == node_len && g_plan_cache.windows == windows &&
+            g_plan_cache.flags == flags && (int32_t)g_plan_cache.plans.size() == windows) {
+            cached.swap(g_plan_cache.plans);
+            g_plan_cache.windows = -1;
+        }
+    }
     std::vector<int> bad((size_t)std::max(windows, 1), 0);
     for_windows(windows, threads, [&](int32_t w) {
-        CompactPlan pl;
+        CompactPlan local;
         const uint32_t *x = x_bits + x_off[w], *len = node_len + len_off[w];
-        compact_plan(n[w], m[w], pitch_words[w], x, len, pl);
+        if (cached.empty()) compact_plan(n[w], m[w], pitch_words[w], x, len, flags, local);
+        const CompactPlan &pl = cached.empty() ? local : cached[w];
         const int32_t op = out_pitch_words[w];
-        if ((int64_t)op * 32 < pl.m_out || pl.const_len > 0xffffffffull) { bad[w] = 1; return; }
+        if (pl.bad || (int64_t)op * 32 < pl.m_out || (affine && pl.total >= (1ull << 31))) { bad[w] = 1; return; }
         uint32_t *lo = len_out + out_len_off[w];
-        const int32_t nv = (int32_t)pl.order.size();
-        for (int32_t j = 0; j < nv; ++j) lo[j] = len[pl.order[j]];
-        if (pl.const_len > 0) lo[nv] = (uint32_t)pl.const_len;
-        const int32_t m_pad = op * 32;                        // lengths of the padding columns: 0 (the caller sizes len_out per pitch)
-        (void)m_pad;
+        const int32_t nv = pl.m_out;
+        for (int32_t j = 0; j < nv; ++j) lo[j] = pl.cols[j].w;
+        if (col_mult_out) {
+            uint8_t *mo = col_mult_out + out_len_off[w];
+            for (int32_t j = 0; j < nv; ++j) mo[j] = pl.cols[j].mult;
+        }
+        if (win_const_out) win_const_out[w] = (int64_t)pl.c;
         // source (word, shift) per output column, then one pass per row
         std::vector<uint32_t> sw((size_t)nv), ss((size_t)nv);
-        for (int32_t j = 0; j < nv; ++j) { sw[j] = (uint32_t)pl.order[j] >> 5; ss[j] = (uint32_t)pl.order[j] & 31u; }
+        std::vector<uint8_t> ones((size_t)nv, 0);
+        for (int32_t j = 0; j < nv; ++j) {
+            const int32_t src = pl.cols[j].src;
+            if (src < 0) { ones[j] = 1; sw[j] = 0; ss[j] = 0; }
+            else { sw[j] = (uint32_t)src >> 5; ss[j] = (uint32_t)src & 31u; }
+        }
+        int32_t *ra = row_adj_out ? row_adj_out + out_row_off[w] : nullptr;
         for (int32_t i = 0; i < n[w]; ++i) {
             const uint32_t *row = x + (size_t)i * pitch_words[w];
             uint32_t *out = x_out + out_x_off[w] + (size_t)i * op;
@@ -639,10 +814,14 @@ int impop_compact_fill(int32_t windows, const int32_t *n, const int32_t *m, cons
             for (int32_t ow = 0; ow < op; ++ow) {
                 uint32_t v = 0u;
                 const int32_t jend = std::min(nv, (ow + 1) * 32);
-                for (; j < jend; ++j) v |= ((row[sw[j]] >> ss[j]) & 1u) << (j & 31);
+                for (; j < jend; ++j) v |= (ones[j] ? 1u : ((row[sw[j]] >> ss[j]) & 1u)) << (j & 31);
                 out[ow] = v;
             }
-            if (pl.const_len > 0) out[nv >> 5] |= 1u << (nv & 31);
+            if (ra) {
+                uint32_t r = 0u;
+                for (const auto &pr : pl.radj) r += ((row[(uint32_t)pr.first >> 5] >> (pr.first & 31)) & 1u) * pr.second;
+                ra[i] = (int32_t)r;
+            }
         }
     });
     for (int32_t w = 0; w < windows; ++w)

@@ -96,7 +96,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
             for (int64_t k = h0 + threadIdx.x; k < h1; k += PREP_THREADS) tab.xh[k] = 0u;
         }
         __syncthreads();
-        if (threadIdx.x == 0 && (s_total >= (1ull << 31) || s_heavy > hpad)) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);
+        if (threadIdx.x == 0) {
+            const int64_t cw = tab.win_const ? tab.win_const[w] : 0;                     // affine form: window constant C
+            if (s_total >= (1ull << 31) || s_heavy > hpad || cw < 0 || cw >= (1ll << 31)) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);
+        }
         const int nh = s_heavy < hpad ? s_heavy : hpad;
         for (int s = nh + threadIdx.x; s < hpad; s += PREP_THREADS) heavy[s] = 0u;
         if (threadIdx.x == 0) tab.heavy_n[w] = nh;
@@ -181,11 +184,16 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
                         const bool lane_ok = lane < pw;
                         const uint32_t *src = x + (size_t)i0 * pitch + w0 + ps * 32 + lane;
                         __syncwarp();
-#pragma unroll 8
-                        for (int r = 0; r < 32; ++r) {
-                            const uint32_t v = (lane_ok && r < nrows) ? __ldg(src + (size_t)r * pitch) : 0u;
-                            tile[r * PR_TILE + lane] = v;
-                            if ((segrows >> r) & 1u) { any[ps] |= v; all[ps] &= v; }
+#pragma unroll 1
+                        for (int rb = 0; rb < 32; rb += 8) {       // eight row loads in flight, then their stores (kept explicit:
+                            uint32_t v[8];                         // left to the scheduler, a load and its store end up back to back)
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = (lane_ok && rb + q < nrows) ? __ldg(src + (size_t)(rb + q) * pitch) : 0u;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                tile[(rb + q) * PR_TILE + lane] = v[q];
+                                if ((segrows >> (rb + q)) & 1u) { any[ps] |= v[q]; all[ps] &= v[q]; }
+                            }
                         }
                         __syncwarp();
                     }
@@ -196,6 +204,9 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
                         const uint32_t v = mine[wd];
                         if (mk == 1u) {
                             acc += (uint32_t)__popc(v & s_pl[ps * 32 + wd][0]);
+                        } else if ((mk & (mk - 1u)) == 0u) {                       // one plane: every node of the word weighs 2^p (or 0)
+                            const int p = __ffs(mk) - 1;
+                            acc += (uint32_t)__popc(v & s_pl[ps * 32 + wd][p]) << p;
                         } else {
                             const uint4 lo4 = *reinterpret_cast<const uint4 *>(&s_pl[ps * 32 + wd][0]);
                             acc += (uint32_t)__popc(v & lo4.x) + ((uint32_t)__popc(v & lo4.y) << 1) +
@@ -227,7 +238,14 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
                         if (valid && touched && hbits) xh[(size_t)i * hwords + hw] |= hbits;   // (xh was zeroed by prep_cols)
                     }
                 }
-                if (valid) A[i] = (int32_t)(acc + (w0 ? (uint32_t)A[i] : 0u));
+                if (valid) {
+                    // affine form: A_i = I_ii = sum_k len_k x_ik + C - 2 R_i
+                    const uint32_t cw = tab.win_const ? (uint32_t)tab.win_const[w] : 0u;
+                    const uint32_t ri = tab.row_adj ? (uint32_t)tab.row_adj[tab.row_off[w] + i] : 0u;
+                    const uint32_t a = acc + (w0 ? (uint32_t)A[i] : cw - 2u * ri);
+                    A[i] = (int32_t)a;
+                    if (w0 + PR_WORDS >= wlim && (int32_t)a < 0) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);   // path length out of range
+                }
             }
 #pragma unroll
             for (int ps = 0; ps < PR_WORDS / 32; ++ps) {
@@ -269,7 +287,12 @@ __global__ void seg_count_kernel(const __grid_constant__ WindowTab tab, int64_t 
                 sg = any & ~all & live;
                 sep = all & live;
             }
-            seg += __popc(sg);
+            if (tab.col_mult) {                                    // a column may stand for several nodes (merged at ingest) or none (a copy)
+                const uint8_t *cm = tab.col_mult + tab.len_off[w] + (size_t)wd * 32;
+                for (uint32_t b = sg; b; b &= b - 1) seg += cm[__ffs(b) - 1];
+            } else {
+                seg += __popc(sg);
+            }
             // word summary: runs that start inside the word, and the kind of its first / last relevant node
             uint32_t rel = sg | sep;
             int internal = 0;
@@ -458,14 +481,13 @@ struct __align__(16) EpiCols {          // everything the epilogue needs of one 
     int32_t n, r0, col0, ncols;         // haplotypes of the window, first row, first column, columns of the item
     int32_t have_acc, last, rev, pad1;  // m > 0 (an accumulator exists); last item of this CTA's visit to the window;
                                         // rev: TMEM lane quarter q holds row quarter 3 - q (see ITEM_REV)
-    uint32_t aj[EPI_COLS];              // path length A_j
-#if IMPOP_EPI_UNION_F64
-    double ajd[EPI_COLS];               // the same as doubles (union formed in fp64)
-#endif
+    uint32_t aj[EPI_COLS];              // column value of the union: A_j - C + R_j (+ 1 for an empty path), see pi_batch
+    uint32_t rj[EPI_COLS];              // R_j (0 for a plain window)
     double fs[EPI_COLS], fa[EPI_COLS], fb[EPI_COLS];   // 1.0 / 0.0: column carries SUBSET / A / B
     uint32_t cmask[EPI_COLS / 16];      // per 16-column chunk: bit 0 all columns valid and in SUBSET, bit 1 any A, bit 2 any B,
                                         // bit 3 all in A, bit 4 all in B (a column carrying a label is a valid column)
-    uint32_t ai[TILE_M];                // path length A_i of the item's rows
+    uint32_t ai[TILE_M];                // row value of the union: A_i + R_i (+ 1 for an empty path)
+    uint32_t ci[TILE_M];                // C - R_i
     uint32_t fi[TILE_M];                // cleaned labels of the item's rows
 };
 
@@ -755,20 +777,18 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 const int n = ext.x, col0 = cur.z, ncols = cur.w;
                 const uint8_t *lab = tab.labels + (size_t)ext.w;
                 const int32_t *Aw = tab.A + (size_t)ext.z;
+                const int32_t *Rw = tab.row_adj ? tab.row_adj + (size_t)ext.z : nullptr;       // affine form (pi_batch)
+                const uint32_t cw = tab.win_const ? (uint32_t)__ldg(tab.win_const + cur.x) : 0u;
                 // issue the global loads before waiting for the slot
-                uint32_t cf[EPI_COLS / 32], ca[EPI_COLS / 32], rf[TILE_M / 32], ra_[TILE_M / 32];
+                uint32_t cf[EPI_COLS / 32], ca[EPI_COLS / 32], cr[EPI_COLS / 32];
 #pragma unroll
                 for (int ps = 0; ps < EPI_COLS / 32; ++ps) {
                     const int cc = ps * 32 + lane, j = col0 + cc;
                     const bool ok = cc < ncols && j < n;
                     cf[ps] = ok ? clean_label(__ldg(lab + j)) : 0u;
-                    ca[ps] = ok ? max((uint32_t)__ldg(Aw + j), 1u) : 1u;     // empty path: 1 instead of 0 (see pi_batch)
-                }
-#pragma unroll
-                for (int ps = 0; ps < TILE_M / 32; ++ps) {
-                    const int i = (cur.y & ITEM_BI_MASK) * TILE_M + ps * 32 + lane;
-                    rf[ps] = i < n ? clean_label(__ldg(lab + i)) : 0u;
-                    ra_[ps] = i < n ? max((uint32_t)__ldg(Aw + i), 1u) : 1u;
+                    const uint32_t a = ok ? (uint32_t)__ldg(Aw + j) : 1u, r = (ok && Rw) ? (uint32_t)__ldg(Rw + j) : 0u;
+                    ca[ps] = ok ? a - cw + r + (a == 0u ? 1u : 0u) : 1u;     // empty path: + 1 (see pi_batch)
+                    cr[ps] = r;
                 }
                 if (alive) alive = mbar_wait<100>(&sh.tbl_empty[slot], ((uint32_t)(k / WS_TABLES) & 1u) ^ 1u, tab.err);
                 EpiCols &col = sh.col[slot];
@@ -777,9 +797,7 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     const int cc = ps * 32 + lane;
                     const uint32_t f = cf[ps];
                     col.aj[cc] = ca[ps];
-#if IMPOP_EPI_UNION_F64
-                    col.ajd[cc] = (double)ca[ps];
-#endif
+                    col.rj[cc] = cr[ps];
                     col.fs[cc] = (f & IMPOP_LAB_SUBSET) ? 1.0 : 0.0;
                     col.fa[cc] = (f & IMPOP_LAB_A) ? 1.0 : 0.0;
                     col.fb[cc] = (f & IMPOP_LAB_B) ? 1.0 : 0.0;
@@ -794,7 +812,13 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                     }
                 }
 #pragma unroll
-                for (int ps = 0; ps < TILE_M / 32; ++ps) { col.ai[ps * 32 + lane] = ra_[ps]; col.fi[ps * 32 + lane] = rf[ps]; }
+                for (int ps = 0; ps < TILE_M / 32; ++ps) {     // the row side (loaded here: this warp runs items ahead, and has 48 registers)
+                    const int i = (cur.y & ITEM_BI_MASK) * TILE_M + ps * 32 + lane;
+                    const uint32_t a = i < n ? (uint32_t)__ldg(Aw + i) : 1u, r = (i < n && Rw) ? (uint32_t)__ldg(Rw + i) : 0u;
+                    col.ai[ps * 32 + lane] = i < n ? a + r + (a == 0u ? 1u : 0u) : 1u;
+                    col.ci[ps * 32 + lane] = i < n ? cw - r : 0u;
+                    col.fi[ps * 32 + lane] = i < n ? clean_label(__ldg(lab + i)) : 0u;
+                }
                 if (lane == 0) {
                     col.n = n; col.r0 = (cur.y & ITEM_BI_MASK) * TILE_M; col.col0 = col0; col.ncols = ncols;
                     col.have_acc = ext.y > 0 ? 1 : 0; col.last = (nxt.x != cur.x) ? 1 : 0; col.rev = (cur.y & ITEM_REV) ? 1 : 0;
@@ -884,15 +908,13 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
             const int rq = col.rev ? 3 - q4 : q4;                         // row quarter behind this warp's TMEM lanes
             const int r0 = geo.y + rq * 32;
             const int i = r0 + lane;
-            const uint32_t ai = col.ai[rq * 32 + lane];
-#if IMPOP_EPI_UNION_F64
-            const double dai = (double)ai;
-#endif
+            const uint32_t ai = col.ai[rq * 32 + lane], ci = col.ci[rq * 32 + lane];
             const uint32_t fi = col.fi[rq * 32 + lane];
             // this quarter's valid chunks [c_lo, c_hi): columns below n, not entirely left of the diagonal; split in two
             int c_lo = 0, c_hi = 0;
+            const int cwidth = min(geo.w, n - col0);                      // columns of the item inside the matrix
             if (r0 < n) {
-                const int width = min(geo.w, n - col0);
+                const int width = cwidth;
                 c_hi = (width + 15) >> 4;
                 c_lo = max(0, (r0 - col0) >> 4);
                 if (c_lo > c_hi) c_lo = c_hi;
@@ -925,31 +947,19 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                              double &call) {
                 constexpr bool FAST = decltype(fast_tag)::value;
                 const int jbase = col0 + cc;
-                uint32_t aj[IMPOP_EPI_NP];
+                uint32_t aj[IMPOP_EPI_NP], rj[IMPOP_EPI_NP];
                 double p[IMPOP_EPI_NP];
-#if IMPOP_EPI_UNION_F64 && !defined(IMPOP_DBG_NO_EPI)
-                double daj[IMPOP_EPI_NP];
-#pragma unroll
-                for (int k2 = 0; k2 < IMPOP_EPI_NP / 2; ++k2) {
-                    const double2 q = *reinterpret_cast<const double2 *>(&col.ajd[cc + g0 + 2 * k2]);
-                    daj[2 * k2] = q.x; daj[2 * k2 + 1] = q.y;
-                }
-                if (DUMP) {
-#pragma unroll
-                    for (int q = 0; q < IMPOP_EPI_NP; ++q) aj[q] = col.aj[cc + g0 + q];
-                }
-                pi_batch_f64<IMPOP_EPI_NP>(r, dai, daj, p);
-#else
                 {
                     const uint4 q = *reinterpret_cast<const uint4 *>(&col.aj[cc + g0]);
                     aj[0] = q.x; aj[1] = q.y; aj[2] = q.z; aj[3] = q.w;
+                    const uint4 t = *reinterpret_cast<const uint4 *>(&col.rj[cc + g0]);
+                    rj[0] = t.x; rj[1] = t.y; rj[2] = t.z; rj[3] = t.w;
                 }
 #ifdef IMPOP_DBG_NO_EPI      // timing experiment only: skip the fp64 math
 #pragma unroll
-                for (int q = 0; q < IMPOP_EPI_NP; ++q) p[q] = __hiloint2double(r[q] + aj[q], ai);
+                for (int q = 0; q < IMPOP_EPI_NP; ++q) p[q] = __hiloint2double(r[q] + aj[q] - rj[q], ai + ci);
 #else
-                pi_batch<IMPOP_EPI_NP>(r, ai, aj, p);
-#endif
+                pi_batch<IMPOP_EPI_NP>(r, ai, aj, ci, rj, p);
 #endif
                 if (on_diag) {
 #pragma unroll
@@ -957,7 +967,8 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 }
                 if (DUMP) {
 #pragma unroll
-                    for (int q = 0; q < IMPOP_EPI_NP; ++q) pair_dump(prm, n, i, jbase + g0 + q, r[q], ai, aj[q]);
+                    for (int q = 0; q < IMPOP_EPI_NP; ++q)      // true intersection; ai + ci and aj - rj leave the union as it is
+                        pair_dump(prm, n, i, jbase + g0 + q, r[q] + ci - rj[q], ai + ci, aj[q] - rj[q]);
                 }
                 if (FAST) {                                     // plain pairwise tree over the group, shared by the classes
                     call = __dadd_rn(call, __dadd_rn(__dadd_rn(p[0], p[1]), __dadd_rn(p[2], p[3])));
@@ -981,28 +992,26 @@ window_pairs_tc_kernel(const __grid_constant__ WindowTab tab, const __grid_const
                 const bool fast = false;
 #else
                 // every column in SUBSET, and A (B) holds all of them or none
-                const bool fast = (cm & 1u) && ((cm & (2u | 8u)) != 2u) && ((cm & (4u | 16u)) != 4u);
+                // (a window without columns has no accumulator: its chunks take the general body, which tests for that)
+                const bool fast = have_acc && (cm & 1u) && ((cm & (2u | 8u)) != 2u) && ((cm & (4u | 16u)) != 4u);
 #endif
                 const int cc = c << 4;
                 const bool on_diag = col0 + cc <= r0 + 31;         // the chunk touches the diagonal of this warp's rows
                 double cs = 0.0, ca = 0.0, cb = 0.0, call = 0.0;   // sums over the chunk's SUBSET / A / B / all columns
                 if (fast) {
                     uint32_t r[16];
-                    if (have_acc) {
-                        tmem_ld16(tm0 + (uint32_t)cc, r);
-                        tmem_ld_wait();
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) r[q] = 0u;
-                    }
+                    tmem_ld16(tm0 + (uint32_t)cc, r);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int g0 = 0; g0 < 16; g0 += IMPOP_EPI_NP) group(r + g0, cc, g0, on_diag, std::true_type{}, cs, ca, cb, call);
                     esum_add(ts, call);                             // fast implies all 16 columns in SUBSET
                     if (cm & 8u) esum_add(ta, call);
                     if (cm & 16u) esum_add(tb, call);
                 } else {
+                    // the last chunk of a row block usually holds only a few columns of the matrix: groups beyond them are skipped
+                    const int glim = min(16, (cwidth - cc + IMPOP_EPI_NP - 1) & ~(IMPOP_EPI_NP - 1));
 #pragma unroll 1
-                    for (int g0 = 0; g0 < 16; g0 += IMPOP_EPI_NP) {
+                    for (int g0 = 0; g0 < glim; g0 += IMPOP_EPI_NP) {
                         uint32_t r[IMPOP_EPI_NP];
                         if (have_acc) {
                             tmem_ld4(tm0 + (uint32_t)(cc + g0), r);
@@ -1092,6 +1101,8 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const _
         const bool rvalid = i < n;
         const uint32_t ai = rvalid ? (uint32_t)Aw[i] : 0u;
         const uint32_t fi = rvalid ? clean_label(lab[i]) : 0u;
+        const int32_t *Rw = tab.row_adj ? tab.row_adj + tab.row_off[it.w] : nullptr;         // affine form: I = cnt + C - R_i - R_j
+        const uint32_t ci = (tab.win_const ? (uint32_t)tab.win_const[it.w] : 0u) - ((rvalid && Rw) ? (uint32_t)Rw[i] : 0u);
         const bool dump = (prm.dumpI != nullptr) || (prm.dumpPi != nullptr);
         dd ts = {0.0, 0.0}, ta = {0.0, 0.0}, tb = {0.0, 0.0};
 
@@ -1152,13 +1163,14 @@ __global__ void __launch_bounds__(SIMT_THREADS) window_pairs_simt_kernel(const _
                 const bool jv = j < n;
                 const uint32_t aj = jv ? (uint32_t)__ldg(Aw + j) : 0u;
                 const uint32_t fj = jv ? clean_label(__ldg(lab + j)) : 0u;
+                const uint32_t inter = cnt[k] + ci - ((jv && Rw) ? (uint32_t)__ldg(Rw + j) : 0u);
                 if (fj != 0u) {
-                    const double p = (rvalid && j > i) ? pi_from_counts(cnt[k], ai, aj) : 0.0;
+                    const double p = (rvalid && j > i) ? pi_from_counts(inter, ai, aj) : 0.0;
                     if (fj & IMPOP_LAB_SUBSET) cs = __dadd_rn(cs, p);
                     if (fj & IMPOP_LAB_A) ca = __dadd_rn(ca, p);
                     if (fj & IMPOP_LAB_B) cb = __dadd_rn(cb, p);
                 }
-                if (dump) pair_dump(prm, n, i, j, cnt[k], ai, aj);
+                if (dump) pair_dump(prm, n, i, j, inter, ai, aj);
             }
             dd_add(ts, cs); dd_add(ta, ca); dd_add(tb, cb);
         }
@@ -1296,6 +1308,26 @@ __global__ void division_selftest_kernel(uint64_t seed, int64_t count, unsigned 
             b2 = (b2 & 0x7FFFFFFFu) ? (b2 & 0x7FFFFFFFu) : 1u;
             const double da = u32_to_double(a2), db = u32_to_double(b2);
             if (__double_as_longlong(__ddiv_rn(da, db)) != __double_as_longlong(div_rn_int31(da, db))) ++bad;
+        }
+        {   // the epilogue's own code path (pi_batch: four chains, seeds whose low words are the integers, affine operands):
+            // the pair above plus three derived ones, each split at random into accumulator, row and column values
+            uint32_t acc4[4], aj4[4], rj4[4], want_i[4], want_ai[4], want_aj[4];
+            const uint32_t ai_t = (uint32_t)(z2 >> 3), ci = (uint32_t)(z >> 17) * 2654435761u;
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t a_i = q == 0 ? ai : (ai >> q) + (uint32_t)q, a_j = q == 0 ? aj : (aj >> (q ^ 1)) + 1u;
+                const uint32_t lm = a_i < a_j ? a_i : a_j;
+                const uint32_t it = q == 0 ? inter : (lm ? (uint32_t)((z2 >> (8 + q)) % ((uint64_t)lm + 1u)) : 0u);
+                uint32_t un = a_i + a_j - it;
+                un = un ? un : 1u;
+                rj4[q] = (uint32_t)(z2 >> (11 * q)) ^ (uint32_t)z;
+                acc4[q] = it - ci + rj4[q];                       // inter = acc + ci - rj
+                aj4[q] = un + acc4[q] - ai_t;                     // union = ai + aj - acc
+                want_i[q] = it; want_ai[q] = a_i; want_aj[q] = a_j;
+            }
+            double p4[4];
+            pi_batch<4>(acc4, ai_t, aj4, ci, rj4, p4);
+            for (int q = 0; q < 4; ++q)
+                if (__double_as_longlong(pi_from_counts(want_i[q], want_ai[q], want_aj[q])) != __double_as_longlong(p4[q])) ++bad;
         }
     }
     if (bad) atomicAdd(out, bad);

@@ -217,7 +217,8 @@ class WindowBatch:
     """
 
     def __init__(self, ctx: Context, n, m, pitch_words, x_off, len_off, lab_off, length,
-                 x: torch.Tensor, node_len: torch.Tensor, labels: torch.Tensor, node_len_host=None, stream=None, site_runs=None):
+                 x: torch.Tensor, node_len: torch.Tensor, labels: torch.Tensor, node_len_host=None, stream=None, site_runs=None,
+                 row_adj=None, win_const=None, col_mult=None):
         self.ctx = ctx
         self.n = np.ascontiguousarray(n, dtype=np.int32)
         self.m = np.ascontiguousarray(m, dtype=np.int32)
@@ -230,9 +231,14 @@ class WindowBatch:
         self.x, self.node_len, self.labels = x, node_len, labels      # keep the device buffers alive
         # site_runs: IMPOP_ST_S_BUBBLES per window as counted at ingest on the original node order (None: counted on the device)
         self.site_runs = None if site_runs is None else np.ascontiguousarray(site_runs, dtype=np.int64)
+        # affine form of the windows (ingest.compact_batch(pairs=True)): row terms R_i (device int32, the windows' rows in batch order), window
+        # constants C (host int64), column multiplicities for S (device uint8, columns at len_off); None: a plain batch
+        self.row_adj, self.col_mult = row_adj, col_mult
+        self.win_const = None if win_const is None else np.ascontiguousarray(win_const, dtype=np.int64)
         d = N.BatchDesc(self.windows, _ptr(self.n), _ptr(self.m), _ptr(self.pitch_words), _ptr(self.x_off),
                         _ptr(self.len_off), _ptr(self.lab_off), _ptr(self.length), _ptr(x), _ptr(node_len),
-                        _ptr(labels), _ptr(node_len_host), _stream_ptr(stream), _ptr(self.site_runs))
+                        _ptr(labels), _ptr(node_len_host), _stream_ptr(stream), _ptr(self.site_runs),
+                        _ptr(row_adj), _ptr(self.win_const), _ptr(col_mult))
         h = C.c_void_p()
         rc = ctx.lib.impop_batch_create(ctx.handle, C.byref(d), C.byref(h))
         if rc != 0:
@@ -242,29 +248,46 @@ class WindowBatch:
     # ------------------------------------------------------------------ constructors
     @classmethod
     def from_uniform(cls, ctx: Context, x_bits, node_len, labels, length, m: int | None = None, node_len_host=None,
-                     stream=None, site_runs=None):
-        """W same-shape windows: x_bits [W, n, pitch] u32, node_len [W, m_pad] u32, labels [n] or [W, n] u8.
+                     stream=None, site_runs=None, row_adj=None, win_const=None, col_mult=None):
+        """W same-shape windows: x_bits [W, n, pitch] u32, node_len [W, m_pad] u32, labels [n] or [W, n] u8; m: columns in use,
+        one number or one per window (default: all m_pad; columns beyond m must have length 0 and cost nothing when given).
 
-        Arguments may be numpy arrays (copied to the device) or device tensors (used in place).
+        Arguments may be numpy arrays (copied to the device) or device tensors (used in place).  Affine form
+        (ingest.compact_uniform(pairs=True)): row_adj [W, n] i32, win_const [W] i64 (host), col_mult [W, m_pad] u8.
         """
         W, n, pitch = x_bits.shape
         m_pad = node_len.shape[1]
         as_dev = lambda a, dt: ctx.upload(np.ascontiguousarray(a, dtype=dt).view(np.int32 if dt == np.uint32 else dt)) if isinstance(a, np.ndarray) else a
         xd, ld, lab = as_dev(x_bits, np.uint32), as_dev(node_len, np.uint32), as_dev(labels, np.uint8)
         per_window_labels = lab.dim() == 2
+        if row_adj is not None:
+            row_adj = as_dev(row_adj, np.int32)
+        if col_mult is not None:
+            col_mult = as_dev(col_mult, np.uint8)
         ar = np.arange(W, dtype=np.int64)
         L = np.full(W, int(length or 0), dtype=np.int64) if np.isscalar(length) or length is None else np.asarray(length)
-        return cls(ctx, np.full(W, n), np.full(W, m_pad if m is None else m), np.full(W, pitch), ar * (n * pitch),
+        m_w = np.full(W, m_pad) if m is None else (np.full(W, int(m)) if np.isscalar(m) else np.asarray(m, dtype=np.int32))
+        return cls(ctx, np.full(W, n), m_w, np.full(W, pitch), ar * (n * pitch),
                    ar * m_pad, ar * n if per_window_labels else np.zeros(W, dtype=np.int64), L, xd, ld, lab,
-                   node_len_host=node_len_host, stream=stream, site_runs=site_runs)
+                   node_len_host=node_len_host, stream=stream, site_runs=site_runs, row_adj=row_adj, win_const=win_const,
+                   col_mult=col_mult)
 
     @classmethod
     def from_windows(cls, ctx: Context, windows, site_runs=None):
-        """Ragged batch from a list of (x_bits [n, pitch] u32, node_len [m] u32, labels [n] u8, L) host arrays."""
+        """Ragged batch from a list of (x_bits [n, pitch] u32, node_len [m] u32, labels [n] u8, L) host arrays; a window
+        in affine form (ingest.compact_window) appends (row_adj [n] i32, win_const, col_mult [m] u8)."""
         n, m, pitch, x_off, len_off, lab_off, L = [], [], [], [], [], [], []
         xs, ls, labs = [], [], []
+        radj, wconst, cmult = [], [], []
+        affine = any(len(wd) > 4 and wd[4] is not None for wd in windows)
         xo = lo = bo = 0
-        for xb, nl, lab, length in windows:
+        for wd in windows:
+            xb, nl, lab, length = wd[:4]
+            if affine:
+                has = len(wd) > 4 and wd[4] is not None
+                radj.append(np.asarray(wd[4], dtype=np.int32) if has else np.zeros(len(lab), dtype=np.int32))
+                wconst.append(int(wd[5]) if has else 0)
+                cmult.append(np.asarray(wd[6], dtype=np.uint8) if has else np.ones(len(nl), dtype=np.uint8))
             xb = np.ascontiguousarray(xb, dtype=np.uint32)
             if xb.ndim != 2:
                 xb = xb.reshape(len(lab), -1)
@@ -283,7 +306,11 @@ class WindowBatch:
         x = ctx.upload(cat(xs, np.uint32).view(np.int32))
         nl = ctx.upload(cat(ls, np.uint32).view(np.int32))
         lab = ctx.upload(cat(labs, np.uint8))
-        return cls(ctx, n, m, pitch, x_off, len_off, lab_off, L, x, nl, lab, site_runs=site_runs)
+        extra = {}
+        if affine:
+            extra = dict(row_adj=ctx.upload(cat(radj, np.int32)), win_const=np.array(wconst, dtype=np.int64),
+                         col_mult=ctx.upload(cat(cmult, np.uint8)))
+        return cls(ctx, n, m, pitch, x_off, len_off, lab_off, L, x, nl, lab, site_runs=site_runs, **extra)
 
     # ------------------------------------------------------------------ life cycle
     def close(self):

@@ -28,6 +28,9 @@ class GraphWindow:
     region: str | None = None
     length: int = 0        # window length L in bp (BED end - start); 0 = unknown
     site_runs: int = -1    # variant sites (bubble-like runs of segregating nodes) counted before compaction; -1: not counted
+    row_adj: np.ndarray | None = None   # affine form (compact_window): R_i [n] int32, window constant C, column multiplicities [m] uint8
+    win_const: int = 0
+    col_mult: np.ndarray | None = None
 
     @property
     def n(self) -> int:
@@ -127,9 +130,10 @@ def save_batch(path, windows) -> None:
     names = "\n".join("\t".join(w.names) for w in windows)
     regions = "\n".join(w.region or "" for w in windows)
     L = np.array([w.length for w in windows], dtype=np.int64)
-    np.savez(path, format=np.array([1]), n=n, m=m, pitch=pitch, x=x.astype(np.uint32), node_len=nl.astype(np.uint32),
+    radj, wconst, cmult, runs = _affine_arrays(windows)
+    np.savez(path, format=np.array([2]), n=n, m=m, pitch=pitch, x=x.astype(np.uint32), node_len=nl.astype(np.uint32),
              names=np.frombuffer(names.encode(), dtype=np.uint8), regions=np.frombuffer(regions.encode(), dtype=np.uint8),
-             length=L)
+             length=L, row_adj=radj, win_const=wconst, col_mult=cmult, site_runs=runs)
 
 
 def load_batch(path) -> list:
@@ -138,24 +142,45 @@ def load_batch(path) -> list:
     x_all, len_all, L_all = z["x"], z["node_len"], z["length"]        # NpzFile re-reads a member on every access: once each
     names = z["names"].tobytes().decode().split("\n") if len(n) else []
     regions = z["regions"].tobytes().decode().split("\n") if len(n) else []
-    out, xo, lo = [], 0, 0
+    affine = "row_adj" in z.files
+    if affine:
+        radj, wconst, cmult, runs = z["row_adj"], z["win_const"], z["col_mult"], z["site_runs"]
+    out, xo, lo, ro = [], 0, 0, 0
     for w in range(len(n)):
         xs = int(n[w]) * int(pitch[w])
-        out.append(GraphWindow(names[w].split("\t") if names[w] else [],
-                               x_all[xo:xo + xs].reshape(int(n[w]), int(pitch[w])).copy(),
-                               len_all[lo:lo + int(m[w])].copy(), None, regions[w] or None, int(L_all[w])))
+        g = GraphWindow(names[w].split("\t") if names[w] else [],
+                        x_all[xo:xo + xs].reshape(int(n[w]), int(pitch[w])).copy(),
+                        len_all[lo:lo + int(m[w])].copy(), None, regions[w] or None, int(L_all[w]))
+        if affine:
+            g.site_runs = int(runs[w])
+            g.row_adj, g.win_const, g.col_mult = radj[ro:ro + int(n[w])].copy(), int(wconst[w]), cmult[lo:lo + int(m[w])].copy()
+        out.append(g)
         xo += xs
         lo += int(m[w])
+        ro += int(n[w])
     return out
+
+
+def _affine_arrays(windows):
+    """(row_adj int32 [rows], win_const int64 [W], col_mult uint8 [nodes], site_runs int64 [W]) of a GraphWindow list; a
+    plain window contributes R = 0, C = 0, multiplicity 1."""
+    radj = [np.asarray(w.row_adj, dtype=np.int32) if w.row_adj is not None else np.zeros(w.n, dtype=np.int32) for w in windows]
+    cmult = [np.asarray(w.col_mult, dtype=np.uint8) if w.col_mult is not None else np.ones(w.m, dtype=np.uint8) for w in windows]
+    cat = lambda parts, dt: np.concatenate(parts).astype(dt, copy=False) if parts else np.zeros(0, dtype=dt)
+    return (cat(radj, np.int32), np.array([int(w.win_const) for w in windows], dtype=np.int64), cat(cmult, np.uint8),
+            np.array([int(w.site_runs) for w in windows], dtype=np.int64))
 
 
 # ------------------------------------------------------------------------------------------------------------
 # Flat container: one file, fixed little-endian layout, every array usable in place (np.memmap) -- a chromosome's
 # windows go from disk to one WindowBatch without a per-window Python loop and without copies.
-#   header  8 x int64: magic, version, W, rows (sum n), x words, nodes (sum m), unique names U, text bytes
-#   int64   n[W] m[W] pitch[W] x_off[W] len_off[W] row_off[W] length[W]
+#   header  8 x int64: magic, version (2), W, rows (sum n), x words, nodes (sum m), unique names U, text bytes
+#   int64   n[W] m[W] pitch[W] x_off[W] len_off[W] row_off[W] length[W] site_runs[W] win_const[W]
 #   int32   name_id[rows]            index of the row's haplotype in the unique-name table
-#   uint32  node_len[nodes]  then  x[x words]   (x starts on a 64-byte boundary)
+#   int32   row_adj[rows]            affine form (impop_batch_desc_t): R_i; a plain window has R = 0, C = 0, multiplicity 1
+#   uint32  node_len[nodes]
+#   uint8   col_mult[nodes]          (padded to 4 bytes)
+#   uint32  x[x words]               (starts on a 64-byte boundary)
 #   text    unique names ('\n' joined; a row name = unique name + ':' + the window's coordinates when the source had them)
 #           + '\x00' + regions ('\n' joined) + '\x00' + per-window coordinate suffixes ('\n' joined)
 # ------------------------------------------------------------------------------------------------------------
@@ -177,6 +202,10 @@ class FlatBatch:
     uniq: list
     regions: list
     suffix: list
+    site_runs: np.ndarray | None = None
+    win_const: np.ndarray | None = None
+    row_adj: np.ndarray | None = None
+    col_mult: np.ndarray | None = None
 
     @property
     def windows(self) -> int:
@@ -202,8 +231,14 @@ class FlatBatch:
     def window(self, w: int) -> GraphWindow:
         xs, pw, nn = int(self.x_off[w]), int(self.pitch[w]), int(self.n[w])
         lo = int(self.len_off[w])
-        return GraphWindow(self.names(w), np.asarray(self.x[xs:xs + nn * pw]).reshape(nn, pw), np.asarray(self.node_len[lo:lo + int(self.m[w])]),
-                           None, self.regions[w] or None, int(self.length[w]))
+        g = GraphWindow(self.names(w), np.asarray(self.x[xs:xs + nn * pw]).reshape(nn, pw), np.asarray(self.node_len[lo:lo + int(self.m[w])]),
+                        None, self.regions[w] or None, int(self.length[w]))
+        if self.row_adj is not None:
+            ro = int(self.row_off[w])
+            g.site_runs = int(self.site_runs[w])
+            g.row_adj, g.win_const = np.asarray(self.row_adj[ro:ro + nn]), int(self.win_const[w])
+            g.col_mult = np.asarray(self.col_mult[lo:lo + int(self.m[w])])
+        return g
 
 
 def _split_name(name: str):
@@ -243,13 +278,16 @@ def save_flat(path, windows) -> None:
     text = ("\n".join(uniq) + "\x00" + "\n".join(w.region or "" for w in windows) + "\x00" + "\n".join(suffix)).encode()
     node_len = np.concatenate([w.node_len for w in windows]).astype(np.uint32) if W else np.zeros(0, np.uint32)
     x = np.concatenate([w.x_bits.reshape(-1) for w in windows]).astype(np.uint32) if W else np.zeros(0, np.uint32)
-    hdr = np.array([FLAT_MAGIC, 1, W, int(n.sum()), int(x.size), int(m.sum()), len(uniq), len(text)], dtype=np.int64)
+    radj, wconst, cmult, runs = _affine_arrays(windows)
+    hdr = np.array([FLAT_MAGIC, 2, W, int(n.sum()), int(x.size), int(m.sum()), len(uniq), len(text)], dtype=np.int64)
     with open(path, "wb") as fh:
         fh.write(hdr.tobytes())
-        for a in (n, m, pitch, x_off, len_off, row_off, length):
+        for a in (n, m, pitch, x_off, len_off, row_off, length, runs, wconst):
             fh.write(a.tobytes())
         fh.write(name_id.tobytes())
+        fh.write(radj.tobytes())
         fh.write(node_len.tobytes())
+        fh.write(cmult.tobytes())
         fh.write(b"\x00" * ((-fh.tell()) % 64))
         fh.write(x.tobytes())
         fh.write(text)
@@ -259,18 +297,27 @@ def load_flat(path, mmap: bool = True) -> FlatBatch:
     """Flat container -> FlatBatch whose arrays are views of the file (np.memmap) -- no per-window work."""
     buf = np.memmap(path, dtype=np.uint8, mode="r") if mmap else np.fromfile(path, dtype=np.uint8)
     hdr = np.frombuffer(buf, dtype=np.int64, count=8)
-    if int(hdr[0]) != FLAT_MAGIC or int(hdr[1]) != 1:
+    if int(hdr[0]) != FLAT_MAGIC or int(hdr[1]) not in (1, 2):
         raise ValueError(f"{path}: not an impop window container")
+    v2 = int(hdr[1]) == 2
     W, rows, xw, nodes, U, tb = (int(v) for v in hdr[2:8])
     off = 64
     out = []
-    for _ in range(7):
+    for _ in range(9 if v2 else 7):
         out.append(np.frombuffer(buf, dtype=np.int64, count=W, offset=off))
         off += 8 * W
+    runs, wconst = (out.pop(7), out.pop(7)) if v2 else (None, None)
     name_id = np.frombuffer(buf, dtype=np.int32, count=rows, offset=off)
     off += 4 * rows
+    radj = cmult = None
+    if v2:
+        radj = np.frombuffer(buf, dtype=np.int32, count=rows, offset=off)
+        off += 4 * rows
     node_len = np.frombuffer(buf, dtype=np.uint32, count=nodes, offset=off)
     off += 4 * nodes
+    if v2:
+        cmult = np.frombuffer(buf, dtype=np.uint8, count=nodes, offset=off)
+        off += nodes
     off += (-off) % 64
     x = np.frombuffer(buf, dtype=np.uint32, count=xw, offset=off)
     off += 4 * xw
@@ -280,7 +327,7 @@ def load_flat(path, mmap: bool = True) -> FlatBatch:
         regions = [""] * W
     if W and not suffix:
         suffix = [""] * W
-    return FlatBatch(*out, name_id, node_len, x, uniq, regions, suffix)
+    return FlatBatch(*out, name_id, node_len, x, uniq, regions, suffix, runs, wconst, radj, cmult)
 
 
 def labels_from_names(names, pop_a=None, pop_b=None, subset=None, seg=None) -> np.ndarray:
@@ -337,14 +384,35 @@ def _host_threads(threads):
     return max(1, int(threads))
 
 
-def compact_batch(n, m, pitch_words, x_off, len_off, x_bits, node_len, threads=None, uniform_pitch: bool = False):
+@dataclass
+class Compacted:
+    """What impop_compact_scan / _fill return for a host batch; the affine form (pairs=True) adds row_adj / win_const /
+    col_mult (see impop_batch_desc_t), which a batch built from x_out / len_out MUST be given."""
+    m_out: np.ndarray
+    pitch_out: np.ndarray
+    x_off_out: np.ndarray
+    len_off_out: np.ndarray
+    x_out: np.ndarray
+    len_out: np.ndarray
+    site_runs: np.ndarray
+    row_off_out: np.ndarray | None = None
+    row_adj: np.ndarray | None = None      # int32, the windows' rows in batch order
+    win_const: np.ndarray | None = None    # int64 [W]
+    col_mult: np.ndarray | None = None     # uint8, laid out like len_out
+
+
+def compact_batch(n, m, pitch_words, x_off, len_off, x_bits, node_len, threads=None, uniform_pitch: bool = False,
+                  pairs: bool = True, replicate: bool = True) -> Compacted:
     """Compact every window of a host batch (descriptor arrays as WindowBatch takes them; x_bits / node_len flat uint32).
 
     Nodes carried by every haplotype of a window are merged into one node of their summed length, nodes carried by
     none (or of length 0) are dropped, the rest is ordered by length: every I_ij, A_i, U_ij, S and statistic is
     unchanged, while an HPRC-shaped window loses the third of its columns that is backbone.
-    Returns (m_out, pitch_out, x_off_out, len_off_out, x_out, len_out); len_out rows are padded with zeros to
-    32 * pitch_out nodes so that a window's lengths can be sliced like its presence words."""
+    pairs=True (affine form): identical columns are merged and the two complementary columns of a bi-allelic bubble
+    become one (row terms R_i, window constant C, column multiplicities for S); replicate=True also spreads weights
+    >= 255 over copies of their column where the copies fit into the chunk padding (include/impop_b200.h).
+    len_out rows are padded with zeros to 32 * pitch_out nodes so that a window's lengths can be sliced like its
+    presence words."""
     L = lib()
     n = np.ascontiguousarray(n, dtype=np.int32)
     m = np.ascontiguousarray(m, dtype=np.int32)
@@ -355,10 +423,11 @@ def compact_batch(n, m, pitch_words, x_off, len_off, x_bits, node_len, threads=N
     node_len = np.ascontiguousarray(node_len).view(np.uint32).reshape(-1)
     W = int(n.shape[0])
     th = _host_threads(threads)
+    flags = (_native.COMPACT_PAIRS | (_native.COMPACT_REPLICATE if replicate else 0)) if pairs else 0
     m_out = np.zeros(W, dtype=np.int32)
     runs = np.zeros(W, dtype=np.int64)
     rc = L.impop_compact_scan(W, n.ctypes.data, m.ctypes.data, pitch_words.ctypes.data, x_off.ctypes.data,
-                              len_off.ctypes.data, x_bits.ctypes.data, node_len.ctypes.data, th, m_out.ctypes.data,
+                              len_off.ctypes.data, x_bits.ctypes.data, node_len.ctypes.data, th, flags, m_out.ctypes.data,
                               runs.ctypes.data)
     compact_batch.last_site_runs = runs              # variant sites (bubble-like runs) of each window in its original node order
     if rc:
@@ -372,33 +441,69 @@ def compact_batch(n, m, pitch_words, x_off, len_off, x_bits, node_len, threads=N
     len_off_out = np.concatenate([[0], np.cumsum(cols)[:-1]]).astype(np.int64) if W else np.zeros(0, np.int64)
     x_out = np.zeros(int(rows.sum()) if W else 0, dtype=np.uint32)
     len_out = np.zeros(int(cols.sum()) if W else 0, dtype=np.uint32)
+    out = Compacted(m_out, pitch_out, x_off_out, len_off_out, x_out, len_out, runs)
+    if pairs:
+        n64 = n.astype(np.int64)
+        out.row_off_out = np.concatenate([[0], np.cumsum(n64)[:-1]]).astype(np.int64) if W else np.zeros(0, np.int64)
+        out.row_adj = np.zeros(int(n64.sum()) if W else 0, dtype=np.int32)
+        out.win_const = np.zeros(W, dtype=np.int64)
+        out.col_mult = np.zeros(len_out.shape[0], dtype=np.uint8)
+    ptr = lambda a: a.ctypes.data if a is not None else None
     rc = L.impop_compact_fill(W, n.ctypes.data, m.ctypes.data, pitch_words.ctypes.data, x_off.ctypes.data,
-                              len_off.ctypes.data, x_bits.ctypes.data, node_len.ctypes.data, th, pitch_out.ctypes.data,
-                              x_off_out.ctypes.data, len_off_out.ctypes.data, x_out.ctypes.data, len_out.ctypes.data)
+                              len_off.ctypes.data, x_bits.ctypes.data, node_len.ctypes.data, th, flags, pitch_out.ctypes.data,
+                              x_off_out.ctypes.data, len_off_out.ctypes.data, x_out.ctypes.data, len_out.ctypes.data,
+                              ptr(out.row_off_out), ptr(out.row_adj), ptr(out.win_const), ptr(out.col_mult))
     if rc:
         raise NativeError(rc, "impop_compact_fill")
-    return m_out, pitch_out, x_off_out, len_off_out, x_out, len_out
+    return out
 
 
-def compact_uniform(x_bits: np.ndarray, node_len: np.ndarray, threads=None):
+@dataclass
+class CompactedUniform:
+    """compact_uniform's result: same-shape windows.  Build the batch with
+    WindowBatch.from_uniform(ctx, c.x, c.node_len, labels, L, **c.batch_kwargs())."""
+    x: np.ndarray            # [W, n, pitch_out] uint32
+    node_len: np.ndarray     # [W, 32 * pitch_out] uint32
+    m: np.ndarray            # [W] columns in use
+    site_runs: np.ndarray    # [W] variant sites counted on the original node order
+    row_adj: np.ndarray | None = None     # [W, n] int32
+    win_const: np.ndarray | None = None   # [W] int64
+    col_mult: np.ndarray | None = None    # [W, 32 * pitch_out] uint8
+
+    def batch_kwargs(self, lo: int = 0, hi: int | None = None, upload=None) -> dict:
+        """Keyword arguments of WindowBatch.from_uniform for windows [lo, hi) beyond x / node_len; `upload` (host array ->
+        device array) is applied to the arrays the batch reads on the device (default: from_uniform uploads them)."""
+        sl = slice(lo, hi)
+        up = upload or (lambda a: a)
+        kw = {"site_runs": self.site_runs[sl], "m": self.m[sl]}
+        if self.row_adj is not None:
+            kw.update(row_adj=up(self.row_adj[sl]), win_const=self.win_const[sl], col_mult=up(self.col_mult[sl]))
+        return kw
+
+
+def compact_uniform(x_bits: np.ndarray, node_len: np.ndarray, threads=None, pairs: bool = True, replicate: bool = True) -> CompactedUniform:
     """Same-shape windows x_bits [W, n, pitch] / node_len [W, m_pad] (host uint32) -> compacted same-shape windows
-    (x_out [W, n, pitch_out], len_out [W, 32 * pitch_out], m_out [W]); pitch_out fits the widest compacted window."""
+    (x [W, n, pitch_out], node_len [W, 32 * pitch_out], m [W] + the affine arrays); pitch_out fits the widest compacted window."""
     W, n, pitch = x_bits.shape
     m_pad = node_len.shape[1]
     ar = np.arange(W, dtype=np.int64)
-    m_out, pitch_out, _, _, x_out, len_out = compact_batch(np.full(W, n), np.full(W, m_pad), np.full(W, pitch),
-                                                           ar * (n * pitch), ar * m_pad, x_bits, node_len, threads,
-                                                           uniform_pitch=True)
-    po = int(pitch_out[0]) if W else 4
-    compact_uniform.last_site_runs = compact_batch.last_site_runs
-    return x_out.reshape(W, n, po), len_out.reshape(W, po * 32), m_out
+    c = compact_batch(np.full(W, n), np.full(W, m_pad), np.full(W, pitch), ar * (n * pitch), ar * m_pad, x_bits, node_len, threads,
+                      uniform_pitch=True, pairs=pairs, replicate=replicate)
+    po = int(c.pitch_out[0]) if W else 4
+    compact_uniform.last_site_runs = c.site_runs
+    out = CompactedUniform(c.x_out.reshape(W, n, po), c.len_out.reshape(W, po * 32), c.m_out, c.site_runs)
+    if pairs:
+        out.row_adj, out.win_const, out.col_mult = c.row_adj.reshape(W, n), c.win_const, c.col_mult.reshape(W, po * 32)
+    return out
 
 
-def compact_window(win: GraphWindow) -> GraphWindow:
+def compact_window(win: GraphWindow, pairs: bool = True, replicate: bool = True) -> GraphWindow:
     """One GraphWindow -> its compacted form (visit counts are not carried over: expand multisets first)."""
-    m_out, pitch_out, _, _, x_out, len_out = compact_batch([win.n], [win.m], [win.x_bits.shape[1]], [0], [0], win.x_bits,
-                                                           win.node_len, threads=1)
-    mo, po = int(m_out[0]), int(pitch_out[0])
-    out = GraphWindow(list(win.names), x_out.reshape(win.n, po), len_out[:mo].copy(), None, win.region, win.length)
-    out.site_runs = int(compact_batch.last_site_runs[0])     # counted on the original node order (IMPOP_ST_S_BUBBLES)
+    c = compact_batch([win.n], [win.m], [win.x_bits.shape[1]], [0], [0], win.x_bits, win.node_len, threads=1, pairs=pairs,
+                      replicate=replicate)
+    mo, po = int(c.m_out[0]), int(c.pitch_out[0])
+    out = GraphWindow(list(win.names), c.x_out.reshape(win.n, po), c.len_out[:mo].copy(), None, win.region, win.length)
+    out.site_runs = int(c.site_runs[0])     # counted on the original node order (IMPOP_ST_S_BUBBLES)
+    if pairs:
+        out.row_adj, out.win_const, out.col_mult = c.row_adj.copy(), int(c.win_const[0]), c.col_mult[:mo].copy()
     return out

@@ -96,7 +96,7 @@ def batch_from_graphs(ctx, graphs, pop_a_ids=None, pop_b_ids=None, subset_ids=No
         pb = expand_population(pop_b_ids, g.names)[0] if pop_b_ids else None
         sub = expand_population(subset_ids, g.names)[0] if subset_ids else None
         lab = ingest.labels_from_names(g.names, pa, pb, sub, sub)
-        wins.append((g.x_bits, g.node_len, lab, g.length))
+        wins.append((g.x_bits, g.node_len, lab, g.length, g.row_adj, g.win_const, g.col_mult))     # affine form when compacted
     runs = [getattr(g, "site_runs", -1) for g in graphs]      # counted before compaction (the node order is gone afterwards)
     return WindowBatch.from_windows(ctx, wins, site_runs=runs if any(r >= 0 for r in runs) else None)
 
@@ -116,8 +116,13 @@ def batch_from_flat(ctx, flat, pop_a_ids=None, pop_b_ids=None, subset_ids=None):
     lab = np.where(both, lab & ~np.uint8(6), lab).astype(np.uint8)
     x = ctx.upload(np.ascontiguousarray(flat.x).view(np.int32))
     nl = ctx.upload(np.ascontiguousarray(flat.node_len).view(np.int32))
+    extra = {}
+    if flat.row_adj is not None:                           # affine form + the variant-site counts taken before compaction
+        runs = np.ascontiguousarray(flat.site_runs)
+        extra = dict(row_adj=ctx.upload(np.ascontiguousarray(flat.row_adj)), win_const=np.ascontiguousarray(flat.win_const),
+                     col_mult=ctx.upload(np.ascontiguousarray(flat.col_mult)), site_runs=runs if (runs >= 0).any() else None)
     return WindowBatch(ctx, flat.n, flat.m, flat.pitch, flat.x_off, flat.len_off, flat.row_off, flat.length, x, nl,
-                       ctx.upload(lab), node_len_host=np.ascontiguousarray(flat.node_len))
+                       ctx.upload(lab), node_len_host=np.ascontiguousarray(flat.node_len), **extra)
 
 
 def stats_disjoint_absent(ctx, batch, labels_host, lab_off):

@@ -101,6 +101,16 @@ typedef struct {
                                         stream the kernels will run on */
     const int64_t *site_runs_host;   /* optional [windows]: IMPOP_ST_S_BUBBLES of each window as counted at ingest on the
                                         original node order (impop_compact_scan); < 0 or NULL: counted on the device */
+    /* Affine form of a window (optional; what impop_compact_fill writes with IMPOP_COMPACT_PAIRS): the intersection is
+     *     I_ij = sum_k node_len_k x_ik x_jk + C - R_i - R_j ,   A_i = I_ii ,   U_ij = A_i + A_j - I_ij
+     * with a window constant C and a row term R_i, all exact integers: nodes every haplotype visits live in C alone,
+     * and the two branches of a bi-allelic bubble (complementary columns) share one column.  All three NULL: C = R = 0
+     * and every column stands for one node.  Requirements: sum(node_len) < 2^31 and 0 <= I, A, U < 2^31 as before. */
+    const int32_t *row_adj_dev;      /* R_i per haplotype row: the rows of all windows in batch order (window w starts at n_0 + .. + n_{w-1}) */
+    const int64_t *win_const_host;   /* C per window */
+    const uint8_t *col_mult_dev;     /* per column, offsets len_off_host: how many nodes of positive length the column stands
+                                        for in the segregating-node count S (1 = a plain node, 2 = a merged bubble, 0 = a
+                                        further copy of a column whose weight was split) */
 } impop_batch_desc_t;
 
 int impop_version(void);
@@ -244,16 +254,29 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
  * the same constant to every intersection and path length), nodes visited by none and nodes of length 0 are dropped,
  * the rest is ordered by length (original order within equal lengths).  Exact: I, A, U, segregating-node counts and all
  * statistics of the compacted window equal those of the original.
+ * flags = IMPOP_COMPACT_PAIRS writes the affine form of impop_batch_desc_t instead (row_adj_out / win_const_out /
+ * col_mult_out are then required): the constant nodes go into C, nodes with identical presence columns are merged, and
+ * two columns that are complementary over the window's rows -- the two branches of a bi-allelic bubble, x_r = 1 - x_a --
+ * become ONE column of weight len_r + len_a with len_r added to C and len_r x_ai to R_i
+ * (len_r x_ri x_rj + len_a x_ai x_aj = len_r - len_r x_ai - len_r x_aj + (len_r + len_a) x_ai x_aj): an HPRC-shaped
+ * window keeps about a quarter of its columns.  | IMPOP_COMPACT_REPLICATE additionally spreads a weight >= 255 over
+ * copies of its column with byte weights (col_mult 0 for the further copies) when the copies fit into the padding of
+ * the window's 128-column chunks, so that the device needs no separate heavy columns for it.  Still exact.
  * Descriptor arrays as in impop_batch_desc_t, but every pointer is a HOST pointer.  impop_compact_scan reports the node
  * count of every compacted window; the caller sizes the outputs (out_pitch_words[w] * 32 >= m_out[w], a multiple of 4
- * words; len_out zero-filled beyond m_out) and impop_compact_fill writes them.  `threads` host threads share the windows. */
+ * words; len_out zero-filled beyond m_out; col_mult_out shares out_len_off, row_adj_out starts at out_row_off[w]) and
+ * impop_compact_fill writes them (it reuses the plans of a scan over the same arrays and flags).  `threads` host
+ * threads share the windows.  IMPOP_ERR_RANGE: a window's visited nodes sum to 2^31 or more. */
+#define IMPOP_COMPACT_PAIRS 1u
+#define IMPOP_COMPACT_REPLICATE 2u
 int impop_compact_scan(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
-                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
+                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads, uint32_t flags,
                        int32_t *m_out, int64_t *site_runs_out /* nullable: IMPOP_ST_S_BUBBLES over all rows, original order */);
 int impop_compact_fill(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
-                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads,
+                       const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len, int32_t threads, uint32_t flags,
                        const int32_t *out_pitch_words, const int64_t *out_x_off, const int64_t *out_len_off,
-                       uint32_t *x_out, uint32_t *len_out);
+                       uint32_t *x_out, uint32_t *len_out, const int64_t *out_row_off /* nullable with flags == 0 */,
+                       int32_t *row_adj_out, int64_t *win_const_out, uint8_t *col_mult_out);
 
 /* All-pairs similarity table (the TSV the similarity tools print; pica2.py:6-58 and h-fst.py:84-119 parse it with
  * csv.DictReader, 47-92 % of those scripts' run time at 466 haplotypes) -> names in sorted order + dense n x n identity

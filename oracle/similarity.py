@@ -160,3 +160,24 @@ def compact_columns(x: np.ndarray, node_len: np.ndarray):
         cols.append(np.ones((n, 1), dtype=np.uint8))
         lens.append(np.array([c], dtype=np.int64))
     return np.concatenate(cols, axis=1), np.concatenate(lens)
+
+
+def pairwise_affine(x: np.ndarray, node_len: np.ndarray, row_adj, win_const: int):
+    """A window in the affine form of include/impop_b200.h (what impop_compact_fill writes with IMPOP_COMPACT_PAIRS):
+    I_ij = sum_k len_k x_ik x_jk + C - R_i - R_j, A_i = I_ii, then the contract's U, J, identity, pi.  The ingest step's
+    claim -- checked in tests/test_ingest_cpu.py -- is that this equals pairwise() of the original window bit for bit."""
+    r = np.asarray(row_adj).astype(np.int64)
+    inter = intersections(x, node_len) + int(win_const) - r[:, None] - r[None, :]
+    a = np.diagonal(inter).copy()
+    union, jac, ident, pi = identity_from_counts(inter, a)
+    return {"I": inter, "A": a, "U": union, "J": jac, "identity": ident, "pi": pi}
+
+
+def segregating_nodes_affine(x: np.ndarray, node_len: np.ndarray, col_mult, rows=None) -> int:
+    """S of a window whose columns stand for col_mult nodes each (merged bubbles: 2, copies of a split weight: 0)."""
+    xs = x if rows is None else x[np.asarray(rows)]
+    if xs.shape[0] == 0:
+        return 0
+    cnt = xs.astype(np.int64).sum(axis=0)
+    seg = (cnt > 0) & (cnt < xs.shape[0]) & (np.asarray(node_len) > 0)
+    return int(np.asarray(col_mult).astype(np.int64)[seg].sum())

@@ -66,18 +66,24 @@ def test_round_digits_through_the_table_path(ctx):
 
 
 def test_compacted_batch_gives_the_same_rows(ctx):
-    """Ingest-time column compaction (impop_compact_scan / _fill) leaves every count and statistic of the fused path as it
-    was: ragged windows with constant, empty, zero-length and heavy columns, both algorithms."""
+    """Ingest-time column compaction (impop_compact_scan / _fill), plain and affine form (bubbles merged, constants in C,
+    weights spread over copies), leaves every count and statistic of the fused path as it was: ragged windows with
+    constant, empty, zero-length, heavy, identical and complementary columns, both algorithms."""
     from impop_b200 import ingest
     from impop_b200.engine import ALGO_SIMT, ALGO_TCGEN05, WindowBatch
     from oracle import similarity
     rng = np.random.default_rng(77)
-    wins, cwins = [], []
+    wins, cwins, awins = [], [], []
     for n, m, heavy in ((37, 70, False), (130, 300, True), (466, 1009, False), (200, 1500, True), (5, 3, False)):
         x = (rng.random((n, m)) < rng.random(m)[None, :]).astype(np.uint8)
         kind = rng.random(m)
         x[:, kind < 0.3] = 1
         x[:, (kind >= 0.3) & (kind < 0.4)] = 0
+        for k in range(1, m - 1, 3):                         # bubbles (complementary columns) and variants in perfect linkage
+            if kind[k] >= 0.4 and kind[k] < 0.7:
+                x[:, k + 1] = 1 - x[:, k]
+            elif kind[k] >= 0.95:
+                x[:, k + 1] = x[:, k]
         nl = rng.integers(1, 100000 if heavy else 60, size=m).astype(np.uint32)
         nl[rng.random(m) < 0.5] = 1
         nl[rng.random(m) < 0.1] = 0
@@ -87,25 +93,33 @@ def test_compacted_batch_gives_the_same_rows(ctx):
         lab[rng.random(n) < 0.1] &= 0xF6                     # a few rows outside SUBSET / SEG
         bits = similarity.pack_bits(x)
         wins.append((bits, nl, lab, 1234))
-        g = ingest.compact_window(ingest.GraphWindow([f"h{i}" for i in range(n)], bits, nl))
+        win = ingest.GraphWindow([f"h{i}" for i in range(n)], bits, nl)
+        g = ingest.compact_window(win, pairs=False)
         assert g.m < m
         cwins.append((g.x_bits, g.node_len, lab, 1234))
-    a, b = WindowBatch.from_windows(ctx, wins), WindowBatch.from_windows(ctx, cwins)
-    for algo in (ALGO_TCGEN05, ALGO_SIMT):
-        sa, ca = a.stats(algo)
-        sb, cb = b.stats(algo)
-        ctx.check()
-        assert np.array_equal(ca.cpu().numpy(), cb.cpu().numpy())
-        sa, sb = sa.cpu().numpy()[:, :19], sb.cpu().numpy()[:, :19]       # column 19 (variant sites) depends on the node order
-        assert np.array_equal(np.isnan(sa), np.isnan(sb))
-        ok = np.isnan(sa) | (np.abs(sa - sb) <= 1e-13 * np.maximum(np.abs(sa), np.abs(sb)))
-        assert ok.all(), np.argwhere(~ok)[:5]
-    I0, A0, p0 = a.pairwise(1)
-    I1, A1, p1 = b.pairwise(1)
-    ctx.check()
-    assert np.array_equal(I0.cpu().numpy(), I1.cpu().numpy()) and np.array_equal(A0.cpu().numpy(), A1.cpu().numpy())
-    assert np.array_equal(p0.cpu().numpy(), p1.cpu().numpy())            # pi_ij bit for bit
-    a.close(); b.close()
+        h = ingest.compact_window(win)
+        assert int((h.col_mult > 0).sum()) < g.m or n < 10      # fewer columns before weights are spread over copies
+        awins.append((h.x_bits, h.node_len, lab, 1234, h.row_adj, h.win_const, h.col_mult))
+    a = WindowBatch.from_windows(ctx, wins)
+    for other in (cwins, awins, [awins[0], wins[1], awins[2], wins[3], awins[4]]):      # (the last: affine and plain windows in one batch)
+        b = WindowBatch.from_windows(ctx, other)
+        for algo in (ALGO_TCGEN05, ALGO_SIMT):
+            sa, ca = a.stats(algo)
+            sb, cb = b.stats(algo)
+            ctx.check()
+            assert np.array_equal(ca.cpu().numpy(), cb.cpu().numpy())
+            sa, sb = sa.cpu().numpy()[:, :19], sb.cpu().numpy()[:, :19]       # column 19 (variant sites) depends on the node order
+            assert np.array_equal(np.isnan(sa), np.isnan(sb))
+            ok = np.isnan(sa) | (np.abs(sa - sb) <= 1e-13 * np.maximum(np.abs(sa), np.abs(sb)))
+            assert ok.all(), np.argwhere(~ok)[:5]
+            for w in (1, 4):
+                I0, A0, p0 = a.pairwise(w, algo)
+                I1, A1, p1 = b.pairwise(w, algo)
+                ctx.check()
+                assert np.array_equal(I0.cpu().numpy(), I1.cpu().numpy()) and np.array_equal(A0.cpu().numpy(), A1.cpu().numpy())
+                assert np.array_equal(p0.cpu().numpy(), p1.cpu().numpy())            # pi_ij bit for bit
+        b.close()
+    a.close()
 
 
 def test_command_lines_run_without_torch(tmp_path):
@@ -201,9 +215,8 @@ def test_variant_sites_column(ctx):
     assert ws_[:, 19].astype(int).tolist() == want                          # the C oracle states the same definition
     b.close()
     ws = synth.make_windows(60, 20000, 4, seed=3)
-    xc, lc, mo = ingest.compact_uniform(ws.x_bits, ws.node_len)
-    runs = ingest.compact_uniform.last_site_runs
-    b = WindowBatch.from_uniform(ctx, xc, lc, np.full(60, 9, dtype=np.uint8), 20000, site_runs=runs)
+    c = ingest.compact_uniform(ws.x_bits, ws.node_len)
+    b = WindowBatch.from_uniform(ctx, c.x, c.node_len, np.full(60, 9, dtype=np.uint8), 20000, **c.batch_kwargs())
     st = b.stats()[0].cpu().numpy()
     ctx.check()
     assert st[:, ST["S_bubbles"]].astype(int).tolist() == [similarity.site_runs(ws.dense(w), ws.node_len[w]) for w in range(4)]

@@ -178,7 +178,7 @@ def test_compact_columns_matches_oracle_and_keeps_every_count(n, m, heavy):
     rng = np.random.default_rng(n * 1000 + m)
     x, nl = _rand_window(rng, n, m, heavy=heavy)
     win = ingest.GraphWindow([f"h{i}" for i in range(n)], similarity.pack_bits(x) if (m and n) else np.zeros((n, 4), np.uint32), nl)
-    got = ingest.compact_window(win)
+    got = ingest.compact_window(win, pairs=False)
     x2, nl2 = similarity.compact_columns(x, nl)
     assert got.m == x2.shape[1] and got.x_bits.shape[1] % 4 == 0
     assert np.array_equal(got.node_len.astype(np.int64), nl2)
@@ -196,9 +196,100 @@ def test_compact_columns_matches_oracle_and_keeps_every_count(n, m, heavy):
         assert (np.diff(got.node_len[:got.m - 1].astype(np.int64)) >= 0).all()                      # ordered by length
 
 
+def _bubble_window(rng, n, sites, extra, heavy=False, dup=True):
+    """A window with the shapes the affine compaction acts on: backbone nodes, bi-allelic bubbles (complementary
+    columns), columns in perfect linkage (identical), a tri-allelic site and unrelated columns."""
+    cols, lens = [np.ones(n, np.uint8)], [int(rng.integers(1, 500))]
+    for s_ in range(sites):
+        alt = (rng.random(n) < rng.random()).astype(np.uint8)
+        cols += [1 - alt, alt, np.ones(n, np.uint8)]
+        lens += [int(rng.integers(1, 30)), int(rng.integers(1, 100000 if heavy and s_ % 5 == 0 else 60)), int(rng.integers(0, 200))]
+        if dup and s_ % 4 == 0:                            # a second variant carried by exactly the same haplotypes
+            cols += [1 - alt, alt]
+            lens += [1, 1]
+    a = rng.integers(0, 3, size=n)                         # three alleles: no two columns are complementary
+    cols += [(a == 0).astype(np.uint8), (a == 1).astype(np.uint8), (a == 2).astype(np.uint8)]
+    lens += [2, 3, 4]
+    for _ in range(extra):
+        cols.append((rng.random(n) < rng.random()).astype(np.uint8))
+        lens.append(int(rng.integers(0, 40)))
+    x = np.stack(cols, axis=1) if n else np.zeros((0, len(cols)), np.uint8)
+    return x, np.array(lens, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("n,sites,extra,heavy,replicate", [(2, 3, 2, False, True), (3, 1, 0, False, True), (17, 20, 5, False, True),
+                                                           (60, 90, 10, True, True), (60, 90, 10, True, False), (466, 280, 0, True, True),
+                                                           (130, 40, 300, False, True), (1, 4, 3, False, True)])
+def test_affine_compaction_is_exact(n, sites, extra, heavy, replicate):
+    """impop_compact_fill with IMPOP_COMPACT_PAIRS (identical columns merged, the two branches of a bubble in one column,
+    constants in C, optionally weights spread over copies): intersections, path lengths, unions, pi_ij and the
+    segregating-node count of the affine form equal those of the original window, for every subset of rows."""
+    rng = np.random.default_rng(n * 7919 + sites * 31 + extra)
+    x, nl = _bubble_window(rng, n, sites, extra, heavy=heavy)
+    win = ingest.GraphWindow([f"h{i}" for i in range(n)], similarity.pack_bits(x), nl)
+    got = ingest.compact_window(win, replicate=replicate)
+    x2 = similarity.unpack_bits(got.x_bits, got.m)
+    assert not similarity.unpack_bits(got.x_bits, got.x_bits.shape[1] * 32)[:, got.m:].any()
+    a, b = similarity.pairwise(x, nl), similarity.pairwise_affine(x2, got.node_len, got.row_adj, got.win_const)
+    for key in ("I", "A", "U"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.array_equal(a["pi"], b["pi"])
+    assert similarity.segregating_nodes(x, nl) == similarity.segregating_nodes_affine(x2, got.node_len, got.col_mult)
+    if n >= 4:
+        rows = np.arange(0, n, 2)
+        assert similarity.segregating_nodes(x, nl, rows) == similarity.segregating_nodes_affine(x2, got.node_len, got.col_mult, rows)
+    assert got.site_runs == similarity.site_runs(x, nl)
+    # fully reduced: no constant / empty / zero-length column is left, and (before weights are spread over copies) no two
+    # columns are identical or complementary
+    cnt = x2.astype(np.int64).sum(axis=0)
+    assert ((cnt > 0) & (cnt < max(n, 1))).all() or n <= 1
+    assert (got.node_len[:got.m] > 0).all()
+    if n > 1:
+        keys = {bytes(c) for c in x2.T[got.col_mult[:got.m] > 0]}
+        assert len(keys) == int((got.col_mult[:got.m] > 0).sum())
+        assert not any(bytes(1 - c) in keys for c in x2.T)
+    if sites >= 3 and n >= 17 and extra <= sites:
+        assert got.m < x.shape[1] // 2                     # bubbles and backbone gone: well under half the columns
+    if replicate and heavy and n >= 17:
+        # every weight the copies could absorb inside the chunk padding is a byte weight now
+        assert (got.col_mult[:got.m] == 0).any()
+    legacy = ingest.compact_window(win, pairs=False)
+    assert legacy.row_adj is None and legacy.m >= got.m - int((got.col_mult[:got.m] == 0).sum())
+
+
+def test_affine_compaction_leaves_incomplete_bubbles_alone():
+    """A haplotype that visits neither branch (a gap in its assembly) or both breaks the complement: the columns stay."""
+    x = np.array([[1, 0, 1], [0, 1, 1], [0, 0, 1], [1, 0, 0]], dtype=np.uint8)
+    nl = np.array([5, 7, 11], dtype=np.uint32)
+    got = ingest.compact_window(ingest.GraphWindow(list("abcd"), similarity.pack_bits(x), nl))
+    assert got.m == 3 and got.win_const == 0 and not got.row_adj.any() and got.col_mult.tolist() == [1, 1, 1]
+    x[2, 1] = 1                                             # now columns 0 and 1 are complementary
+    got = ingest.compact_window(ingest.GraphWindow(list("abcd"), similarity.pack_bits(x), nl))
+    assert got.m == 2 and got.win_const == 7 and sorted(got.col_mult.tolist()) == [1, 2]
+    assert np.array_equal(similarity.pairwise(x, nl)["I"],
+                          similarity.pairwise_affine(similarity.unpack_bits(got.x_bits, got.m), got.node_len, got.row_adj, got.win_const)["I"])
+
+
+def test_compact_range_error():
+    x = np.array([[1, 0], [0, 1]], dtype=np.uint8)
+    nl = np.array([1 << 30, 1 << 30], dtype=np.uint32)
+    with pytest.raises(NativeError):
+        ingest.compact_window(ingest.GraphWindow(["a", "b"], similarity.pack_bits(x), nl))
+
+
 def test_compact_uniform_batch_threads():
     ws = synth.make_windows(60, 20000, 5, seed=91)
-    xo, lo, mo = ingest.compact_uniform(ws.x_bits, ws.node_len, threads=3)
+    aff = ingest.compact_uniform(ws.x_bits, ws.node_len, threads=3)
+    assert aff.row_adj.shape == (5, 60) and aff.win_const.shape == (5,) and aff.col_mult.shape == aff.node_len.shape
+    for w in range(5):
+        x2 = similarity.unpack_bits(aff.x[w], int(aff.m[w]))
+        a = similarity.pairwise(ws.dense(w), ws.node_len[w])
+        b = similarity.pairwise_affine(x2, aff.node_len[w, :aff.m[w]], aff.row_adj[w], aff.win_const[w])
+        assert np.array_equal(a["I"], b["I"]) and np.array_equal(a["pi"], b["pi"])
+        assert aff.m[w] <= (ws.m - 1) // 3 + 64           # one column per segregating site (+ copies of split weights)
+    plain = ingest.compact_uniform(ws.x_bits, ws.node_len, threads=3, pairs=False)
+    xo, lo, mo = plain.x, plain.node_len, plain.m
+    assert plain.row_adj is None
     assert xo.shape[0] == 5 and xo.shape[1] == 60 and lo.shape[1] == xo.shape[2] * 32
     K = (ws.m - 1) // 3
     for w in range(5):

@@ -80,9 +80,10 @@ with tempfile.TemporaryDirectory() as tmp:
             g.names = [f"{b}:{w * L}-{(w + 1) * L}" for b in base_names]
     t0 = time.perf_counter()
     xb = np.stack([g.x_bits for g in graphs]); nl = np.zeros((F, big.m_pad), np.uint32); nl[:, :big.m] = np.stack([g.node_len for g in graphs])
-    xc, lc, mo = ingest.compact_uniform(xb, nl)
+    cu = ingest.compact_uniform(xb, nl)                      # affine form: bubbles merged, constants in C
     t1 = time.perf_counter()
-    cg = [ingest.GraphWindow(g.names, xc[w], lc[w, :int(mo[w])], None, g.region, L) for w, g in enumerate(graphs)]
+    cg = [ingest.GraphWindow(g.names, cu.x[w], cu.node_len[w, :int(cu.m[w])], None, g.region, L, int(cu.site_runs[w]),
+                             cu.row_adj[w], int(cu.win_const[w]), cu.col_mult[w, :int(cu.m[w])]) for w, g in enumerate(graphs)]
     flat_path = os.path.join(tmp, "chr2.impw")
     t2 = time.perf_counter()
     ingest.save_flat(flat_path, cg)

@@ -17,18 +17,22 @@ ap.add_argument("--algo", type=int, default=0)
 ap.add_argument("--n", type=int, default=466)
 ap.add_argument("--length", type=int, default=50000)
 ap.add_argument("--compact", action="store_true", help="compact the columns at ingest (impop_compact_scan / _fill)")
+ap.add_argument("--plain", action="store_true", help="with --compact: the plain form (constant columns merged only)")
 args = ap.parse_args()
 ctx = Context(0)
 x, nl, pops, m, m_pad = synth.make_windows_device(ctx, args.n, args.length, args.windows, seed=0xB201)
+KW = {}
 if args.compact:
     from impop_b200 import ingest  # noqa: E402
-    xc, lc, mo = ingest.compact_uniform(x.cpu().numpy().view(np.uint32), nl.cpu().numpy().view(np.uint32))
-    x = torch.from_numpy(xc.view(np.int32)).to(ctx.torch_device)
-    nl = torch.from_numpy(lc.view(np.int32)).to(ctx.torch_device)
+    cu = ingest.compact_uniform(x.cpu().numpy().view(np.uint32), nl.cpu().numpy().view(np.uint32), pairs=not args.plain)
+    x = torch.from_numpy(cu.x.view(np.int32)).to(ctx.torch_device)
+    nl = torch.from_numpy(cu.node_len.view(np.int32)).to(ctx.torch_device)
+    KW = cu.batch_kwargs(upload=lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.torch_device))
+    print("compacted: nodes", m, "->", int(cu.m.max()), flush=True)
 lab = np.full(args.n, 9, dtype=np.uint8)
 lab[pops == 0] |= 2
 lab[pops == 2] |= 4
-batch = WindowBatch.from_uniform(ctx, x, nl, torch.from_numpy(lab).to(ctx.torch_device), args.length)
+batch = WindowBatch.from_uniform(ctx, x, nl, torch.from_numpy(lab).to(ctx.torch_device), args.length, **KW)
 for _ in range(args.reps):
     stats, counts = batch.stats(args.algo)
 ctx.check()

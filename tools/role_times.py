@@ -8,14 +8,16 @@ from impop_b200 import synth
 from impop_b200.engine import Context, WindowBatch
 W = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 4854
 ctx = Context(0)
+KW = {}
 x, nl, pops, m, m_pad = synth.make_windows_device(ctx, 466, 50000, W, seed=0xB201)
 if "--compact" in sys.argv:            # columns compacted at ingest (impop_compact_scan / _fill)
     from impop_b200 import ingest
-    xc, lc, mo = ingest.compact_uniform(x.cpu().numpy().view(np.uint32), nl.cpu().numpy().view(np.uint32))
-    x = torch.from_numpy(xc.view(np.int32)).to(ctx.torch_device); nl = torch.from_numpy(lc.view(np.int32)).to(ctx.torch_device)
-    print("compacted: nodes", m, "->", int(mo.max()))
+    cu = ingest.compact_uniform(x.cpu().numpy().view(np.uint32), nl.cpu().numpy().view(np.uint32), pairs="--plain" not in sys.argv)
+    x = torch.from_numpy(cu.x.view(np.int32)).to(ctx.torch_device); nl = torch.from_numpy(cu.node_len.view(np.int32)).to(ctx.torch_device)
+    KW = cu.batch_kwargs(upload=lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.torch_device))
+    print("compacted: nodes", m, "->", int(cu.m.max()))
 lab = np.full(466, 9, dtype=np.uint8); lab[pops == 0] |= 2; lab[pops == 2] |= 4
-b = WindowBatch.from_uniform(ctx, x, nl, torch.from_numpy(lab).to(ctx.torch_device), 50000)
+b = WindowBatch.from_uniform(ctx, x, nl, torch.from_numpy(lab).to(ctx.torch_device), 50000, **KW)
 for _ in range(3):
     b.stats(0)
 ctx.check()

@@ -16,7 +16,7 @@ print("selftest mismatches:", ctx.selftest_division(1 << 24, 3))
 ctx.close()
 dbg = subprocess.run([sys.executable, "tools/gpu_debug.py"], capture_output=True, text=True).stdout
 print("debug: exact tc lines", dbg.count("tc: A ok=True I mismatches=0") , "of 5;", "pi exact" , dbg.count("pi exact=True"), "of 10")
-out = subprocess.run([sys.executable, "bench.py", "--steps", "10", "--warmup", "3", "--no-cpu"], capture_output=True, text=True)
+out = subprocess.run([sys.executable, "bench.py", "--steps", "10", "--warmup", "3", "--no-cpu", "--no-others"], capture_output=True, text=True)
 try:
     d = json.loads(out.stdout.strip().splitlines()[-1])
     r = d["roofline"]
