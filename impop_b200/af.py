@@ -35,16 +35,43 @@ def load_pairs(path):
     return rows, sorted(samples)
 
 
-def cluster(rows, samples, threshold, ctx=None):
+def load_table_fast(path):
+    """The table through libimpop_b200's native reader (tables.read_table_fast) when that is equivalent to load_pairs:
+    machine-clean text, every row a distinct pair of two different samples (then "any row reaching the threshold links",
+    af.py:37-39, and "the last row of a pair stays" coincide) and names that stay distinct once cut at the first ':'
+    (af.py:13-14).  None otherwise -- the caller reads the rows as the reference does."""
+    from .tables import read_table_fast
+    got = read_table_fast(path)
+    if got is None:
+        return None
+    table, data_rows = got
+    n = len(table.names)
+    if n == 0 or np.count_nonzero(~np.isnan(table.matrix[np.triu_indices(n, 1)])) != data_rows:
+        return None                                             # repeated pairs or self pairs: rows are not one per pair
+    if not np.isnan(np.diagonal(table.matrix)).all():
+        return None
+    short = [s.split(":", 1)[0] for s in table.names]
+    if len(set(short)) != n:
+        return None
+    order = sorted(range(n), key=lambda i: short[i])           # cutting the coordinates can change the sort order
+    if order != list(range(n)):
+        table = SimilarityTable([short[i] for i in order], np.ascontiguousarray(table.matrix[np.ix_(order, order)]))
+    else:
+        table = SimilarityTable(short, table.matrix)
+    return table
+
+
+def cluster(rows, samples, threshold, ctx=None, table=None):
     """Connected components of {identity >= threshold}, as lists of names ordered like af.py:35-44."""
     ctx = ctx or default_context()
-    samples = list(samples)
-    if not samples:
-        return []
-    table = SimilarityTable.from_rows(rows, combine="max")     # any row reaching the threshold links (af.py:37-39)
-    extra = sorted(set(samples) - set(table.names))
-    if extra:                                                   # samples that occur in no row stay singletons
-        table = _with_names(table, extra)
+    if table is None:
+        samples = list(samples)
+        if not samples:
+            return []
+        table = SimilarityTable.from_rows(rows, combine="max")     # any row reaching the threshold links (af.py:37-39)
+        extra = sorted(set(samples) - set(table.names))
+        if extra:                                                   # samples that occur in no row stay singletons
+            table = _with_names(table, extra)
     comp = ctx.cluster(table.device(ctx), threshold)
     ctx.check()
     comp = comp.cpu().numpy()
@@ -129,8 +156,12 @@ def main(argv=None):
     args = parser.parse_args(argv)
     if args.sites:
         return _run_sites(args)
-    rows, samples = load_pairs(args.input)
-    clusters = cluster(rows, samples, args.threshold)
+    table = load_table_fast(args.input)
+    if table is not None:
+        clusters = cluster(None, None, args.threshold, table=table)
+    else:
+        rows, samples = load_pairs(args.input)
+        clusters = cluster(rows, samples, args.threshold)
     summary = build_summary(clusters)
     if args.output:
         with open(args.output, "w", newline="") as handle:

@@ -180,7 +180,33 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
                 for (int ps = 0; ps < PR_WORDS / 32; ++ps) {
                     const int pw = min(32, gw - ps * 32);           // words of this pass
                     if (pw <= 0) break;
-                    {   // load: lane = word
+                    // rows that lie back to back in memory and fit one pass (every window compacted at ingest): the 32 rows are ONE
+                    // contiguous block -- read with all 32 lanes, 128 bytes per load, and scattered into the tile; the any / all
+                    // words over the SEG rows are then folded in the compute phase (lane = row) with a warp reduction per word
+                    const bool contig = (w0 == 0) && (pitch == gw) && (gw <= 32);
+                    if (contig) {
+                        const uint32_t *src = x + (size_t)i0 * pitch;
+                        const int total = nrows * pitch;
+                        // tile slot of block word idx: row idx / pitch (exact as (idx * M) >> 16 for idx < 1024, pitch <= 32), column
+                        // idx % pitch -> idx + row * (PR_TILE - pitch)
+                        const uint32_t M = 65536u / (uint32_t)pitch + 1u, skew = (uint32_t)(PR_TILE - pitch);
+                        __syncwarp();
+#pragma unroll 1
+                        for (int b0 = 0; b0 < pitch; b0 += 16) {    // a full block is `pitch` loads per lane; sixteen in flight: a window
+                            uint32_t v[16];                         // of <= 512 columns costs ONE memory latency per 32 rows
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                const int k = lane + 32 * (b0 + q);
+                                v[q] = (b0 + q < pitch && k < total) ? __ldg(src + k) : 0u;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {          // (rows past the slice get zeros; every slot written lies in the tile)
+                                const uint32_t k = (uint32_t)(lane + 32 * (b0 + q));
+                                if (b0 + q < pitch) tile[k + ((k * M) >> 16) * skew] = v[q];
+                            }
+                        }
+                        __syncwarp();
+                    } else {   // load: lane = word
                         const bool lane_ok = lane < pw;
                         const uint32_t *src = x + (size_t)i0 * pitch + w0 + ps * 32 + lane;
                         __syncwarp();
@@ -198,8 +224,15 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
                         __syncwarp();
                     }
                     const uint32_t *mine = tile + lane * PR_TILE;   // compute: lane = row
+                    const bool myseg = (segrows >> lane) & 1u;
                     for (int wd = 0; wd < pw; ++wd) {
                         const uint32_t mk = s_mk[ps * 32 + wd];
+                        if (contig) {
+                            const uint32_t vv = mine[wd];
+                            const uint32_t ra = __reduce_or_sync(0xffffffffu, myseg ? vv : 0u);
+                            const uint32_t rl = __reduce_and_sync(0xffffffffu, myseg ? vv : 0xffffffffu);
+                            if (lane == wd) { any[ps] |= ra; all[ps] &= rl; }
+                        }
                         if (!mk) continue;
                         const uint32_t v = mine[wd];
                         if (mk == 1u) {

@@ -75,6 +75,9 @@ def _check_table_case(case, path):
         assert len(summary) == len(want)
         for (cid, cnt, fr, mem), (wcid, wcnt, wfr, wmem) in zip(summary, want):
             assert cid == wcid and cnt == wcnt and mem == wmem and fr == unhex(wfr)
+        fast = af.load_table_fast(path)                       # the command line's native reader path gives the same clusters
+        if fast is not None:
+            assert af.build_summary(af.cluster(None, None, row["threshold"], table=fast)) == summary
     return names
 
 

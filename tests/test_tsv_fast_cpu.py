@@ -112,3 +112,26 @@ def test_scan_memo_is_not_reused_for_other_text():
     text[text.index(b"0.25"):text.index(b"0.25") + 4] = b"0.35"   # same address, same length, other content
     m = fill()
     assert m[0, 1] == 0.35 and m[1, 0] == 0.35 and m[0, 2] == 0.5 and m[1, 2] == 0.75 and np.isnan(m[0, 0])
+
+
+def test_af_fast_table_only_when_equivalent(tmp_path):
+    """af.py's native reader path (af.load_table_fast) is taken only when it cannot differ from af.py:7-19 + 35-44: one
+    row per pair of different samples, names distinct after the cut at ':'; the matrix follows the CUT names' order."""
+    from impop_b200 import af
+    hdr = "group.a\tgroup.b\testimated.identity\n"
+    p = tmp_path / "t.tsv"
+    p.write_text(hdr + "b#1#x:9-20\ta#1#y:9-20\t0.5\nb#1#x:9-20\tc:9-20\t0.75\na#1#y:9-20\tc:9-20\t1.0\n")
+    t = af.load_table_fast(str(p))
+    assert t is not None and t.names == ["a#1#y", "b#1#x", "c"]
+    assert t.matrix[0, 1] == 0.5 and t.matrix[1, 2] == 0.75 and t.matrix[0, 2] == 1.0 and t.matrix[2, 0] == 1.0
+    rows, samples = af.load_pairs(str(p))
+    assert samples == t.names and sorted(r[2] for r in rows) == [0.5, 0.75, 1.0]
+    # cutting the coordinates reorders: 'a:5' < 'a#1:5' as full names ('#' < ':' is false for the cut names' first difference)
+    p.write_text(hdr + "s10:1-2\ts1#x:1-2\t0.25\n")
+    t = af.load_table_fast(str(p))
+    assert t is not None and t.names == sorted(["s10", "s1#x"]) and t.matrix[0, 1] == 0.25
+    for body in ("a:1-2\tb:1-2\t0.5\na:1-2\tb:1-2\t0.9\n",            # a repeated pair: any row may link (max), not the last
+                 "a:1-2\ta:1-2\t1.0\na:1-2\tb:1-2\t0.5\n",            # a self pair
+                 "a:1-2\tb:1-2\t0.5\na:3-4\tc:1-2\t0.5\n"):           # two full names of one sample
+        p.write_text(hdr + body)
+        assert af.load_table_fast(str(p)) is None
