@@ -16,9 +16,12 @@ every rank owns its own chromosome-length batch (weak scaling) and the result ro
   --config 1   pica2.py on one 90-haplotype similarity table: latency of the drop-in CLI (N = 1 only)
 
 Ingest: the windows are generated as full presence matrices (every node a column); `impop_compact_scan / _fill`
-(host, once per window, timed and reported as `ingest`) merges the columns every haplotype carries, drops empty ones
-and orders the rest by length.  Every result is unchanged (the line carries the comparison with the oracle run on the
-ORIGINAL columns); the roofline counts algorithmic operations from the ORIGINAL node count.
+(host, once per window, timed and reported as `ingest`) writes the affine form of include/impop_b200.h: the columns every
+haplotype carries go into a window constant, identical columns are merged, the two complementary columns of a bi-allelic
+bubble become one (I = acc + C - R_i - R_j), empty columns are dropped, the rest is ordered by weight and weights >= 255 are
+spread over column copies; every window keeps its own row pitch.  Every result is unchanged (the line carries the
+comparison with the oracle run on the ORIGINAL columns); the roofline counts algorithmic operations from the ORIGINAL
+node count.  The CPU oracle port is given the plain compacted form (constant columns merged only).
 
 Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = through the public API with
 host buffers, roofline = dominant kernel vs its bound, cpu_baseline = the CPU oracle port timed on this box's host
@@ -743,7 +746,9 @@ def run_ours(args):
             "peak_source": "64 fp64 lanes / clk / SM (tools/micro/pi_bench.cu: 2.0 cycles per warp DFMA and sub-partition) x SMs x max SM clock / 18 instructions per pair"}
     hbm = {"algorithmic_bytes_per_launch": bytes_launch, "achieved_gbs": bytes_launch / pairs_s / 1e9, "peak_gbs": peaks["hbm_gbs"],
            "frac": bytes_launch / pairs_s / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["hbm_src"]}
-    bound = "tensor" if args.config == 5 else "fp64"
+    # the binding pipe: fp64 (pair epilogues) unless the tensor pipe is the busier one on what it really executes (before the
+    # affine compaction config 5 was tensor-bound; with a fifth of its columns left it is fp64-bound like the others)
+    bound = "tensor" if tensor["frac_executed"] > fp64["frac"] else "fp64"
     head = tensor if bound == "tensor" else fp64
     roofline = {"bound": bound, "achieved": head["achieved"], "peak": head["peak"], "unit": head["unit"], "frac": head["frac"],
                 "traffic": None, "kernel": "window_pairs_tc_kernel" if algo == ALGO_TCGEN05 else "window_pairs_simt_kernel",
