@@ -188,6 +188,20 @@ def make_workload(gen, cfg: dict, windows: int, seed: int, threads: int, keep_or
     t1 = time.perf_counter()
     x_off = np.concatenate([[0], np.cumsum(n * pitch_w.astype(np.int64))]).astype(np.int64)
     len_off = np.concatenate([[0], np.cumsum(32 * pitch_w.astype(np.int64))]).astype(np.int64)
+    # transfer form of the presence bits: tight rows (ceil(m / 32) words each); impop_repitch_rows pads them to the
+    # 16-byte rows the kernels read once they are on the device
+    tp_w = np.maximum(1, (m_out.astype(np.int64) + 31) // 32).astype(np.int32)
+    xt_off = np.concatenate([[0], np.cumsum((n * tp_w.astype(np.int64) + 31) // 32 * 32)]).astype(np.int64)     # windows start on 128 bytes
+    x_tight = None
+    if affine:
+        xflat = xc.reshape(-1)
+        x_tight = np.zeros(int(xt_off[-1]), dtype=np.uint32)
+        for pw in np.unique(pitch_w):                      # windows of one pitch at a time (a handful of pitches)
+            for tw in np.unique(tp_w[pitch_w == pw]):
+                sel = np.flatnonzero((pitch_w == pw) & (tp_w == tw))
+                src = (x_off[sel][:, None] + np.arange(n * int(pw))[None, :]).reshape(len(sel), n, int(pw))[:, :, :int(tw)]
+                dst = (xt_off[sel][:, None] + np.arange(n * int(tw))[None, :])
+                x_tight[dst.reshape(-1)] = xflat[src.reshape(-1)]
     pl = ingest.compact_uniform(xh[:plain], lh[:plain], threads=threads, pairs=False) if (plain and affine) else None
     lflat = lc.reshape(-1).astype(np.int64)
     hv = (lflat // 255 + 254) // 255                                               # heavy-table entries per column
@@ -196,46 +210,76 @@ def make_workload(gen, cfg: dict, windows: int, seed: int, threads: int, keep_or
     nl_max = int(lh.max()) if lh.size else 0
     planes = 1 if nl_max < 256 else (2 if nl_max < 65536 else (3 if nl_max < (1 << 24) else 4))
     aff_bytes = int(row_adj.nbytes + col_mult.nbytes + win_const.nbytes) if affine else 0
+    x_bytes = int(x_tight.nbytes) if affine else int(xc.nbytes)
     return {"x": xc, "len": lc, "m_out": m_out, "site_runs": site_runs, "pops": pops, "labels": labels_for(cfg["labels"], pops), "n": n, "L": L,
             "row_adj": row_adj, "win_const": win_const, "col_mult": col_mult, "pitch_w": pitch_w, "x_off": x_off, "len_off": len_off,
+            "x_tight": x_tight, "tp_w": tp_w, "xt_off": xt_off,
             "m_in": int(m), "m_pad_in": int(m_pad), "pitch": int(pitch_w.max()) if W else 4, "m_pad": int(pitch_w.max()) * 32 if W else 128,
             "planes": planes, "k_exec": k_exec, "ingest_s": t1 - t0, "ingest_threads": threads,
             "plain_x": pl.x if pl is not None else None, "plain_len": pl.node_len if pl is not None else None,
             "plain_m_out": int(pl.m.max()) if (pl is not None and len(pl.m)) else 0,
             "orig_x": xh[:keep_original].copy() if keep_original else None,
             "orig_len": lh[:keep_original].copy() if keep_original else None,
-            "bytes_in": int(xh.nbytes + lh.nbytes), "bytes_out": int(xc.nbytes + lc.nbytes) + aff_bytes}
+            "bytes_in": int(xh.nbytes + lh.nbytes), "bytes_out": x_bytes + int(lc.nbytes) + aff_bytes}
 
 
 class DeviceWindows:
-    """The ingested windows of a workload as flat device (or pinned host) arrays + what a WindowBatch over windows [lo, hi) needs."""
+    """The ingested windows of a workload as flat device (or pinned host) arrays + what a WindowBatch over windows [lo, hi)
+    needs.  The pinned host copy holds the presence bits in their transfer form (tight rows, `xt`); on the device they
+    are padded to the 16-byte rows the kernels read (`x`, impop_repitch_rows)."""
 
-    def __init__(self, torch, wl, where):
-        mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if where == "pinned" else \
+    def __init__(self, torch, wl, where, tight=True):
+        pinned = where == "pinned"
+        mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()) if pinned else \
              (lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(where))
-        self.x = mk(wl["x"].reshape(-1).view(np.int32))
+        self.x = None if (pinned and tight) else mk(wl["x"].reshape(-1).view(np.int32))
+        self.xt = mk(wl["x_tight"].view(np.int32)) if (pinned and tight) else None
+        self._tabs = {}
         self.len = mk(wl["len"].reshape(-1).view(np.int32))
         self.row_adj = mk(wl["row_adj"].reshape(-1))
         self.col_mult = mk(wl["col_mult"].reshape(-1))
 
     @property
     def nbytes(self):
-        return sum(int(t.numel()) * t.element_size() for t in (self.x, self.len, self.row_adj, self.col_mult))
+        return sum(int(t.numel()) * t.element_size() for t in (self.x, self.xt, self.len, self.row_adj, self.col_mult) if t is not None)
 
-    def empty_like(self, torch, dev):
+    def empty_like(self, torch, dev, xt_words=0):
         out = object.__new__(DeviceWindows)
         for k in ("x", "len", "row_adj", "col_mult"):
             setattr(out, k, torch.empty(getattr(self, k).shape, dtype=getattr(self, k).dtype, device=dev))
+        out.xt = torch.empty(int(xt_words), dtype=torch.int32, device=dev) if xt_words else None      # landing area of the tight rows
+        out._tabs = {}
         return out
 
-    def copy_from(self, src, wl, lo, hi):
-        """Enqueue the copies of windows [lo, hi) from `src` (pinned host) on the current stream: small arrays first."""
+    def copy_from(self, ctx, src, wl, lo, hi):
+        """Enqueue the copies of windows [lo, hi) from `src` (pinned host) on the current stream: small arrays first, then the
+        presence rows (tight: padded on the device afterwards, see repitch)."""
         n = wl["n"]
-        x0, x1, l0, l1 = int(wl["x_off"][lo]), int(wl["x_off"][hi]), int(wl["len_off"][lo]), int(wl["len_off"][hi])
+        x0, l0, l1 = int(wl["x_off"][lo]), int(wl["len_off"][lo]), int(wl["len_off"][hi])
+        t0, t1 = int(wl["xt_off"][lo]), int(wl["xt_off"][hi])
         self.len[l0:l1].copy_(src.len[l0:l1], non_blocking=True)
         self.row_adj[lo * n:hi * n].copy_(src.row_adj[lo * n:hi * n], non_blocking=True)
         self.col_mult[l0:l1].copy_(src.col_mult[l0:l1], non_blocking=True)
-        self.x[x0:x1].copy_(src.x[x0:x1], non_blocking=True)
+        x1 = int(wl["x_off"][hi])
+        if src.xt is None:                                  # rows transferred as the kernels read them (16-byte multiples)
+            self.x[x0:x1].copy_(src.x[x0:x1], non_blocking=True)
+            return
+        self.xt[t0:t1].copy_(src.xt[t0:t1], non_blocking=True)
+
+    def repitch(self, ctx, wl, lo, hi):
+        """Pad the tight rows of windows [lo, hi) (already copied) to 16-byte rows.  Called AFTER the batch is created: a kernel
+        between the big copy and the batch's small table upload would let that upload queue up behind the other stream's
+        next big copy on the copy engine."""
+        if self.xt is None:
+            return
+        n = wl["n"]
+        x0, x1, t0, t1 = int(wl["x_off"][lo]), int(wl["x_off"][hi]), int(wl["xt_off"][lo]), int(wl["xt_off"][hi])
+        tabs = self._tabs.get((lo, hi))
+        if tabs is None:                                    # per-window tables of this window range: built once
+            tabs = self._tabs[(lo, hi)] = (np.full(hi - lo, n, dtype=np.int32), np.ascontiguousarray(wl["tp_w"][lo:hi], dtype=np.int32),
+                                           np.ascontiguousarray(wl["pitch_w"][lo:hi], dtype=np.int32),
+                                           np.ascontiguousarray(wl["xt_off"][lo:hi] - t0), np.ascontiguousarray(wl["x_off"][lo:hi] - x0))
+        ctx.repitch_rows(self.xt[t0:t1], self.x[x0:x1], *tabs)
 
     def batch(self, ctx, WindowBatch, wl, labels, lo, hi, stream=None, host=None, with_runs=True):
         n, L = wl["n"], wl["L"]
@@ -521,9 +565,9 @@ def run_ours(args):
         keep = min(W, 1)
         if rank == 0:
             wl = make_workload(ctx, cfg, W, cfg["seed"], host_threads(), keep_original=0)
-            host = DeviceWindows(torch, wl, "pinned")
+            host = DeviceWindows(torch, wl, "pinned", tight=args.transfer == "tight")
             meta = [wl["m_in"], wl["m_pad_in"], wl["planes"], int(wl["m_out"].max()), int(wl["k_exec"].max()), wl["pitch"],
-                    host.x.numel(), host.len.numel()]
+                    int(wl["x_off"][-1]), int(wl["len_off"][-1])]
             tabs = np.stack([wl["m_out"].astype(np.int64), wl["pitch_w"].astype(np.int64), wl["x_off"][:-1], wl["len_off"][:-1],
                              wl["win_const"], wl["site_runs"]])
         else:
@@ -541,8 +585,10 @@ def run_ours(args):
         res = object.__new__(DeviceWindows)
         res.x = torch.empty(xw, dtype=torch.int32, device=dev); res.len = torch.empty(lw, dtype=torch.int32, device=dev)
         res.row_adj = torch.empty(W * n, dtype=torch.int32, device=dev); res.col_mult = torch.empty(lw, dtype=torch.uint8, device=dev)
+        res.xt = None
         if rank == 0:
-            for k_ in ("x", "len", "row_adj", "col_mult"):
+            res.x.copy_(torch.from_numpy(wl["x"].reshape(-1).view(np.int32)))
+            for k_ in ("len", "row_adj", "col_mult"):
                 getattr(res, k_).copy_(getattr(host, k_))
         if world > 1:
             for k_ in ("x", "len", "row_adj", "col_mult"):
@@ -559,7 +605,7 @@ def run_ours(args):
         pitch, m_pad, m_in, m_pad_in, planes = wl["pitch"], wl["m_pad"], wl["m_in"], wl["m_pad_in"], wl["planes"]
         m_out_max, k_exec = int(wl["m_out"].max()), wl["k_exec"]
         lab_host = wl["labels"]
-        host = DeviceWindows(torch, wl, "pinned")          # the ingested windows in pinned host memory (what the e2e leg uploads)
+        host = DeviceWindows(torch, wl, "pinned", tight=args.transfer == "tight")     # the ingested windows in pinned host memory (what the e2e leg uploads)
         res = DeviceWindows(torch, wl, dev)                # ... and resident in HBM (the device-timed leg)
         ingest = {"seconds": wl["ingest_s"], "threads": wl["ingest_threads"], "bytes_in": wl["bytes_in"], "bytes_out": wl["bytes_out"]}
         sizes = torch.tensor([W], dtype=torch.int64, device=dev)
@@ -630,16 +676,18 @@ def run_ours(args):
     hs = torch.empty((W, NSTATS), dtype=torch.float64, pin_memory=True)
     hc = torch.empty((W, NCOUNTS), dtype=torch.int64, pin_memory=True)
     hlab = torch.from_numpy(lab_host).pin_memory()
-    dwin = res.empty_like(torch, dev)                      # the e2e leg's own device buffers
+    dwin = res.empty_like(torch, dev, xt_words=wl["xt_off"][-1] if (args.transfer == "tight" and (not split or rank == 0)) else 0)   # the e2e leg's own device buffers
     ds, dc = torch.empty_like(stats), torch.empty_like(counts)
     pending = []          # batches of the previous step: closed while this step's copies and kernels run
+    host_busy = [0.0]
     if split:
         dlab = torch.empty_like(labels)
         nsub = 1
 
         def e2e_step():
             if rank == 0:
-                dwin.copy_from(host, wl, 0, W)
+                dwin.copy_from(ctx, host, wl, 0, W)
+                dwin.repitch(ctx, wl, 0, W)
             dlab.copy_(hlab, non_blocking=True)
             if world > 1:
                 for k_ in ("x", "len", "row_adj", "col_mult"):
@@ -663,6 +711,7 @@ def run_ours(args):
         dlabs = [torch.empty_like(labels) for _ in range(nsub)]
 
         def e2e_step():
+            t_in = time.perf_counter()
             live = []
             for k in range(nsub):
                 lo, hi = cuts[k], cuts[k + 1]
@@ -673,14 +722,16 @@ def run_ours(args):
                     # this sub-batch's copies first, its set-up (host-side tables + their small upload) while they run: the copy
                     # engine is the bottleneck of the step and must never wait for the host
                     dlabs[k].copy_(hlab, non_blocking=True)
-                    dwin.copy_from(host, wl, lo, hi)
+                    dwin.copy_from(ctx, host, wl, lo, hi)
                     b = dwin.batch(ctx, WindowBatch, wl, dlabs[k], lo, hi, stream=st, host=host)
+                    dwin.repitch(ctx, wl, lo, hi)
                     b.stats(algo, stream=st, out_stats=ds[lo:hi], out_counts=dc[lo:hi])
                     hs[lo:hi].copy_(ds[lo:hi], non_blocking=True)
                     hc[lo:hi].copy_(dc[lo:hi], non_blocking=True)
                 live.append(b)
             while pending:                      # host work hidden behind the copies just enqueued
                 pending.pop().close()
+            host_busy[0] += time.perf_counter() - t_in         # host time spent enqueueing (the rest of a step waits for the GPU)
             for st in streams:
                 st.synchronize()
             pending.extend(live)
@@ -689,6 +740,7 @@ def run_ours(args):
     for _ in range(3):
         e2e_step()
     barrier()
+    host_busy[0] = 0.0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -821,7 +873,8 @@ def run_ours(args):
                        "l2": l2_note,
                        "algo": args.algo, "ingest": ingest, "rank0_cpu_affinity": numa},
             "e2e": {"value": units_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": nsub, "matches_resident_run": same,
+                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "sub_batches": nsub, "transfer": args.transfer,
+                    "host_enqueue_ms_per_step": host_busy[0] / e2e_steps * 1e3, "matches_resident_run": same,
                     "bitwise_equal_to_resident_run": bitwise,
                     "h2d_bytes_per_step_without_ingest": int(windows_job * (n * (m_pad_in // 8) + m_pad_in * 4)) if not split else None},
             "gpu_launches": int(launches),
@@ -875,7 +928,9 @@ def main():
     ap.add_argument("--windows", type=int, default=0, help="windows per GPU (weak) / in total (strong); default: the config's own")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the short measurements of the other BASELINE configs")
-    ap.add_argument("--sub-batches", type=int, default=8, help="e2e leg: sub-batches alternating between two streams")
+    ap.add_argument("--sub-batches", type=int, default=4, help="e2e leg: sub-batches alternating between two streams (more than ~4 and the host's enqueue time per step, reported as e2e.host_enqueue_ms_per_step, exceeds the copy time)")
+    ap.add_argument("--transfer", default="tight", choices=["tight", "aligned"],
+                    help="e2e leg: presence rows uploaded tight (ceil(m / 32) words, padded on the device by impop_repitch_rows) or as the kernels read them")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

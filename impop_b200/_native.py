@@ -70,6 +70,7 @@ SIGNATURES = {
     "impop_debug_role_times": (C.c_int, [_p, _p, _i32]),
     "impop_greedy_groups": (C.c_int, [_p, _p, _i32, _i64, _f64, _p, _p, _p]),
     "impop_round_decimal": (C.c_int, [_p, _p, _i64, _i32, _p]),
+    "impop_repitch_rows": (C.c_int, [_p, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "impop_dev_alloc": (C.c_int, [_p, _i64, C.POINTER(_p)]),
     "impop_dev_free": (C.c_int, [_p, _p]),
     "impop_dev_copy": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),

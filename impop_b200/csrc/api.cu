@@ -26,6 +26,7 @@ cudaError_t launch_window_sums(const WindowTab &, const double *, int, int, doub
 cudaError_t launch_finalize(const WindowTab &, const double *, int, const int64_t *, double *, int, cudaStream_t);
 cudaError_t launch_export_a(const int32_t *, int32_t, int64_t *, cudaStream_t);
 cudaError_t launch_pack_bits(const uint8_t *, int32_t, int32_t, int64_t, uint32_t *, int32_t, int, cudaStream_t);
+cudaError_t launch_repitch_rows(const RepitchDesc *, int32_t, const uint32_t *, uint32_t *, int, cudaStream_t);
 int reduce_identity_blocks(int32_t n, int sm_count);
 cudaError_t launch_reduce_identity(const double *, int32_t, int64_t, const uint8_t *, const double *, int64_t, double,
                                    const double2 *, int32_t, double *, int, double *, int64_t *, double *, cudaStream_t);
@@ -718,6 +719,39 @@ int impop_round_decimal(impop_ctx_t *ctx, double *values_dev, int64_t count, int
     CU(cudaSetDevice(ctx->device));
     CU(launch_round_decimal(values_dev, count, digits, ctx->sm_count, (cudaStream_t)stream));
     ctx->launches += (count > 0);
+    return IMPOP_OK;
+}
+
+int impop_repitch_rows(impop_ctx_t *ctx, int32_t windows, const int32_t *rows_host, const int32_t *src_pitch_words_host,
+                       const int32_t *dst_pitch_words_host, const int64_t *src_off_host, const int64_t *dst_off_host,
+                       const uint32_t *src_dev, uint32_t *dst_dev, void *stream) {
+    if (!ctx) return IMPOP_ERR_ARG;
+    if (windows < 0 || (windows > 0 && (!rows_host || !src_pitch_words_host || !dst_pitch_words_host || !src_off_host ||
+                                        !dst_off_host || !src_dev || !dst_dev)))
+        return fail(ctx, IMPOP_ERR_ARG, "impop_repitch_rows: null argument");
+    if (windows == 0) return IMPOP_OK;
+    for (int32_t w = 0; w < windows; ++w)
+        if (rows_host[w] < 0 || src_pitch_words_host[w] < 0 || dst_pitch_words_host[w] < src_pitch_words_host[w] ||
+            dst_pitch_words_host[w] % 4 != 0 || src_off_host[w] < 0 || dst_off_host[w] < 0 || dst_off_host[w] % 4 != 0)
+            return fail(ctx, IMPOP_ERR_ARG, "impop_repitch_rows: pitches (dst a multiple of 4 words, >= src) / offsets out of range");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t bytes = sizeof(RepitchDesc) * (size_t)windows;
+    impop_ctx::Staging *sg = staging_get(ctx, bytes);
+    void *table = pool_get(ctx, bytes, st);
+    if (!sg || !table) {
+        if (table) pool_put(ctx, table, st);
+        return fail(ctx, IMPOP_ERR_NOMEM, "impop_repitch_rows: out of memory (tables)");
+    }
+    RepitchDesc *hd = (RepitchDesc *)sg->host;
+    for (int32_t w = 0; w < windows; ++w)
+        hd[w] = RepitchDesc{src_off_host[w], dst_off_host[w], rows_host[w], src_pitch_words_host[w], dst_pitch_words_host[w], 0};
+    cudaError_t e = cudaMemcpyAsync(table, hd, bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) { e = cudaEventRecord(sg->done, st); sg->busy = true; }
+    if (e == cudaSuccess) e = launch_repitch_rows((const RepitchDesc *)table, windows, src_dev, dst_dev, ctx->sm_count, st);
+    pool_put(ctx, table, st);                      // reused at once only by work on `st`, by other streams after the event
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "impop_repitch_rows");
+    ctx->launches += 1;
     return IMPOP_OK;
 }
 

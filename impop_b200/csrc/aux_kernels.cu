@@ -372,6 +372,25 @@ cudaError_t launch_round_decimal(double *v, int64_t count, int32_t digits, int s
     return cudaGetLastError();
 }
 
+// Tight rows (as stored / transferred) -> the 16-byte-multiple rows the window kernels read, zero padded.
+__global__ void repitch_rows_kernel(const RepitchDesc *desc, int32_t windows, const uint32_t *src, uint32_t *dst) {
+    for (int w = blockIdx.x; w < windows; w += gridDim.x) {
+        const RepitchDesc d = desc[w];
+        const int64_t total = (int64_t)d.rows * d.dst_pitch;
+        for (int64_t t = threadIdx.x; t < total; t += blockDim.x) {
+            const int r = (int)(t / d.dst_pitch), c = (int)(t - (int64_t)r * d.dst_pitch);
+            dst[d.dst_off + t] = c < d.src_pitch ? __ldg(src + d.src_off + (int64_t)r * d.src_pitch + c) : 0u;
+        }
+    }
+}
+
+cudaError_t launch_repitch_rows(const RepitchDesc *desc, int32_t windows, const uint32_t *src, uint32_t *dst, int sm_count,
+                                cudaStream_t st) {
+    if (windows == 0) return cudaSuccess;
+    repitch_rows_kernel<<<min(windows, sm_count * 8), 256, 0, st>>>(desc, windows, src, dst);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack_bits(const uint8_t *dense, int32_t n, int32_t m, int64_t dpitch, uint32_t *x,
                              int32_t pitch_words, int sm_count, cudaStream_t st) {
     int64_t total = (int64_t)n * pitch_words;

@@ -185,6 +185,14 @@ class Context:
         self._call("impop_round_decimal", _ptr(values), values.numel(), int(digits), _stream_ptr(stream))
         return values
 
+    def repitch_rows(self, src, dst, rows, src_pitch, dst_pitch, src_off, dst_off, stream=None):
+        """Tight rows (as stored / transferred: src_pitch words per haplotype) -> the 16-byte-multiple rows the kernels read,
+        zero padded (impop_repitch_rows).  src / dst: device u32 (int32) arrays; the tables are host arrays, one entry per window."""
+        tabs = [np.ascontiguousarray(a, dtype=dt) for a, dt in ((rows, np.int32), (src_pitch, np.int32), (dst_pitch, np.int32),
+                                                                (src_off, np.int64), (dst_off, np.int64))]
+        self._call("impop_repitch_rows", int(tabs[0].shape[0]), *[_ptr(t) for t in tabs], _ptr(src), _ptr(dst), _stream_ptr(stream))
+        return dst
+
     def selftest_division(self, count: int = 1 << 24, seed: int = 1, stream=None) -> int:
         """Mismatches between the epilogue's in-range division and __ddiv_rn over `count` random triples."""
         bad = C.c_int64(-1)

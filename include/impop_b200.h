@@ -197,6 +197,15 @@ int impop_tajima_d(impop_ctx_t *ctx, const int64_t *n_dev, const double *S_dev, 
  * nearest double.  0 <= digits <= 22.  NaN (pair absent) and infinities stay. */
 int impop_round_decimal(impop_ctx_t *ctx, double *values_dev, int64_t count, int32_t digits, void *stream);
 
+/* Rows as they are stored and transferred -- tight: `src_pitch_words` >= ceil(m / 32) words per haplotype, any number --
+ * into the rows the kernels read (16-byte multiples: `dst_pitch_words` a multiple of 4, >= src), zero padded.  A window of
+ * 286 columns travels as 9 words per row instead of 12: a quarter of the presence bits less to upload.  All tables are
+ * HOST arrays of length `windows` (offsets in 32-bit words into src_dev / dst_dev); one small table upload and one kernel
+ * on `stream`.  No counterpart in the reference (the hand-off there is text). */
+int impop_repitch_rows(impop_ctx_t *ctx, int32_t windows, const int32_t *rows_host, const int32_t *src_pitch_words_host,
+                       const int32_t *dst_pitch_words_host, const int64_t *src_off_host, const int64_t *dst_off_host,
+                       const uint32_t *src_dev, uint32_t *dst_dev, void *stream);
+
 /* Plain device memory for callers without a tensor library (the TSV-mode command lines: scripts/pica2.py, h-fst.py,
  * af.py, tj_d.py, hud.py run without importing torch).  impop_dev_copy: kind 0 host -> device, 1 device -> host,
  * 2 device -> device; synchronous with respect to `stream`. */

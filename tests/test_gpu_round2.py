@@ -222,3 +222,26 @@ def test_variant_sites_column(ctx):
     assert st[:, ST["S_bubbles"]].astype(int).tolist() == [similarity.site_runs(ws.dense(w), ws.node_len[w]) for w in range(4)]
     assert (2 * st[:, ST["S_bubbles"]] == st[:, ST["S"]]).all()              # bi-allelic bubbles: two segregating nodes per site
     b.close()
+
+
+def test_repitch_rows(ctx):
+    """impop_repitch_rows: tight rows (as stored / transferred) -> 16-byte-multiple rows, zero padded; ragged windows."""
+    import torch
+    rng = np.random.default_rng(11)
+    rows = np.array([5, 0, 466, 37, 1], dtype=np.int32)
+    sp = np.array([9, 3, 11, 1, 4], dtype=np.int32)
+    dp = np.array([12, 4, 12, 4, 4], dtype=np.int32)
+    so = np.concatenate([[0], np.cumsum(rows.astype(np.int64) * sp)])
+    do = np.concatenate([[0], np.cumsum(rows.astype(np.int64) * dp)])
+    src = rng.integers(0, 2 ** 32, size=int(so[-1]), dtype=np.uint64).astype(np.uint32)
+    dsrc = torch.from_numpy(src.view(np.int32)).to(ctx.torch_device)
+    ddst = torch.full((int(do[-1]),), -1, dtype=torch.int32, device=ctx.torch_device)
+    ctx.repitch_rows(dsrc, ddst, rows, sp, dp, so[:-1], do[:-1])
+    ctx.check()
+    got = ddst.cpu().numpy().view(np.uint32)
+    for w in range(len(rows)):
+        a = src[so[w]:so[w + 1]].reshape(rows[w], sp[w])
+        b = got[do[w]:do[w + 1]].reshape(rows[w], dp[w])
+        assert np.array_equal(b[:, :sp[w]], a) and not b[:, sp[w]:].any(), w
+    with pytest.raises(Exception):
+        ctx.repitch_rows(dsrc, ddst, rows, sp, dp - 1, so[:-1], do[:-1])      # destination pitch not a multiple of 4 words

@@ -18,6 +18,7 @@ ap.add_argument("--n", type=int, default=466)
 ap.add_argument("--length", type=int, default=50000)
 ap.add_argument("--compact", action="store_true", help="compact the columns at ingest (impop_compact_scan / _fill)")
 ap.add_argument("--plain", action="store_true", help="with --compact: the plain form (constant columns merged only)")
+ap.add_argument("--full-pitch", action="store_true", help="with --compact: every window uses all columns of the shared pitch (rows contiguous: prep_rows' block path)")
 args = ap.parse_args()
 ctx = Context(0)
 x, nl, pops, m, m_pad = synth.make_windows_device(ctx, args.n, args.length, args.windows, seed=0xB201)
@@ -28,6 +29,8 @@ if args.compact:
     x = torch.from_numpy(cu.x.view(np.int32)).to(ctx.torch_device)
     nl = torch.from_numpy(cu.node_len.view(np.int32)).to(ctx.torch_device)
     KW = cu.batch_kwargs(upload=lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.torch_device))
+    if args.full_pitch:
+        KW["m"] = None
     print("compacted: nodes", m, "->", int(cu.m.max()), flush=True)
 lab = np.full(args.n, 9, dtype=np.uint8)
 lab[pops == 0] |= 2
