@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_cols_kernel(const __grid_co
 // PR_WORDS presence words (2048 nodes) of planes are staged per group.
 constexpr int PR_WORDS = 64;
 constexpr int PR_TILE = 33;                   // tile row pitch in words (32 + 1: lane = row reads hit 32 banks)
+constexpr int PR_FAST_HEAVY = 8;              // register path: at most this many heavy entries per window (probed one by one)
 
 #ifndef IMPOP_PREP_OCC
 #define IMPOP_PREP_OCC 4
@@ -170,6 +171,70 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
             uint32_t any[PR_WORDS / 32], all[PR_WORDS / 32];        // lane = word of pass ps
 #pragma unroll
             for (int ps = 0; ps < PR_WORDS / 32; ++ps) { any[ps] = 0u; all[ps] = 0xffffffffu; }
+            // Register path (every window compacted at ingest takes it: rows back to back, <= 1 024 columns, a handful of heavy
+            // entries at most): lane = row, the row's words arrive 16 bytes at a time straight into registers (next group
+            // requested before the current one is processed) -- no shared tile, no transposition.  The bit planes and the
+            // plane mask of a word are the same for all lanes (shared memory, broadcast, warp-uniform branches); the any / all
+            // words over the SEG rows take one warp reduction each per word and 32 rows and are kept by lane = word.
+            const bool fast = (pitch == wlim) && (pitch <= 32) && (heavy_n <= PR_FAST_HEAVY);
+            if (fast) {
+                const int G = pitch >> 2;                           // 16-byte groups per row
+                for (int i0 = row_lo + warp * 32; i0 < row_hi; i0 += PREP_THREADS) {
+                    const int i = i0 + lane;
+                    const bool valid = i < row_hi;
+                    const bool seg = valid && (lab[valid ? i : row_lo] & IMPOP_LAB_SEG);
+                    const uint4 *rowp = reinterpret_cast<const uint4 *>(x + (size_t)(valid ? i : row_lo) * pitch);
+                    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+                    uint32_t acc = 0u;
+                    uint4 nxt = valid ? __ldg(rowp) : zero4;
+#pragma unroll 1
+                    for (int g = 0; g < G; ++g) {
+                        const uint4 cur = nxt;
+                        if (g + 1 < G) nxt = valid ? __ldg(rowp + g + 1) : zero4;
+                        const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int wd = 4 * g + t;
+                            const uint32_t v = wv[t];
+                            const uint32_t ra = __reduce_or_sync(0xffffffffu, seg ? v : 0u);
+                            const uint32_t rl = __reduce_and_sync(0xffffffffu, seg ? v : 0xffffffffu);
+                            if (lane == wd) { any[0] |= ra; all[0] &= rl; }
+                            const uint32_t mk = s_mk[wd];
+                            if (!mk) continue;
+                            if ((mk & (mk - 1u)) == 0u) {                              // one plane: every node of the word weighs 2^p (or 0)
+                                const int pl = __ffs(mk) - 1;
+                                acc += (uint32_t)__popc(v & s_pl[wd][pl]) << pl;
+                            } else {
+                                const uint4 lo4 = *reinterpret_cast<const uint4 *>(&s_pl[wd][0]);
+                                acc += (uint32_t)__popc(v & lo4.x) + ((uint32_t)__popc(v & lo4.y) << 1) +
+                                       ((uint32_t)__popc(v & lo4.z) << 2) + ((uint32_t)__popc(v & lo4.w) << 3);
+                                if (mk >> 4) {
+                                    const uint4 hi4 = *reinterpret_cast<const uint4 *>(&s_pl[wd][4]);
+                                    acc += ((uint32_t)__popc(v & hi4.x) << 4) + ((uint32_t)__popc(v & hi4.y) << 5) +
+                                           ((uint32_t)__popc(v & hi4.z) << 6) + ((uint32_t)__popc(v & hi4.w) << 7);
+                                }
+                            }
+                        }
+                    }
+                    uint32_t hbits = 0u;                            // the few heavy entries: their words come back from L1
+                    for (int e = 0; e < heavy_n; ++e) {
+                        const uint32_t ent = __ldg(heavy + e);
+                        if (!(ent & 255u)) continue;
+                        const uint32_t wvv = valid ? __ldg(x + (size_t)i * pitch + (ent >> 13)) : 0u;
+                        const uint32_t on = (wvv >> ((ent >> 8) & 31u)) & 1u;
+                        acc += on * (HEAVY_Q * (ent & 255u));
+                        hbits |= on << e;
+                    }
+                    if (valid) {
+                        if (hbits) xh[(size_t)i * hwords] |= hbits;                   // (xh was zeroed by prep_cols; heavy_n <= 32: one word)
+                        const uint32_t cw = tab.win_const ? (uint32_t)tab.win_const[w] : 0u;
+                        const uint32_t ri = tab.row_adj ? (uint32_t)tab.row_adj[tab.row_off[w] + i] : 0u;
+                        const uint32_t a = acc + cw - 2u * ri;                        // affine form: A_i = sum_k len_k x_ik + C - 2 R_i
+                        A[i] = (int32_t)a;
+                        if ((int32_t)a < 0) atomicExch(tab.err, (int32_t)DEV_ERR_RANGE);
+                    }
+                }
+            } else
             for (int i0 = row_lo + warp * 32; i0 < row_hi; i0 += PREP_THREADS) {
                 const int i = i0 + lane;
                 const bool valid = i < row_hi;
@@ -180,33 +245,7 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
                 for (int ps = 0; ps < PR_WORDS / 32; ++ps) {
                     const int pw = min(32, gw - ps * 32);           // words of this pass
                     if (pw <= 0) break;
-                    // rows that lie back to back in memory and fit one pass (every window compacted at ingest): the 32 rows are ONE
-                    // contiguous block -- read with all 32 lanes, 128 bytes per load, and scattered into the tile; the any / all
-                    // words over the SEG rows are then folded in the compute phase (lane = row) with a warp reduction per word
-                    const bool contig = (w0 == 0) && (pitch == gw) && (gw <= 32);
-                    if (contig) {
-                        const uint32_t *src = x + (size_t)i0 * pitch;
-                        const int total = nrows * pitch;
-                        // tile slot of block word idx: row idx / pitch (exact as (idx * M) >> 16 for idx < 1024, pitch <= 32), column
-                        // idx % pitch -> idx + row * (PR_TILE - pitch)
-                        const uint32_t M = 65536u / (uint32_t)pitch + 1u, skew = (uint32_t)(PR_TILE - pitch);
-                        __syncwarp();
-#pragma unroll 1
-                        for (int b0 = 0; b0 < pitch; b0 += 16) {    // a full block is `pitch` loads per lane; sixteen in flight: a window
-                            uint32_t v[16];                         // of <= 512 columns costs ONE memory latency per 32 rows
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) {
-                                const int k = lane + 32 * (b0 + q);
-                                v[q] = (b0 + q < pitch && k < total) ? __ldg(src + k) : 0u;
-                            }
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) {          // (rows past the slice get zeros; every slot written lies in the tile)
-                                const uint32_t k = (uint32_t)(lane + 32 * (b0 + q));
-                                if (b0 + q < pitch) tile[k + ((k * M) >> 16) * skew] = v[q];
-                            }
-                        }
-                        __syncwarp();
-                    } else {   // load: lane = word
+                    {   // load: lane = word
                         const bool lane_ok = lane < pw;
                         const uint32_t *src = x + (size_t)i0 * pitch + w0 + ps * 32 + lane;
                         __syncwarp();
@@ -224,15 +263,8 @@ __global__ void __launch_bounds__(PREP_THREADS, IMPOP_PREP_OCC) prep_rows_kernel
                         __syncwarp();
                     }
                     const uint32_t *mine = tile + lane * PR_TILE;   // compute: lane = row
-                    const bool myseg = (segrows >> lane) & 1u;
                     for (int wd = 0; wd < pw; ++wd) {
                         const uint32_t mk = s_mk[ps * 32 + wd];
-                        if (contig) {
-                            const uint32_t vv = mine[wd];
-                            const uint32_t ra = __reduce_or_sync(0xffffffffu, myseg ? vv : 0u);
-                            const uint32_t rl = __reduce_and_sync(0xffffffffu, myseg ? vv : 0xffffffffu);
-                            if (lane == wd) { any[ps] |= ra; all[ps] &= rl; }
-                        }
                         if (!mk) continue;
                         const uint32_t v = mine[wd];
                         if (mk == 1u) {
