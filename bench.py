@@ -699,7 +699,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             b.close()
     else:
-        nsub = max(1, min(args.sub_batches, W))
+        nsub = max(1, min(args.sub_batches or (4 if world <= 2 else 8), W))
         if nsub < 4:
             cuts = [int(v) for v in np.linspace(0, W, nsub + 1)]
         else:
@@ -928,7 +928,9 @@ def main():
     ap.add_argument("--windows", type=int, default=0, help="windows per GPU (weak) / in total (strong); default: the config's own")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the short measurements of the other BASELINE configs")
-    ap.add_argument("--sub-batches", type=int, default=4, help="e2e leg: sub-batches alternating between two streams (more than ~4 and the host's enqueue time per step, reported as e2e.host_enqueue_ms_per_step, exceeds the copy time)")
+    ap.add_argument("--sub-batches", type=int, default=0,
+                    help="e2e leg: sub-batches alternating between two streams; default 4 on one or two GPUs (with more, the host's enqueue time per step, "
+                         "e2e.host_enqueue_ms_per_step, exceeds the copy time) and 8 on four or eight (the copies share the host's memory bandwidth and are the slower side)")
     ap.add_argument("--transfer", default="tight", choices=["tight", "aligned"],
                     help="e2e leg: presence rows uploaded tight (ceil(m / 32) words, padded on the device by impop_repitch_rows) or as the kernels read them")
     args = ap.parse_args()

@@ -18,7 +18,7 @@ if [ $rc -eq 0 ]; then
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:window_pairs_tc_kernel -c 1 -s 1 -f \
         -o gpurun_out/prof_pairs_${R} python tools/profile_step.py --windows 1184 --reps 2 --compact > gpurun_out/ncu_pairs.log 2>&1
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:prep_rows_kernel -c 1 -s 1 -f \
-        -o gpurun_out/prof_prep_${R} python tools/profile_step.py --windows 1184 --reps 2 --compact > gpurun_out/ncu_prep.log 2>&1
+        -o gpurun_out/prof_prep_${R} python tools/profile_step.py --windows 1184 --reps 2 --compact --full-pitch > gpurun_out/ncu_prep.log 2>&1
   }
 fi
 tail -2 gpurun_out/pytest.log; cat gpurun_out/smoke.log | tail -1; python - <<PY
