@@ -583,13 +583,48 @@ inline uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
-void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const uint32_t *len, uint32_t flags, CompactPlan &pl) {
+// 32 x 32 bit transpose, least significant bit first: out[c] bit r = in[r] bit c.
+inline void transpose32(uint32_t A[32]) {
+    uint32_t m = 0x0000FFFFu;
+    for (int j = 16; j != 0; j >>= 1, m ^= (m << j))
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            const uint32_t t = ((A[k] >> j) ^ A[k + j]) & m;
+            A[k] ^= t << j;
+            A[k + j] ^= t;
+        }
+}
+
+// The window column by column: column k = nb words, bit (i & 31) of word i >> 5 = haplotype i carries node k.
+// (The compaction compares, merges and gathers COLUMNS; the caller's matrix is row-major.)
+struct ColMajor {
+    int nb = 0;
+    uint32_t last_mask = 0xffffffffu;           // valid rows of the last word
+    std::vector<uint32_t> w;
+    const uint32_t *col(int32_t k) const { return w.data() + (size_t)k * nb; }
+    uint32_t mask(int i) const { return i == nb - 1 ? last_mask : 0xffffffffu; }
+};
+
+void to_columns(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, ColMajor &cm) {
     const int words = (m + 31) / 32;
-    std::vector<uint32_t> any((size_t)words, 0u), all((size_t)words, 0xffffffffu);
-    for (int32_t i = 0; i < n; ++i) {
-        const uint32_t *row = x + (size_t)i * pitch;
-        for (int w = 0; w < words; ++w) { any[w] |= row[w]; all[w] &= row[w]; }
+    cm.nb = (n + 31) / 32;
+    cm.last_mask = (n & 31) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+    cm.w.assign((size_t)words * 32 * (size_t)cm.nb, 0u);
+    uint32_t A[32];
+    for (int rb = 0; rb < cm.nb; ++rb) {
+        const int r0 = rb * 32, nr = std::min(32, n - r0);
+        for (int wc = 0; wc < words; ++wc) {
+            for (int r = 0; r < nr; ++r) A[r] = x[(size_t)(r0 + r) * pitch + wc];
+            for (int r = nr; r < 32; ++r) A[r] = 0u;
+            transpose32(A);
+            for (int c = 0; c < 32; ++c) cm.w[((size_t)wc * 32 + c) * cm.nb + rb] = A[c];
+        }
     }
+}
+
+void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const uint32_t *len, uint32_t flags, CompactPlan &pl,
+                  ColMajor &cm) {
+    to_columns(n, m, pitch, x, cm);
+    const int nb = cm.nb;
     pl.cols.clear(); pl.radj.clear();
     pl.c = 0; pl.total = 0; pl.site_runs = 0; pl.bad = false;
     uint64_t const_len = 0;
@@ -597,9 +632,11 @@ void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const 
     bool in_run = false;
     for (int32_t k = 0; k < m; ++k) {
         if (len[k] == 0u) continue;
-        const uint32_t bit = 1u << (k & 31);
-        if (n > 0 && (all[k >> 5] & bit)) { const_len += len[k]; pl.total += len[k]; in_run = false; }
-        else if (any[k >> 5] & bit) {
+        const uint32_t *c = cm.col(k);
+        bool any = false, all = n > 0;
+        for (int i = 0; i < nb; ++i) { any |= c[i] != 0u; all &= c[i] == cm.mask(i); }
+        if (all) { const_len += len[k]; pl.total += len[k]; in_run = false; }
+        else if (any) {
             var.push_back(k);
             pl.total += len[k];
             if (!in_run) { ++pl.site_runs; in_run = true; }
@@ -609,58 +646,47 @@ void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const 
     if (!affine) {
         for (int32_t k : var) pl.cols.push_back(CompactCol{k, len[k], 1});
     } else {
-        // column signatures: h_k = sum of a random 64-bit value per row over the rows that carry k; a column and its
-        // complement add up to the sum over all rows.  Candidates are verified bit by bit.
-        std::vector<uint64_t> h((size_t)m, 0ull);
-        std::vector<uint32_t> vmask((size_t)words, 0u);
-        for (int32_t k : var) vmask[k >> 5] |= 1u << (k & 31);
-        uint64_t tsum = 0;
-        for (int32_t i = 0; i < n; ++i) {
-            const uint64_t r = mix64((uint64_t)i);
-            tsum += r;
-            const uint32_t *row = x + (size_t)i * pitch;
-            for (int w = 0; w < words; ++w) {
-                uint32_t b = row[w] & vmask[w];
-                while (b) { h[(size_t)w * 32 + __builtin_ctz(b)] += r; b &= b - 1; }
-            }
-        }
-        auto related = [&](int32_t a, int32_t b, uint32_t want) {          // want 0: identical columns, 1: complementary
-            const int wa = a >> 5, sa = a & 31, wb = b >> 5, sb = b & 31;
-            for (int32_t i = 0; i < n; ++i) {
-                const uint32_t *row = x + (size_t)i * pitch;
-                if ((((row[wa] >> sa) ^ (row[wb] >> sb)) & 1u) != want) return false;
-            }
+        // column signatures: a hash of the column's words, and of its complement's; candidates are verified word by word
+        auto sig = [&](const uint32_t *c, bool complement) {
+            uint64_t h = 0x243f6a8885a308d3ull;
+            for (int i = 0; i < nb; ++i) h = mix64(h ^ (uint64_t)(complement ? (~c[i] & cm.mask(i)) : c[i]));
+            return h;
+        };
+        auto related = [&](int32_t a, int32_t b, bool complement) {
+            const uint32_t *ca = cm.col(a), *cb = cm.col(b);
+            for (int i = 0; i < nb; ++i)
+                if ((ca[i] ^ cb[i]) != (complement ? cm.mask(i) : 0u)) return false;
             return true;
         };
-        struct Group { int32_t rep; uint64_t len; uint32_t cnt; uint64_t h; bool used; };
+        struct Group { int32_t rep; uint64_t len; uint32_t cnt; bool used; };
         std::vector<Group> groups;
         std::unordered_map<uint64_t, int32_t> by_hash;
         by_hash.reserve(var.size() * 2);
         for (int32_t k : var) {
-            auto it = by_hash.find(h[k]);
+            const uint64_t h = sig(cm.col(k), false);
+            auto it = by_hash.find(h);
             if (it != by_hash.end()) {
                 Group &g = groups[it->second];
-                if (g.cnt < 127u && related(g.rep, k, 0u)) { g.len += len[k]; ++g.cnt; continue; }
-                groups.push_back(Group{k, len[k], 1u, h[k], false});        // same signature, different column: stays alone
+                if (g.cnt < 127u && related(g.rep, k, false)) { g.len += len[k]; ++g.cnt; continue; }
+                groups.push_back(Group{k, len[k], 1u, false});              // same signature, different column: stays alone
                 continue;
             }
-            by_hash.emplace(h[k], (int32_t)groups.size());
-            groups.push_back(Group{k, len[k], 1u, h[k], false});
+            by_hash.emplace(h, (int32_t)groups.size());
+            groups.push_back(Group{k, len[k], 1u, false});
         }
         pl.c = const_len;
         for (size_t gi = 0; gi < groups.size(); ++gi) {
             Group &g = groups[gi];
             if (g.used) continue;
             g.used = true;
-            auto it = by_hash.find(tsum - g.h);
+            auto it = by_hash.find(sig(cm.col(g.rep), true));
             if (it != by_hash.end() && (size_t)it->second != gi) {
                 Group &o = groups[it->second];
-                if (!o.used && related(g.rep, o.rep, 1u)) {
+                if (!o.used && related(g.rep, o.rep, true)) {
                     o.used = true;
-                    pl.cols.push_back(CompactCol{g.rep, 0u, (uint8_t)(g.cnt + o.cnt)});
                     const uint64_t wsum = g.len + o.len;
-                    if (wsum > 0xffffffffull || o.len > 0xffffffffull) { pl.bad = true; return; }
-                    pl.cols.back().w = (uint32_t)wsum;
+                    if (wsum > 0xffffffffull) { pl.bad = true; return; }
+                    pl.cols.push_back(CompactCol{g.rep, (uint32_t)wsum, (uint8_t)(g.cnt + o.cnt)});
                     pl.c += o.len;
                     pl.radj.emplace_back(g.rep, (uint32_t)o.len);
                     continue;
@@ -748,7 +774,8 @@ int impop_compact_scan(int32_t windows, const int32_t *n, const int32_t *m, cons
     std::vector<CompactPlan> plans((size_t)windows);
     for_windows(windows, threads, [&](int32_t w) {
         CompactPlan &pl = plans[w];
-        compact_plan(n[w], m[w], pitch_words[w], x_bits + x_off[w], node_len + len_off[w], flags, pl);
+        ColMajor cm;
+        compact_plan(n[w], m[w], pitch_words[w], x_bits + x_off[w], node_len + len_off[w], flags, pl, cm);
         m_out[w] = pl.m_out;
         if (site_runs_out) site_runs_out[w] = pl.site_runs;
     });
@@ -785,42 +812,46 @@ int impop_compact_fill(int32_t windows, const int32_t *n, const int32_t *m, cons
     std::vector<int> bad((size_t)std::max(windows, 1), 0);
     for_windows(windows, threads, [&](int32_t w) {
         CompactPlan local;
+        ColMajor cm;
         const uint32_t *x = x_bits + x_off[w], *len = node_len + len_off[w];
-        if (cached.empty()) compact_plan(n[w], m[w], pitch_words[w], x, len, flags, local);
+        if (cached.empty()) compact_plan(n[w], m[w], pitch_words[w], x, len, flags, local, cm);
+        else to_columns(n[w], m[w], pitch_words[w], x, cm);
         const CompactPlan &pl = cached.empty() ? local : cached[w];
         const int32_t op = out_pitch_words[w];
         if (pl.bad || (int64_t)op * 32 < pl.m_out || (affine && pl.total >= (1ull << 31))) { bad[w] = 1; return; }
         uint32_t *lo = len_out + out_len_off[w];
-        const int32_t nv = pl.m_out;
+        const int32_t nv = pl.m_out, nn = n[w];
         for (int32_t j = 0; j < nv; ++j) lo[j] = pl.cols[j].w;
         if (col_mult_out) {
             uint8_t *mo = col_mult_out + out_len_off[w];
             for (int32_t j = 0; j < nv; ++j) mo[j] = pl.cols[j].mult;
         }
         if (win_const_out) win_const_out[w] = (int64_t)pl.c;
-        // source (word, shift) per output column, then one pass per row
-        std::vector<uint32_t> sw((size_t)nv), ss((size_t)nv);
-        std::vector<uint8_t> ones((size_t)nv, 0);
-        for (int32_t j = 0; j < nv; ++j) {
-            const int32_t src = pl.cols[j].src;
-            if (src < 0) { ones[j] = 1; sw[j] = 0; ss[j] = 0; }
-            else { sw[j] = (uint32_t)src >> 5; ss[j] = (uint32_t)src & 31u; }
-        }
-        int32_t *ra = row_adj_out ? row_adj_out + out_row_off[w] : nullptr;
-        for (int32_t i = 0; i < n[w]; ++i) {
-            const uint32_t *row = x + (size_t)i * pitch_words[w];
-            uint32_t *out = x_out + out_x_off[w] + (size_t)i * op;
-            int32_t j = 0;
+        // output rows: 32 output columns x 32 rows at a time, gathered as column words and transposed back
+        uint32_t *xo = x_out + out_x_off[w];
+        uint32_t A[32];
+        for (int rb = 0; rb < cm.nb; ++rb) {
+            const int r0 = rb * 32, nr = std::min(32, nn - r0);
             for (int32_t ow = 0; ow < op; ++ow) {
-                uint32_t v = 0u;
-                const int32_t jend = std::min(nv, (ow + 1) * 32);
-                for (; j < jend; ++j) v |= (ones[j] ? 1u : ((row[sw[j]] >> ss[j]) & 1u)) << (j & 31);
-                out[ow] = v;
+                bool nonzero = false;
+                for (int c = 0; c < 32; ++c) {
+                    const int32_t j = ow * 32 + c;
+                    uint32_t v = 0u;
+                    if (j < nv) v = pl.cols[j].src < 0 ? cm.mask(rb) : cm.col(pl.cols[j].src)[rb];
+                    A[c] = v;
+                    nonzero |= v != 0u;
+                }
+                if (nonzero) transpose32(A);
+                for (int r = 0; r < nr; ++r) xo[(size_t)(r0 + r) * op + ow] = A[r];
             }
-            if (ra) {
-                uint32_t r = 0u;
-                for (const auto &pr : pl.radj) r += ((row[(uint32_t)pr.first >> 5] >> (pr.first & 31)) & 1u) * pr.second;
-                ra[i] = (int32_t)r;
+        }
+        if (row_adj_out) {
+            int32_t *ra = row_adj_out + out_row_off[w];
+            for (int32_t i = 0; i < nn; ++i) ra[i] = 0;
+            for (const auto &pr : pl.radj) {
+                const uint32_t *c = cm.col(pr.first);
+                for (int rb = 0; rb < cm.nb; ++rb)
+                    for (uint32_t b = c[rb]; b; b &= b - 1) ra[rb * 32 + __builtin_ctz(b)] += (int32_t)pr.second;
             }
         }
     });
