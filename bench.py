@@ -213,7 +213,7 @@ def make_workload(gen, cfg: dict, windows: int, seed: int, threads: int, keep_or
     x_bytes = int(x_tight.nbytes) if affine else int(xc.nbytes)
     return {"x": xc, "len": lc, "m_out": m_out, "site_runs": site_runs, "pops": pops, "labels": labels_for(cfg["labels"], pops), "n": n, "L": L,
             "row_adj": row_adj, "win_const": win_const, "col_mult": col_mult, "pitch_w": pitch_w, "x_off": x_off, "len_off": len_off,
-            "x_tight": x_tight, "tp_w": tp_w, "xt_off": xt_off,
+            "x_tight": x_tight, "tp_w": tp_w, "xt_off": xt_off, "heavy": heavy.astype(np.int32),
             "m_in": int(m), "m_pad_in": int(m_pad), "pitch": int(pitch_w.max()) if W else 4, "m_pad": int(pitch_w.max()) * 32 if W else 128,
             "planes": planes, "k_exec": k_exec, "ingest_s": t1 - t0, "ingest_threads": threads,
             "plain_x": pl.x if pl is not None else None, "plain_len": pl.node_len if pl is not None else None,
@@ -289,7 +289,8 @@ class DeviceWindows:
                            np.zeros(Wn, dtype=np.int64), np.full(Wn, L), self.x[x0:x1], self.len[l0:l1], labels,
                            node_len_host=None if host is None else host.len[l0:l1], stream=stream,
                            site_runs=wl["site_runs"][lo:hi] if with_runs else None, row_adj=self.row_adj[lo * n:hi * n],
-                           win_const=wl["win_const"][lo:hi], col_mult=self.col_mult[l0:l1])
+                           win_const=wl["win_const"][lo:hi], col_mult=self.col_mult[l0:l1],
+                           heavy_entries=None if wl.get("heavy") is None else wl["heavy"][lo:hi])
 
 
 def item_geometry(n: int):

@@ -31,7 +31,7 @@ class BatchDesc(C.Structure):
     _fields_ = [("windows", _i32), ("n_host", _p), ("m_host", _p), ("pitch_words_host", _p), ("x_off_host", _p),
                 ("len_off_host", _p), ("lab_off_host", _p), ("length_host", _p), ("x_dev", _p), ("node_len_dev", _p),
                 ("labels_dev", _p), ("node_len_host", _p), ("stream", _p), ("site_runs_host", _p),
-                ("row_adj_dev", _p), ("win_const_host", _p), ("col_mult_dev", _p)]
+                ("row_adj_dev", _p), ("win_const_host", _p), ("col_mult_dev", _p), ("heavy_entries_host", _p)]
 
 
 class GfaInfo(C.Structure):

@@ -463,7 +463,12 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     // ---- heavy-entry counts: from the caller's host copy of node_len when given (no synchronisation),
     //      else counted on the device and read back (one stream synchronisation)
     int32_t *cnt = (int32_t *)(hb + o_cnt);
-    if (W > 0 && d->node_len_host) {
+    if (W > 0 && d->heavy_entries_host) {
+        for (int32_t w = 0; w < W; ++w) {
+            if (d->heavy_entries_host[w] < 0) return bail(IMPOP_ERR_ARG, "impop_batch_create: negative heavy_entries_host");
+            cnt[w] = d->heavy_entries_host[w];
+        }
+    } else if (W > 0 && d->node_len_host) {
         // branch-free so that the compiler vectorises it; a few host threads for large batches
         auto count_range = [&](int32_t w0, int32_t w1) {
             for (int32_t w = w0; w < w1; ++w) {

@@ -226,7 +226,7 @@ class WindowBatch:
 
     def __init__(self, ctx: Context, n, m, pitch_words, x_off, len_off, lab_off, length,
                  x: torch.Tensor, node_len: torch.Tensor, labels: torch.Tensor, node_len_host=None, stream=None, site_runs=None,
-                 row_adj=None, win_const=None, col_mult=None):
+                 row_adj=None, win_const=None, col_mult=None, heavy_entries=None):
         self.ctx = ctx
         self.n = np.ascontiguousarray(n, dtype=np.int32)
         self.m = np.ascontiguousarray(m, dtype=np.int32)
@@ -243,10 +243,13 @@ class WindowBatch:
         # constants C (host int64), column multiplicities for S (device uint8, columns at len_off); None: a plain batch
         self.row_adj, self.col_mult = row_adj, col_mult
         self.win_const = None if win_const is None else np.ascontiguousarray(win_const, dtype=np.int64)
+        # heavy_entries: per window, sum over its nodes of ceil(floor(len / 255) / 255), when known from ingest (heavy_entries()
+        # below): batch set-up then skips its host pass over the node lengths
+        self.heavy_entries = None if heavy_entries is None else np.ascontiguousarray(heavy_entries, dtype=np.int32)
         d = N.BatchDesc(self.windows, _ptr(self.n), _ptr(self.m), _ptr(self.pitch_words), _ptr(self.x_off),
                         _ptr(self.len_off), _ptr(self.lab_off), _ptr(self.length), _ptr(x), _ptr(node_len),
                         _ptr(labels), _ptr(node_len_host), _stream_ptr(stream), _ptr(self.site_runs),
-                        _ptr(row_adj), _ptr(self.win_const), _ptr(col_mult))
+                        _ptr(row_adj), _ptr(self.win_const), _ptr(col_mult), _ptr(self.heavy_entries))
         h = C.c_void_p()
         rc = ctx.lib.impop_batch_create(ctx.handle, C.byref(d), C.byref(h))
         if rc != 0:
@@ -256,7 +259,7 @@ class WindowBatch:
     # ------------------------------------------------------------------ constructors
     @classmethod
     def from_uniform(cls, ctx: Context, x_bits, node_len, labels, length, m: int | None = None, node_len_host=None,
-                     stream=None, site_runs=None, row_adj=None, win_const=None, col_mult=None):
+                     stream=None, site_runs=None, row_adj=None, win_const=None, col_mult=None, heavy_entries=None):
         """W same-shape windows: x_bits [W, n, pitch] u32, node_len [W, m_pad] u32, labels [n] or [W, n] u8; m: columns in use,
         one number or one per window (default: all m_pad; columns beyond m must have length 0 and cost nothing when given).
 
@@ -278,7 +281,7 @@ class WindowBatch:
         return cls(ctx, np.full(W, n), m_w, np.full(W, pitch), ar * (n * pitch),
                    ar * m_pad, ar * n if per_window_labels else np.zeros(W, dtype=np.int64), L, xd, ld, lab,
                    node_len_host=node_len_host, stream=stream, site_runs=site_runs, row_adj=row_adj, win_const=win_const,
-                   col_mult=col_mult)
+                   col_mult=col_mult, heavy_entries=heavy_entries)
 
     @classmethod
     def from_windows(cls, ctx: Context, windows, site_runs=None):

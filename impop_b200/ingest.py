@@ -475,10 +475,17 @@ class CompactedUniform:
         device array) is applied to the arrays the batch reads on the device (default: from_uniform uploads them)."""
         sl = slice(lo, hi)
         up = upload or (lambda a: a)
-        kw = {"site_runs": self.site_runs[sl], "m": self.m[sl]}
+        kw = {"site_runs": self.site_runs[sl], "m": self.m[sl], "heavy_entries": heavy_entries(self.node_len[sl])}
         if self.row_adj is not None:
             kw.update(row_adj=up(self.row_adj[sl]), win_const=self.win_const[sl], col_mult=up(self.col_mult[sl]))
         return kw
+
+
+def heavy_entries(node_len: np.ndarray) -> np.ndarray:
+    """Heavy-table entries per window of node lengths [W, m]: sum of ceil(floor(len / 255) / 255) (impop_batch_desc_t
+    heavy_entries_host: with it batch set-up never reads the lengths on the host)."""
+    l = np.asarray(node_len).astype(np.int64)
+    return ((l // 255 + 254) // 255).sum(axis=-1).astype(np.int32)
 
 
 def compact_uniform(x_bits: np.ndarray, node_len: np.ndarray, threads=None, pairs: bool = True, replicate: bool = True) -> CompactedUniform:

@@ -111,6 +111,10 @@ typedef struct {
     const uint8_t *col_mult_dev;     /* per column, offsets len_off_host: how many nodes of positive length the column stands
                                         for in the segregating-node count S (1 = a plain node, 2 = a merged bubble, 0 = a
                                         further copy of a column whose weight was split) */
+    const int32_t *heavy_entries_host; /* optional [windows]: heavy-table entries of each window, sum over its nodes of
+                                        ceil(floor(node_len / 255) / 255), when the caller knows it from ingest: batch set-up
+                                        then never reads node_len on the host.  Too small a number is caught on the
+                                        device (IMPOP_ERR_RANGE at impop_check), a larger one only costs scratch. */
 } impop_batch_desc_t;
 
 int impop_version(void);

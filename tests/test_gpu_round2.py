@@ -245,3 +245,32 @@ def test_repitch_rows(ctx):
         assert np.array_equal(b[:, :sp[w]], a) and not b[:, sp[w]:].any(), w
     with pytest.raises(Exception):
         ctx.repitch_rows(dsrc, ddst, rows, sp, dp - 1, so[:-1], do[:-1])      # destination pitch not a multiple of 4 words
+
+
+def test_heavy_entry_counts_from_the_caller(ctx):
+    """impop_batch_desc_t.heavy_entries_host: with the caller's counts batch set-up skips its pass over the node lengths; the
+    results are the same, and counts that are too small are caught on the device."""
+    from impop_b200 import ingest, synth
+    from impop_b200.engine import WindowBatch
+    from impop_b200._native import NativeError
+    ws = synth.make_windows(40, 20000, 3, seed=21)
+    nl = ws.node_len.copy()
+    nl[:, 5] = 70000                                          # nodes of >= 255 bp: heavy entries
+    nl[1, 9] = 300
+    lab = np.full(40, 9, dtype=np.uint8)
+    ref = WindowBatch.from_uniform(ctx, ws.x_bits, nl, lab, 20000)
+    s0, c0 = ref.stats()
+    ctx.check()
+    he = ingest.heavy_entries(nl)
+    assert he.tolist() == [int(((l.astype(np.int64) // 255 + 254) // 255).sum()) for l in nl] and he.min() >= 2
+    b = WindowBatch.from_uniform(ctx, ws.x_bits, nl, lab, 20000, heavy_entries=he)
+    s1, c1 = b.stats()
+    ctx.check()
+    assert np.array_equal(c0.cpu().numpy(), c1.cpu().numpy())
+    a, bb = s0.cpu().numpy(), s1.cpu().numpy()
+    assert np.array_equal(np.isnan(a), np.isnan(bb)) and np.array_equal(a[~np.isnan(a)], bb[~np.isnan(bb)])
+    bad = WindowBatch.from_uniform(ctx, ws.x_bits, nl, lab, 20000, heavy_entries=np.zeros(3, dtype=np.int32))
+    bad.stats()
+    with pytest.raises(NativeError):
+        ctx.check()
+    ref.close(); b.close(); bad.close()
