@@ -321,7 +321,9 @@ class WindowBatch:
         if affine:
             extra = dict(row_adj=ctx.upload(cat(radj, np.int32)), win_const=np.array(wconst, dtype=np.int64),
                          col_mult=ctx.upload(cat(cmult, np.uint8)))
-        return cls(ctx, n, m, pitch, x_off, len_off, lab_off, L, x, nl, lab, site_runs=site_runs, **extra)
+        # heavy-table sizes from the host copies at hand: batch set-up then needs neither a device pass nor a host pass of its own
+        heavy = np.array([int(((l.astype(np.int64) // 255 + 254) // 255).sum()) for l in ls], dtype=np.int32)
+        return cls(ctx, n, m, pitch, x_off, len_off, lab_off, L, x, nl, lab, site_runs=site_runs, heavy_entries=heavy, **extra)
 
     # ------------------------------------------------------------------ life cycle
     def close(self):

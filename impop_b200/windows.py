@@ -121,8 +121,12 @@ def batch_from_flat(ctx, flat, pop_a_ids=None, pop_b_ids=None, subset_ids=None):
         runs = np.ascontiguousarray(flat.site_runs)
         extra = dict(row_adj=ctx.upload(np.ascontiguousarray(flat.row_adj)), win_const=np.ascontiguousarray(flat.win_const),
                      col_mult=ctx.upload(np.ascontiguousarray(flat.col_mult)), site_runs=runs if (runs >= 0).any() else None)
+    q = (np.asarray(flat.node_len).astype(np.int64) // 255 + 254) // 255        # heavy-table entries per node -> per window
+    csum = np.concatenate([[0], np.cumsum(q)])
+    lo = np.asarray(flat.len_off, dtype=np.int64)
+    heavy = (csum[lo + np.asarray(flat.m, dtype=np.int64)] - csum[lo]).astype(np.int32)
     return WindowBatch(ctx, flat.n, flat.m, flat.pitch, flat.x_off, flat.len_off, flat.row_off, flat.length, x, nl,
-                       ctx.upload(lab), node_len_host=np.ascontiguousarray(flat.node_len), **extra)
+                       ctx.upload(lab), heavy_entries=heavy, **extra)
 
 
 def stats_disjoint_absent(ctx, batch, labels_host, lab_off):

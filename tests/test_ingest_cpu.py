@@ -354,3 +354,29 @@ def test_site_runs_on_hand_built_graphs():
         poly = sum(1 for s in range(K) if 0 < d[:, 2 + 3 * s].sum() < 40)          # sites whose alt allele segregates
         assert similarity.site_runs(d, ws.node_len[w, :ws.m]) == poly
         assert 2 * poly == similarity.segregating_nodes(d, ws.node_len[w, :ws.m])
+
+
+def test_containers_carry_the_affine_form(tmp_path):
+    """A compacted window (affine form) survives both containers: row terms, window constant, column multiplicities and the
+    variant-site count taken on the original node order come back as they went in; a plain window reads back as R = 0,
+    C = 0, multiplicity 1."""
+    ws = synth.make_windows(30, 20000, 3, seed=8)
+    wins = []
+    for w in range(3):
+        g = ingest.GraphWindow(synth.haplotype_names(30, "chr2", 1000 * w, 1000 * w + 20000), ws.x_bits[w], ws.node_len[w, :ws.m].copy(),
+                               None, f"chr2:{1000 * w}-{1000 * w + 20000}", 20000)
+        wins.append(ingest.compact_window(g) if w != 1 else g)               # window 1 stays plain
+    assert wins[0].row_adj is not None and wins[0].win_const > 0 and wins[1].row_adj is None
+    ingest.save_flat(tmp_path / "w.impw", wins)
+    ingest.save_batch(tmp_path / "w.npz", wins)
+    fb = ingest.load_flat(tmp_path / "w.impw")
+    for back in ([fb.window(w) for w in range(3)], ingest.load_batch(tmp_path / "w.npz")):
+        for g, h in zip(wins, back):
+            assert np.array_equal(h.x_bits, g.x_bits) and np.array_equal(h.node_len, g.node_len) and h.names == g.names
+            assert h.site_runs == g.site_runs
+            if g.row_adj is None:
+                assert not np.asarray(h.row_adj).any() and h.win_const == 0 and (np.asarray(h.col_mult) == 1).all()
+            else:
+                assert np.array_equal(h.row_adj, g.row_adj) and h.win_const == g.win_const and np.array_equal(h.col_mult, g.col_mult)
+    he = ingest.heavy_entries(np.array([[0, 254, 255, 510, 65024, 65025, 65026 + 255]], dtype=np.uint32))
+    assert he.tolist() == [0 + 0 + 1 + 1 + 1 + 1 + 2]
