@@ -381,6 +381,8 @@ int impop_batch_create(impop_ctx_t *ctx, const impop_batch_desc_t *d, impop_batc
     }
     if ((any_rows && any_nodes && !d->x_dev) || (any_nodes && !d->node_len_dev) || (any_rows && !d->labels_dev))
         return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: null device array");
+    if (((uintptr_t)d->x_dev & 15u) != 0u)          // rows are read 16 bytes at a time (cp.async in the pairs kernel, uint4 in prep_rows)
+        return fail(ctx, IMPOP_ERR_ARG, "impop_batch_create: x_dev must be 16-byte aligned");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)d->stream;
     // prep row slices: one per window when the batch has enough windows to fill the GPU, else windows are cut

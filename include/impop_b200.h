@@ -92,7 +92,7 @@ typedef struct {
     const int64_t *len_off_host;     /* offset of the window in node_len_dev (elements) */
     const int64_t *lab_off_host;     /* offset of the window in labels_dev (bytes) */
     const int64_t *length_host;      /* BED window length L per window (0 = no per-site normalisation) */
-    const uint32_t *x_dev;
+    const uint32_t *x_dev;           /* 16-byte aligned (rows are read 16 bytes at a time) */
     const uint32_t *node_len_dev;
     const uint8_t *labels_dev;
     const uint32_t *node_len_host;   /* optional host copy of node_len (same offsets): lets batch set-up run without
