@@ -202,16 +202,19 @@ inline bool path_name(char kind, const Line &ln, std::string &out) {
 inline int steps_field(char kind) { return kind == 'P' ? 2 : 6; }
 
 inline uint64_t text_hash(const char *text, int64_t bytes) {
-    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes;
+    uint64_t h0 = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes, h1 = 0xC2B2AE3D27D4EB4Full, h2 = 0x165667B19E3779F9ull, h3 = 0x27D4EB2F165667C5ull;
     int64_t i = 0;
-    for (; i + 8 <= bytes; i += 8) {
-        uint64_t w;
-        memcpy(&w, text + i, 8);
-        h = (h ^ w) * 0xD6E8FEB86659FD93ull;
-        h ^= h >> 29;
+    for (; i + 32 <= bytes; i += 32) {                           // four independent lanes: the multiplies overlap
+        uint64_t w[4];
+        memcpy(w, text + i, 32);
+        h0 = (h0 ^ w[0]) * 0xD6E8FEB86659FD93ull; h0 ^= h0 >> 29;
+        h1 = (h1 ^ w[1]) * 0xD6E8FEB86659FD93ull; h1 ^= h1 >> 29;
+        h2 = (h2 ^ w[2]) * 0xD6E8FEB86659FD93ull; h2 ^= h2 >> 29;
+        h3 = (h3 ^ w[3]) * 0xD6E8FEB86659FD93ull; h3 ^= h3 >> 29;
     }
+    uint64_t h = h0 ^ (h1 * 0x9E3779B97F4A7C15ull) ^ (h2 * 0xBF58476D1CE4E5B9ull) ^ (h3 * 0x94D049BB133111EBull);
     for (; i < bytes; ++i) h = (h ^ (unsigned char)text[i]) * 0x100000001B3ull;
-    return h;
+    return h ^ (h >> 31);
 }
 
 // What impop_gfa_scan found, kept for the impop_gfa_fill that follows on the same thread with the same text (pointer,
@@ -246,9 +249,12 @@ int impop_gfa_scan(const char *text, int64_t bytes, impop_gfa_info_t *info) {
             if (!path_name(kind, ln, name)) { out.error_line = lineno; *info = out; return IMPOP_ERR_ARG; }
             const char *sp, *se;
             if (!field(ln, steps_field(kind), sp, se)) { out.error_line = lineno; *info = out; return IMPOP_ERR_ARG; }
+            // steps by their separators (a loop the compiler vectorises); malformed steps are reported by impop_gfa_fill,
+            // which walks them anyway
             int64_t steps = 0;
-            if (!for_each_step(kind, sp, se, [&](const char *, const char *) { ++steps; return true; })) {
-                out.error_line = lineno; *info = out; return IMPOP_ERR_ARG;
+            if (!(se - sp == 1 && *sp == '*')) {
+                if (kind == 'P') { steps = se > sp ? 1 : 0; for (const char *q = sp; q < se; ++q) steps += *q == ','; }
+                else for (const char *q = sp; q < se; ++q) steps += (*q == '>') | (*q == '<');
             }
             ++out.paths;
             out.name_bytes += (int64_t)name.size() + 1;
@@ -315,8 +321,44 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
         uint32_t *xr = x_bits_host + (size_t)row * (size_t)pitch_words;
         uint16_t *cr = counts_host ? counts_host + (size_t)row * (size_t)info.segments : nullptr;
         const char *sp, *se;
-        field(ln, steps_field(kind), sp, se);
-        const bool ok = for_each_step(kind, sp, se, [&](const char *a, const char *b) {
+        if (!field(ln, steps_field(kind), sp, se)) { if (error_line) *error_line = lineno; return IMPOP_ERR_ARG; }
+        // P line over numbered segments (what graph builders write): digits, sign and comma in ONE pass over the bytes, the
+        // node by array index.  Anything unusual -- a token that is not a canonical number, a missing sign -- and the line is
+        // done again by the general tokenizer below, which decides what is an error.
+        bool done = false;
+        if (kind == 'P' && map.use_direct && !(se - sp == 1 && *sp == '*')) {
+            const char *p = sp;
+            const uint32_t lo = map.lo, span = map.hi - map.lo;
+            const int32_t *direct = map.direct.data();
+            done = true;
+            int32_t cw = -1;                                          // presence word being filled (steps mostly ascend: one
+            uint32_t cbits = 0u;                                      // store per word instead of a read-modify-write per step)
+            while (p < se) {
+                uint32_t v = 0;
+                const char *q = p;
+                unsigned d;
+                while (q < se && (d = (unsigned)(*q - '0')) <= 9u) { v = v * 10u + d; ++q; }
+                const size_t nd = (size_t)(q - p);
+                if (nd == 0 || nd > 9 || (nd > 1 && *p == '0') || q >= se || (*q != '+' && *q != '-') || (q + 1 < se && q[1] != ',')) { done = false; break; }
+                const uint32_t rel = v - lo;
+                const int32_t k = rel <= span ? direct[rel] : -1;
+                if (k < 0) { done = false; break; }
+                if ((k >> 5) != cw) {
+                    if (cw >= 0) xr[cw] |= cbits;
+                    cw = k >> 5;
+                    cbits = 0u;
+                }
+                cbits |= 1u << (k & 31);
+                if (cr && cr[k] != 0xFFFFu) ++cr[k];
+                p = q + 2;                                            // past the sign and the comma (or the end)
+            }
+            if (done && cw >= 0) xr[cw] |= cbits;
+            if (!done) {                                              // start the row over
+                memset(xr, 0, sizeof(uint32_t) * (size_t)pitch_words);
+                if (cr) memset(cr, 0, sizeof(uint16_t) * (size_t)info.segments);
+            }
+        }
+        const bool ok = done || for_each_step(kind, sp, se, [&](const char *a, const char *b) {
             const int32_t k = map.find(a, (size_t)(b - a));
             if (k < 0) return false;                      // step over a segment the file does not define
             xr[k >> 5] |= 1u << (k & 31);
