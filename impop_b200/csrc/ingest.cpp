@@ -798,8 +798,25 @@ struct PlanCache {
     const void *x = nullptr, *len = nullptr;
     int32_t windows = -1;
     uint32_t flags = 0;
+    uint64_t key = 0;                // content of the descriptor arrays, of every node length and of a sample of the presence words
     std::vector<CompactPlan> plans;
 } g_plan_cache;
+
+// Guard of the plan cache: pointers and sizes alone would accept another batch that happens to live at the same addresses.
+uint64_t batch_key(int32_t windows, const int32_t *n, const int32_t *m, const int32_t *pitch_words, const int64_t *x_off,
+                   const int64_t *len_off, const uint32_t *x_bits, const uint32_t *node_len) {
+    uint64_t h = text_hash((const char *)n, 4 * (int64_t)windows) ^ mix64(text_hash((const char *)m, 4 * (int64_t)windows)) ^
+                 mix64(text_hash((const char *)pitch_words, 4 * (int64_t)windows) + 1) ^ mix64(text_hash((const char *)x_off, 8 * (int64_t)windows) + 2) ^
+                 mix64(text_hash((const char *)len_off, 8 * (int64_t)windows) + 3);
+    for (int32_t w = 0; w < windows; ++w) {
+        h = mix64(h ^ text_hash((const char *)(node_len + len_off[w]), 4 * (int64_t)m[w]));
+        if (n[w] > 0 && pitch_words[w] > 0) {                       // first and last row of the window
+            h = mix64(h ^ text_hash((const char *)(x_bits + x_off[w]), 4 * (int64_t)pitch_words[w]));
+            h = mix64(h ^ text_hash((const char *)(x_bits + x_off[w] + (int64_t)(n[w] - 1) * pitch_words[w]), 4 * (int64_t)pitch_words[w]));
+        }
+    }
+    return h;
+}
 
 }  // namespace
 
@@ -826,6 +843,7 @@ int impop_compact_scan(int32_t windows, const int32_t *n, const int32_t *m, cons
     {
         std::lock_guard<std::mutex> lk(g_plan_cache.mu);
         g_plan_cache.x = x_bits; g_plan_cache.len = node_len; g_plan_cache.windows = windows; g_plan_cache.flags = flags;
+        g_plan_cache.key = batch_key(windows, n, m, pitch_words, x_off, len_off, x_bits, node_len);
         g_plan_cache.plans.swap(plans);
     }
     return bad ? IMPOP_ERR_RANGE : IMPOP_OK;
@@ -846,7 +864,8 @@ int impop_compact_fill(int32_t windows, const int32_t *n, const int32_t *m, cons
     {
         std::lock_guard<std::mutex> lk(g_plan_cache.mu);
         if (g_plan_cache.x == x_bits && g_plan_cache.len == node_len && g_plan_cache.windows == windows &&
-            g_plan_cache.flags == flags && (int32_t)g_plan_cache.plans.size() == windows) {
+            g_plan_cache.flags == flags && (int32_t)g_plan_cache.plans.size() == windows &&
+            g_plan_cache.key == batch_key(windows, n, m, pitch_words, x_off, len_off, x_bits, node_len)) {
             cached.swap(g_plan_cache.plans);
             g_plan_cache.windows = -1;
         }

@@ -380,3 +380,34 @@ def test_containers_carry_the_affine_form(tmp_path):
                 assert np.array_equal(h.row_adj, g.row_adj) and h.win_const == g.win_const and np.array_equal(h.col_mult, g.col_mult)
     he = ingest.heavy_entries(np.array([[0, 254, 255, 510, 65024, 65025, 65026 + 255]], dtype=np.uint32))
     assert he.tolist() == [0 + 0 + 1 + 1 + 1 + 1 + 2]
+
+
+def test_compaction_plan_cache_is_guarded_by_content():
+    """impop_compact_fill reuses the plans of the preceding impop_compact_scan only for the same CONTENT: a batch changed in
+    place between the two calls (same addresses, same sizes) is planned again."""
+    from impop_b200._native import lib, COMPACT_PAIRS, COMPACT_REPLICATE
+    L = lib()
+    rng = np.random.default_rng(3)
+    xa, nla = _bubble_window(rng, 40, 12, 4)
+    xb, nlb = _bubble_window(rng, 40, 12, 4)
+    assert xa.shape == xb.shape
+    bits = similarity.pack_bits(xa).copy()
+    nl = nla.copy()
+    n, m, pitch = np.array([40], np.int32), np.array([xa.shape[1]], np.int32), np.array([bits.shape[1]], np.int32)
+    zero = np.zeros(1, np.int64)
+    flags = COMPACT_PAIRS | COMPACT_REPLICATE
+    m_out, runs = np.zeros(1, np.int32), np.zeros(1, np.int64)
+    assert L.impop_compact_scan(1, n.ctypes.data, m.ctypes.data, pitch.ctypes.data, zero.ctypes.data, zero.ctypes.data, bits.ctypes.data,
+                                nl.ctypes.data, 1, flags, m_out.ctypes.data, runs.ctypes.data) == 0
+    bits[:] = similarity.pack_bits(xb)                      # another window at the same addresses
+    nl[:] = nlb
+    want = ingest.compact_window(ingest.GraphWindow([f"h{i}" for i in range(40)], similarity.pack_bits(xb), nlb))
+    op = np.array([max(4, (max(int(m_out[0]), want.m) + 127) // 128 * 4)], np.int32)
+    x_out, len_out = np.zeros(40 * int(op[0]), np.uint32), np.zeros(32 * int(op[0]), np.uint32)
+    ra, wc, cmult = np.zeros(40, np.int32), np.zeros(1, np.int64), np.zeros(32 * int(op[0]), np.uint8)
+    assert L.impop_compact_fill(1, n.ctypes.data, m.ctypes.data, pitch.ctypes.data, zero.ctypes.data, zero.ctypes.data, bits.ctypes.data,
+                                nl.ctypes.data, 1, flags, op.ctypes.data, zero.ctypes.data, zero.ctypes.data, x_out.ctypes.data,
+                                len_out.ctypes.data, zero.ctypes.data, ra.ctypes.data, wc.ctypes.data, cmult.ctypes.data) == 0
+    assert np.array_equal(len_out[:want.m], want.node_len) and not len_out[want.m:].any()
+    assert int(wc[0]) == want.win_const and np.array_equal(ra, want.row_adj)
+    assert np.array_equal(x_out.reshape(40, -1)[:, :want.x_bits.shape[1]], want.x_bits)
