@@ -514,3 +514,31 @@ def compact_window(win: GraphWindow, pairs: bool = True, replicate: bool = True)
     if pairs:
         out.row_adj, out.win_const, out.col_mult = c.row_adj.copy(), int(c.win_const[0]), c.col_mult[:mo].copy()
     return out
+
+
+def compact_windows(windows, threads=None, pairs: bool = True, replicate: bool = True) -> list:
+    """A list of GraphWindows -> their compacted forms, all windows in ONE native call that spreads them over the host
+    threads (compact_window one by one is a Python loop on one core: seconds per chromosome)."""
+    windows = list(windows)
+    if not windows:
+        return []
+    n = np.array([w.n for w in windows], dtype=np.int32)
+    m = np.array([w.m for w in windows], dtype=np.int32)
+    pitch = np.array([w.x_bits.shape[1] for w in windows], dtype=np.int32)
+    xs = n.astype(np.int64) * pitch
+    x_off = np.concatenate([[0], np.cumsum(xs)[:-1]]).astype(np.int64)
+    len_off = np.concatenate([[0], np.cumsum(m.astype(np.int64))[:-1]]).astype(np.int64)
+    x = np.concatenate([np.ascontiguousarray(w.x_bits, dtype=np.uint32).reshape(-1) for w in windows]) if xs.sum() else np.zeros(4, np.uint32)
+    nl = np.concatenate([np.asarray(w.node_len, dtype=np.uint32) for w in windows]) if m.sum() else np.zeros(4, np.uint32)
+    c = compact_batch(n, m, pitch, x_off, len_off, x, nl, threads=threads, pairs=pairs, replicate=replicate)
+    out = []
+    for k, w in enumerate(windows):
+        mo, po, nn = int(c.m_out[k]), int(c.pitch_out[k]), int(n[k])
+        xo, lo = int(c.x_off_out[k]), int(c.len_off_out[k])
+        g = GraphWindow(list(w.names), c.x_out[xo:xo + nn * po].reshape(nn, po), c.len_out[lo:lo + mo], None, w.region, w.length)
+        g.site_runs = int(c.site_runs[k])
+        if pairs:
+            ro = int(c.row_off_out[k])
+            g.row_adj, g.win_const, g.col_mult = c.row_adj[ro:ro + nn], int(c.win_const[k]), c.col_mult[lo:lo + mo]
+        out.append(g)
+    return out

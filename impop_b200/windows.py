@@ -236,7 +236,7 @@ def main(argv=None):
                 graphs = [ingest.multiset_expand(g) if (g.counts is not None and g.counts.size and int(g.counts.max()) > 1) else g
                           for g in graphs]
         if not args.no_compact:
-            graphs = [ingest.compact_window(g) for g in graphs]
+            graphs = ingest.compact_windows(graphs)           # one native call, all host threads
         mark("ingest")
     if args.save_batch:
         src_graphs = graphs if graphs is not None else [flat.window(w) for w in range(flat.windows)]

@@ -411,3 +411,23 @@ def test_compaction_plan_cache_is_guarded_by_content():
     assert np.array_equal(len_out[:want.m], want.node_len) and not len_out[want.m:].any()
     assert int(wc[0]) == want.win_const and np.array_equal(ra, want.row_adj)
     assert np.array_equal(x_out.reshape(40, -1)[:, :want.x_bits.shape[1]], want.x_bits)
+
+
+def test_compact_windows_equals_one_by_one():
+    """ingest.compact_windows (one native call over a ragged list, all host threads) gives what compact_window gives."""
+    rng = np.random.default_rng(17)
+    wins = []
+    for n, sites, extra in ((5, 3, 2), (40, 30, 6), (1, 2, 0), (130, 60, 40), (0, 1, 1)):
+        x, nl = _bubble_window(rng, n, sites, extra, heavy=n > 30)
+        wins.append(ingest.GraphWindow([f"h{i}" for i in range(n)], similarity.pack_bits(x) if n else np.zeros((0, 4), np.uint32), nl, None, f"r{n}", 1000 + n))
+    for pairs in (True, False):
+        many = ingest.compact_windows(wins, threads=3, pairs=pairs)
+        for w, g in zip(wins, many):
+            one = ingest.compact_window(w, pairs=pairs)
+            assert g.m == one.m and g.names == one.names and g.region == one.region and g.length == one.length and g.site_runs == one.site_runs
+            assert np.array_equal(g.x_bits, one.x_bits) and np.array_equal(g.node_len, one.node_len)
+            if pairs:
+                assert np.array_equal(g.row_adj, one.row_adj) and g.win_const == one.win_const and np.array_equal(g.col_mult, one.col_mult)
+            else:
+                assert g.row_adj is None
+    assert ingest.compact_windows([]) == []
