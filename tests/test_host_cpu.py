@@ -192,3 +192,30 @@ def test_pooled_fst_text_matches_the_wrapper_snippets():
     for a, b, c, avg, fst in cases:
         assert windows.pooled_fst_text(a, b, c) == (avg, fst)
         assert popstats.pooled_fst_text(a, b, c) == (avg, fst)
+
+
+def test_bench_workload_forms_agree():
+    """bench.make_workload on the host generator: the affine form it hands to the GPU arm, the tight transfer rows of the
+    end-to-end leg and the plain form the CPU oracle is given describe the same windows."""
+    import bench
+    from impop_b200 import synth
+    from oracle import similarity
+    cfg = dict(bench.CONFIGS[2])
+    wl = bench.make_workload(synth.HostGenerator(), cfg, 6, 11, 2, keep_original=6, plain=6)
+    n = wl["n"]
+    assert wl["x_off"].shape == (7,) and wl["xt_off"].shape == (7,) and (wl["xt_off"] % 32 == 0).all() and (wl["pitch_w"] % 4 == 0).all()
+    for w in range(6):
+        pw, tw, mo = int(wl["pitch_w"][w]), int(wl["tp_w"][w]), int(wl["m_out"][w])
+        assert tw == max(1, (mo + 31) // 32) and pw * 32 >= mo
+        a = wl["x"][wl["x_off"][w]:wl["x_off"][w + 1]].reshape(n, pw)
+        t = wl["x_tight"][wl["xt_off"][w]:wl["xt_off"][w] + n * tw].reshape(n, tw)
+        assert np.array_equal(a[:, :tw], t) and not a[:, tw:].any()
+        lens = wl["len"][wl["len_off"][w]:wl["len_off"][w + 1]]
+        assert int(wl["heavy"][w]) == int(((lens.astype(np.int64) // 255 + 254) // 255).sum()) and not lens[mo:].any()
+        # affine form == original window == plain form (intersections and pi_ij, bit for bit)
+        orig = similarity.pairwise(similarity.unpack_bits(wl["orig_x"][w], wl["m_pad_in"]), wl["orig_len"][w])
+        aff = similarity.pairwise_affine(similarity.unpack_bits(a, mo), lens[:mo], wl["row_adj"][w * n:(w + 1) * n], wl["win_const"][w])
+        pl = similarity.pairwise(similarity.unpack_bits(wl["plain_x"][w], wl["plain_len"].shape[1]), wl["plain_len"][w])
+        for other in (aff, pl):
+            assert np.array_equal(orig["I"], other["I"]) and np.array_equal(orig["pi"], other["pi"])
+    assert wl["bytes_out"] < wl["bytes_in"] // 2
