@@ -274,3 +274,37 @@ def test_heavy_entry_counts_from_the_caller(ctx):
     with pytest.raises(NativeError):
         ctx.check()
     ref.close(); b.close(); bad.close()
+
+
+def test_affine_window_without_columns(ctx):
+    """A window whose nodes every haplotype visits (and one that loses all but a bubble): the affine form has no column
+    left -- everything is in the window constant -- and still gives the plain batch's rows."""
+    from impop_b200 import ingest
+    from impop_b200.engine import ALGO_SIMT, ALGO_TCGEN05, WindowBatch
+    from oracle import similarity
+    lab = np.array([9, 11, 13, 9, 11, 13], dtype=np.uint8)
+    xs = [np.ones((6, 4), np.uint8),
+          np.array([[1, 1, 0, 1], [1, 0, 1, 1], [1, 1, 0, 1], [1, 0, 1, 1], [1, 1, 0, 1], [1, 1, 0, 1]], np.uint8)]
+    nls = [np.array([3, 5, 7, 0], np.uint32), np.array([100, 1, 1, 50], np.uint32)]
+    plain, aff = [], []
+    for x, nl in zip(xs, nls):
+        bits = similarity.pack_bits(x)
+        plain.append((bits, nl, lab, 200))
+        g = ingest.compact_window(ingest.GraphWindow([f"h{i}" for i in range(6)], bits, nl))
+        aff.append((g.x_bits, g.node_len, lab, 200, g.row_adj, g.win_const, g.col_mult))
+    assert aff[0][1].shape[0] == 0 and aff[0][5] == 15 and aff[1][1].tolist() == [2] and aff[1][5] == 151
+    a, b = WindowBatch.from_windows(ctx, plain), WindowBatch.from_windows(ctx, aff)
+    for algo in (ALGO_TCGEN05, ALGO_SIMT):
+        sa, ca = a.stats(algo)
+        sb, cb = b.stats(algo)
+        ctx.check()
+        assert np.array_equal(ca.cpu().numpy(), cb.cpu().numpy())
+        sa, sb = sa.cpu().numpy()[:, :19], sb.cpu().numpy()[:, :19]
+        assert np.array_equal(np.isnan(sa), np.isnan(sb)) and np.array_equal(sa[~np.isnan(sa)], sb[~np.isnan(sb)])
+        for w in range(2):
+            I0, A0, p0 = a.pairwise(w, algo)
+            I1, A1, p1 = b.pairwise(w, algo)
+            ctx.check()
+            assert np.array_equal(I0.cpu().numpy(), I1.cpu().numpy()) and np.array_equal(A0.cpu().numpy(), A1.cpu().numpy())
+            assert np.array_equal(p0.cpu().numpy(), p1.cpu().numpy())
+    a.close(); b.close()
