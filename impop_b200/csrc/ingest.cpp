@@ -709,9 +709,11 @@ void compact_plan(int32_t n, int32_t m, int32_t pitch, const uint32_t *x, const 
             auto it = by_hash.find(h);
             if (it != by_hash.end()) {
                 Group &g = groups[it->second];
-                if (g.cnt < 127u && related(g.rep, k, false)) { g.len += len[k]; ++g.cnt; continue; }
-                groups.push_back(Group{k, len[k], 1u, false});              // same signature, different column: stays alone
-                continue;
+                const bool same = related(g.rep, k, false);
+                if (same && g.cnt < 127u) { g.len += len[k]; ++g.cnt; continue; }
+                groups.push_back(Group{k, len[k], 1u, false});
+                if (same) it->second = (int32_t)groups.size() - 1;          // the group is full: further copies join its successor
+                continue;                                                   // (same signature, different column: stays alone)
             }
             by_hash.emplace(h, (int32_t)groups.size());
             groups.push_back(Group{k, len[k], 1u, false});

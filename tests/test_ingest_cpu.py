@@ -431,3 +431,22 @@ def test_compact_windows_equals_one_by_one():
             else:
                 assert g.row_adj is None
     assert ingest.compact_windows([]) == []
+
+
+def test_affine_compaction_with_hundreds_of_identical_columns():
+    """More identical columns than one multiplicity byte can count: they are merged in groups of at most 127 (a pair of
+    complementary groups: 254), and every count stays exact."""
+    rng = np.random.default_rng(5)
+    n = 20
+    a = (rng.random(n) < 0.4).astype(np.uint8)
+    a[0], a[1] = 0, 1
+    cols = [a] * 300 + [1 - a] * 290 + [(rng.random(n) < 0.5).astype(np.uint8)]
+    x = np.stack(cols, axis=1)
+    nl = rng.integers(1, 9, size=x.shape[1]).astype(np.uint32)
+    got = ingest.compact_window(ingest.GraphWindow([f"h{i}" for i in range(n)], similarity.pack_bits(x), nl))
+    x2 = similarity.unpack_bits(got.x_bits, got.m)
+    assert got.col_mult.max() <= 254 and int(got.col_mult.sum()) == x.shape[1]        # every node of positive length is counted once
+    a0, b0 = similarity.pairwise(x, nl), similarity.pairwise_affine(x2, got.node_len, got.row_adj, got.win_const)
+    assert np.array_equal(a0["I"], b0["I"]) and np.array_equal(a0["A"], b0["A"]) and np.array_equal(a0["pi"], b0["pi"])
+    assert similarity.segregating_nodes(x, nl) == similarity.segregating_nodes_affine(x2, got.node_len, got.col_mult)
+    assert int((got.col_mult > 0).sum()) <= 6              # 3 + 3 groups, one pair merged, + the unrelated column (the rest: copies of split weights)
