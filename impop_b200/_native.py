@@ -77,7 +77,7 @@ SIGNATURES = {
     "impop_tsv_scan": (C.c_int, [C.c_char_p, _i64, C.POINTER(TsvInfo)]),
     "impop_tsv_fill": (C.c_int, [C.c_char_p, _i64, _p, _p, _p]),
     "impop_gfa_scan": (C.c_int, [C.c_char_p, _i64, C.POINTER(GfaInfo)]),
-    "impop_gfa_fill": (C.c_int, [C.c_char_p, _i64, _i32, _p, _p, _p, _p, _p, C.POINTER(_i64)]),
+    "impop_gfa_fill": (C.c_int, [C.c_char_p, _i64, _i32, _p, _p, _p, _p, _p, C.POINTER(_i64), C.POINTER(_i32)]),
     "impop_compact_scan": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32, C.c_uint32, _p, _p]),
     "impop_compact_fill": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _i32, C.c_uint32, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }

@@ -267,8 +267,10 @@ int impop_gfa_scan(const char *text, int64_t bytes, impop_gfa_info_t *info) {
 }
 
 int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_t *x_bits_host, uint32_t *node_len_host,
-                   uint16_t *counts_host, char *names_host, int64_t *name_off_host, int64_t *error_line) {
+                   uint16_t *counts_host, char *names_host, int64_t *name_off_host, int64_t *error_line, int32_t *revisits) {
     if (error_line) *error_line = 0;
+    if (revisits) *revisits = 0;
+    bool revisit = false;
     if (!text || bytes < 0 || pitch_words < 0 || pitch_words % 4 != 0) return IMPOP_ERR_ARG;
     impop_gfa_info_t info;
     if (g_gfa_memo.text == text && g_gfa_memo.bytes == bytes && g_gfa_memo.hash == text_hash(text, bytes)) {
@@ -331,8 +333,9 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
             const uint32_t lo = map.lo, span = map.hi - map.lo;
             const int32_t *direct = map.direct.data();
             done = true;
+            const bool revisit_before = revisit;
             int32_t cw = -1;                                          // presence word being filled (steps mostly ascend: one
-            uint32_t cbits = 0u;                                      // store per word instead of a read-modify-write per step)
+            uint32_t cbits = 0u;                                      // load and one store per word instead of a read-modify-write per step)
             while (p < se) {
                 uint32_t v = 0;
                 const char *q = p;
@@ -344,16 +347,18 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
                 const int32_t k = rel <= span ? direct[rel] : -1;
                 if (k < 0) { done = false; break; }
                 if ((k >> 5) != cw) {
-                    if (cw >= 0) xr[cw] |= cbits;
+                    if (cw >= 0) xr[cw] = cbits;
                     cw = k >> 5;
-                    cbits = 0u;
+                    cbits = xr[cw];
                 }
+                revisit |= (cbits >> (k & 31)) & 1u;                  // the path has been here before
                 cbits |= 1u << (k & 31);
                 if (cr && cr[k] != 0xFFFFu) ++cr[k];
                 p = q + 2;                                            // past the sign and the comma (or the end)
             }
-            if (done && cw >= 0) xr[cw] |= cbits;
+            if (done && cw >= 0) xr[cw] = cbits;
             if (!done) {                                              // start the row over
+                revisit = revisit_before;
                 memset(xr, 0, sizeof(uint32_t) * (size_t)pitch_words);
                 if (cr) memset(cr, 0, sizeof(uint16_t) * (size_t)info.segments);
             }
@@ -361,6 +366,7 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
         const bool ok = done || for_each_step(kind, sp, se, [&](const char *a, const char *b) {
             const int32_t k = map.find(a, (size_t)(b - a));
             if (k < 0) return false;                      // step over a segment the file does not define
+            revisit |= (xr[k >> 5] >> (k & 31)) & 1u;
             xr[k >> 5] |= 1u << (k & 31);
             if (cr && cr[k] != 0xFFFFu) ++cr[k];
             return true;
@@ -369,6 +375,7 @@ int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_
         ++row;
     }
     if (info.paths) name_off_host[row] = off;
+    if (revisits) *revisits = revisit ? 1 : 0;
     return IMPOP_OK;
 }
 

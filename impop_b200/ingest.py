@@ -31,6 +31,7 @@ class GraphWindow:
     row_adj: np.ndarray | None = None   # affine form (compact_window): R_i [n] int32, window constant C, column multiplicities [m] uint8
     win_const: int = 0
     col_mult: np.ndarray | None = None
+    revisits: bool = False  # some path visits a node more than once (reported by the reader; multiset coverage then differs from presence)
 
     @property
     def n(self) -> int:
@@ -45,9 +46,11 @@ def _pitch_for(m: int) -> int:
     return max(4, ((m + 127) // 128) * 4)
 
 
-def parse_gfa(text, want_counts: bool = False, region: str | None = None, length: int = 0) -> GraphWindow:
+def parse_gfa(text, want_counts=False, region: str | None = None, length: int = 0) -> GraphWindow:
     """GFA v1 text (bytes / str / path-like object with .read) -> GraphWindow.  Raises NativeError with the
-    offending line number on malformed input."""
+    offending line number on malformed input.  want_counts: True / False, or "auto" = visit counts only when some path
+    revisits a node (the window is then read a second time: rare, and a chromosome's worth of count matrices is
+    gigabytes)."""
     if hasattr(text, "read"):
         text = text.read()
     if isinstance(text, str):
@@ -61,26 +64,30 @@ def parse_gfa(text, want_counts: bool = False, region: str | None = None, length
     pitch = _pitch_for(m)
     x = np.zeros((n, pitch), dtype=np.uint32)
     node_len = np.zeros(m, dtype=np.uint32)
-    counts = np.zeros((n, m), dtype=np.uint16) if want_counts else None
+    counts = np.zeros((n, m), dtype=np.uint16) if want_counts is True else None
     names_buf = np.zeros(max(int(info.name_bytes), 1), dtype=np.uint8)
     name_off = np.zeros(n + 1, dtype=np.int64)
-    err_line = C.c_int64(0)
+    err_line, revisits = C.c_int64(0), C.c_int32(0)
     rc = L.impop_gfa_fill(text, len(text), pitch, x.ctypes.data, node_len.ctypes.data,
                           counts.ctypes.data if counts is not None else None, names_buf.ctypes.data,
-                          name_off.ctypes.data, C.byref(err_line))
+                          name_off.ctypes.data, C.byref(err_line), C.byref(revisits))
     if rc:
         raise NativeError(rc, "impop_gfa_fill", f"malformed GFA at line {err_line.value}")
+    if want_counts == "auto" and revisits.value:
+        return parse_gfa(text, True, region, length)
     raw = names_buf.tobytes()
     names = [raw[name_off[i]:name_off[i + 1] - 1].decode() for i in range(n)]
-    return GraphWindow(names, x, node_len, counts, region, int(length))
+    win = GraphWindow(names, x, node_len, counts, region, int(length))
+    win.revisits = bool(revisits.value)
+    return win
 
 
-def read_gfa(path, want_counts: bool = False, region: str | None = None, length: int = 0) -> GraphWindow:
+def read_gfa(path, want_counts=False, region: str | None = None, length: int = 0) -> GraphWindow:
     with open(path, "rb") as fh:
         return parse_gfa(fh.read(), want_counts, region, length)
 
 
-def read_gfa_many(items, threads: int | None = None, want_counts: bool = False) -> list:
+def read_gfa_many(items, threads: int | None = None, want_counts=False) -> list:
     """[(region, path, length), ...] -> [GraphWindow, ...] in the same order.  The native reader runs outside the GIL
     (ctypes), so the window graphs of a chromosome are parsed on all host cores; `threads=1` reads one by one."""
     import os

@@ -226,7 +226,7 @@ def main(argv=None):
                 todo.append((region, path, int(mt.group(2)) - int(mt.group(1)) if mt else 0))
         # parsed on all host cores (the reader runs outside the GIL), visit counts kept: a path that revisits a node
         # (duplication, inversion, loop) contributes min(count_a, count_b) * len to an intersection
-        graphs = ingest.read_gfa_many(todo, want_counts=not args.presence_only)
+        graphs = ingest.read_gfa_many(todo, want_counts=False if args.presence_only else "auto")   # counts only where a path revisits a node
         mark("parse")
         if not args.presence_only:
             revisits = sum(1 for g in graphs if g.counts is not None and g.counts.size and int(g.counts.max()) > 1)

@@ -256,9 +256,11 @@ int impop_gfa_scan(const char *text, int64_t bytes, impop_gfa_info_t *info);
 /* Caller-owned host buffers sized from impop_gfa_scan: x_bits [paths x pitch_words] u32 (pitch_words a multiple of 4,
  * 32 * pitch_words >= segments; zeroed here), node_len [segments], names [name_bytes] with name_off [paths + 1],
  * counts (optional, may be NULL) [paths x segments] u16 = how often the path visits the node (saturating; the
- * multiset coverage a cyclic graph needs). */
+ * multiset coverage a cyclic graph needs).  revisits (optional): set to 1 when some path visits a node more than once,
+ * else 0 -- a reader that wants visit counts only for such windows parses without them first (a chromosome's worth of
+ * count matrices is gigabytes). */
 int impop_gfa_fill(const char *text, int64_t bytes, int32_t pitch_words, uint32_t *x_bits_host, uint32_t *node_len_host,
-                   uint16_t *counts_host, char *names_host, int64_t *name_off_host, int64_t *error_line);
+                   uint16_t *counts_host, char *names_host, int64_t *name_off_host, int64_t *error_line, int32_t *revisits);
 
 /* ---- Ingest (host side, no device work): column compaction of a batch of windows ---------------------------------
  * The similarity tools walk paths (run_pica2_odgi.sh:96 `odgi similarity -i tmp.gfa`, run_h-fst.sh:65-67); a presence

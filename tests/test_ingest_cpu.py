@@ -450,3 +450,21 @@ def test_affine_compaction_with_hundreds_of_identical_columns():
     assert np.array_equal(a0["I"], b0["I"]) and np.array_equal(a0["A"], b0["A"]) and np.array_equal(a0["pi"], b0["pi"])
     assert similarity.segregating_nodes(x, nl) == similarity.segregating_nodes_affine(x2, got.node_len, got.col_mult)
     assert int((got.col_mult > 0).sum()) <= 6              # 3 + 3 groups, one pair merged, + the unrelated column (the rest: copies of split weights)
+
+
+def test_reader_reports_revisits_and_auto_counts():
+    """impop_gfa_fill tells whether some path visits a node more than once; want_counts="auto" then reads the visit counts
+    only for such windows (P and W lines, named and numbered segments, a revisit far from the first visit)."""
+    plain = "S\t1\tAC\nS\t2\tG\nS\t3\tTT\nP\ta\t1+,2+,3+\t*\nP\tb\t1+,3+\t*\n"
+    loop = "S\t1\tAC\nS\t2\tG\nS\t3\tTT\nP\ta\t1+,2+,3+,1-\t*\nP\tb\t1+,3+\t*\n"
+    walk = "S\ts1\tAC\nS\ts2\tG\nW\tx\t1\tc\t0\t5\t>s1>s2<s1\n"
+    big = "".join(f"S\t{k}\tA\n" for k in range(1, 200)) + "P\tp\t" + ",".join(f"{k}+" for k in list(range(1, 200)) + [7]) + "\t*\n"
+    for text, want in ((plain, False), (loop, True), (walk, True), (big, True)):
+        g = ingest.parse_gfa(text)
+        assert g.revisits is want and g.counts is None
+        a = ingest.parse_gfa(text, want_counts="auto")
+        assert a.revisits is want and (a.counts is not None) is want
+        if want:
+            full = ingest.parse_gfa(text, want_counts=True)
+            assert np.array_equal(a.counts, full.counts) and int(a.counts.max()) == 2
+        assert np.array_equal(a.x_bits, g.x_bits)
